@@ -1,0 +1,229 @@
+/*
+ * b200_sixdof.h — C ABI of the B200-native 6DOF rigid-body integrator.
+ *
+ * This library replaces, on the six_dof() hot path only, the executor seam of
+ * elodin-sys/elodin's nox-py host:
+ *
+ *   enum WorldExec { Jax, Cranelift }            libs/nox-py/src/exec.rs:53-94
+ *   CraneliftExec::invoke_batch(world, n, ..)    libs/nox-py/src/cranelift_exec.rs:129-195
+ *   type TickFn = unsafe extern "C" fn(*const *const u8, *mut *mut u8)
+ *                                                libs/nox-py/src/cranelift_exec.rs:11
+ *   ExecMetadata{arg_ids, ret_ids, arg_slots}    libs/nox-py/src/exec.rs:18-29
+ *
+ * Everything below is plain C: opaque handle, POD descriptors, raw pointers and
+ * sizes.  No C++/torch types cross the boundary; no exceptions cross it either
+ * (every entry point returns an int status, 0 = ok, message via b200_last_error()).
+ *
+ * Data model (mirrors libs/nox-py/src/world.rs:25-29 `Column{buffer, entity_ids}`):
+ *   a column is a dense little-endian f64 array [n_worlds][n_entities][width],
+ *   row i of a world = i-th spawned entity that owns the component.  The
+ *   reference has no world axis (one OS process per Monte-Carlo world,
+ *   libs/monte-carlo/src/lib.rs:2083); n_worlds = 1 reproduces its layout
+ *   byte for byte.  Columns are addressed by ComponentId = FNV-1a-64(name) with
+ *   bit 63 cleared (libs/impeller2/src/types.rs:36-45).
+ *
+ * On the device every column is stored SoA: `width` planes of
+ * n_worlds*n_entities doubles each (body index b = world*n_entities + entity).
+ *
+ * Threading: a handle is single-thread-affine, like the reference executor
+ * ("moved once, never shared", cranelift_exec.rs:31-51).  One handle per GPU.
+ */
+#ifndef B200_SIXDOF_H
+#define B200_SIXDOF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_SIXDOF_ABI_VERSION 1u
+
+/* ---- status codes (0 = ok).  Names follow libs/nox-py/src/error.rs:7-44 ---- */
+enum {
+    B200_OK = 0,
+    B200_ERR_COMPONENT_NOT_FOUND = 1, /* Error::ComponentNotFound            */
+    B200_ERR_VALUE_SIZE_MISMATCH = 2, /* Error::ValueSizeMismatch            */
+    B200_ERR_INVALID_ARGUMENT = 3,    /* Error::UnexpectedInput / MissingArg */
+    B200_ERR_UNSUPPORTED = 4,         /* effector / integrator not built in  */
+    B200_ERR_CUDA = 5,                /* Error::CraneliftBackend(String) analogue: backend failure (sticky per handle) */
+    B200_ERR_NO_DEVICE = 6,           /* no CUDA device: there is NO CPU fallback */
+    B200_ERR_OUT_OF_MEMORY = 7
+};
+
+/* ---- well-known component ids (FNV-1a-64 & ~(1<<63)); SURVEY §8a-7 ---- */
+#define B200_ID_WORLD_ACCEL          0x019091805bc057f4ull
+#define B200_ID_SIMULATION_TIME_STEP 0x08e7ddbb2cceaab5ull
+#define B200_ID_TICK                 0x1e7683ef2ebc7684ull
+#define B200_ID_WORLD_VEL            0x4b03b28a841edd5full
+#define B200_ID_WORLD_POS            0x5d1c198a8e96e26eull
+#define B200_ID_INERTIA              0x5fd14829c04c0f91ull
+#define B200_ID_FORCE                0x675ad8afb3eeebe4ull
+
+/* ---- integrators: libs/nox-py/src/integrator/{rk4,semi_implicit}.rs ---- */
+enum {
+    B200_INTEGRATOR_RK4 = 0,          /* Rk4::compile, rk4.rs:77-125 (incl. the v0-stage behaviour) */
+    B200_INTEGRATOR_SEMI_IMPLICIT = 1 /* semi_implicit_euler, semi_implicit.rs:42-62 */
+};
+
+/* ---- arithmetic mode ---- */
+enum {
+    /* literal operation order of libs/nox/src/{spatial,quaternion}.rs, no FMA
+     * contraction, IEEE div/sqrt: bit-identical to oracle/sixdof_oracle.c */
+    B200_MATH_EXACT = 0,
+    /* FMA contraction + hoisted reciprocals + rotation-matrix form of the
+     * inertia apply; agrees with EXACT to <= 1e-12 relative per tick
+     * (tests/test_parity_gpu.py states and checks the tolerance) */
+    B200_MATH_FAST = 1
+};
+
+/* ---- built-in effectors.  Evaluated in array order
+ * inside every integrator stage on the stage state, accumulating into Force
+ * after clear_forces (libs/nox-py/src/six_dof.rs:148-150,195). ---- */
+enum {
+    /* F.lin += g * m           examples/ball/sim.py:56-58, examples/rocket/main.py:292-294
+     * p[0..2] = g */
+    B200_EFF_GRAVITY_CONST = 1,
+    /* quadratic drag on the stage velocity, examples/ball/sim.py:99-116
+     * p[0] = Cd*rho, p[1] = area; column (optional, width 3) = wind;
+     * NOTE (reference behaviour): result torque is reset to 0. */
+    B200_EFF_DRAG_QUADRATIC = 2,
+    /* F.lin += (q @ axis) * thrust      examples/rocket/main.py:429-431
+     * p[0..2] = body axis; column (width 1) = thrust per body */
+    B200_EFF_THRUST_BODY = 3,
+    /* F += q @ wrench (body -> world)   examples/rocket/main.py:407-413 (layout [tau,f])
+     *                                   examples/falcon9/sim.py:659-672 (layout [f,tau], flag below)
+     * column (width 6) = body-frame wrench per body */
+    B200_EFF_WRENCH_BODY = 4,
+    /* point-mass gravity + Coriolis + centrifugal in a rotating frame,
+     * examples/falcon9/sim.py:350-361 + frames.py:91-109
+     * p[0] = mu, p[1..3] = frame angular velocity */
+    B200_EFF_GRAVITY_FRAME = 5,
+    /* GraphQuery.edge_fold gravity, sequential fold per source body over its
+     * out-edges in spawn order (libs/nox-py/src/graph.rs:177-236,
+     * python/elodin/__init__.py:454-557); Force := fold(init 0).
+     * NEWTON  : examples/three-body/main.py:63-70    p[0] = G
+     * SOFTENED: examples/n-body/sim.py:349-361       p[0] = K^2, p[1] = softening */
+    B200_EFF_GRAVITY_EDGES_NEWTON = 6,
+    B200_EFF_GRAVITY_EDGES_SOFTENED = 7
+};
+
+#define B200_EFF_FLAG_WRENCH_LINEAR_FIRST 1u /* wrench column is [f(3), tau(3)] (falcon9) */
+
+#define B200_MAX_EFFECTORS 8u
+
+typedef struct b200_effector {
+    uint32_t kind;          /* B200_EFF_*                                           */
+    uint32_t flags;         /* B200_EFF_FLAG_*                                      */
+    double   p[8];          /* constants, meaning per kind                          */
+    uint64_t column_id;     /* ComponentId of the per-body input column, 0 = none   */
+    uint32_t column_width;  /* f64 per body in that column                          */
+    uint32_t reserved;
+    uint64_t n_edges;       /* GRAVITY_EDGES_*: directed edges, spawn order         */
+    const uint32_t *edge_from; /* entity row index within a world                   */
+    const uint32_t *edge_to;
+} b200_effector;
+
+typedef struct b200_sixdof_desc {
+    uint32_t abi_version;      /* B200_SIXDOF_ABI_VERSION                            */
+    uint32_t integrator;       /* B200_INTEGRATOR_*                                  */
+    uint32_t math_mode;        /* B200_MATH_*                                        */
+    uint32_t n_effectors;      /* <= B200_MAX_EFFECTORS                              */
+    uint64_t n_entities;       /* bodies per world (rows of every Body column)       */
+    uint64_t n_worlds;         /* Monte-Carlo world batch (>= 1)                     */
+    double   sim_time_step;    /* SimulationTimeStep component (globals.rs:9); stage dt, rk4.rs:90 */
+    double   time_step;        /* six_dof(time_step=..) override of the final combine dt (rk4.rs:83);
+                                  NaN = none (use sim_time_step)                      */
+    const b200_effector *effectors;
+    int32_t  device;           /* CUDA ordinal, -1 = current device                  */
+    uint32_t max_fused_ticks;  /* ticks one launch may keep in registers (0/1 = one tick per launch);
+                                  only used when no effector couples bodies          */
+    uint32_t trajectory_every; /* 0 = off; k = record (pos,vel) every k ticks         */
+    uint32_t reserved;
+    uint64_t trajectory_capacity; /* samples the device ring can hold                 */
+} b200_sixdof_desc;
+
+typedef struct b200_timings {  /* TickTimings analogue, libs/nox-py/src/profile.rs */
+    double h2d_upload_ms;
+    double kernel_invoke_ms;
+    double d2h_download_ms;
+    uint64_t kernel_launches;  /* launches of this library's kernels since create   */
+    uint64_t ticks;            /* ticks integrated since create                      */
+} b200_timings;
+
+typedef struct b200_sixdof b200_sixdof; /* opaque */
+
+/* FNV-1a-64(name) & ~(1<<63): ComponentId::new, libs/impeller2/src/types.rs:40-45 */
+uint64_t b200_component_id(const char *name);
+
+/* thread-local message of the last failing call (never NULL) */
+const char *b200_last_error(void);
+
+/* number of visible CUDA devices, or a negative status; never falls back to CPU */
+int b200_device_count(void);
+
+/* Build an executor for one world batch.  Replaces CraneliftExec::new
+ * (cranelift_exec.rs:54-127): allocates device-resident SoA columns and the
+ * output tables.  All columns start zeroed except inertia-independent defaults;
+ * callers upload initial state with b200_sixdof_upload / _invoke_batch. */
+int b200_sixdof_create(const b200_sixdof_desc *desc, b200_sixdof **out);
+void b200_sixdof_destroy(b200_sixdof *h);
+
+/* ExecMetadata.arg_ids / ret_ids (exec.rs:18-29).  Inputs in first-init order,
+ * outputs sorted by ComponentId (BTreeMap order) — SURVEY §8a-7.  Returns the
+ * count; writes at most `cap` ids. */
+uint32_t b200_sixdof_input_ids(const b200_sixdof *h, uint64_t *ids, uint32_t cap);
+uint32_t b200_sixdof_output_ids(const b200_sixdof *h, uint64_t *ids, uint32_t cap);
+/* byte length of a column's host buffer (n_worlds*n_entities*width*8; 8 for the
+ * two globals), 0 if the handle has no such column */
+uint64_t b200_sixdof_column_bytes(const b200_sixdof *h, uint64_t component_id);
+
+/* Host (or device: the copy direction is inferred, cudaMemcpyDefault) AoS column
+ * -> device SoA planes, and back.  `bytes` must equal b200_sixdof_column_bytes
+ * (else B200_ERR_VALUE_SIZE_MISMATCH, as cranelift_exec.rs:175-177,188-190). */
+int b200_sixdof_upload(b200_sixdof *h, uint64_t component_id, const void *src, uint64_t bytes);
+int b200_sixdof_download(b200_sixdof *h, uint64_t component_id, void *dst, uint64_t bytes);
+
+/* Advance the device-resident world n_ticks (asynchronous on the handle's
+ * stream).  tick += n_ticks. */
+int b200_sixdof_step(b200_sixdof *h, uint64_t n_ticks);
+int b200_sixdof_sync(b200_sixdof *h);
+
+/* The reference-shaped call: CraneliftExec::invoke_batch (cranelift_exec.rs:129-195).
+ * in_cols[i]  = host buffer of input_ids[i]  (borrowed for the call only)
+ * out_cols[j] = host buffer of output_ids[j] (caller-owned, never aliasing an input)
+ * Uploads every input column, integrates max(n_ticks,1) ticks on the device,
+ * downloads every output column, synchronises. */
+int b200_sixdof_invoke_batch(b200_sixdof *h, const uint8_t *const *in_cols,
+                             uint8_t *const *out_cols, uint64_t n_ticks);
+
+/* TickFn-shaped shim (cranelift_exec.rs:11): one tick, bound to a thread-local
+ * handle.  Returns void like the reference; errors are sticky on the handle. */
+int b200_sixdof_bind_tick(b200_sixdof *h);
+void b200_sixdof_tick(const uint8_t *const *in_cols, uint8_t **out_cols);
+
+/* Trajectory ring: samples of (world_pos[7], world_vel[6]) taken every
+ * `trajectory_every` ticks.  Download layout [samples][n_worlds][n_entities][13]. */
+uint64_t b200_sixdof_trajectory_len(const b200_sixdof *h);
+int b200_sixdof_trajectory_download(b200_sixdof *h, void *dst, uint64_t bytes);
+int b200_sixdof_trajectory_reset(b200_sixdof *h);
+
+/* plumbing */
+uint64_t b200_sixdof_tick_count(const b200_sixdof *h);
+int b200_sixdof_set_stream(b200_sixdof *h, void *cuda_stream); /* cudaStream_t; NULL = own stream */
+int b200_sixdof_timings(const b200_sixdof *h, b200_timings *out);
+int b200_sixdof_status(const b200_sixdof *h);                  /* sticky status of the handle */
+/* raw device plane pointer (plane p of a column), for zero-copy interop (NCCL gather) */
+void *b200_sixdof_device_plane(b200_sixdof *h, uint64_t component_id, uint32_t plane);
+uint64_t b200_sixdof_plane_stride(const b200_sixdof *h); /* doubles between planes */
+
+/* FP64 / HBM probes used by bench.py to report the roofs next to the kernel
+ * numbers (device-timed, returns GB/s resp. GFLOP/s, <0 on error) */
+double b200_probe_copy_gbs(int device, uint64_t bytes, int iters);
+double b200_probe_fp64_gflops(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_SIXDOF_H */

@@ -1,0 +1,466 @@
+/*
+ * TEST INFRASTRUCTURE — NOT PRODUCT CODE.  See sixdof_oracle.h for the parity
+ * status ("pinned" for the free-body / three-body / rocket / ball paths).
+ *
+ * Plain-C restatement of the reference arithmetic, one IEEE operation per
+ * source operation, in the reference's evaluation order.  Build with
+ *   gcc -O2 -ffp-contract=off -fno-fast-math      (oracle/Makefile)
+ * so no multiply-add is ever contracted.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "sixdof_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+/* ---- libs/nox/src/quaternion.rs:268-281 — Mul for &Quaternion; storage [i,j,k,w]
+ * (quaternion.rs:100,134-138).  Rust `a + b + c - d` associates left to right. */
+void orc_qmul(const double l[4], const double r[4], double out[4])
+{
+    const double li = l[0], lj = l[1], lk = l[2], lw = l[3];
+    const double ri = r[0], rj = r[1], rk = r[2], rw = r[3];
+    const double i = ((lw * ri + li * rw) + lj * rk) - lk * rj;
+    const double j = ((lw * rj - li * rk) + lj * rw) + lk * ri;
+    const double k = ((lw * rk + li * rj) - lj * ri) + lk * rw;
+    const double w = ((lw * rw - li * ri) - lj * rj) - lk * rk;
+    out[0] = i; out[1] = j; out[2] = k; out[3] = w;
+}
+
+/* 4-element dot.  dot_general of two rank-1 tensors is a left fold from 0.0
+ * (libs/cranelift-mlir/src/lower.rs:9357-9366): ((a0*b0 + a1*b1) + a2*b2) + a3*b3. */
+static double dot4_plain(const double a[4], const double b[4])
+{
+    return ((a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]) + a[3] * b[3];
+}
+
+/* The same fold as the reference JIT's *pointer-ABI* runtime evaluates it:
+ * tensor_matmul_f64 (libs/cranelift-mlir/src/tensor_rt.rs:1141-1163) uses
+ * `d.algebraic_add(a.algebraic_mul(b))`, which the Rust compiler contracts to a
+ * fused multiply-add on hosts that have one.  The reference's golden rocket
+ * telemetry was produced that way (see orc_set_dot_mode). */
+static double dot4_fused(const double a[4], const double b[4])
+{
+    double d = a[0] * b[0];
+    d = fma(a[1], b[1], d);
+    d = fma(a[2], b[2], d);
+    d = fma(a[3], b[3], d);
+    return d;
+}
+
+/* 0 = ORC_DOT_PLAIN (canonical: no contraction anywhere).
+ * 1 = ORC_DOT_GOLDEN_HOST: quaternion norm_squared inside the Rust-defined
+ *     systems that nox inlines into `main` (the (+) of spatial.rs:530-549 and
+ *     calc_accel, six_dof.rs:137-146) is FMA-contracted, while Python @el.map
+ *     effectors (private scalar-ABI functions) stay plain.  With this mode the
+ *     oracle reproduces scripts/ci/baseline/rocket-csv bit for bit (100/100
+ *     one-step predictions); plain mode differs from it by <= 1e-15 relative. */
+static int g_dot_mode = 0;
+void orc_set_dot_mode(int mode) { g_dot_mode = mode; }
+int orc_get_dot_mode(void) { return g_dot_mode; }
+
+static double dot4_sys(const double a[4], const double b[4])
+{
+    return g_dot_mode ? dot4_fused(a, b) : dot4_plain(a, b);
+}
+
+static double dot3(const double a[3], const double b[3])
+{
+    return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
+}
+
+typedef double (*dot4_fn)(const double *, const double *);
+
+/* libs/nox/src/quaternion.rs:141-155 — conjugate() / norm_squared(); no unit-norm assumption */
+static void qinv_with(dot4_fn dot, const double q[4], double out[4])
+{
+    const double n2 = dot(q, q);
+    out[0] = -q[0] / n2;
+    out[1] = -q[1] / n2;
+    out[2] = -q[2] / n2;
+    out[3] = q[3] / n2;
+}
+
+/* libs/nox/src/quaternion.rs:283-305 — Quaternion * Vector3: (q * [v,0]) * q.inverse(),
+ * the inverse is recomputed on every call. */
+static void qrot_with(dot4_fn dot, const double q[4], const double v[3], double out[3])
+{
+    const double vq[4] = {v[0], v[1], v[2], 0.0};
+    double inv[4], t[4], r[4];
+    qinv_with(dot, q, inv);
+    orc_qmul(q, vq, t);
+    orc_qmul(t, inv, r);
+    out[0] = r[0]; out[1] = r[1]; out[2] = r[2];
+}
+
+/* libs/nox/src/quaternion.rs:147-149 + vector.rs:115-122 — q / sqrt(dot(q,q)) */
+static void qnormalize_with(dot4_fn dot, const double q[4], double out[4])
+{
+    const double n = sqrt(dot(q, q));
+    out[0] = q[0] / n; out[1] = q[1] / n; out[2] = q[2] / n; out[3] = q[3] / n;
+}
+
+/* public primitives: canonical (plain) arithmetic */
+void orc_qinv(const double q[4], double out[4]) { qinv_with(dot4_plain, q, out); }
+void orc_qrot(const double q[4], const double v[3], double out[3]) { qrot_with(dot4_plain, q, v, out); }
+void orc_qnormalize(const double q[4], double out[4]) { qnormalize_with(dot4_plain, q, out); }
+
+/* libs/nox/src/spatial.rs:530-549 — SpatialTransform + SpatialMotion:
+ * h = [omega/2, 0]; q' = normalize(q + h*q); x' = x + v */
+void orc_transform_add_motion(const double pos[7], const double m[6], double out[7])
+{
+    const double h[4] = {m[0] / 2.0, m[1] / 2.0, m[2] / 2.0, 0.0};
+    double hq[4], s[4];
+    orc_qmul(h, pos, hq);
+    s[0] = pos[0] + hq[0]; s[1] = pos[1] + hq[1]; s[2] = pos[2] + hq[2]; s[3] = pos[3] + hq[3];
+    qnormalize_with(dot4_sys, s, out);
+    out[4] = pos[4] + m[3];
+    out[5] = pos[5] + m[4];
+    out[6] = pos[6] + m[5];
+}
+
+/* libs/nox-py/src/six_dof.rs:137-146 calc_accel, with
+ * Quaternion * SpatialForce (spatial.rs:587-593), SpatialForce / SpatialInertia
+ * (spatial.rs:353-361) and Quaternion * SpatialMotion (spatial.rs:571-577). */
+void orc_calc_accel(const double pos[7], const double force[6], const double inertia[7], double accel[6])
+{
+    double qi[4], tb[3], fb[3], ab_ang[3], ab_lin[3];
+    qinv_with(dot4_sys, pos, qi);              /* q.inverse() */
+    qrot_with(dot4_sys, qi, force, tb);        /* body-frame torque */
+    qrot_with(dot4_sys, qi, force + 3, fb);    /* body-frame force  */
+    ab_lin[0] = fb[0] / inertia[6]; ab_lin[1] = fb[1] / inertia[6]; ab_lin[2] = fb[2] / inertia[6];
+    ab_ang[0] = tb[0] / inertia[0]; ab_ang[1] = tb[1] / inertia[1]; ab_ang[2] = tb[2] / inertia[2];
+    qrot_with(dot4_sys, pos, ab_ang, accel);
+    qrot_with(dot4_sys, pos, ab_lin, accel + 3);
+}
+
+/* ------------------------------------------------------------------ effectors */
+
+static void cross3(const double a[3], const double b[3], double o[3])
+{
+    /* jnp.cross / libs/nox/src/vector.rs:84-91 */
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+/* examples/ball/sim.py:56-58, examples/rocket/main.py:292-294:
+ *   f + SpatialForce(linear=g * inertia.mass())   (torque part adds +0.0) */
+static void eff_gravity_const(const orc_effector *e, const double inertia[7], double F[6])
+{
+    const double m = inertia[6];
+    F[0] = F[0] + 0.0; F[1] = F[1] + 0.0; F[2] = F[2] + 0.0;
+    F[3] = F[3] + e->p[0] * m;
+    F[4] = F[4] + e->p[1] * m;
+    F[5] = F[5] + e->p[2] * m;
+}
+
+/* examples/ball/sim.py:99-116 apply_drag; calculate_drag = 0.5*(Cd*r*V**2*A).
+ * Cd*r is a Python constant (p[0]); returns SpatialForce(linear=...) => torque 0. */
+static void eff_drag_quadratic(const orc_effector *e, const double *wind, const double vel[6], double F[6])
+{
+    double fl[3];
+    const double w0 = wind ? wind[0] : 0.0, w1 = wind ? wind[1] : 0.0, w2 = wind ? wind[2] : 0.0;
+    fl[0] = w0 - vel[3]; fl[1] = w1 - vel[4]; fl[2] = w2 - vel[5];
+    const double speed = sqrt(dot3(fl, fl));
+    const double drag = 0.5 * ((e->p[0] * (speed * speed)) * e->p[1]);
+    const double d0 = fl[0] / speed, d1 = fl[1] / speed, d2 = fl[2] / speed;
+    F[0] = 0.0; F[1] = 0.0; F[2] = 0.0;
+    F[3] = F[3] + drag * d0;
+    F[4] = F[4] + drag * d1;
+    F[5] = F[5] + drag * d2;
+}
+
+/* examples/rocket/main.py:429-431: f + SpatialForce(linear=p.angular() @ axis * thrust) */
+static void eff_thrust_body(const orc_effector *e, const double *thrust, const double pos[7], double F[6])
+{
+    double d[3];
+    const double t = thrust ? thrust[0] : 0.0;
+    orc_qrot(pos, e->p, d);
+    F[0] = F[0] + 0.0; F[1] = F[1] + 0.0; F[2] = F[2] + 0.0;
+    F[3] = F[3] + d[0] * t;
+    F[4] = F[4] + d[1] * t;
+    F[5] = F[5] + d[2] * t;
+}
+
+/* examples/rocket/main.py:407-413: f + p.angular() @ f_aero   (column [tau, f])
+ * examples/falcon9/sim.py:659-672: force + SpatialForce(linear=q@total[:3], torque=q@total[3:]) */
+static void eff_wrench_body(const orc_effector *e, const double *wr, const double pos[7], double F[6])
+{
+    double tw[3], fw[3];
+    const double zero[6] = {0, 0, 0, 0, 0, 0};
+    if (!wr) wr = zero;
+    if (e->flags & ORC_FLAG_WRENCH_LINEAR_FIRST) {
+        orc_qrot(pos, wr + 3, tw);
+        orc_qrot(pos, wr, fw);
+    } else {
+        orc_qrot(pos, wr, tw);
+        orc_qrot(pos, wr + 3, fw);
+    }
+    F[0] = F[0] + tw[0]; F[1] = F[1] + tw[1]; F[2] = F[2] + tw[2];
+    F[3] = F[3] + fw[0]; F[4] = F[4] + fw[1]; F[5] = F[5] + fw[2];
+}
+
+/* examples/falcon9/sim.py:350-361 + frames.py:91-109 (parity unpinned: no golden) */
+static void eff_gravity_frame(const orc_effector *e, const double pos[7], const double vel[6],
+                              const double inertia[7], double F[6])
+{
+    const double mu = e->p[0];
+    const double *om = e->p + 1;
+    const double *r = pos + 4, *v = vel + 3;
+    const double rn = sqrt(dot3(r, r));
+    const double rn3 = (rn * rn) * rn;
+    double g[3], c[3], cr[3], c2[3], acc[3];
+    g[0] = ((-mu) * r[0]) / rn3; g[1] = ((-mu) * r[1]) / rn3; g[2] = ((-mu) * r[2]) / rn3;
+    cross3(om, v, c);
+    cross3(om, r, cr);
+    cross3(om, cr, c2);
+    for (int k = 0; k < 3; ++k) {
+        const double cor = -2.0 * c[k];
+        const double cen = -c2[k];
+        const double frame = cor + cen;
+        acc[k] = g[k] + frame;
+    }
+    const double m = inertia[6];
+    F[0] = F[0] + 0.0; F[1] = F[1] + 0.0; F[2] = F[2] + 0.0;
+    F[3] = F[3] + acc[0] * m; F[4] = F[4] + acc[1] * m; F[5] = F[5] + acc[2] * m;
+}
+
+/* examples/three-body/main.py:63-70 gravity_fn (fold accumulator in, out) */
+static void fold_newton(double G, const double *a_pos, const double *a_in, const double *b_pos,
+                        const double *b_in, double acc[6])
+{
+    double r[3];
+    r[0] = a_pos[4] - b_pos[4]; r[1] = a_pos[5] - b_pos[5]; r[2] = a_pos[6] - b_pos[6];
+    const double m = a_in[6], M = b_in[6];
+    const double norm = sqrt(dot3(r, r));
+    const double s = (G * M) * m;
+    const double d = (norm * norm) * norm;
+    acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0;       /* el.Force(linear=...) => zero torque */
+    acc[3] = acc[3] - (s * r[0]) / d;
+    acc[4] = acc[4] - (s * r[1]) / d;
+    acc[5] = acc[5] - (s * r[2]) / d;
+}
+
+/* examples/n-body/sim.py:349-361 gravity_fn (parity unpinned above N=3: no golden) */
+static void fold_softened(double K2, double soft, const double *a_pos, const double *a_in,
+                          const double *b_pos, const double *b_in, double acc[6])
+{
+    double r[3];
+    r[0] = b_pos[4] - a_pos[4]; r[1] = b_pos[5] - a_pos[5]; r[2] = b_pos[6] - a_pos[6];
+    const double dist_sq = dot3(r, r) + soft;
+    const double inv = 1.0 / sqrt(dist_sq);
+    const double inv3 = (inv * inv) * inv;
+    const double scalar = ((K2 * a_in[6]) * b_in[6]) * inv3;
+    acc[0] = acc[0] + 0.0; acc[1] = acc[1] + 0.0; acc[2] = acc[2] + 0.0;
+    acc[3] = acc[3] + scalar * r[0];
+    acc[4] = acc[4] + scalar * r[1];
+    acc[5] = acc[5] + scalar * r[2];
+}
+
+/* GraphQuery.edge_fold: per source entity, sequential left fold over its
+ * out-edges in spawn order, init = zero Force; the result REPLACES that
+ * entity's Force (libs/nox-py/src/graph.rs:177-236, __init__.py:454-557). */
+static void eff_gravity_edges(const orc_effector *e, uint64_t n, const double *pos,
+                              const double *inertia, double *F, unsigned char *has_edge)
+{
+    memset(has_edge, 0, n);
+    for (uint64_t k = 0; k < e->n_edges; ++k)
+        if (e->edge_from[k] < n) has_edge[e->edge_from[k]] = 1;
+    for (uint64_t i = 0; i < n; ++i)
+        if (has_edge[i]) memset(F + 6 * i, 0, 6 * sizeof(double));
+    for (uint64_t k = 0; k < e->n_edges; ++k) {
+        const uint64_t a = e->edge_from[k], b = e->edge_to[k];
+        if (a >= n || b >= n) continue;
+        if (e->kind == ORC_EFF_GRAVITY_EDGES_NEWTON)
+            fold_newton(e->p[0], pos + 7 * a, inertia + 7 * a, pos + 7 * b, inertia + 7 * b, F + 6 * a);
+        else
+            fold_softened(e->p[0], e->p[1], pos + 7 * a, inertia + 7 * a, pos + 7 * b, inertia + 7 * b,
+                          F + 6 * a);
+    }
+}
+
+/* clear_forces | effectors | calc_accel  (six_dof.rs:195) on one world's stage state */
+static void eval_pipe(uint64_t n, uint64_t world, const double *inertia, uint32_t n_eff,
+                      const orc_effector *effs, const double *pos, const double *vel, double *F,
+                      double *A, unsigned char *scratch)
+{
+    for (uint64_t i = 0; i < 6 * n; ++i) F[i] = 0.0; /* clear_forces, six_dof.rs:148-150 */
+    for (uint32_t k = 0; k < n_eff; ++k) {
+        const orc_effector *e = &effs[k];
+        if (e->kind == ORC_EFF_GRAVITY_EDGES_NEWTON || e->kind == ORC_EFF_GRAVITY_EDGES_SOFTENED) {
+            eff_gravity_edges(e, n, pos, inertia, F, scratch);
+            continue;
+        }
+        for (uint64_t i = 0; i < n; ++i) {
+            const double *col = e->column ? e->column + (world * n + i) * e->column_width : 0;
+            switch (e->kind) {
+            case ORC_EFF_GRAVITY_CONST: eff_gravity_const(e, inertia + 7 * i, F + 6 * i); break;
+            case ORC_EFF_DRAG_QUADRATIC: eff_drag_quadratic(e, col, vel + 6 * i, F + 6 * i); break;
+            case ORC_EFF_THRUST_BODY: eff_thrust_body(e, col, pos + 7 * i, F + 6 * i); break;
+            case ORC_EFF_WRENCH_BODY: eff_wrench_body(e, col, pos + 7 * i, F + 6 * i); break;
+            case ORC_EFF_GRAVITY_FRAME:
+                eff_gravity_frame(e, pos + 7 * i, vel + 6 * i, inertia + 7 * i, F + 6 * i);
+                break;
+            default: break;
+            }
+        }
+    }
+    for (uint64_t i = 0; i < n; ++i) orc_calc_accel(pos + 7 * i, F + 6 * i, inertia + 7 * i, A + 6 * i);
+}
+
+void orc_eval_stage(const orc_world *w, uint64_t world, uint32_t n_eff, const orc_effector *effs,
+                    const double *pos, const double *vel, double *force, double *accel)
+{
+    unsigned char *scratch = (unsigned char *)malloc(w->n ? w->n : 1);
+    eval_pipe(w->n, world, w->inertia + world * w->n * 7, n_eff, effs, pos, vel, force, accel, scratch);
+    free(scratch);
+}
+
+/* ------------------------------------------------------------------ RK4
+ * libs/nox-py/src/integrator/rk4.rs:77-125.  `init_u.insert_into_builder`
+ * (rk4.rs:105,107,109) restores WorldPos/WorldVel to (x0, v0) before each
+ * `step` binds `du = (vars[WorldVel], vars[WorldAccel])`, so every stage
+ * position is advanced with v0 and every stage velocity with the previous
+ * stage's acceleration (stage 1: the WorldAccel column, times 0):
+ *   a_s = A(x0 (+) (dt*f_s)*v0 ,  v0 + (dt*f_s)*a_{s-1}),   f = 0, .5, .5, 1
+ *   k_s = (stage velocity, a_s)
+ *   u1  = u0 + (dt_final*(1/6)) * (((k1 + 2.0*k2) + 2.0*k3) + k4)
+ * Force and WorldAccel leave the tick holding their stage-4 values. */
+static void rk4_world_tick(uint64_t n, uint64_t world, double *pos, double *vel, double *accel,
+                           double *force, const double *inertia, uint32_t n_eff,
+                           const orc_effector *effs, double dt_stage, double dt_final, double *tmp,
+                           unsigned char *scratch)
+{
+    double *sx = tmp;            /* [n,7] stage position  */
+    double *sv = sx + 7 * n;     /* [n,6] stage velocity  */
+    double *sa = sv + 6 * n;     /* [n,6] stage accel     */
+    double *sf = sa + 6 * n;     /* [n,6] stage force     */
+    double *kv = sf + 6 * n;     /* [n,6] running sum of k.v */
+    double *ka = kv + 6 * n;     /* [n,6] running sum of k.a */
+    static const double fac[4] = {0.0, 0.5, 0.5, 1.0};
+
+    memcpy(sa, accel, 6 * n * sizeof(double)); /* du.a before stage 1 = WorldAccel column */
+    for (int s = 0; s < 4; ++s) {
+        const double dtf = dt_stage * fac[s]; /* rk4.rs:90 */
+        for (uint64_t i = 0; i < n; ++i) {
+            double mv[6];
+            for (int k = 0; k < 6; ++k) mv[k] = dtf * vel[6 * i + k];           /* dt*du.v (six_dof.rs:62-70) */
+            orc_transform_add_motion(pos + 7 * i, mv, sx + 7 * i);               /* U+DU: x (+) v (six_dof.rs:40-49) */
+            for (int k = 0; k < 6; ++k) sv[6 * i + k] = vel[6 * i + k] + dtf * sa[6 * i + k];
+        }
+        eval_pipe(n, world, inertia, n_eff, effs, sx, sv, sf, sa, scratch);
+        for (uint64_t i = 0; i < 6 * n; ++i) {
+            if (s == 0) { kv[i] = sv[i]; ka[i] = sa[i]; }
+            else if (s == 3) { kv[i] = kv[i] + sv[i]; ka[i] = ka[i] + sa[i]; }
+            else { kv[i] = kv[i] + 2.0 * sv[i]; ka[i] = ka[i] + 2.0 * sa[i]; }
+        }
+    }
+    const double c = dt_final * (1.0 / 6.0); /* rk4.rs:119 */
+    for (uint64_t i = 0; i < n; ++i) {
+        double mv[6], nx[7];
+        for (int k = 0; k < 6; ++k) mv[k] = c * kv[6 * i + k];
+        orc_transform_add_motion(pos + 7 * i, mv, nx);
+        memcpy(pos + 7 * i, nx, sizeof nx);
+        for (int k = 0; k < 6; ++k) vel[6 * i + k] = vel[6 * i + k] + c * ka[6 * i + k];
+    }
+    memcpy(accel, sa, 6 * n * sizeof(double));
+    memcpy(force, sf, 6 * n * sizeof(double));
+}
+
+/* libs/nox-py/src/integrator/semi_implicit.rs:42-62: v' = v + dt*a ; x' = x (+) dt*v' */
+static void semi_world_tick(uint64_t n, uint64_t world, double *pos, double *vel, double *accel,
+                            double *force, const double *inertia, uint32_t n_eff,
+                            const orc_effector *effs, double dt, unsigned char *scratch)
+{
+    eval_pipe(n, world, inertia, n_eff, effs, pos, vel, force, accel, scratch);
+    for (uint64_t i = 0; i < n; ++i) {
+        double mv[6], nx[7];
+        for (int k = 0; k < 6; ++k) vel[6 * i + k] = vel[6 * i + k] + dt * accel[6 * i + k];
+        for (int k = 0; k < 6; ++k) mv[k] = dt * vel[6 * i + k];
+        orc_transform_add_motion(pos + 7 * i, mv, nx);
+        memcpy(pos + 7 * i, nx, sizeof nx);
+    }
+}
+
+/* ---- world-parallel driver (bench baseline only): static partition of the
+ * world axis over pthreads, mirroring `elodin monte-carlo` workers = logical
+ * cores (libs/monte-carlo/src/lib.rs:2530-2538). ---- */
+int orc_max_threads(void)
+{
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n > 0 ? (int)n : 1;
+}
+
+typedef struct orc_job {
+    orc_world *w;
+    uint32_t n_eff;
+    const orc_effector *effs;
+    double dt_stage, dt_final;
+    uint64_t n_ticks;
+    uint64_t m0, m1;
+    int semi;
+} orc_job;
+
+static void *orc_worker(void *arg)
+{
+    orc_job *j = (orc_job *)arg;
+    orc_world *w = j->w;
+    const uint64_t n = w->n;
+    double *tmp = (double *)malloc((37 * n + 1) * sizeof(double));
+    unsigned char *scratch = (unsigned char *)malloc(n ? n : 1);
+    for (uint64_t m = j->m0; m < j->m1; ++m) {
+        for (uint64_t t = 0; t < j->n_ticks; ++t) {
+            if (j->semi)
+                semi_world_tick(n, m, w->pos + m * n * 7, w->vel + m * n * 6, w->accel + m * n * 6,
+                                w->force + m * n * 6, w->inertia + m * n * 7, j->n_eff, j->effs,
+                                j->dt_stage, scratch);
+            else
+                rk4_world_tick(n, m, w->pos + m * n * 7, w->vel + m * n * 6, w->accel + m * n * 6,
+                               w->force + m * n * 6, w->inertia + m * n * 7, j->n_eff, j->effs,
+                               j->dt_stage, j->dt_final, tmp, scratch);
+        }
+    }
+    free(tmp);
+    free(scratch);
+    return 0;
+}
+
+static void orc_run(orc_world *w, uint32_t n_eff, const orc_effector *effs, double dt_stage,
+                    double dt_final, uint64_t n_ticks, int n_threads, int semi)
+{
+    const uint64_t M = w->n_worlds;
+    if (n_threads < 1) n_threads = 1;
+    if ((uint64_t)n_threads > M) n_threads = (int)(M ? M : 1);
+    orc_job *jobs = (orc_job *)calloc((size_t)n_threads, sizeof(orc_job));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    for (int t = 0; t < n_threads; ++t) {
+        jobs[t].w = w; jobs[t].n_eff = n_eff; jobs[t].effs = effs;
+        jobs[t].dt_stage = dt_stage; jobs[t].dt_final = dt_final; jobs[t].n_ticks = n_ticks;
+        jobs[t].m0 = M * (uint64_t)t / (uint64_t)n_threads;
+        jobs[t].m1 = M * (uint64_t)(t + 1) / (uint64_t)n_threads;
+        jobs[t].semi = semi;
+    }
+    if (n_threads == 1) {
+        orc_worker(&jobs[0]);
+    } else {
+        for (int t = 0; t < n_threads; ++t) pthread_create(&th[t], 0, orc_worker, &jobs[t]);
+        for (int t = 0; t < n_threads; ++t) pthread_join(th[t], 0);
+    }
+    free(jobs);
+    free(th);
+}
+
+void orc_rk4_ticks(orc_world *w, uint32_t n_eff, const orc_effector *effs, double dt_stage,
+                   double dt_final, uint64_t n_ticks, int n_threads)
+{
+    orc_run(w, n_eff, effs, dt_stage, dt_final, n_ticks, n_threads, 0);
+}
+
+void orc_semi_implicit_ticks(orc_world *w, uint32_t n_eff, const orc_effector *effs, double dt,
+                             uint64_t n_ticks, int n_threads)
+{
+    orc_run(w, n_eff, effs, dt, dt, n_ticks, n_threads, 1);
+}

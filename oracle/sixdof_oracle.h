@@ -1,0 +1,96 @@
+/*
+ * TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, f64, no FMA contraction) of the arithmetic of
+ * elodin-sys/elodin's six_dof() path.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this.  The
+ * product (elodin_b200/csrc) never links or calls it.
+ *
+ * Parity status: PINNED against the reference's own golden telemetry
+ * (scripts/ci/baseline/{three-body,rocket,ball}-csv, repacked under
+ * tests/golden/ by tests/golden/make_golden.py) and its known-answer tests
+ * (libs/nox/src/spatial.rs:630-676, libs/nox/src/quaternion.rs:352-388,
+ * libs/nox-py/python/tests/test_all.py:67-83,228-291,342-366).
+ * UNPINNED (no golden in the reference): softened n-body gravity at N>3 and the
+ * falcon9 frame-force effector — oracle-vs-kernel only.
+ *
+ * The reference implementation itself (Rust + JAX + Cranelift) cannot be built
+ * or imported in this image (no cargo/rustc/jax), so there is no oracle/_ref.
+ */
+#ifndef SIXDOF_ORACLE_H
+#define SIXDOF_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* effector kinds: same numbering as include/b200_sixdof.h */
+enum {
+    ORC_EFF_GRAVITY_CONST = 1,
+    ORC_EFF_DRAG_QUADRATIC = 2,
+    ORC_EFF_THRUST_BODY = 3,
+    ORC_EFF_WRENCH_BODY = 4,
+    ORC_EFF_GRAVITY_FRAME = 5,
+    ORC_EFF_GRAVITY_EDGES_NEWTON = 6,
+    ORC_EFF_GRAVITY_EDGES_SOFTENED = 7
+};
+#define ORC_FLAG_WRENCH_LINEAR_FIRST 1u
+
+typedef struct orc_effector {
+    uint32_t kind;
+    uint32_t flags;
+    double p[8];
+    const double *column;  /* [n_worlds][n][width] AoS, may be NULL */
+    uint32_t column_width;
+    uint32_t reserved;
+    uint64_t n_edges;
+    const uint32_t *edge_from;
+    const uint32_t *edge_to;
+} orc_effector;
+
+/* AoS columns [n_worlds][n][width], exactly the host layout of the C ABI */
+typedef struct orc_world {
+    uint64_t n;        /* bodies per world */
+    uint64_t n_worlds;
+    double *pos;       /* [..,7]  q(i,j,k,w), x,y,z */
+    double *vel;       /* [..,6]  omega, v          */
+    double *accel;     /* [..,6]                    */
+    double *force;     /* [..,6]  tau, f            */
+    const double *inertia; /* [..,7] diag(3), momentum(3), mass */
+} orc_world;
+
+/* dot evaluation mode, see sixdof_oracle.c: 0 = plain IEEE (canonical),
+ * 1 = reproduce the FMA-contracted `dot` of the host JIT that generated the
+ * reference's golden rocket telemetry (test pinning only) */
+#define ORC_DOT_PLAIN 0
+#define ORC_DOT_GOLDEN_HOST 1
+void orc_set_dot_mode(int mode);
+int orc_get_dot_mode(void);
+
+/* primitives (exposed for the known-answer tests) */
+void orc_qmul(const double l[4], const double r[4], double out[4]);
+void orc_qinv(const double q[4], double out[4]);
+void orc_qrot(const double q[4], const double v[3], double out[3]);
+void orc_qnormalize(const double q[4], double out[4]);
+void orc_transform_add_motion(const double pos[7], const double motion[6], double out[7]);
+void orc_calc_accel(const double pos[7], const double force[6], const double inertia[7], double accel[6]);
+
+/* one tick of six_dof(Rk4) / six_dof(SemiImplicit) over every world.
+ * dt_stage = SimulationTimeStep, dt_final = six_dof(time_step=) or dt_stage.
+ * n_threads > 1 parallelises over worlds with pthreads (bench baseline only). */
+void orc_rk4_ticks(orc_world *w, uint32_t n_eff, const orc_effector *effs,
+                   double dt_stage, double dt_final, uint64_t n_ticks, int n_threads);
+void orc_semi_implicit_ticks(orc_world *w, uint32_t n_eff, const orc_effector *effs,
+                             double dt, uint64_t n_ticks, int n_threads);
+
+/* evaluate only the effector pipe + calc_accel on the given state (one "stage") */
+void orc_eval_stage(const orc_world *w, uint64_t world, uint32_t n_eff, const orc_effector *effs,
+                    const double *pos, const double *vel, double *force, double *accel);
+
+int orc_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,58 @@
+"""Repack the reference's own CI golden telemetry into compact fixtures.
+
+Run in the build container (where /root/reference is mounted):
+
+    python tests/golden/make_golden.py
+
+Reads  /root/reference/scripts/ci/baseline/{three-body,rocket,ball}-csv/*.csv
+       (101 rows each, written by the reference's `bench --ticks 100` +
+        `elodin-db export --format csv --flatten`, scripts/ci/regress.sh)
+Writes tests/golden/elodin_ci_baseline.npz   (f64 arrays, bit-exact copies of
+       the CSV values; the `time` column is dropped, as compare_baseline_csv.py does).
+
+Nothing under tests/ reads /root/reference at run time: only this script does.
+"""
+
+import csv
+import os
+import sys
+
+import numpy as np
+
+REF = os.environ.get("ELODIN_REFERENCE", "/root/reference")
+BASE = os.path.join(REF, "scripts", "ci", "baseline")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "elodin_ci_baseline.npz")
+
+
+def read(sim: str, stem: str) -> np.ndarray:
+    path = os.path.join(BASE, f"{sim}-csv", f"{stem}.csv")
+    with open(path, newline="") as f:
+        rows = list(csv.reader(f))
+    data = np.array([[float(x) for x in r[1:]] for r in rows[1:]], dtype=np.float64)
+    return data
+
+
+def main() -> int:
+    out = {}
+    for ent in "abc":
+        for comp in ("world_pos", "world_vel", "world_accel", "force", "inertia"):
+            out[f"three_body.{ent}.{comp}"] = read("three-body", f"{ent}.{comp}")
+    edges = []
+    for name in ("a_to_b", "b_to_a", "a_to_c", "b_to_c", "c_to_a", "c_to_b"):  # spawn order, main.py:82-89
+        edges.append(read("three-body", f"{name}.gravity_edge")[0])
+    out["three_body.edges_entity_ids"] = np.array(edges, dtype=np.float64)
+    out["three_body.simulation_time_step"] = read("three-body", "globals.simulation_time_step")
+    out["three_body.tick"] = read("three-body", "globals.tick")
+    for comp in ("world_pos", "world_vel", "world_accel", "force", "inertia", "thrust", "aero_force"):
+        out[f"rocket.{comp}"] = read("rocket", f"rocket.{comp}")
+    out["rocket.simulation_time_step"] = read("rocket", "globals.simulation_time_step")
+    for comp in ("world_pos", "world_vel", "world_accel", "force", "inertia", "wind"):
+        out[f"ball.{comp}"] = read("ball", f"ball.{comp}")
+    out["ball.simulation_time_step"] = read("ball", "globals.simulation_time_step")
+    np.savez_compressed(OUT, **out)
+    print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT)} bytes")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

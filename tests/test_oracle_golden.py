@@ -1,0 +1,244 @@
+"""Pin the CPU oracle against the reference's own golden vectors (CPU only).
+
+Golden telemetry: scripts/ci/baseline/{three-body,rocket,ball}-csv of the
+reference, repacked by tests/golden/make_golden.py.  Known-answer vectors:
+libs/nox/src/spatial.rs:630-676, libs/nox/src/quaternion.rs:352-388,
+libs/nox-py/python/tests/test_all.py:67-83,228-291,342-366.
+"""
+
+import numpy as np
+import pytest
+
+THREE_BODY_EDGES = np.array([[0, 1], [1, 0], [0, 2], [1, 2], [2, 0], [2, 1]])  # main.py:82-89
+G_NEWTON = 6.6743e-11
+
+
+def _three_body_cols(golden):
+    def col(c):
+        return np.stack([golden[f"three_body.{e}.{c}"] for e in "abc"], 1)
+
+    return [col(c) for c in ("world_pos", "world_vel", "world_accel", "force", "inertia")]
+
+
+def test_three_body_100_ticks_bit_exact(golden, oracle):
+    """RK4 (incl. the v0-stage behaviour) + edge_fold gravity: every one of the
+    100 recorded ticks is reproduced bit for bit (pos, vel, force, accel)."""
+    O = oracle
+    pos, vel, acc, frc, ine = _three_body_cols(golden)
+    dt = float(golden["three_body.simulation_time_step"][0, 0])
+    assert dt == 0.008333333  # Duration-quantised 1/120 s (world_builder.rs:221)
+    w = O.World(pos[0], vel[0], ine[0], acc[0], frc[0])
+    eff = [O.Effector(O.EFF_GRAVITY_EDGES_NEWTON, p=(G_NEWTON,), edges=THREE_BODY_EDGES)]
+    for t in range(1, 101):
+        w.rk4(dt, 1, eff)
+        assert np.array_equal(w.pos[0], pos[t]), t
+        assert np.array_equal(w.vel[0], vel[t]), t
+        assert np.array_equal(w.force[0], frc[t]), t
+        assert np.array_equal(w.accel[0], acc[t]), t
+    # entity ids of the recorded edges: a=1, b=2, c=3 (entity 0 = Globals, world.rs:174-183)
+    assert np.array_equal(golden["three_body.edges_entity_ids"], THREE_BODY_EDGES + 1)
+    assert np.array_equal(golden["three_body.tick"][:, 0], np.arange(101))
+
+
+def test_textbook_rk4_is_not_the_reference(golden, oracle):
+    """Guard against 'fixing' the scheme: advancing stage positions with the
+    stage velocity (textbook RK4) misses the golden by ~5e-8 after one tick."""
+    O = oracle
+    pos, vel, acc, frc, ine = _three_body_cols(golden)
+    dt = float(golden["three_body.simulation_time_step"][0, 0])
+    eff = [O.Effector(O.EFF_GRAVITY_EDGES_NEWTON, p=(G_NEWTON,), edges=THREE_BODY_EDGES)]
+
+    def A(x, v):
+        w = O.World(x, v, ine[0])
+        return w.eval_stage(0, eff)[1]
+
+    x0, v0 = pos[0], vel[0]
+    k1v, k1a = v0, A(x0, v0)
+    x2 = x0.copy(); x2[:, 4:] += 0.5 * dt * k1v[:, 3:]
+    k2v, k2a = v0 + 0.5 * dt * k1a, A(x2, v0 + 0.5 * dt * k1a)
+    x3 = x0.copy(); x3[:, 4:] += 0.5 * dt * k2v[:, 3:]
+    k3v, k3a = v0 + 0.5 * dt * k2a, A(x3, v0 + 0.5 * dt * k2a)
+    x4 = x0.copy(); x4[:, 4:] += dt * k3v[:, 3:]
+    k4v = v0 + dt * k3a
+    x1 = x0[:, 4:] + dt / 6 * (k1v + 2 * k2v + 2 * k3v + k4v)[:, 3:]
+    err = np.max(np.abs(x1 - pos[1][:, 4:]))
+    assert 1e-11 < err < 1e-6
+
+
+def _rocket_step(O, golden, t):
+    g = golden
+    w = O.World(g["rocket.world_pos"][t][None], g["rocket.world_vel"][t][None],
+                g["rocket.inertia"][t][None], g["rocket.world_accel"][t][None],
+                g["rocket.force"][t][None])
+    eff = [  # examples/rocket/main.py:575  effectors = gravity | apply_thrust | apply_aero_forces
+        O.Effector(O.EFF_GRAVITY_CONST, p=(0.0, 0.0, -9.81)),
+        O.Effector(O.EFF_THRUST_BODY, p=(-1.0, 0.0, 0.0), column=g["rocket.thrust"][t + 1].reshape(1, 1, 1)),
+        O.Effector(O.EFF_WRENCH_BODY, column=g["rocket.aero_force"][t + 1].reshape(1, 1, 6)),
+    ]
+    w.rk4(float(g["rocket.simulation_time_step"][0, 0]), 1, eff)
+    return w
+
+
+def test_rocket_one_step_predictions(golden, oracle):
+    """Attitude kinematics, torque / diagonal inertia, body->world rotation with
+    the recorded thrust / aero_force as stage-constant inputs.
+
+    Canonical (plain IEEE) oracle: within 1e-15 x max|value| of every recorded vector.
+    Golden-host mode (FMA-contracted `dot` where the reference JIT's pointer-ABI
+    runtime contracts it, tensor_rt.rs:1141-1163): 100/100 steps bit-exact."""
+    O = oracle
+    g = golden
+    names = ("world_pos", "world_vel", "force", "world_accel")
+    try:
+        O.set_dot_mode(0)
+        exact = 0
+        for t in range(100):
+            w = _rocket_step(O, g, t)
+            got = (w.pos[0, 0], w.vel[0, 0], w.force[0, 0], w.accel[0, 0])
+            ok = True
+            for name, a in zip(names, got):
+                ref = g[f"rocket.{name}"][t + 1]
+                scale = np.max(np.abs(ref))
+                assert np.max(np.abs(a - ref)) <= 1e-15 * scale, (t, name)
+                ok &= np.array_equal(a, ref)
+            exact += ok
+        assert exact >= 60
+        O.set_dot_mode(1)
+        for t in range(100):
+            w = _rocket_step(O, g, t)
+            got = (w.pos[0, 0], w.vel[0, 0], w.force[0, 0], w.accel[0, 0])
+            for name, a in zip(names, got):
+                assert np.array_equal(a, g[f"rocket.{name}"][t + 1]), (t, name)
+    finally:
+        O.set_dot_mode(0)
+
+
+def test_ball_one_step_predictions_bit_exact(golden, oracle):
+    """const-g + quadratic drag evaluated on the *stage* velocity
+    (examples/ball/sim.py:56-58,99-116) with the recorded wind; `bounce`
+    (sim.py:64-72) edits vel before six_dof and is replayed on the host."""
+    O = oracle
+    g = golden
+    dt = float(g["ball.simulation_time_step"][0, 0])
+    for t in range(100):
+        v = g["ball.world_vel"][t].copy()
+        if max(g["ball.world_pos"][t][6], v[5]) < 0.0:
+            v = np.concatenate([np.zeros(3), v[3:] * np.array([1.0, 1.0, -1.0]) * 0.85])
+        w = O.World(g["ball.world_pos"][t][None], v[None], g["ball.inertia"][t][None],
+                    g["ball.world_accel"][t][None], g["ball.force"][t][None])
+        eff = [O.Effector(O.EFF_GRAVITY_CONST, p=(0.0, 0.0, -9.81)),
+               O.Effector(O.EFF_DRAG_QUADRATIC, p=(0.5 * 1.225, 2 * 3.1415 * 0.2 ** 2),
+                          column=g["ball.wind"][t + 1].reshape(1, 1, 3))]
+        w.rk4(dt, 1, eff)
+        assert np.array_equal(w.pos[0, 0], g["ball.world_pos"][t + 1]), t
+        assert np.array_equal(w.vel[0, 0], g["ball.world_vel"][t + 1]), t
+        assert np.array_equal(w.force[0, 0], g["ball.force"][t + 1]), t
+        assert np.array_equal(w.accel[0, 0], g["ball.world_accel"][t + 1]), t
+
+
+# ---- known-answer tests of the primitives -------------------------------------
+
+
+def _axis_angle(axis, angle):
+    axis = np.asarray(axis, float)
+    axis = axis / np.sqrt(axis @ axis)
+    return np.concatenate([axis * np.sin(angle / 2), [np.cos(angle / 2)]])
+
+
+def test_quat_known_answers(oracle):
+    O = oracle
+    # quaternion.rs:352-361 test_quat_mult
+    out = O.qmul(_axis_angle([1, 0, 0], 3.0), _axis_angle([1, 0, 0], 1.0))
+    assert np.array_equal(out, [0.9092974268256817, 0.0, 0.0, -0.4161468365471424])
+    # quaternion.rs:363-370 test_quat_inverse
+    out = O.qinv(_axis_angle([1, 0, 0], 3.0))
+    assert np.array_equal(out, [-0.9974949866040544, -0.0, -0.0, 0.0707372016677029])
+    # quaternion.rs:372-381 test_quat_vec_mult
+    out = O.qrot(_axis_angle([1, 0, 0], 3.0), [1.0, 2.0, 3.0])
+    assert np.allclose(out, [1.0, -2.4033450173804924, -2.6877374736816018], atol=1e-6)
+    # quaternion.rs:383-388 convention i*j = k
+    assert np.array_equal(O.qmul([1.0, 0, 0, 0], [0, 1.0, 0, 0]), [0, 0, 1.0, 0])
+
+
+def test_spatial_transform_add_known_answers(oracle):
+    O = oracle
+    # spatial.rs:630-650 test_spatial_transform_add (assert_eq! => exact)
+    out = O.transform_add_motion([0, 0, 0, 1.0, 0, 0, 0], [0, 0, 1.0, 0, 0, 0])
+    assert np.array_equal(out, [0.0, 0.0, 0.4472135954999579, 0.8944271909999159, 0.0, 0.0, 0.0])
+    # spatial.rs:652-676 test_spatial_transform_integrate
+    p = np.array([0, 0, 0, 1.0, 0, 0, 0])
+    for _ in range(20):
+        p = O.transform_add_motion(p, [0, 0, 0.25 / 20.0, 0, 0, 0])
+    assert np.allclose(p, [0, 0, 0.12467473338522769, 0.992197667229329, 0, 0, 0], atol=1e-5)
+
+
+def _body(O, vel, inertia=None):
+    pos = np.array([[0, 0, 0, 1.0, 0, 0, 0]])
+    ine = np.array([[1.0, 1.0, 1.0, 0, 0, 0, 1.0]]) if inertia is None else inertia
+    return O.World(pos, np.array([vel], float), ine)
+
+
+def test_six_dof_kats_from_test_all(oracle):
+    O = oracle
+    # test_all.py:67-83 test_six_dof: x = dt after one tick of six_dof(1/60)
+    w = _body(O, [0, 0, 0, 1.0, 0, 0]).rk4(0.01, 1, dt_final=1.0 / 60.0)
+    assert np.allclose(w.pos[0, 0, :4], [0, 0, 0, 1.0])
+    assert np.allclose(w.pos[0, 0, 4:], [0.01666667, 0, 0])
+    # test_all.py:228-291 test_six_dof_ang_vel_int (Julia/Simulink values, rtol 1e-5)
+    dt = 0.008333333
+    for omega, want in [
+        ([0, 0, 1.0], [0.0, 0.0, 0.479425538604203, 0.8775825618903728]),
+        ([0, 1.0, 0], [0.0, 0.479425538604203, 0.0, 0.8775825618903728]),
+        ([1.0, 1.0, 0], [0.45936268493243, 0.45936268493243, 0.0, 0.76024459707606]),
+    ]:
+        w = _body(O, omega + [0, 0, 0]).rk4(dt, 120, dt_final=1.0 / 120.0)
+        assert np.isclose(w.pos[0, 0, :4], want, rtol=1e-5).all()
+    # test_all.py:342-366 test_six_dof_force: x = 0.5 after 1 s of unit force
+    class ConstForce:  # constant world-frame force == GRAVITY_CONST with g = F/m, m = 1
+        pass
+
+    w = _body(O, [0, 0, 0, 0, 0, 0]).rk4(dt, 120, [O.Effector(O.EFF_GRAVITY_CONST, p=(1.0, 0, 0))],
+                                         dt_final=1.0 / 120.0)
+    assert np.isclose(w.pos[0, 0], [0, 0, 0, 1.0, 0.5, 0, 0], rtol=1e-5).all()
+
+
+def test_semi_implicit_matches_definition(oracle):
+    """semi_implicit.rs:42-62: v' = v + dt*a ; x' = x (+) dt*v'."""
+    O = oracle
+    rng = np.random.default_rng(3)
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    pos = np.concatenate([q, rng.normal(size=3)])[None]
+    vel = rng.normal(size=(1, 6))
+    ine = np.array([[0.5, 2.0, 3.0, 0, 0, 0, 4.0]])
+    eff = [O.Effector(O.EFF_GRAVITY_CONST, p=(0.1, -0.2, -9.81))]
+    w = O.World(pos, vel, ine)
+    F, A = w.eval_stage(0, eff)
+    v1 = vel[0] + 0.01 * A[0]
+    x1 = O.transform_add_motion(pos[0], 0.01 * v1)
+    w.semi_implicit(0.01, 1, eff)
+    assert np.array_equal(w.vel[0, 0], v1)
+    assert np.array_equal(w.pos[0, 0], x1)
+    assert np.array_equal(w.force[0, 0], F[0]) and np.array_equal(w.accel[0, 0], A[0])
+
+
+def test_oracle_world_axis_and_threads(oracle):
+    """M stacked worlds == M independent runs; thread count does not change bits."""
+    O = oracle
+    rng = np.random.default_rng(11)
+    M, N = 6, 5
+    q = rng.normal(size=(M, N, 4)); q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    pos = np.concatenate([q, rng.normal(size=(M, N, 3))], -1)
+    vel = rng.normal(size=(M, N, 6))
+    ine = np.concatenate([rng.uniform(0.1, 10, (M, N, 3)), np.zeros((M, N, 3)), rng.uniform(0.5, 50, (M, N, 1))], -1)
+    edges = np.array([[i, j] for i in range(N) for j in range(N) if i != j])
+    thrust = rng.uniform(0, 5, (M, N, 1))
+    eff = [O.Effector(O.EFF_GRAVITY_EDGES_SOFTENED, p=(1e-3, 1e-10), edges=edges),
+           O.Effector(O.EFF_THRUST_BODY, p=(-1.0, 0, 0), column=thrust)]
+    a = O.World(pos, vel, ine).rk4(0.01, 7, eff, threads=1)
+    b = O.World(pos, vel, ine).rk4(0.01, 7, eff, threads=4)
+    assert np.array_equal(a.pos, b.pos) and np.array_equal(a.vel, b.vel)
+    for m in range(M):
+        e1 = [O.Effector(O.EFF_GRAVITY_EDGES_SOFTENED, p=(1e-3, 1e-10), edges=edges),
+              O.Effector(O.EFF_THRUST_BODY, p=(-1.0, 0, 0), column=thrust[m:m + 1])]
+        c = O.World(pos[m], vel[m], ine[m]).rk4(0.01, 7, e1)
+        assert np.array_equal(c.pos[0], a.pos[m]) and np.array_equal(c.vel[0], a.vel[m])
