@@ -1,0 +1,693 @@
+// Host runtime + C ABI of libb200_sixdof (include/b200_sixdof.h).
+//
+// Replaces CraneliftExec (libs/nox-py/src/cranelift_exec.rs:54-195) on the
+// six_dof() path: owns device-resident SoA columns, maps the reference's host
+// column buffers in and out, and drives the sm_100a kernels.  There is no CPU
+// fallback anywhere in this file: without a CUDA device every entry point fails
+// with B200_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sixdof_internal.h"
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_last_error = "";
+thread_local b200_sixdof *g_tick_handle = nullptr;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+struct Column {
+    uint64_t id;
+    uint32_t width;     // f64 per body (globals: 1)
+    bool global;        // tick / simulation_time_step: one 8-byte scalar, host resident
+    double *dev;        // width planes of ld doubles
+};
+
+uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+} // namespace
+
+struct b200_sixdof {
+    b200_sixdof_desc desc{};
+    std::vector<b200_effector> effectors;
+    int device = 0;
+    uint64_t n_bodies = 0;
+    uint64_t ld = 0;
+    std::vector<Column> cols;
+    std::vector<uint64_t> input_ids, output_ids;
+    double sim_time_step = 0.0;   // SimulationTimeStep column value
+    uint64_t tick = 0;            // Tick column value
+    uint64_t ticks_done = 0;      // ticks since create / trajectory reset (trajectory slot index base)
+    // graph effector
+    int graph_eff = -1;
+    bool graph_dense = false;
+    uint32_t *row_ptr = nullptr, *col_idx = nullptr;
+    uint8_t *has_edge = nullptr;
+    double *gforce = nullptr;
+    // staging for AoS <-> SoA
+    double *staging = nullptr;
+    uint64_t staging_bytes = 0;
+    // trajectory
+    double *traj = nullptr;
+    // plumbing
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int status = B200_OK;
+    b200_timings timings{};
+
+    Column *find(uint64_t id)
+    {
+        for (auto &c : cols) if (c.id == id) return &c;
+        return nullptr;
+    }
+    const Column *find(uint64_t id) const
+    {
+        for (auto &c : cols) if (c.id == id) return &c;
+        return nullptr;
+    }
+};
+
+namespace {
+
+int cuda_fail(b200_sixdof *h, cudaError_t e, const char *what)
+{
+    if (h) h->status = B200_ERR_CUDA;
+    return fail(e == cudaErrorMemoryAllocation ? B200_ERR_OUT_OF_MEMORY : B200_ERR_CUDA, "CUDA error in %s: %s", what,
+                cudaGetErrorString(e));
+}
+
+#define CU(h, call)                                                        \
+    do {                                                                   \
+        cudaError_t e_ = (call);                                           \
+        if (e_ != cudaSuccess) return cuda_fail((h), e_, #call);           \
+    } while (0)
+
+int ensure_staging(b200_sixdof *h, uint64_t bytes)
+{
+    if (h->staging_bytes >= bytes) return B200_OK;
+    if (h->staging) { CU(h, cudaFree(h->staging)); h->staging = nullptr; h->staging_bytes = 0; }
+    CU(h, cudaMalloc(&h->staging, bytes));
+    h->staging_bytes = bytes;
+    return B200_OK;
+}
+
+uint64_t column_bytes(const b200_sixdof *h, const Column &c)
+{
+    return c.global ? 8ull : h->n_bodies * c.width * 8ull;
+}
+
+bool is_graph_kind(uint32_t k) { return k == B200_EFF_GRAVITY_EDGES_NEWTON || k == B200_EFF_GRAVITY_EDGES_SOFTENED; }
+
+// The reference's free six_dof() system has inputs (first-init order)
+//   tick, force, inertia, world_pos, world_accel, simulation_time_step, world_vel
+// (cranelift-mlir/tests/three_body_e2e.rs:15-16); effector
+// columns are inserted after `force` in effector order.  Outputs are every
+// variable of the builder, ordered by ComponentId (BTreeMap, system.rs).
+void build_id_tables(b200_sixdof *h)
+{
+    std::vector<uint64_t> in = {B200_ID_TICK, B200_ID_FORCE};
+    for (auto &e : h->effectors)
+        if (e.column_id && std::find(in.begin(), in.end(), e.column_id) == in.end()) in.push_back(e.column_id);
+    for (uint64_t id : {B200_ID_INERTIA, B200_ID_WORLD_POS, B200_ID_WORLD_ACCEL, B200_ID_SIMULATION_TIME_STEP,
+                        B200_ID_WORLD_VEL})
+        if (std::find(in.begin(), in.end(), id) == in.end()) in.push_back(id);
+    h->input_ids = in;
+    h->output_ids = in;
+    std::sort(h->output_ids.begin(), h->output_ids.end());
+}
+
+int add_column(b200_sixdof *h, uint64_t id, uint32_t width, bool global)
+{
+    if (h->find(id)) return B200_OK;
+    Column c{id, width, global, nullptr};
+    if (!global && h->n_bodies) {
+        const uint64_t bytes = (uint64_t)width * h->ld * 8ull;
+        CU(h, cudaMalloc(&c.dev, bytes));
+        CU(h, cudaMemsetAsync(c.dev, 0, bytes, h->stream));
+    }
+    h->cols.push_back(c);
+    return B200_OK;
+}
+
+int build_graph(b200_sixdof *h, const b200_effector &e)
+{
+    const uint32_t N = (uint32_t)h->desc.n_entities;
+    std::vector<uint32_t> row(N + 1, 0), col;
+    std::vector<std::vector<uint32_t>> adj(N);
+    for (uint64_t k = 0; k < e.n_edges; ++k) {
+        const uint32_t a = e.edge_from[k], b = e.edge_to[k];
+        if (a >= N || b >= N) return fail(B200_ERR_INVALID_ARGUMENT, "edge %llu (%u -> %u) out of range (n_entities=%u)",
+                                          (unsigned long long)k, a, b, N);
+        adj[a].push_back(b); // spawn order preserved per source (graph.rs:194-197)
+    }
+    std::vector<uint8_t> has(N ? N : 1, 0);
+    bool dense = N > 1;
+    for (uint32_t i = 0; i < N; ++i) {
+        row[i + 1] = row[i] + (uint32_t)adj[i].size();
+        col.insert(col.end(), adj[i].begin(), adj[i].end());
+        has[i] = !adj[i].empty();
+        if (adj[i].size() != N - 1) dense = false;
+        else {
+            uint32_t want = 0;
+            for (uint32_t t : adj[i]) { if (want == i) ++want; if (t != want) { dense = false; break; } ++want; }
+        }
+    }
+    h->graph_dense = dense;
+    CU(h, cudaMalloc(&h->row_ptr, (N + 1) * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&h->col_idx, std::max<size_t>(col.size(), 1) * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&h->has_edge, has.size()));
+    CU(h, cudaMemcpy(h->row_ptr, row.data(), (N + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!col.empty()) CU(h, cudaMemcpy(h->col_idx, col.data(), col.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->has_edge, has.data(), has.size(), cudaMemcpyHostToDevice));
+    CU(h, cudaMalloc(&h->gforce, 9ull * h->ld * 8ull));
+    CU(h, cudaMemset(h->gforce, 0, 9ull * h->ld * 8ull));
+    return B200_OK;
+}
+
+void fill_step_params(b200_sixdof *h, StepParams &P)
+{
+    std::memset(&P, 0, sizeof P);
+    P.pos = h->find(B200_ID_WORLD_POS)->dev;
+    P.vel = h->find(B200_ID_WORLD_VEL)->dev;
+    P.acc = h->find(B200_ID_WORLD_ACCEL)->dev;
+    P.frc = h->find(B200_ID_FORCE)->dev;
+    P.ine = h->find(B200_ID_INERTIA)->dev;
+    P.gforce = h->gforce;
+    P.has_edge = h->has_edge;
+    P.ld = h->ld;
+    P.n_bodies = h->n_bodies;
+    P.n_entities = (uint32_t)h->desc.n_entities;
+    P.n_eff = (uint32_t)h->effectors.size();
+    P.dt_stage = h->sim_time_step;
+    P.dt_final = std::isnan(h->desc.time_step) ? h->sim_time_step : h->desc.time_step;
+    P.traj = h->traj;
+    P.traj_capacity = h->desc.trajectory_capacity;
+    P.traj_every = h->traj ? h->desc.trajectory_every : 0;
+    for (size_t i = 0; i < h->effectors.size(); ++i) {
+        const b200_effector &e = h->effectors[i];
+        P.eff[i].kind = e.kind;
+        P.eff[i].flags = e.flags;
+        std::memcpy(P.eff[i].p, e.p, sizeof e.p);
+        const Column *c = e.column_id ? h->find(e.column_id) : nullptr;
+        P.eff[i].col = c ? c->dev : nullptr;
+    }
+}
+
+int do_step(b200_sixdof *h, uint64_t n_ticks)
+{
+    if (h->status != B200_OK) return fail(h->status, "handle is in a failed state");
+    if (n_ticks == 0 || h->n_bodies == 0) { h->tick += n_ticks; h->ticks_done += n_ticks; return B200_OK; }
+    StepParams P;
+    fill_step_params(h, P);
+    const bool exact = h->desc.math_mode == B200_MATH_EXACT;
+    const bool graph = h->graph_eff >= 0;
+    const uint64_t fuse = graph ? 1 : std::max<uint32_t>(1u, h->desc.max_fused_ticks);
+    uint64_t left = n_ticks;
+    while (left) {
+        const uint64_t n = std::min(left, fuse);
+        if (graph) {
+            const b200_effector &e = h->effectors[h->graph_eff];
+            GraphParams G{};
+            G.pos = P.pos; G.vel = P.vel; G.ine = P.ine; G.gforce = h->gforce;
+            G.ld = h->ld; G.n_entities = P.n_entities; G.n_worlds = (uint32_t)h->desc.n_worlds;
+            G.dt_stage = P.dt_stage; G.kind = e.kind; G.integrator = h->desc.integrator;
+            G.p0 = e.p[0]; G.p1 = e.p[1]; G.row_ptr = h->row_ptr; G.col_idx = h->col_idx;
+            CU(h, launch_graph_force(G, h->desc.math_mode, h->graph_dense, h->stream));
+            h->timings.kernel_launches++;
+        }
+        P.n_ticks = (uint32_t)n;
+        P.tick0 = h->ticks_done;
+        P.write_fa = (exact || left == n) ? 1u : 0u; // Force/WorldAccel are only host-visible after the batch
+        CU(h, launch_body_step(P, (int)h->desc.integrator, (int)h->desc.math_mode, h->stream));
+        h->timings.kernel_launches++;
+        h->ticks_done += n;
+        h->tick += n;
+        h->timings.ticks += n;
+        left -= n;
+    }
+    return B200_OK;
+}
+
+int do_upload(b200_sixdof *h, uint64_t id, const void *src, uint64_t bytes)
+{
+    Column *c = h->find(id);
+    if (!c) return fail(B200_ERR_COMPONENT_NOT_FOUND, "component not found: 0x%016llx", (unsigned long long)id);
+    if (bytes != column_bytes(h, *c))
+        return fail(B200_ERR_VALUE_SIZE_MISMATCH, "component value had wrong size: 0x%016llx has %llu bytes, got %llu",
+                    (unsigned long long)id, (unsigned long long)column_bytes(h, *c), (unsigned long long)bytes);
+    if (!src) return fail(B200_ERR_INVALID_ARGUMENT, "null source buffer");
+    if (c->global) {
+        uint64_t raw;
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+            CU(h, cudaMemcpy(&raw, src, 8, cudaMemcpyDeviceToHost));
+        } else {
+            (void)cudaGetLastError();
+            std::memcpy(&raw, src, 8);
+        }
+        if (id == B200_ID_TICK) h->tick = raw;
+        else std::memcpy(&h->sim_time_step, &raw, 8);
+        return B200_OK;
+    }
+    if (bytes == 0) return B200_OK;
+    int rc = ensure_staging(h, bytes);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(h->staging, src, bytes, cudaMemcpyDefault, h->stream));
+    CU(h, launch_aos_to_soa(h->staging, c->dev, h->n_bodies, c->width, h->ld, h->stream));
+    h->timings.kernel_launches++;
+    return B200_OK;
+}
+
+int do_download(b200_sixdof *h, uint64_t id, void *dst, uint64_t bytes)
+{
+    Column *c = h->find(id);
+    if (!c) return fail(B200_ERR_COMPONENT_NOT_FOUND, "component not found: 0x%016llx", (unsigned long long)id);
+    if (bytes != column_bytes(h, *c))
+        return fail(B200_ERR_VALUE_SIZE_MISMATCH, "component value had wrong size: 0x%016llx has %llu bytes, got %llu",
+                    (unsigned long long)id, (unsigned long long)column_bytes(h, *c), (unsigned long long)bytes);
+    if (!dst) return fail(B200_ERR_INVALID_ARGUMENT, "null destination buffer");
+    if (c->global) {
+        uint64_t raw;
+        if (id == B200_ID_TICK) raw = h->tick;
+        else std::memcpy(&raw, &h->sim_time_step, 8);
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+            CU(h, cudaMemcpy(dst, &raw, 8, cudaMemcpyHostToDevice));
+        } else {
+            (void)cudaGetLastError();
+            std::memcpy(dst, &raw, 8);
+        }
+        return B200_OK;
+    }
+    if (bytes == 0) return B200_OK;
+    int rc = ensure_staging(h, bytes);
+    if (rc) return rc;
+    CU(h, launch_soa_to_aos(c->dev, h->staging, h->n_bodies, c->width, h->ld, h->stream));
+    h->timings.kernel_launches++;
+    CU(h, cudaMemcpyAsync(dst, h->staging, bytes, cudaMemcpyDefault, h->stream));
+    // the staging buffer is reused by the next transfer; the copy must have left it first
+    CU(h, cudaStreamSynchronize(h->stream));
+    return B200_OK;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+} // namespace
+
+// ===================================================================== C ABI
+
+extern "C" {
+
+uint64_t b200_component_id(const char *name)
+{
+    uint64_t h = 0xcbf29ce484222325ull; // FNV-1a 64 offset basis
+    if (name)
+        for (const unsigned char *p = (const unsigned char *)name; *p; ++p) { h ^= *p; h *= 0x100000001b3ull; }
+    return h & ~(1ull << 63); // types.rs:43
+}
+
+const char *b200_last_error(void) { return g_last_error.c_str(); }
+
+int b200_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return -fail(B200_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e)); }
+    return n;
+}
+
+void *b200_host_alloc(uint64_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        fail(B200_ERR_OUT_OF_MEMORY, "cudaHostAlloc(%llu) failed: %s", (unsigned long long)bytes,
+             cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+
+void b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
+{
+    if (!d || !out) return fail(B200_ERR_INVALID_ARGUMENT, "null descriptor / out pointer");
+    *out = nullptr;
+    if (d->abi_version != B200_SIXDOF_ABI_VERSION)
+        return fail(B200_ERR_INVALID_ARGUMENT, "ABI version mismatch: library %u, caller %u", B200_SIXDOF_ABI_VERSION,
+                    d->abi_version);
+    if (d->integrator > B200_INTEGRATOR_SEMI_IMPLICIT) return fail(B200_ERR_UNSUPPORTED, "unknown integrator %u", d->integrator);
+    if (d->math_mode > B200_MATH_FAST) return fail(B200_ERR_UNSUPPORTED, "unknown math mode %u", d->math_mode);
+    if (d->n_effectors > B200_MAX_EFFECTORS) return fail(B200_ERR_UNSUPPORTED, "too many effectors (%u > %u)", d->n_effectors, B200_MAX_EFFECTORS);
+    if (d->n_effectors && !d->effectors) return fail(B200_ERR_INVALID_ARGUMENT, "n_effectors > 0 but effectors is null");
+    if (d->n_worlds == 0) return fail(B200_ERR_INVALID_ARGUMENT, "n_worlds must be >= 1");
+    if (d->n_entities > 0xffffffffull || d->n_worlds > 0xffffffffull) return fail(B200_ERR_UNSUPPORTED, "n_entities / n_worlds exceed 2^32-1");
+    if (!(d->sim_time_step > 0.0) || !std::isfinite(d->sim_time_step))
+        return fail(B200_ERR_INVALID_ARGUMENT, "invalid time step: %g", d->sim_time_step); // Error::InvalidTimeStep
+
+    int ndev = b200_device_count();
+    if (ndev <= 0) return fail(B200_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    int dev = d->device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) return fail(B200_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", dev, ndev);
+
+    b200_sixdof *h = new (std::nothrow) b200_sixdof();
+    if (!h) return fail(B200_ERR_OUT_OF_MEMORY, "out of host memory");
+    h->desc = *d;
+    h->device = dev;
+    h->effectors.assign(d->effectors, d->effectors + d->n_effectors);
+    h->desc.effectors = nullptr;
+    h->n_bodies = d->n_entities * d->n_worlds;
+    h->ld = round_up(std::max<uint64_t>(h->n_bodies, 1), 32);
+    h->sim_time_step = d->sim_time_step;
+
+    int rc = B200_OK;
+    auto bail = [&](int code) { b200_sixdof_destroy(h); return code; };
+    if (cudaSetDevice(dev) != cudaSuccess) return bail(cuda_fail(nullptr, cudaGetLastError(), "cudaSetDevice"));
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(cuda_fail(nullptr, cudaGetLastError(), "cudaStreamCreate"));
+    for (auto &e : h->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return bail(cuda_fail(nullptr, cudaGetLastError(), "cudaEventCreate"));
+
+    // validate effectors
+    int n_drag = 0, n_frame = 0;
+    for (size_t i = 0; i < h->effectors.size(); ++i) {
+        b200_effector &e = h->effectors[i];
+        uint32_t want_w = 0;
+        switch (e.kind) {
+        case B200_EFF_GRAVITY_CONST: case B200_EFF_GRAVITY_FRAME: want_w = 0; break;
+        case B200_EFF_DRAG_QUADRATIC: want_w = 3; ++n_drag; break;
+        case B200_EFF_THRUST_BODY: want_w = 1; break;
+        case B200_EFF_WRENCH_BODY: want_w = 6; break;
+        case B200_EFF_GRAVITY_EDGES_NEWTON: case B200_EFF_GRAVITY_EDGES_SOFTENED:
+            if (h->graph_eff >= 0) return bail(fail(B200_ERR_UNSUPPORTED, "only one edge_fold gravity effector is supported"));
+            if (e.n_edges && (!e.edge_from || !e.edge_to)) return bail(fail(B200_ERR_INVALID_ARGUMENT, "edge arrays are null"));
+            if (d->math_mode == B200_MATH_FAST && i != 0)
+                return bail(fail(B200_ERR_UNSUPPORTED, "FAST math: the edge_fold gravity effector must come first (it overwrites Force)"));
+            h->graph_eff = (int)i;
+            break;
+        default:
+            return bail(fail(B200_ERR_UNSUPPORTED, "effector kind %u is not built in (no CPU fallback, no JIT)", e.kind));
+        }
+        if (e.kind == B200_EFF_GRAVITY_FRAME) ++n_frame;
+        if (e.column_id) {
+            if (e.column_width != want_w)
+                return bail(fail(B200_ERR_VALUE_SIZE_MISMATCH, "effector %zu: column width %u, kind %u needs %u", i, e.column_width, e.kind, want_w));
+        } else if (e.kind == B200_EFF_THRUST_BODY || e.kind == B200_EFF_WRENCH_BODY) {
+            return bail(fail(B200_ERR_INVALID_ARGUMENT, "effector %zu (kind %u) needs an input column", i, e.kind));
+        }
+    }
+    if (d->math_mode == B200_MATH_FAST && (n_drag > 1 || n_frame > 1))
+        return bail(fail(B200_ERR_UNSUPPORTED, "FAST math supports at most one drag and one frame effector"));
+
+    // columns
+    if ((rc = add_column(h, B200_ID_TICK, 1, true))) return bail(rc);
+    if ((rc = add_column(h, B200_ID_SIMULATION_TIME_STEP, 1, true))) return bail(rc);
+    if ((rc = add_column(h, B200_ID_WORLD_POS, 7, false))) return bail(rc);
+    if ((rc = add_column(h, B200_ID_WORLD_VEL, 6, false))) return bail(rc);
+    if ((rc = add_column(h, B200_ID_WORLD_ACCEL, 6, false))) return bail(rc);
+    if ((rc = add_column(h, B200_ID_FORCE, 6, false))) return bail(rc);
+    if ((rc = add_column(h, B200_ID_INERTIA, 7, false))) return bail(rc);
+    for (auto &e : h->effectors)
+        if (e.column_id) {
+            const Column *c = h->find(e.column_id);
+            if (c && c->width != e.column_width)
+                return bail(fail(B200_ERR_VALUE_SIZE_MISMATCH, "column 0x%016llx declared with two widths", (unsigned long long)e.column_id));
+            if ((rc = add_column(h, e.column_id, e.column_width, false))) return bail(rc);
+        }
+    build_id_tables(h);
+
+    if (h->graph_eff >= 0) {
+        // copy the edge arrays' content now: the caller's pointers are only valid for this call
+        if ((rc = build_graph(h, h->effectors[h->graph_eff]))) return bail(rc);
+        h->effectors[h->graph_eff].edge_from = h->effectors[h->graph_eff].edge_to = nullptr;
+    }
+    if (d->trajectory_every && d->trajectory_capacity) {
+        if (cudaMalloc(&h->traj, d->trajectory_capacity * 13ull * h->ld * 8ull) != cudaSuccess)
+            return bail(cuda_fail(nullptr, cudaGetLastError(), "cudaMalloc(trajectory)"));
+    }
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(cuda_fail(nullptr, cudaGetLastError(), "create sync"));
+    *out = h;
+    return B200_OK;
+}
+
+void b200_sixdof_destroy(b200_sixdof *h)
+{
+    if (!h) return;
+    if (g_tick_handle == h) g_tick_handle = nullptr;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto &c : h->cols) if (c.dev) cudaFree(c.dev);
+    if (h->row_ptr) cudaFree(h->row_ptr);
+    if (h->col_idx) cudaFree(h->col_idx);
+    if (h->has_edge) cudaFree(h->has_edge);
+    if (h->gforce) cudaFree(h->gforce);
+    if (h->staging) cudaFree(h->staging);
+    if (h->traj) cudaFree(h->traj);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+    (void)cudaGetLastError();
+    delete h;
+}
+
+uint32_t b200_sixdof_input_ids(const b200_sixdof *h, uint64_t *ids, uint32_t cap)
+{
+    if (!h) return 0;
+    for (uint32_t i = 0; i < cap && i < h->input_ids.size(); ++i) ids[i] = h->input_ids[i];
+    return (uint32_t)h->input_ids.size();
+}
+
+uint32_t b200_sixdof_output_ids(const b200_sixdof *h, uint64_t *ids, uint32_t cap)
+{
+    if (!h) return 0;
+    for (uint32_t i = 0; i < cap && i < h->output_ids.size(); ++i) ids[i] = h->output_ids[i];
+    return (uint32_t)h->output_ids.size();
+}
+
+uint64_t b200_sixdof_column_bytes(const b200_sixdof *h, uint64_t id)
+{
+    if (!h) return 0;
+    const Column *c = h->find(id);
+    return c ? column_bytes(h, *c) : 0;
+}
+
+int b200_sixdof_upload(b200_sixdof *h, uint64_t id, const void *src, uint64_t bytes)
+{
+    if (!h) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+    CU(h, cudaSetDevice(h->device));
+    return do_upload(h, id, src, bytes);
+}
+
+int b200_sixdof_download(b200_sixdof *h, uint64_t id, void *dst, uint64_t bytes)
+{
+    if (!h) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+    CU(h, cudaSetDevice(h->device));
+    return do_download(h, id, dst, bytes);
+}
+
+int b200_sixdof_step(b200_sixdof *h, uint64_t n_ticks)
+{
+    if (!h) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+    CU(h, cudaSetDevice(h->device));
+    return do_step(h, n_ticks);
+}
+
+int b200_sixdof_sync(b200_sixdof *h)
+{
+    if (!h) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return B200_OK;
+}
+
+int b200_sixdof_invoke_batch(b200_sixdof *h, const uint8_t *const *in_cols, uint8_t *const *out_cols, uint64_t n_ticks)
+{
+    if (!h) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+    if (!in_cols || !out_cols) return fail(B200_ERR_INVALID_ARGUMENT, "null column tables");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaEventRecord(h->ev[0], h->stream));
+    for (size_t i = 0; i < h->input_ids.size(); ++i) {
+        const Column *c = h->find(h->input_ids[i]);
+        int rc = do_upload(h, c->id, in_cols[i], column_bytes(h, *c));
+        if (rc) return rc;
+    }
+    CU(h, cudaEventRecord(h->ev[1], h->stream));
+    int rc = do_step(h, std::max<uint64_t>(n_ticks, 1)); // `n.max(1)`, cranelift_exec.rs:135
+    if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev[2], h->stream));
+    for (size_t i = 0; i < h->output_ids.size(); ++i) {
+        const Column *c = h->find(h->output_ids[i]);
+        rc = do_download(h, c->id, out_cols[i], column_bytes(h, *c));
+        if (rc) return rc;
+    }
+    CU(h, cudaEventRecord(h->ev[3], h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->timings.h2d_upload_ms = ev_ms(h->ev[0], h->ev[1]);
+    h->timings.kernel_invoke_ms = ev_ms(h->ev[1], h->ev[2]);
+    h->timings.d2h_download_ms = ev_ms(h->ev[2], h->ev[3]);
+    return B200_OK;
+}
+
+int b200_sixdof_bind_tick(b200_sixdof *h)
+{
+    g_tick_handle = h;
+    return B200_OK;
+}
+
+void b200_sixdof_tick(const uint8_t *const *in_cols, uint8_t **out_cols)
+{
+    b200_sixdof *h = g_tick_handle;
+    if (!h) { fail(B200_ERR_INVALID_ARGUMENT, "b200_sixdof_tick: no handle bound on this thread"); return; }
+    (void)b200_sixdof_invoke_batch(h, in_cols, out_cols, 1); // errors stay sticky on the handle / last_error
+}
+
+uint64_t b200_sixdof_trajectory_len(const b200_sixdof *h)
+{
+    if (!h || !h->traj || !h->desc.trajectory_every) return 0;
+    return std::min<uint64_t>(h->ticks_done / h->desc.trajectory_every, h->desc.trajectory_capacity);
+}
+
+int b200_sixdof_trajectory_download(b200_sixdof *h, void *dst, uint64_t bytes)
+{
+    if (!h) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+    CU(h, cudaSetDevice(h->device));
+    const uint64_t n = b200_sixdof_trajectory_len(h);
+    const uint64_t want = n * h->n_bodies * 13ull * 8ull;
+    if (bytes != want) return fail(B200_ERR_VALUE_SIZE_MISMATCH, "trajectory is %llu bytes, got %llu", (unsigned long long)want, (unsigned long long)bytes);
+    if (want == 0) return B200_OK;
+    // convert in chunks through the staging buffer
+    const uint64_t per_sample = h->n_bodies * 13ull * 8ull;
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (256ull << 20) / per_sample));
+    int rc = ensure_staging(h, chunk * per_sample);
+    if (rc) return rc;
+    for (uint64_t s0 = 0; s0 < n; s0 += chunk) {
+        const uint64_t ns = std::min(chunk, n - s0);
+        CU(h, launch_traj_to_aos(h->traj + s0 * 13ull * h->ld, h->staging, ns, h->n_bodies, h->ld, h->stream));
+        h->timings.kernel_launches++;
+        CU(h, cudaMemcpyAsync((char *)dst + s0 * per_sample, h->staging, ns * per_sample, cudaMemcpyDefault, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
+    return B200_OK;
+}
+
+int b200_sixdof_trajectory_reset(b200_sixdof *h)
+{
+    if (!h) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+    h->ticks_done = 0;
+    return B200_OK;
+}
+
+uint64_t b200_sixdof_tick_count(const b200_sixdof *h) { return h ? h->tick : 0; }
+
+int b200_sixdof_set_stream(b200_sixdof *h, void *cuda_stream)
+{
+    if (!h) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (cuda_stream) {
+        if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+        h->stream = (cudaStream_t)cuda_stream;
+        h->own_stream = false;
+    } else if (!h->own_stream) {
+        CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    return B200_OK;
+}
+
+int b200_sixdof_timings(const b200_sixdof *h, b200_timings *out)
+{
+    if (!h || !out) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+    *out = h->timings;
+    return B200_OK;
+}
+
+int b200_sixdof_status(const b200_sixdof *h) { return h ? h->status : B200_ERR_INVALID_ARGUMENT; }
+
+void *b200_sixdof_device_plane(b200_sixdof *h, uint64_t id, uint32_t plane)
+{
+    if (!h) return nullptr;
+    Column *c = h->find(id);
+    if (!c || c->global || plane >= c->width) return nullptr;
+    return c->dev + (uint64_t)plane * h->ld;
+}
+
+uint64_t b200_sixdof_plane_stride(const b200_sixdof *h) { return h ? h->ld : 0; }
+
+double b200_probe_copy_gbs(int device, uint64_t bytes, int iters)
+{
+    if (b200_device_count() <= 0) return -1.0;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return -1.0;
+    void *a = nullptr, *b = nullptr;
+    if (cudaMalloc(&a, bytes) != cudaSuccess || cudaMalloc(&b, bytes) != cudaSuccess) { cudaFree(a); (void)cudaGetLastError(); return -1.0; }
+    cudaMemset(a, 1, bytes);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int i = 0; i < iters + 2; ++i) {
+        cudaEventRecord(e0);
+        cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (i >= 2 && ms > 0) best = std::max(best, 2.0 * bytes / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(a); cudaFree(b);
+    return best;
+}
+
+double b200_probe_fp64_gflops(int device, int iters)
+{
+    if (b200_device_count() <= 0) return -1.0;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop{};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaGetDeviceProperties(&prop, dev);
+    const int blocks = prop.multiProcessorCount * 8;
+    double *out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * 256 * 8) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int i = 0; i < 5; ++i) {
+        cudaEventRecord(e0);
+        launch_probe_fp64(out, iters, blocks, nullptr);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (i >= 1 && ms > 0) best = std::max(best, 2.0 * 8.0 * iters * blocks * 256.0 / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
+
+} // extern "C"

@@ -1,0 +1,73 @@
+// Host<->kernel parameter blocks of libb200_sixdof (internal; the public surface
+// is include/b200_sixdof.h).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/b200_sixdof.h"
+
+namespace b200 {
+
+// One built-in effector as the kernels see it.  `col` points at the SoA planes
+// of its per-body input column (plane p at col + p*ld), nullptr if none.
+struct EffDev {
+    uint32_t kind;
+    uint32_t flags;
+    double p[8];
+    const double *col;
+};
+
+// Launch parameters of the per-body integrator kernels.  All columns are SoA:
+// plane k of a column lives at base + k*ld, body b at [.. + b].
+struct StepParams {
+    double *pos;        // 7 planes: q.i q.j q.k q.w x y z
+    double *vel;        // 6 planes: omega(3) v(3)
+    double *acc;        // 6 planes (WorldAccel; stage-4 value on output)
+    double *frc;        // 6 planes (Force; stage-4 value on output)
+    const double *ine;  // 7 planes: diag(3) momentum(3) mass
+    const double *gforce; // 9 planes: edge_fold gravity at the 3 distinct stage positions (or nullptr)
+    const uint8_t *has_edge; // [n_entities]: body owns >= 1 out-edge (or nullptr)
+    uint64_t ld;        // plane stride in doubles
+    uint64_t n_bodies;  // n_worlds * n_entities
+    uint32_t n_entities;
+    uint32_t n_eff;
+    double dt_stage;    // SimulationTimeStep (rk4.rs:90)
+    double dt_final;    // six_dof(time_step=) or dt_stage (rk4.rs:83,119)
+    uint32_t n_ticks;   // ticks integrated by this launch (state stays in registers)
+    uint32_t write_fa;  // materialise Force / WorldAccel at the end of the launch
+    // trajectory ring: sample s, plane p at traj + (s*13 + p)*ld
+    double *traj;
+    uint64_t traj_capacity;
+    uint32_t traj_every; // 0 = off
+    uint32_t pad;
+    uint64_t tick0;     // global tick count before this launch
+    EffDev eff[B200_MAX_EFFECTORS];
+};
+
+// Launch parameters of the edge_fold gravity kernels.
+struct GraphParams {
+    const double *pos, *vel, *ine;
+    double *gforce;          // 9 planes out
+    uint64_t ld;
+    uint32_t n_entities;
+    uint32_t n_worlds;
+    double dt_stage;
+    uint32_t kind;           // B200_EFF_GRAVITY_EDGES_*
+    uint32_t integrator;     // B200_INTEGRATOR_*: RK4 evaluates 3 stage positions, semi-implicit 1
+    double p0, p1;           // G | K^2, softening
+    const uint32_t *row_ptr; // CSR over sources (n_entities+1), spawn order kept inside a row
+    const uint32_t *col_idx;
+};
+
+// kernel launchers (sixdof_kernels.cu); every one returns the launch status
+cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode, cudaStream_t s);
+cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, cudaStream_t s);
+cudaError_t launch_aos_to_soa(const double *aos, double *soa, uint64_t n_bodies, uint32_t width, uint64_t ld,
+                              cudaStream_t s);
+cudaError_t launch_soa_to_aos(const double *soa, double *aos, uint64_t n_bodies, uint32_t width, uint64_t ld,
+                              cudaStream_t s);
+cudaError_t launch_traj_to_aos(const double *traj, double *aos, uint64_t n_samples, uint64_t n_bodies, uint64_t ld,
+                               cudaStream_t s);
+cudaError_t launch_probe_fp64(double *out, int iters, int blocks, cudaStream_t s);
+
+} // namespace b200

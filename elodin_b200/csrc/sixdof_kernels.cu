@@ -1,0 +1,663 @@
+// sm_100a kernels of the six_dof() hot path.
+//
+//   body_exact_kernel  K1/K2/K4/K5 of SURVEY §2.4 in EXACT arithmetic: one thread per
+//                      body, the whole tick (clear_forces, effectors x4, calc_accel x4,
+//                      stage advance x4, final combine, renormalise) in registers,
+//                      n_ticks ticks per launch.
+//   body_fast_kernel   the same tick restructured for the FP64 pipe / HBM roofline.
+//   graph_*_kernel     K3: GraphQuery.edge_fold gravity at the 3 distinct stage
+//                      positions of a tick (they depend on x0, v0 only — see below).
+//   aos_to_soa / soa_to_aos   K6: host column layout <-> device planes.
+//
+// Why one launch per tick suffices even with body-body coupling: in the
+// reference's RK4 (libs/nox-py/src/integrator/rk4.rs:85-111) every stage position
+// is x0 (+) (dt*f)*v0 — it never depends on a stage acceleration — so the gravity
+// at all four stages (three distinct positions, f = 0, .5, 1) is a function of
+// the tick's input state alone and needs no grid-wide synchronisation.
+#include "sixdof_device.cuh"
+#include "sixdof_internal.h"
+
+namespace b200 {
+
+static constexpr int kBlock = 256;
+
+// ------------------------------------------------------------------ column access
+__device__ __forceinline__ double ldp(const double *base, uint64_t ld, int plane, uint64_t b)
+{
+    return base[(uint64_t)plane * ld + b];
+}
+__device__ __forceinline__ void stp(double *base, uint64_t ld, int plane, uint64_t b, double v)
+{
+    base[(uint64_t)plane * ld + b] = v;
+}
+
+__device__ __forceinline__ Pose load_pose(const double *p, uint64_t ld, uint64_t b)
+{
+    Pose o;
+    o.q = Quat{ldp(p, ld, 0, b), ldp(p, ld, 1, b), ldp(p, ld, 2, b), ldp(p, ld, 3, b)};
+    o.x = Vec3{ldp(p, ld, 4, b), ldp(p, ld, 5, b), ldp(p, ld, 6, b)};
+    return o;
+}
+__device__ __forceinline__ Motion load_motion(const double *p, uint64_t ld, uint64_t b)
+{
+    Motion m;
+    m.ang = Vec3{ldp(p, ld, 0, b), ldp(p, ld, 1, b), ldp(p, ld, 2, b)};
+    m.lin = Vec3{ldp(p, ld, 3, b), ldp(p, ld, 4, b), ldp(p, ld, 5, b)};
+    return m;
+}
+__device__ __forceinline__ Inertia load_inertia(const double *p, uint64_t ld, uint64_t b)
+{
+    Inertia I;
+    I.diag = Vec3{ldp(p, ld, 0, b), ldp(p, ld, 1, b), ldp(p, ld, 2, b)};
+    I.m = ldp(p, ld, 6, b);
+    return I;
+}
+__device__ __forceinline__ void store_pose(double *p, uint64_t ld, uint64_t b, const Pose &o)
+{
+    stp(p, ld, 0, b, o.q.i); stp(p, ld, 1, b, o.q.j); stp(p, ld, 2, b, o.q.k); stp(p, ld, 3, b, o.q.w);
+    stp(p, ld, 4, b, o.x.x); stp(p, ld, 5, b, o.x.y); stp(p, ld, 6, b, o.x.z);
+}
+__device__ __forceinline__ void store_motion(double *p, uint64_t ld, uint64_t b, const Motion &m)
+{
+    stp(p, ld, 0, b, m.ang.x); stp(p, ld, 1, b, m.ang.y); stp(p, ld, 2, b, m.ang.z);
+    stp(p, ld, 3, b, m.lin.x); stp(p, ld, 4, b, m.lin.y); stp(p, ld, 5, b, m.lin.z);
+}
+
+__device__ __forceinline__ void traj_sample(const StepParams &P, uint64_t b, uint64_t tick_after, const Pose &x,
+                                            const Motion &v)
+{
+    if (P.traj_every == 0 || (tick_after % P.traj_every) != 0) return;
+    const uint64_t s = tick_after / P.traj_every - 1;
+    if (s >= P.traj_capacity) return;
+    double *t = P.traj + s * 13ull * P.ld;
+    store_pose(t, P.ld, b, x);
+    store_motion(t + 7ull * P.ld, P.ld, b, v);
+}
+
+// ================================================================== EXACT body kernel
+
+// clear_forces | effectors (array order) on the stage state; six_dof.rs:148-150,195
+__device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t b, int slot, const Pose &sx,
+                                                  const Motion &sv, const Inertia &I)
+{
+    using namespace ex;
+    Motion F = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+    for (uint32_t e = 0; e < P.n_eff; ++e) {
+        const EffDev &E = P.eff[e];
+        switch (E.kind) {
+        case B200_EFF_GRAVITY_CONST: { // ball/sim.py:56-58: f + SpatialForce(linear=g*m)
+            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+            F.lin = Vec3{add(F.lin.x, mul(E.p[0], I.m)), add(F.lin.y, mul(E.p[1], I.m)),
+                         add(F.lin.z, mul(E.p[2], I.m))};
+            break;
+        }
+        case B200_EFF_DRAG_QUADRATIC: { // ball/sim.py:99-116; result torque is zero
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+            if (E.col) { w0 = ldp(E.col, P.ld, 0, b); w1 = ldp(E.col, P.ld, 1, b); w2 = ldp(E.col, P.ld, 2, b); }
+            const Vec3 fl = {sub(w0, sv.lin.x), sub(w1, sv.lin.y), sub(w2, sv.lin.z)};
+            const double speed = sqr(dot3(fl));
+            const double drag = mul(0.5, mul(mul(E.p[0], mul(speed, speed)), E.p[1]));
+            F.ang = Vec3{0.0, 0.0, 0.0};
+            F.lin = Vec3{add(F.lin.x, mul(drag, div(fl.x, speed))), add(F.lin.y, mul(drag, div(fl.y, speed))),
+                         add(F.lin.z, mul(drag, div(fl.z, speed)))};
+            break;
+        }
+        case B200_EFF_THRUST_BODY: { // rocket/main.py:429-431
+            const double t = E.col ? ldp(E.col, P.ld, 0, b) : 0.0;
+            const Vec3 d = qrot(sx.q, Vec3{E.p[0], E.p[1], E.p[2]});
+            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+            F.lin = Vec3{add(F.lin.x, mul(d.x, t)), add(F.lin.y, mul(d.y, t)), add(F.lin.z, mul(d.z, t))};
+            break;
+        }
+        case B200_EFF_WRENCH_BODY: { // rocket/main.py:407-413, falcon9/sim.py:659-672
+            Vec3 a = {0.0, 0.0, 0.0}, c = {0.0, 0.0, 0.0};
+            if (E.col) {
+                a = Vec3{ldp(E.col, P.ld, 0, b), ldp(E.col, P.ld, 1, b), ldp(E.col, P.ld, 2, b)};
+                c = Vec3{ldp(E.col, P.ld, 3, b), ldp(E.col, P.ld, 4, b), ldp(E.col, P.ld, 5, b)};
+            }
+            const bool lin_first = (E.flags & B200_EFF_FLAG_WRENCH_LINEAR_FIRST) != 0;
+            const Vec3 tw = qrot(sx.q, lin_first ? c : a);
+            const Vec3 fw = qrot(sx.q, lin_first ? a : c);
+            F.ang = Vec3{add(F.ang.x, tw.x), add(F.ang.y, tw.y), add(F.ang.z, tw.z)};
+            F.lin = Vec3{add(F.lin.x, fw.x), add(F.lin.y, fw.y), add(F.lin.z, fw.z)};
+            break;
+        }
+        case B200_EFF_GRAVITY_FRAME: { // falcon9/sim.py:350-361, frames.py:91-109
+            const double mu = E.p[0];
+            const Vec3 om = {E.p[1], E.p[2], E.p[3]};
+            const Vec3 r = sx.x, v = sv.lin;
+            const double rn = sqr(dot3(r));
+            const double rn3 = mul(mul(rn, rn), rn);
+            const Vec3 g = {div(mul(-mu, r.x), rn3), div(mul(-mu, r.y), rn3), div(mul(-mu, r.z), rn3)};
+            const Vec3 c = cross(om, v);
+            const Vec3 c2 = cross(om, cross(om, r));
+            const Vec3 acc = {add(g.x, add(mul(-2.0, c.x), -c2.x)), add(g.y, add(mul(-2.0, c.y), -c2.y)),
+                              add(g.z, add(mul(-2.0, c.z), -c2.z))};
+            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+            F.lin = Vec3{add(F.lin.x, mul(acc.x, I.m)), add(F.lin.y, mul(acc.y, I.m)), add(F.lin.z, mul(acc.z, I.m))};
+            break;
+        }
+        case B200_EFF_GRAVITY_EDGES_NEWTON:
+        case B200_EFF_GRAVITY_EDGES_SOFTENED: { // Force := edge_fold(init 0) for bodies that own an edge
+            if (P.gforce && P.has_edge && P.has_edge[b % P.n_entities]) {
+                F.ang = Vec3{0.0, 0.0, 0.0};
+                F.lin = Vec3{ldp(P.gforce, P.ld, slot * 3 + 0, b), ldp(P.gforce, P.ld, slot * 3 + 1, b),
+                             ldp(P.gforce, P.ld, slot * 3 + 2, b)};
+            }
+            break;
+        }
+        default: break;
+        }
+    }
+    return F;
+}
+
+template <int INTEG>
+__global__ void __launch_bounds__(kBlock) body_exact_kernel(const __grid_constant__ StepParams P)
+{
+    using namespace ex;
+    const uint64_t b = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (b >= P.n_bodies) return;
+
+    Pose x0 = load_pose(P.pos, P.ld, b);
+    Motion v0 = load_motion(P.vel, P.ld, b);
+    Motion a_out = load_motion(P.acc, P.ld, b);
+    Motion f_out = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+    const Inertia I = load_inertia(P.ine, P.ld, b);
+
+    for (uint32_t t = 0; t < P.n_ticks; ++t) {
+        if (INTEG == B200_INTEGRATOR_RK4) {
+            // rk4.rs:85-123 (see the header comment of oracle/sixdof_oracle.c for the derivation)
+            Motion sa = a_out; // du.a before stage 1 is the WorldAccel column
+            Motion kv, ka;
+#pragma unroll 1
+            for (int s = 0; s < 4; ++s) {
+                const double fac = (s == 0) ? 0.0 : ((s == 3) ? 1.0 : 0.5);
+                const double dtf = mul(P.dt_stage, fac);
+                const Pose sx = tadd(x0, scale(dtf, v0));
+                const Motion sv = madd(v0, scale(dtf, sa));
+                const int slot = (s == 0) ? 0 : ((s == 3) ? 2 : 1);
+                f_out = effectors_exact(P, b, slot, sx, sv, I);
+                sa = calc_accel(sx, f_out, I);
+                if (s == 0) { kv = sv; ka = sa; }
+                else if (s == 3) { kv = madd(kv, sv); ka = madd(ka, sa); }
+                else { kv = madd(kv, scale(2.0, sv)); ka = madd(ka, scale(2.0, sa)); }
+            }
+            const double c = mul(P.dt_final, 1.0 / 6.0);
+            x0 = tadd(x0, scale(c, kv));
+            v0 = madd(v0, scale(c, ka));
+            a_out = sa;
+        } else {
+            // semi_implicit.rs:42-62
+            f_out = effectors_exact(P, b, 0, x0, v0, I);
+            a_out = calc_accel(x0, f_out, I);
+            v0 = madd(v0, scale(P.dt_final, a_out));
+            x0 = tadd(x0, scale(P.dt_final, v0));
+        }
+        traj_sample(P, b, P.tick0 + t + 1, x0, v0);
+    }
+    store_pose(P.pos, P.ld, b, x0);
+    store_motion(P.vel, P.ld, b, v0);
+    store_motion(P.acc, P.ld, b, a_out);
+    store_motion(P.frc, P.ld, b, f_out);
+}
+
+// ================================================================== FAST body kernel
+
+// Everything the effector list contributes, folded once per launch:
+//   F_lin(stage) = fw + R(q) fb + drag(v) + m*frame(x, v) + gforce[slot]
+//   a_ang(stage) = R(q) u,   u = (sum of body-frame torques) / diag(I)   (R^-1 then R cancel)
+struct Folded {
+    Vec3 fw;      // world-frame constant force (GRAVITY_CONST: g*m)
+    Vec3 fb;      // body-frame force (THRUST_BODY axis*thrust, WRENCH_BODY force part)
+    Vec3 u;       // body-frame angular acceleration
+    Vec3 wind;    // DRAG_QUADRATIC
+    double kd;    // 0.5*Cd*rho*A
+    double mu;    // GRAVITY_FRAME
+    Vec3 om;
+    bool drag, frame, graph;
+};
+
+__device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b, const Inertia &I, const Vec3 &invI)
+{
+    Folded f;
+    f.fw = f.fb = f.u = f.wind = f.om = Vec3{0.0, 0.0, 0.0};
+    f.kd = f.mu = 0.0;
+    f.drag = f.frame = f.graph = false;
+    Vec3 tb = {0.0, 0.0, 0.0};
+    for (uint32_t e = 0; e < P.n_eff; ++e) {
+        const EffDev &E = P.eff[e];
+        switch (E.kind) {
+        case B200_EFF_GRAVITY_CONST:
+            f.fw.x = fma(E.p[0], I.m, f.fw.x); f.fw.y = fma(E.p[1], I.m, f.fw.y); f.fw.z = fma(E.p[2], I.m, f.fw.z);
+            break;
+        case B200_EFF_DRAG_QUADRATIC:
+            f.drag = true;
+            f.kd = 0.5 * E.p[0] * E.p[1];
+            if (E.col) f.wind = Vec3{ldp(E.col, P.ld, 0, b), ldp(E.col, P.ld, 1, b), ldp(E.col, P.ld, 2, b)};
+            tb = Vec3{0.0, 0.0, 0.0}; // the reference's apply_drag returns SpatialForce(linear=...): torque reset
+            break;
+        case B200_EFF_THRUST_BODY: {
+            const double t = E.col ? ldp(E.col, P.ld, 0, b) : 0.0;
+            f.fb.x = fma(E.p[0], t, f.fb.x); f.fb.y = fma(E.p[1], t, f.fb.y); f.fb.z = fma(E.p[2], t, f.fb.z);
+            break;
+        }
+        case B200_EFF_WRENCH_BODY:
+            if (E.col) {
+                const int to = (E.flags & B200_EFF_FLAG_WRENCH_LINEAR_FIRST) ? 3 : 0;
+                const int fo = 3 - to;
+                tb.x += ldp(E.col, P.ld, to + 0, b); tb.y += ldp(E.col, P.ld, to + 1, b); tb.z += ldp(E.col, P.ld, to + 2, b);
+                f.fb.x += ldp(E.col, P.ld, fo + 0, b); f.fb.y += ldp(E.col, P.ld, fo + 1, b); f.fb.z += ldp(E.col, P.ld, fo + 2, b);
+            }
+            break;
+        case B200_EFF_GRAVITY_FRAME:
+            f.frame = true;
+            f.mu = E.p[0];
+            f.om = Vec3{E.p[1], E.p[2], E.p[3]};
+            break;
+        case B200_EFF_GRAVITY_EDGES_NEWTON:
+        case B200_EFF_GRAVITY_EDGES_SOFTENED: // host guarantees this is effector 0 in FAST mode
+            f.graph = P.gforce && P.has_edge && P.has_edge[b % P.n_entities];
+            break;
+        default: break;
+        }
+    }
+    f.u = Vec3{tb.x * invI.x, tb.y * invI.y, tb.z * invI.z};
+    return f;
+}
+
+// linear acceleration of one stage: everything that depends on (q, x, v)
+__device__ __forceinline__ Vec3 lin_accel_fast(const StepParams &P, const Folded &f, uint64_t b, int slot,
+                                               const Vec3 &fbw, const Vec3 &x, const Vec3 &v, double m, double inv_m)
+{
+    Vec3 F = {f.fw.x + fbw.x, f.fw.y + fbw.y, f.fw.z + fbw.z};
+    if (f.drag) {
+        const Vec3 fl = {f.wind.x - v.x, f.wind.y - v.y, f.wind.z - v.z};
+        const double s2 = fl.x * fl.x + fl.y * fl.y + fl.z * fl.z;
+        // drag*dir = (kd*speed^2) * fl/speed; speed == 0 is 0/0 = NaN in the reference too
+        const double k = (s2 == 0.0) ? __longlong_as_double(0x7ff8000000000000ll) : f.kd * sqrt(s2);
+        F.x = fma(k, fl.x, F.x); F.y = fma(k, fl.y, F.y); F.z = fma(k, fl.z, F.z);
+    }
+    if (f.frame) {
+        const double r2 = x.x * x.x + x.y * x.y + x.z * x.z;
+        const double ir = rsqrt(r2);
+        const double g = -f.mu * ir * ir * ir;
+        const Vec3 c = fa::cross(f.om, v);
+        const Vec3 c2 = fa::cross(f.om, fa::cross(f.om, x));
+        F.x = fma(fma(g, x.x, -2.0 * c.x - c2.x), m, F.x);
+        F.y = fma(fma(g, x.y, -2.0 * c.y - c2.y), m, F.y);
+        F.z = fma(fma(g, x.z, -2.0 * c.z - c2.z), m, F.z);
+    }
+    if (f.graph) {
+        F.x += ldp(P.gforce, P.ld, slot * 3 + 0, b);
+        F.y += ldp(P.gforce, P.ld, slot * 3 + 1, b);
+        F.z += ldp(P.gforce, P.ld, slot * 3 + 2, b);
+    }
+    return Vec3{F.x * inv_m, F.y * inv_m, F.z * inv_m};
+}
+
+// world-frame force this stage's state produced (only materialised when Force is written back)
+__device__ __forceinline__ Motion force_out_fast(const Vec3 &a_lin, const Vec3 &a_ang_body_u, const Quat &q,
+                                                 const Inertia &I)
+{
+    // torque_world = R (I .* u)
+    const Vec3 tb = {a_ang_body_u.x * I.diag.x, a_ang_body_u.y * I.diag.y, a_ang_body_u.z * I.diag.z};
+    Motion F;
+    F.ang = fa::rot(q, tb);
+    F.lin = Vec3{a_lin.x * I.m, a_lin.y * I.m, a_lin.z * I.m};
+    return F;
+}
+
+template <int INTEG>
+__global__ void __launch_bounds__(kBlock) body_fast_kernel(const __grid_constant__ StepParams P)
+{
+    const uint64_t b = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (b >= P.n_bodies) return;
+
+    Pose x0 = load_pose(P.pos, P.ld, b);
+    Motion v0 = load_motion(P.vel, P.ld, b);
+    const Inertia I = load_inertia(P.ine, P.ld, b);
+    const Vec3 invI = {1.0 / I.diag.x, 1.0 / I.diag.y, 1.0 / I.diag.z};
+    const double inv_m = 1.0 / I.m;
+    const Folded f = fold_effectors(P, b, I, invI);
+
+    Motion a_last = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+    Quat q_last = x0.q;
+    const double dt = P.dt_stage;
+
+    for (uint32_t t = 0; t < P.n_ticks; ++t) {
+        if (INTEG == B200_INTEGRATOR_RK4) {
+            const Vec3 w0 = v0.ang, u0 = v0.lin;
+            // the three distinct stage poses depend on (x0, v0) only (rk4.rs:85-111)
+            const Quat q1 = fa::advance(x0.q, Vec3{0.0, 0.0, 0.0});
+            const double h2 = 0.25 * dt, h4 = 0.5 * dt;
+            const Quat q2 = fa::advance(x0.q, Vec3{h2 * w0.x, h2 * w0.y, h2 * w0.z});
+            const Quat q4 = fa::advance(x0.q, Vec3{h4 * w0.x, h4 * w0.y, h4 * w0.z});
+            const Vec3 x2 = {fma(h4, u0.x, x0.x.x), fma(h4, u0.y, x0.x.y), fma(h4, u0.z, x0.x.z)};
+            const Vec3 x4 = {fma(dt, u0.x, x0.x.x), fma(dt, u0.y, x0.x.y), fma(dt, u0.z, x0.x.z)};
+            // angular acceleration R(q) u and rotated body force, once per distinct attitude
+            const Vec3 aa1 = fa::rot(q1, f.u), aa2 = fa::rot(q2, f.u), aa4 = fa::rot(q4, f.u);
+            const Vec3 fb1 = fa::rot(q1, f.fb), fb2 = fa::rot(q2, f.fb), fb4 = fa::rot(q4, f.fb);
+            // stage 1: v = v0
+            const Vec3 al1 = lin_accel_fast(P, f, b, 0, fb1, x0.x, u0, I.m, inv_m);
+            // stage 2: v = v0 + dt/2 a1
+            const Vec3 u2 = {fma(h4, al1.x, u0.x), fma(h4, al1.y, u0.y), fma(h4, al1.z, u0.z)};
+            const Vec3 al2 = lin_accel_fast(P, f, b, 1, fb2, x2, u2, I.m, inv_m);
+            // stage 3: same pose as stage 2, v = v0 + dt/2 a2
+            const Vec3 u3 = {fma(h4, al2.x, u0.x), fma(h4, al2.y, u0.y), fma(h4, al2.z, u0.z)};
+            const Vec3 al3 = lin_accel_fast(P, f, b, 1, fb2, x2, u3, I.m, inv_m);
+            // stage 4: v = v0 + dt a3
+            const Vec3 u4 = {fma(dt, al3.x, u0.x), fma(dt, al3.y, u0.y), fma(dt, al3.z, u0.z)};
+            const Vec3 al4 = lin_accel_fast(P, f, b, 2, fb4, x4, u4, I.m, inv_m);
+            // k.v sum = 6 v0 + dt (a1 + a2 + a3);  k.a sum = a1 + 2 a2 + 2 a3 + a4   (a3.ang == a2.ang)
+            const double c = P.dt_final * (1.0 / 6.0);
+            const Vec3 kw = {fma(dt, aa1.x + 2.0 * aa2.x, 6.0 * w0.x), fma(dt, aa1.y + 2.0 * aa2.y, 6.0 * w0.y),
+                             fma(dt, aa1.z + 2.0 * aa2.z, 6.0 * w0.z)};
+            const Vec3 ku = {fma(dt, al1.x + al2.x + al3.x, 6.0 * u0.x), fma(dt, al1.y + al2.y + al3.y, 6.0 * u0.y),
+                             fma(dt, al1.z + al2.z + al3.z, 6.0 * u0.z)};
+            const double hc = 0.5 * c;
+            x0.q = fa::advance(x0.q, Vec3{hc * kw.x, hc * kw.y, hc * kw.z});
+            x0.x = Vec3{fma(c, ku.x, x0.x.x), fma(c, ku.y, x0.x.y), fma(c, ku.z, x0.x.z)};
+            v0.ang = Vec3{fma(c, aa1.x + 4.0 * aa2.x + aa4.x, w0.x), fma(c, aa1.y + 4.0 * aa2.y + aa4.y, w0.y),
+                          fma(c, aa1.z + 4.0 * aa2.z + aa4.z, w0.z)};
+            v0.lin = Vec3{fma(c, al1.x + 2.0 * (al2.x + al3.x) + al4.x, u0.x),
+                          fma(c, al1.y + 2.0 * (al2.y + al3.y) + al4.y, u0.y),
+                          fma(c, al1.z + 2.0 * (al2.z + al3.z) + al4.z, u0.z)};
+            a_last.ang = aa4; a_last.lin = al4; q_last = q4;
+        } else {
+            // semi_implicit.rs:42-62; calc_accel rotates by q/|q| whatever |q| is
+            const double n2 = x0.q.i * x0.q.i + x0.q.j * x0.q.j + x0.q.k * x0.q.k + x0.q.w * x0.q.w;
+            const double rn = rsqrt(n2);
+            const Quat qn = {x0.q.i * rn, x0.q.j * rn, x0.q.k * rn, x0.q.w * rn};
+            const Vec3 aa = fa::rot(qn, f.u);
+            const Vec3 fbw = fa::rot(qn, f.fb);
+            const Vec3 al = lin_accel_fast(P, f, b, 0, fbw, x0.x, v0.lin, I.m, inv_m);
+            const double d = P.dt_final;
+            v0.ang = Vec3{fma(d, aa.x, v0.ang.x), fma(d, aa.y, v0.ang.y), fma(d, aa.z, v0.ang.z)};
+            v0.lin = Vec3{fma(d, al.x, v0.lin.x), fma(d, al.y, v0.lin.y), fma(d, al.z, v0.lin.z)};
+            const double hd = 0.5 * d;
+            x0.q = fa::advance(x0.q, Vec3{hd * v0.ang.x, hd * v0.ang.y, hd * v0.ang.z});
+            x0.x = Vec3{fma(d, v0.lin.x, x0.x.x), fma(d, v0.lin.y, x0.x.y), fma(d, v0.lin.z, x0.x.z)};
+            a_last.ang = aa; a_last.lin = al; q_last = qn;
+        }
+        traj_sample(P, b, P.tick0 + t + 1, x0, v0);
+    }
+    store_pose(P.pos, P.ld, b, x0);
+    store_motion(P.vel, P.ld, b, v0);
+    if (P.write_fa) {
+        store_motion(P.acc, P.ld, b, a_last);
+        store_motion(P.frc, P.ld, b, force_out_fast(a_last.lin, f.u, q_last, I));
+    }
+}
+
+// ================================================================== edge_fold gravity
+
+// stage position of a body for slot 0/1/2 (f = 0, .5, 1): x (+) (dt*f)*v, linear part
+template <bool EXACT>
+__device__ __forceinline__ Vec3 stage_pos(const Vec3 &x, const Vec3 &v, double dtf)
+{
+    if (EXACT) return Vec3{ex::add(x.x, ex::mul(dtf, v.x)), ex::add(x.y, ex::mul(dtf, v.y)), ex::add(x.z, ex::mul(dtf, v.z))};
+    return Vec3{fma(dtf, v.x, x.x), fma(dtf, v.y, x.y), fma(dtf, v.z, x.z)};
+}
+
+// Dense all-pairs (every body's out-edges are all other bodies, ascending): block =
+// kBlockG source bodies of one world, targets streamed through shared memory in
+// tiles; each thread folds its targets sequentially in ascending order, which is
+// the reference's fold order (graph.rs:177-236) — so EXACT stays bit-exact.
+static constexpr int kBlockG = 128;
+
+template <bool EXACT, bool RK4>
+__global__ void __launch_bounds__(kBlockG) graph_dense_kernel(const __grid_constant__ GraphParams G)
+{
+    constexpr int NS = RK4 ? 3 : 1;
+    __shared__ double sx[NS][3][kBlockG];
+    __shared__ double sm[kBlockG];
+
+    const uint32_t N = G.n_entities;
+    const uint32_t tiles = (N + kBlockG - 1) / kBlockG;
+    const uint32_t world = blockIdx.x / tiles;
+    const uint32_t tile = blockIdx.x % tiles;
+    const uint32_t i = tile * kBlockG + threadIdx.x;
+    const uint64_t wbase = (uint64_t)world * N;
+    const bool active = i < N;
+    const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
+
+    double dtf[3];
+    dtf[0] = EXACT ? ex::mul(G.dt_stage, 0.0) : 0.0;
+    dtf[1] = EXACT ? ex::mul(G.dt_stage, 0.5) : 0.5 * G.dt_stage;
+    dtf[2] = EXACT ? ex::mul(G.dt_stage, 1.0) : G.dt_stage;
+
+    Vec3 xi[NS];
+    double mi = 0.0;
+    Vec3 acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { xi[s] = Vec3{0, 0, 0}; acc[s] = Vec3{0, 0, 0}; }
+    if (active) {
+        const uint64_t b = wbase + i;
+        const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+        const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+        mi = ldp(G.ine, G.ld, 6, b);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) xi[s] = RK4 ? stage_pos<EXACT>(x, v, dtf[s]) : x;
+    }
+
+    for (uint32_t j0 = 0; j0 < N; j0 += kBlockG) {
+        const uint32_t j = j0 + threadIdx.x;
+        __syncthreads();
+        if (j < N) {
+            const uint64_t b = wbase + j;
+            const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+            const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const Vec3 p = RK4 ? stage_pos<EXACT>(x, v, dtf[s]) : x;
+                sx[s][0][threadIdx.x] = p.x; sx[s][1][threadIdx.x] = p.y; sx[s][2][threadIdx.x] = p.z;
+            }
+            sm[threadIdx.x] = ldp(G.ine, G.ld, 6, b);
+        }
+        __syncthreads();
+        const uint32_t jn = min((uint32_t)kBlockG, N - j0);
+        if (active) {
+            for (uint32_t jj = 0; jj < jn; ++jj) {
+                if (j0 + jj == i) continue;
+                const double mj = sm[jj];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const Vec3 xj = {sx[s][0][jj], sx[s][1][jj], sx[s][2][jj]};
+                    if (EXACT) {
+                        if (newton) ex::fold_newton(G.p0, xi[s], mi, xj, mj, acc[s]);
+                        else ex::fold_softened(G.p0, G.p1, xi[s], mi, xj, mj, acc[s]);
+                    } else {
+                        // common factor (G|K^2)*m_i applied after the loop; sign folded in below
+                        const Vec3 r = {xj.x - xi[s].x, xj.y - xi[s].y, xj.z - xi[s].z};
+                        const double d2 = r.x * r.x + r.y * r.y + r.z * r.z + (newton ? 0.0 : G.p1);
+                        const double inv = rsqrt(d2);
+                        const double w = mj * inv * inv * inv;
+                        acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
+                    }
+                }
+            }
+        }
+    }
+    if (active) {
+        const uint64_t b = wbase + i;
+        const double k = EXACT ? 1.0 : G.p0 * mi;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            stp(G.gforce, G.ld, s * 3 + 0, b, EXACT ? acc[s].x : k * acc[s].x);
+            stp(G.gforce, G.ld, s * 3 + 1, b, EXACT ? acc[s].y : k * acc[s].y);
+            stp(G.gforce, G.ld, s * 3 + 2, b, EXACT ? acc[s].z : k * acc[s].z);
+        }
+    }
+}
+
+// General edge list (CSR by source, spawn order inside a row): one thread per
+// (world, source) gathers its targets.  Used for sparse / irregular graphs.
+template <bool EXACT, bool RK4>
+__global__ void __launch_bounds__(kBlockG) graph_csr_kernel(const __grid_constant__ GraphParams G)
+{
+    constexpr int NS = RK4 ? 3 : 1;
+    const uint64_t t = (uint64_t)blockIdx.x * kBlockG + threadIdx.x;
+    const uint64_t total = (uint64_t)G.n_entities * G.n_worlds;
+    if (t >= total) return;
+    const uint32_t i = (uint32_t)(t % G.n_entities);
+    const uint64_t wbase = t - i;
+    const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
+    double dtf[3];
+    dtf[0] = EXACT ? ex::mul(G.dt_stage, 0.0) : 0.0;
+    dtf[1] = EXACT ? ex::mul(G.dt_stage, 0.5) : 0.5 * G.dt_stage;
+    dtf[2] = EXACT ? ex::mul(G.dt_stage, 1.0) : G.dt_stage;
+
+    const Vec3 x = {ldp(G.pos, G.ld, 4, t), ldp(G.pos, G.ld, 5, t), ldp(G.pos, G.ld, 6, t)};
+    const Vec3 v = {ldp(G.vel, G.ld, 3, t), ldp(G.vel, G.ld, 4, t), ldp(G.vel, G.ld, 5, t)};
+    const double mi = ldp(G.ine, G.ld, 6, t);
+    Vec3 xi[NS], acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { xi[s] = RK4 ? stage_pos<EXACT>(x, v, dtf[s]) : x; acc[s] = Vec3{0, 0, 0}; }
+
+    for (uint32_t e = G.row_ptr[i]; e < G.row_ptr[i + 1]; ++e) {
+        const uint64_t bj = wbase + G.col_idx[e];
+        const Vec3 xj0 = {ldp(G.pos, G.ld, 4, bj), ldp(G.pos, G.ld, 5, bj), ldp(G.pos, G.ld, 6, bj)};
+        const Vec3 vj = {ldp(G.vel, G.ld, 3, bj), ldp(G.vel, G.ld, 4, bj), ldp(G.vel, G.ld, 5, bj)};
+        const double mj = ldp(G.ine, G.ld, 6, bj);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const Vec3 xj = RK4 ? stage_pos<EXACT>(xj0, vj, dtf[s]) : xj0;
+            if (EXACT) {
+                if (newton) ex::fold_newton(G.p0, xi[s], mi, xj, mj, acc[s]);
+                else ex::fold_softened(G.p0, G.p1, xi[s], mi, xj, mj, acc[s]);
+            } else {
+                const Vec3 r = {xj.x - xi[s].x, xj.y - xi[s].y, xj.z - xi[s].z};
+                const double d2 = r.x * r.x + r.y * r.y + r.z * r.z + (newton ? 0.0 : G.p1);
+                const double inv = rsqrt(d2);
+                const double w = mj * inv * inv * inv;
+                acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
+            }
+        }
+    }
+    const double k = EXACT ? 1.0 : G.p0 * mi;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        stp(G.gforce, G.ld, s * 3 + 0, t, EXACT ? acc[s].x : k * acc[s].x);
+        stp(G.gforce, G.ld, s * 3 + 1, t, EXACT ? acc[s].y : k * acc[s].y);
+        stp(G.gforce, G.ld, s * 3 + 2, t, EXACT ? acc[s].z : k * acc[s].z);
+    }
+}
+
+// ================================================================== layout kernels (K6)
+
+static constexpr int kTile = 256;
+
+__global__ void __launch_bounds__(kTile) aos_to_soa_kernel(const double *__restrict__ aos, double *__restrict__ soa,
+                                                           uint64_t n_bodies, uint32_t width, uint64_t ld)
+{
+    extern __shared__ double tile[]; // kTile * (width | 1)
+    const uint32_t pitch = width | 1u;
+    const uint64_t base = (uint64_t)blockIdx.x * kTile;
+    const uint32_t nb = (uint32_t)min((uint64_t)kTile, n_bodies - base);
+    const double *src = aos + base * width;
+    for (uint32_t i = threadIdx.x; i < nb * width; i += kTile) tile[(i / width) * pitch + (i % width)] = src[i];
+    __syncthreads();
+    if (threadIdx.x < nb)
+        for (uint32_t k = 0; k < width; ++k) soa[(uint64_t)k * ld + base + threadIdx.x] = tile[threadIdx.x * pitch + k];
+}
+
+// gridDim.y = samples; a sample's planes start at soa + y*width*ld, its rows at aos + y*n_bodies*width
+__global__ void __launch_bounds__(kTile) soa_to_aos_kernel(const double *__restrict__ soa, double *__restrict__ aos,
+                                                           uint64_t n_bodies, uint32_t width, uint64_t ld)
+{
+    extern __shared__ double tile[];
+    const uint32_t pitch = width | 1u;
+    const uint64_t base = (uint64_t)blockIdx.x * kTile;
+    const uint32_t nb = (uint32_t)min((uint64_t)kTile, n_bodies - base);
+    const double *s = soa + (uint64_t)blockIdx.y * width * ld;
+    double *dst = aos + (uint64_t)blockIdx.y * n_bodies * width + base * width;
+    if (threadIdx.x < nb)
+        for (uint32_t k = 0; k < width; ++k) tile[threadIdx.x * pitch + k] = s[(uint64_t)k * ld + base + threadIdx.x];
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nb * width; i += kTile) dst[i] = tile[(i / width) * pitch + (i % width)];
+}
+
+// FP64 FMA throughput probe: 8 independent chains per thread
+__global__ void __launch_bounds__(256) probe_fp64_kernel(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(uint64_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ================================================================== launchers
+
+cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode, cudaStream_t s)
+{
+    if (P.n_bodies == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((P.n_bodies + kBlock - 1) / kBlock);
+    const bool rk4 = integrator == B200_INTEGRATOR_RK4;
+    if (math_mode == B200_MATH_EXACT) {
+        if (rk4) body_exact_kernel<B200_INTEGRATOR_RK4><<<grid, kBlock, 0, s>>>(P);
+        else body_exact_kernel<B200_INTEGRATOR_SEMI_IMPLICIT><<<grid, kBlock, 0, s>>>(P);
+    } else {
+        if (rk4) body_fast_kernel<B200_INTEGRATOR_RK4><<<grid, kBlock, 0, s>>>(P);
+        else body_fast_kernel<B200_INTEGRATOR_SEMI_IMPLICIT><<<grid, kBlock, 0, s>>>(P);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, cudaStream_t s)
+{
+    const bool exact = math_mode == B200_MATH_EXACT;
+    const bool rk4 = G.integrator == B200_INTEGRATOR_RK4;
+    if (G.n_entities == 0 || G.n_worlds == 0) return cudaSuccess;
+    if (dense) {
+        const unsigned tiles = (G.n_entities + kBlockG - 1) / kBlockG;
+        const unsigned grid = tiles * G.n_worlds;
+        if (exact) { if (rk4) graph_dense_kernel<true, true><<<grid, kBlockG, 0, s>>>(G); else graph_dense_kernel<true, false><<<grid, kBlockG, 0, s>>>(G); }
+        else { if (rk4) graph_dense_kernel<false, true><<<grid, kBlockG, 0, s>>>(G); else graph_dense_kernel<false, false><<<grid, kBlockG, 0, s>>>(G); }
+    } else {
+        const uint64_t total = (uint64_t)G.n_entities * G.n_worlds;
+        const unsigned grid = (unsigned)((total + kBlockG - 1) / kBlockG);
+        if (exact) { if (rk4) graph_csr_kernel<true, true><<<grid, kBlockG, 0, s>>>(G); else graph_csr_kernel<true, false><<<grid, kBlockG, 0, s>>>(G); }
+        else { if (rk4) graph_csr_kernel<false, true><<<grid, kBlockG, 0, s>>>(G); else graph_csr_kernel<false, false><<<grid, kBlockG, 0, s>>>(G); }
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_aos_to_soa(const double *aos, double *soa, uint64_t n_bodies, uint32_t width, uint64_t ld, cudaStream_t s)
+{
+    if (n_bodies == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n_bodies + kTile - 1) / kTile);
+    aos_to_soa_kernel<<<grid, kTile, kTile * (width | 1u) * sizeof(double), s>>>(aos, soa, n_bodies, width, ld);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_soa_to_aos(const double *soa, double *aos, uint64_t n_bodies, uint32_t width, uint64_t ld, cudaStream_t s)
+{
+    if (n_bodies == 0) return cudaSuccess;
+    const dim3 grid((unsigned)((n_bodies + kTile - 1) / kTile), 1);
+    soa_to_aos_kernel<<<grid, kTile, kTile * (width | 1u) * sizeof(double), s>>>(soa, aos, n_bodies, width, ld);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_traj_to_aos(const double *traj, double *aos, uint64_t n_samples, uint64_t n_bodies, uint64_t ld, cudaStream_t s)
+{
+    if (n_bodies == 0 || n_samples == 0) return cudaSuccess;
+    for (uint64_t s0 = 0; s0 < n_samples; s0 += 32768) {
+        const unsigned ny = (unsigned)min((uint64_t)32768, n_samples - s0);
+        const dim3 grid((unsigned)((n_bodies + kTile - 1) / kTile), ny);
+        soa_to_aos_kernel<<<grid, kTile, kTile * 13 * sizeof(double), s>>>(traj + s0 * 13 * ld, aos + s0 * n_bodies * 13,
+                                                                          n_bodies, 13, ld);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_probe_fp64(double *out, int iters, int blocks, cudaStream_t s)
+{
+    probe_fp64_kernel<<<blocks, 256, 0, s>>>(out, iters);
+    return cudaGetLastError();
+}
+
+} // namespace b200

@@ -1,0 +1,176 @@
+"""Built-in effectors of the B200 six_dof() path.
+
+In the reference an effector is an arbitrary JAX function traced by
+`@el.map` / `@el.system` (python/elodin/__init__.py:160,360) and lowered through
+XLA / Cranelift.  The B200 path has no tracing compiler: the effectors its
+kernels know are the shapes SURVEY §8a-12 / §8a-8 list, each a faithful
+restatement of the reference example it cites.  Anything else is rejected with
+an error (no CPU fallback).
+
+Effectors compose with `|` exactly like reference systems (`gravity | apply_drag`)
+and are passed to `six_dof(sys=...)`.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+class System:
+    """Common base so effectors pipe with `|` (reference: System.pipe / __or__)."""
+
+    def pipe(self, other: "System") -> "Pipe":
+        return Pipe(_flatten(self) + _flatten(other))
+
+    def __or__(self, other: "System") -> "Pipe":
+        return self.pipe(other)
+
+
+def _flatten(s) -> list:
+    if s is None:
+        return []
+    if isinstance(s, Pipe):
+        return list(s.systems)
+    if isinstance(s, System):
+        return [s]
+    raise TypeError(
+        f"{s!r} is not a built-in B200 effector: the B200 backend cannot trace arbitrary Python/JAX systems "
+        "(see elodin_b200.effectors for the supported set; there is no CPU fallback)"
+    )
+
+
+@dataclass
+class Pipe(System):
+    systems: list = field(default_factory=list)
+
+
+@dataclass
+class Effector(System):
+    def lower(self, world) -> "_lib.Effector":  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def column_name(self) -> Optional[str]:
+        return getattr(self, "column", None)
+
+
+def _base(kind, p=(), flags=0, column: Optional[str] = None, width=0) -> _lib.Effector:
+    e = _lib.Effector()
+    e.kind, e.flags = kind, flags
+    for i, v in enumerate(p):
+        e.p[i] = float(v)
+    if column:
+        e.column_id = _lib.component_id(column)
+        e.column_width = width
+    return e
+
+
+@dataclass
+class GravityConst(Effector):
+    """`f + SpatialForce(linear=g * inertia.mass())` — examples/ball/sim.py:56-58,
+    examples/rocket/main.py:292-294."""
+
+    g: Sequence[float] = (0.0, 0.0, -9.81)
+
+    def lower(self, world):
+        return _base(_lib.EFF_GRAVITY_CONST, self.g)
+
+
+@dataclass
+class DragQuadratic(Effector):
+    """apply_drag of examples/ball/sim.py:99-116: drag = 0.5*(Cd*rho*V**2*A) along the
+    fluid-relative velocity `wind - v`, evaluated on the stage velocity.  Like the
+    reference it returns SpatialForce(linear=...): accumulated torque is reset."""
+
+    cd_rho: float = 0.5 * 1.225
+    area: float = 2 * 3.1415 * 0.2 ** 2
+    column: Optional[str] = "wind"
+
+    def lower(self, world):
+        return _base(_lib.EFF_DRAG_QUADRATIC, (self.cd_rho, self.area), column=self.column, width=3)
+
+
+@dataclass
+class ThrustBody(Effector):
+    """`f + SpatialForce(linear=p.angular() @ axis * thrust)` — examples/rocket/main.py:429-431."""
+
+    axis: Sequence[float] = (-1.0, 0.0, 0.0)
+    column: str = "thrust"
+
+    def lower(self, world):
+        return _base(_lib.EFF_THRUST_BODY, self.axis, column=self.column, width=1)
+
+
+@dataclass
+class WrenchBody(Effector):
+    """Body-frame wrench rotated into the world frame.
+    layout "torque_first": `f + p.angular() @ f_aero` (examples/rocket/main.py:407-413)
+    layout "linear_first": falcon9 apply_body_wrenches (examples/falcon9/sim.py:659-672)."""
+
+    column: str = "aero_force"
+    layout: str = "torque_first"
+
+    def lower(self, world):
+        if self.layout not in ("torque_first", "linear_first"):
+            raise ValueError(f"unknown wrench layout {self.layout!r}")
+        flags = _lib.EFF_FLAG_WRENCH_LINEAR_FIRST if self.layout == "linear_first" else 0
+        return _base(_lib.EFF_WRENCH_BODY, flags=flags, column=self.column, width=6)
+
+
+@dataclass
+class GravityFrame(Effector):
+    """Point-mass gravity + Coriolis + centrifugal of a rotating frame —
+    gravity_and_frame_forces, examples/falcon9/sim.py:350-361 + frames.py:91-109."""
+
+    mu: float = 3.986004418e14
+    omega: Sequence[float] = (0.0, 0.0, 7.292115e-5)
+
+    def lower(self, world):
+        return _base(_lib.EFF_GRAVITY_FRAME, (self.mu, *self.omega))
+
+
+@dataclass
+class GravityEdges(Effector):
+    """GraphQuery.edge_fold gravity (python/elodin/__init__.py:454-557).
+
+    kind "newton":   examples/three-body/main.py:63-70   (G)
+    kind "softened": examples/n-body/sim.py:349-361      (k_squared, softening)
+    `edges` are (from_entity_row, to_entity_row) pairs in spawn order; when None the
+    world's spawned `GravityConstraint`-style edges are used."""
+
+    kind: str = "newton"
+    G: float = 6.6743e-11
+    k_squared: float = 2.9591220828e-4 / (86400.0 * 86400.0)
+    softening: float = 1.0e-10
+    edges: Optional[np.ndarray] = None
+    _keep: list = field(default_factory=list, repr=False, compare=False)
+
+    def lower(self, world):
+        edges = self.edges if self.edges is not None else (world.edge_rows() if world is not None else None)
+        if edges is None:
+            raise ValueError("GravityEdges needs an edge list")
+        ed = np.asarray(edges, dtype=np.uint32).reshape(-1, 2)
+        f = np.ascontiguousarray(ed[:, 0])
+        t = np.ascontiguousarray(ed[:, 1])
+        self._keep[:] = [f, t]
+        if self.kind == "newton":
+            e = _base(_lib.EFF_GRAVITY_EDGES_NEWTON, (self.G,))
+        elif self.kind == "softened":
+            e = _base(_lib.EFF_GRAVITY_EDGES_SOFTENED, (self.k_squared, self.softening))
+        else:
+            raise ValueError(f"unknown gravity kind {self.kind!r}")
+        e.n_edges = len(f)
+        e.edge_from = f.ctypes.data
+        e.edge_to = t.ctypes.data
+        return e
+
+
+def all_pairs_edges(n: int) -> np.ndarray:
+    """Edges of examples/n-body/sim.py:334-338: for src, for dst != src."""
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    m = i != j
+    return np.stack([i[m], j[m]], 1).astype(np.uint32)

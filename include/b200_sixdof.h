@@ -163,6 +163,11 @@ const char *b200_last_error(void);
 /* number of visible CUDA devices, or a negative status; never falls back to CPU */
 int b200_device_count(void);
 
+/* Page-locked host memory for column buffers (optional: any host pointer works,
+ * pinned ones copy at full PCIe speed and asynchronously). */
+void *b200_host_alloc(uint64_t bytes);
+void b200_host_free(void *p);
+
 /* Build an executor for one world batch.  Replaces CraneliftExec::new
  * (cranelift_exec.rs:54-127): allocates device-resident SoA columns and the
  * output tables.  All columns start zeroed except inertia-independent defaults;

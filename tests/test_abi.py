@@ -1,0 +1,91 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/b200_sixdof.h
+declares, and fails loudly (no CPU fallback) when there is no GPU."""
+
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import elodin_b200 as el
+from elodin_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b200_sixdof.h")
+
+
+def _header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "elodin_b200", "csrc")], check=True)
+    return ctypes.CDLL(_lib.LIB_PATH)
+
+
+def test_header_symbols_all_exported(built_lib):
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(built_lib, s), f"{s} declared in include/b200_sixdof.h but not exported"
+    assert sorted(_lib.SYMBOLS) == syms  # the ctypes binding covers the whole header
+
+
+def test_component_id_matches_reference_table(built_lib):
+    """FNV-1a-64 & ~(1<<63): the ids SURVEY §8a-7 lists, host (pure Python) and library agree."""
+    want = {"world_accel": 0x019091805BC057F4, "simulation_time_step": 0x08E7DDBB2CCEAAB5, "tick": 0x1E7683EF2EBC7684,
+            "world_vel": 0x4B03B28A841EDD5F, "world_pos": 0x5D1C198A8E96E26E, "inertia": 0x5FD14829C04C0F91,
+            "force": 0x675AD8AFB3EEEBE4}
+    built_lib.b200_component_id.restype = ctypes.c_uint64
+    built_lib.b200_component_id.argtypes = [ctypes.c_char_p]
+    for name, cid in want.items():
+        assert el.component_id(name) == cid
+        assert built_lib.b200_component_id(name.encode()) == cid
+    ordered = sorted(want, key=want.get)
+    assert ordered == ["world_accel", "simulation_time_step", "tick", "world_vel", "world_pos", "inertia", "force"]
+    # from_pair("a","b") == new("a.b") (types.rs:47-57)
+    assert el.component_id("a.b") == built_lib.b200_component_id(b"a.b")
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.Effector) == 4 + 4 + 64 + 8 + 4 + 4 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.Desc) == 16 + 16 + 16 + 8 + 4 + 4 + 4 + 4 + 8
+    assert ctypes.sizeof(_lib.Timings) == 40
+
+
+def test_no_gpu_means_loud_failure_not_cpu_fallback(built_lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert el.device_count() == 0
+    with pytest.raises(el.B200Error) as ei:
+        el.B200Exec(3, 1, 0.01)
+    assert ei.value.code == _lib.ERR_NO_DEVICE
+    w = el.World()
+    w.spawn(el.Body(), name="e1")
+    with pytest.raises(el.B200Error):
+        w.build(el.six_dof())
+
+
+def test_product_never_imports_the_oracle():
+    """The product package must not import, link, dlopen or call anything under oracle/
+    (comments may cite it as the thing the EXACT mode is bit-identical to)."""
+    pkg = os.path.join(ROOT, "elodin_b200")
+    banned = [r"^\s*(from|import)\s+oracle", r"libsixdof_oracle", r"\borc_[a-z0-9_]+\s*\(", r"#include\s+[\"<].*oracle",
+              r"sixdof_oracle\.h", r"importlib.*oracle", r"[\"']oracle[\"'/]"]
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                for pat in banned:
+                    assert not re.search(pat, src, flags=re.M), f"{f} matches {pat}"
+    # and the shared library does not depend on it
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out

@@ -1,0 +1,473 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI
+(libb200_sixdof.so), against the CPU oracle and the reference's golden telemetry.
+
+Bars:
+  * B200_MATH_EXACT: bit-identical to the oracle (which reproduces the reference's
+    three-body / ball golden CSVs bit for bit) — `np.array_equal`.
+  * B200_MATH_FAST: <= FAST_TOL_TICK vector-relative per tick vs EXACT/oracle
+    (stated tolerance 1e-12), and <= FAST_TOL_1000 after 1000 ticks.
+"""
+
+import numpy as np
+import pytest
+
+import elodin_b200 as el
+from elodin_b200.executor import FORCE, INERTIA, WORLD_ACCEL, WORLD_POS, WORLD_VEL
+from tests.util import effector_pair, max_rel, random_world
+
+pytestmark = pytest.mark.gpu
+
+FAST_TOL_TICK = 1e-12
+FAST_TOL_1000 = 1e-9
+THREE_BODY_EDGES = np.array([[0, 1], [1, 0], [0, 2], [1, 2], [2, 0], [2, 1]])
+
+
+def _run_gpu(pos, vel, ine, effs, cols, dt, n_ticks, math="exact", integrator="rk4", time_step=None, fused=1,
+             accel=None):
+    M, N, _ = pos.shape
+    with el.B200Exec(N, M, dt, time_step, effs, integrator, math, max_fused_ticks=fused) as ex:
+        ex.set_state(pos, vel, ine, accel=accel, **cols)
+        ex.step(n_ticks, sync=True)
+        return (ex.download(WORLD_POS), ex.download(WORLD_VEL), ex.download(WORLD_ACCEL), ex.download(FORCE))
+
+
+def _run_oracle(O, pos, vel, ine, effs, dt, n_ticks, integrator="rk4", time_step=None, accel=None):
+    w = O.World(pos, vel, ine, accel)
+    if integrator == "rk4":
+        w.rk4(dt, n_ticks, effs, dt_final=time_step, threads=4)
+    else:
+        w.semi_implicit(dt if time_step is None else time_step, n_ticks, effs, threads=4)
+    return w.pos, w.vel, w.accel, w.force
+
+
+def _assert_exact(got, want, what=""):
+    for name, a, b in zip(("pos", "vel", "accel", "force"), got, want):
+        assert np.array_equal(a, b), f"{what} {name}: max abs diff {np.max(np.abs(a - b))}"
+
+
+def _assert_close(got, want, tol, what="", check_force=True):
+    names = ("pos_q", "pos_x", "vel", "accel", "force")
+    pairs = [(got[0][..., :4], want[0][..., :4]), (got[0][..., 4:], want[0][..., 4:]), (got[1], want[1]),
+             (got[2], want[2]), (got[3], want[3])]
+    for name, (a, b) in zip(names, pairs):
+        if name == "force" and not check_force:
+            continue
+        # accelerations / forces can cancel to ~0: scale by the batch-wide magnitude
+        scale = max(np.max(np.abs(b)), 1e-300)
+        err = float(np.max(np.abs(a - b)) / scale)
+        assert err <= tol, f"{what} {name}: rel err {err:.3e} > {tol}"
+
+
+# --------------------------------------------------------------------------- golden
+
+
+def test_three_body_golden_bit_exact(golden, oracle):
+    """The GPU EXACT path reproduces all 100 recorded ticks of
+    scripts/ci/baseline/three-body-csv bit for bit, through invoke_batch."""
+    def col(c):
+        return np.stack([golden[f"three_body.{e}.{c}"] for e in "abc"], 1)
+
+    pos, vel, acc, frc, ine = [col(c) for c in ("world_pos", "world_vel", "world_accel", "force", "inertia")]
+    dt = float(golden["three_body.simulation_time_step"][0, 0])
+    eff = el.GravityEdges("newton", G=6.6743e-11, edges=THREE_BODY_EDGES)
+    with el.B200Exec(3, 1, dt, None, [eff], "rk4", "exact") as ex:
+        state = {WORLD_POS: pos[0][None], WORLD_VEL: vel[0][None], WORLD_ACCEL: acc[0][None], FORCE: frc[0][None],
+                 INERTIA: ine[0][None]}
+        tick = 0
+        for t in range(1, 101):
+            ins = []
+            for cid in ex.input_ids:
+                if cid == el.component_id("tick"):
+                    ins.append(np.array([tick], dtype=np.uint64))
+                elif cid == el.component_id("simulation_time_step"):
+                    ins.append(np.array([dt]))
+                else:
+                    ins.append(state[cid])
+            outs = dict(zip(ex.output_ids, ex.invoke_batch(ins, 1)))
+            tick = int(outs[el.component_id("tick")][0])
+            assert tick == t
+            for cid in state:
+                state[cid] = outs[cid]
+            assert np.array_equal(state[WORLD_POS][0], pos[t]), t
+            assert np.array_equal(state[WORLD_VEL][0], vel[t]), t
+            assert np.array_equal(state[FORCE][0], frc[t]), t
+            assert np.array_equal(state[WORLD_ACCEL][0], acc[t]), t
+            assert np.array_equal(state[INERTIA][0], ine[t]), t  # pass-through output
+    # FAST: within tolerance of the golden after 100 ticks
+    got = _run_gpu(pos[0][None], vel[0][None], ine[0][None], [eff], {}, dt, 100, "fast")
+    assert max_rel(got[0][0][:, 4:], pos[100][:, 4:]) < 1e-11
+    assert max_rel(got[1][0][:, 3:], vel[100][:, 3:]) < 1e-11
+
+
+def test_ball_golden_one_step_bit_exact(golden):
+    g = golden
+    dt = float(g["ball.simulation_time_step"][0, 0])
+    effs = [el.GravityConst((0.0, 0.0, -9.81)), el.DragQuadratic(0.5 * 1.225, 2 * 3.1415 * 0.2 ** 2, "wind")]
+    with el.B200Exec(1, 1, dt, None, effs, "rk4", "exact") as ex:
+        for t in range(100):
+            v = g["ball.world_vel"][t].copy()
+            if max(g["ball.world_pos"][t][6], v[5]) < 0.0:  # bounce, examples/ball/sim.py:64-72 (host side)
+                v = np.concatenate([np.zeros(3), v[3:] * np.array([1.0, 1.0, -1.0]) * 0.85])
+            ex.set_state(g["ball.world_pos"][t], v, g["ball.inertia"][t], accel=g["ball.world_accel"][t],
+                         wind=g["ball.wind"][t + 1])
+            ex.step(1, sync=True)
+            assert np.array_equal(ex.download(WORLD_POS)[0, 0], g["ball.world_pos"][t + 1]), t
+            assert np.array_equal(ex.download(WORLD_VEL)[0, 0], g["ball.world_vel"][t + 1]), t
+            assert np.array_equal(ex.download(FORCE)[0, 0], g["ball.force"][t + 1]), t
+            assert np.array_equal(ex.download(WORLD_ACCEL)[0, 0], g["ball.world_accel"][t + 1]), t
+
+
+def test_rocket_golden_one_step(golden, oracle):
+    """EXACT == canonical oracle bit for bit; both within 1e-15 of the recorded rocket
+    telemetry (whose host JIT contracted `dot` with FMA, see oracle/sixdof_oracle.c)."""
+    g = golden
+    dt = float(g["rocket.simulation_time_step"][0, 0])
+    effs = [el.GravityConst((0.0, 0.0, -9.81)), el.ThrustBody((-1.0, 0.0, 0.0), "thrust"), el.WrenchBody("aero_force")]
+    O = oracle
+    with el.B200Exec(1, 1, dt, None, effs, "rk4", "exact") as ex, el.B200Exec(1, 1, dt, None, effs, "rk4", "fast") as fx:
+        for t in range(100):
+            for e in (ex, fx):
+                e.set_state(g["rocket.world_pos"][t], g["rocket.world_vel"][t], g["rocket.inertia"][t],
+                            accel=g["rocket.world_accel"][t], thrust=g["rocket.thrust"][t + 1],
+                            aero_force=g["rocket.aero_force"][t + 1])
+                e.step(1, sync=True)
+            w = O.World(g["rocket.world_pos"][t][None], g["rocket.world_vel"][t][None], g["rocket.inertia"][t][None],
+                        g["rocket.world_accel"][t][None])
+            w.rk4(dt, 1, [O.Effector(O.EFF_GRAVITY_CONST, p=(0, 0, -9.81)),
+                          O.Effector(O.EFF_THRUST_BODY, p=(-1.0, 0, 0), column=g["rocket.thrust"][t + 1].reshape(1, 1, 1)),
+                          O.Effector(O.EFF_WRENCH_BODY, column=g["rocket.aero_force"][t + 1].reshape(1, 1, 6))])
+            got = (ex.download(WORLD_POS), ex.download(WORLD_VEL), ex.download(WORLD_ACCEL), ex.download(FORCE))
+            _assert_exact(got, (w.pos, w.vel, w.accel, w.force), f"rocket t={t}")
+            for name, a in (("world_pos", got[0]), ("world_vel", got[1]), ("world_accel", got[2]), ("force", got[3])):
+                ref = g[f"rocket.{name}"][t + 1]
+                assert np.max(np.abs(a[0, 0] - ref)) <= 1e-15 * np.max(np.abs(ref)), (t, name)
+            fgot = (fx.download(WORLD_POS), fx.download(WORLD_VEL), fx.download(WORLD_ACCEL), fx.download(FORCE))
+            _assert_close(fgot, got, FAST_TOL_TICK, f"rocket fast t={t}")
+
+
+# --------------------------------------------------------------------------- random worlds vs oracle
+
+
+@pytest.mark.parametrize("M,N", [(1, 1), (3, 5), (64, 7), (2, 257), (1000, 1)])
+@pytest.mark.parametrize("combo", ["free", "rocket", "ball", "falcon9", "wrench_then_drag"])
+def test_effector_combos_exact_and_fast(oracle, M, N, combo):
+    O = oracle
+    pos, vel, ine = random_world(100 + M + N, M, N)
+    rng = np.random.default_rng(7)
+    specs = {
+        "free": [],
+        "rocket": [("gravity", {}), ("thrust", {"thrust": rng.uniform(0, 400, (M, N, 1))}),
+                   ("wrench", {"wrench": rng.normal(0, 3, (M, N, 6))})],
+        "ball": [("gravity", {}), ("drag", {"wind": rng.normal(0, 1, (M, N, 3))})],
+        "falcon9": [("frame", {}), ("wrench", {"wrench": rng.normal(0, 1e3, (M, N, 6)), "linear_first": True})],
+        "wrench_then_drag": [("wrench", {"wrench": rng.normal(0, 3, (M, N, 6))}), ("drag", {"wind": rng.normal(0, 1, (M, N, 3))}),
+                             ("thrust", {"thrust": rng.uniform(0, 40, (M, N, 1))})],
+    }[combo]
+    if combo == "falcon9":  # near the Earth's surface, ECEF
+        pos[..., 4:] = pos[..., 4:] * 1e2 + np.array([6.4e6, 0, 0])
+    oeffs, geffs, cols = [], [], {}
+    for kind, kw in specs:
+        o, g, c = effector_pair(O, kind, **kw)
+        oeffs.append(o); geffs.append(g); cols.update(c)
+    dt = 0.008333333
+    acc0 = rng.normal(0, 1, (M, N, 6))
+    want = _run_oracle(O, pos, vel, ine, oeffs, dt, 5, accel=acc0)
+    got = _run_gpu(pos, vel, ine, geffs, cols, dt, 5, "exact", accel=acc0)
+    _assert_exact(got, want, f"{combo} M={M} N={N}")
+    fast = _run_gpu(pos, vel, ine, geffs, cols, dt, 5, "fast", accel=acc0)
+    _assert_close(fast, want, 5 * FAST_TOL_TICK, f"{combo} fast M={M} N={N}")
+
+
+@pytest.mark.parametrize("integrator", ["rk4", "semi_implicit"])
+@pytest.mark.parametrize("time_step", [None, 1.0 / 60.0])
+def test_integrators_and_dt_override(oracle, integrator, time_step):
+    O = oracle
+    M, N = 4, 9
+    pos, vel, ine = random_world(5, M, N, unit_q=(integrator == "rk4"))
+    rng = np.random.default_rng(1)
+    o1, g1, c1 = effector_pair(O, "gravity")
+    o2, g2, c2 = effector_pair(O, "wrench", wrench=rng.normal(0, 2, (M, N, 6)))
+    want = _run_oracle(O, pos, vel, ine, [o1, o2], 0.01, 7, integrator, time_step)
+    got = _run_gpu(pos, vel, ine, [g1, g2], {**c1, **c2}, 0.01, 7, "exact", integrator, time_step)
+    _assert_exact(got, want, f"{integrator} ts={time_step}")
+    fast = _run_gpu(pos, vel, ine, [g1, g2], {**c1, **c2}, 0.01, 7, "fast", integrator, time_step)
+    _assert_close(fast, want, 7 * FAST_TOL_TICK, f"{integrator} fast")
+
+
+@pytest.mark.parametrize("kind", ["softened", "newton"])
+@pytest.mark.parametrize("M,N", [(1, 2), (3, 130), (2, 300)])
+def test_nbody_dense_gravity(oracle, kind, M, N):
+    """All-pairs edge_fold (examples/n-body/sim.py:334-369): the tiled kernel keeps the
+    reference's ascending fold order, so EXACT is bit-exact at any N."""
+    O = oracle
+    pos, vel, ine = random_world(17, M, N)
+    rng = np.random.default_rng(3)
+    pos[..., 4:] = rng.uniform(-30, 30, (M, N, 3))
+    vel[..., 3:] = rng.normal(0, 1e-2, (M, N, 3))
+    ine[..., 6] = 10 ** rng.uniform(-6, -3, (M, N))
+    edges = el.all_pairs_edges(N)
+    kw = {"k2": 2.9591220828e-4, "soft": 1e-10} if kind == "softened" else {"G": 1e-3}
+    o, g, _ = effector_pair(O, kind, edges=edges, **kw)
+    want = _run_oracle(O, pos, vel, ine, [o], 0.05, 4)
+    got = _run_gpu(pos, vel, ine, [g], {}, 0.05, 4, "exact")
+    _assert_exact(got, want, f"{kind} dense N={N}")
+    fast = _run_gpu(pos, vel, ine, [g], {}, 0.05, 4, "fast")
+    _assert_close(fast, want, 1e-11, f"{kind} dense fast N={N}")
+
+
+def test_sparse_graph_csr_and_order(oracle):
+    """Irregular edge list: bodies without out-edges keep the forces of earlier
+    effectors; fold order is the spawn order (deliberately shuffled here)."""
+    O = oracle
+    M, N = 3, 40
+    pos, vel, ine = random_world(23, M, N)
+    rng = np.random.default_rng(9)
+    pos[..., 4:] = rng.uniform(-5, 5, (M, N, 3))
+    edges = np.array([(i, j) for i in range(0, N, 2) for j in rng.permutation(N)[:7] if i != j])
+    rng.shuffle(edges)
+    og, gg, _ = effector_pair(O, "gravity")
+    o, g, _ = effector_pair(O, "softened", edges=edges, k2=0.3, soft=1e-6)
+    want = _run_oracle(O, pos, vel, ine, [og, o], 0.01, 3)
+    got = _run_gpu(pos, vel, ine, [gg, g], {}, 0.01, 3, "exact")
+    _assert_exact(got, want, "sparse graph")
+    # FAST requires the graph effector first; put gravity after it
+    want2 = _run_oracle(O, pos, vel, ine, [o, og], 0.01, 3)
+    fast = _run_gpu(pos, vel, ine, [g, gg], {}, 0.01, 3, "fast")
+    _assert_close(fast, want2, 1e-11, "sparse graph fast")
+    with pytest.raises(el.B200Error):
+        _run_gpu(pos, vel, ine, [gg, g], {}, 0.01, 1, "fast")
+
+
+def test_semi_implicit_nbody(oracle):
+    O = oracle
+    M, N = 2, 33
+    pos, vel, ine = random_world(31, M, N)
+    pos[..., 4:] *= 1e-2
+    o, g, _ = effector_pair(O, "softened", edges=el.all_pairs_edges(N), k2=0.1, soft=1e-4)
+    want = _run_oracle(O, pos, vel, ine, [o], 0.01, 6, "semi_implicit")
+    got = _run_gpu(pos, vel, ine, [g], {}, 0.01, 6, "exact", "semi_implicit")
+    _assert_exact(got, want, "semi-implicit n-body")
+
+
+# --------------------------------------------------------------------------- structure / plumbing
+
+
+def test_fused_ticks_equal_single_ticks():
+    pos, vel, ine = random_world(2, 50, 3)
+    rng = np.random.default_rng(0)
+    effs = [el.GravityConst(), el.ThrustBody((0.0, 0.0, 1.0), "thrust")]
+    cols = {"thrust": rng.uniform(0, 300, (50, 3, 1))}
+    for math in ("exact", "fast"):
+        a = _run_gpu(pos, vel, ine, effs, cols, 1e-3, 37, math, fused=1)
+        b = _run_gpu(pos, vel, ine, effs, cols, 1e-3, 37, math, fused=16)
+        for x, y in zip(a[:2], b[:2]):
+            assert np.array_equal(x, y), math
+        # Force / WorldAccel leave the batch holding the last tick's stage-4 values either way
+        for x, y in zip(a[2:], b[2:]):
+            assert np.array_equal(x, y), math
+
+
+def test_trajectory_ring_matches_states():
+    M, N = 6, 4
+    pos, vel, ine = random_world(4, M, N)
+    effs = [el.GravityConst()]
+    with el.B200Exec(N, M, 0.01, None, effs, "rk4", "exact", max_fused_ticks=8, trajectory_every=5,
+                     trajectory_capacity=10) as ex:
+        ex.set_state(pos, vel, ine)
+        snaps = []
+        for _ in range(12):
+            ex.step(5, sync=True)
+            snaps.append(np.concatenate([ex.download(WORLD_POS), ex.download(WORLD_VEL)], -1))
+        traj = ex.trajectory()
+        assert traj.shape == (10, M, N, 13)  # capacity caps the ring
+        for s in range(10):
+            assert np.array_equal(traj[s], snaps[s]), s
+        assert ex.tick == 60
+
+
+@pytest.mark.parametrize("B", [1, 31, 32, 33, 255, 257, 1000, 4097])
+def test_layout_roundtrip_ragged(B):
+    """K6 aos<->soa: upload then download returns the same bytes for ragged sizes."""
+    rng = np.random.default_rng(B)
+    with el.B200Exec(B, 1, 0.01, None, [el.WrenchBody("aero_force"), el.ThrustBody((1, 0, 0), "thrust")], "rk4", "exact") as ex:
+        for cid, w in ((WORLD_POS, 7), (WORLD_VEL, 6), (INERTIA, 7), ("aero_force", 6), ("thrust", 1)):
+            a = rng.normal(size=(1, B, w))
+            ex.upload(cid, a)
+            assert np.array_equal(ex.download(cid), a)
+
+
+def test_world_axis_is_independent_worlds(oracle):
+    """[M, N] batch == M separate executors (the reference runs one process per world)."""
+    M, N = 5, 6
+    pos, vel, ine = random_world(77, M, N)
+    pos[..., 4:] *= 1e-2
+    eff = lambda: [el.GravityEdges("softened", k_squared=0.2, softening=1e-5, edges=el.all_pairs_edges(N))]
+    both = _run_gpu(pos, vel, ine, eff(), {}, 0.01, 5, "exact")
+    for m in range(M):
+        one = _run_gpu(pos[m:m + 1], vel[m:m + 1], ine[m:m + 1], eff(), {}, 0.01, 5, "exact")
+        for a, b in zip(one, both):
+            assert np.array_equal(a[0], b[m])
+
+
+def test_abi_errors_match_reference_semantics():
+    with el.B200Exec(4, 1, 0.01, None, [], "rk4", "exact") as ex:
+        with pytest.raises(ValueError):  # Error::ValueSizeMismatch -> ValueError (error.rs:46-58)
+            ex.upload(WORLD_POS, np.zeros((1, 3, 7)))
+        with pytest.raises(ValueError):  # Error::ComponentNotFound -> ValueError
+            ex.upload("no_such_component", np.zeros(4))
+        assert ex.input_ids == [el.component_id(n) for n in
+                                ("tick", "force", "inertia", "world_pos", "world_accel", "simulation_time_step", "world_vel")]
+        assert ex.output_ids == sorted(ex.input_ids)
+    with pytest.raises(el.B200Error):
+        el.B200Exec(4, 1, -1.0, None, [], "rk4", "exact")  # Error::InvalidTimeStep
+    with pytest.raises(el.B200Error):
+        el.B200Exec(4, 1, 0.01, None, [el.GravityConst()] * 9, "rk4", "exact")
+    # empty world: legal, ticks still advance
+    with el.B200Exec(0, 1, 0.01, None, [], "rk4", "exact") as ex:
+        ex.step(3, sync=True)
+        assert ex.tick == 3
+
+
+def test_tickfn_shaped_entry():
+    pos, vel, ine = random_world(8, 1, 3)
+    with el.B200Exec(3, 1, 0.01, None, [], "rk4", "exact") as ex:
+        zeros6 = np.zeros((1, 3, 6))
+        table = {el.component_id("tick"): np.array([41], dtype=np.uint64), FORCE: zeros6, INERTIA: ine, WORLD_POS: pos,
+                 WORLD_ACCEL: zeros6, el.component_id("simulation_time_step"): np.array([0.01]), WORLD_VEL: vel}
+        ins = [table[c] for c in ex.input_ids]
+        outs = [np.empty_like(table[c]) for c in ex.output_ids]
+        ex.tick_fn(ins, outs)
+        o = dict(zip(ex.output_ids, outs))
+        assert int(o[el.component_id("tick")][0]) == 42
+        ref = _run_gpu(pos, vel, ine, [], {}, 0.01, 1, "exact")
+        assert np.array_equal(o[WORLD_POS], ref[0]) and np.array_equal(o[WORLD_VEL], ref[1])
+
+
+# --------------------------------------------------------------------------- full-size properties
+
+
+def test_full_size_properties_free_body(oracle):
+    """BASELINE configs[1] batched (2^20 worlds x 1 body, dt = 1e-3): properties that do
+    not need the oracle at full size + an oracle check on a slice."""
+    O = oracle
+    M = 1 << 20
+    pos, vel, ine = random_world(2026, M, 1)
+    for math in ("exact", "fast"):
+        got = _run_gpu(pos, vel, ine, [], {}, 1e-3, 20, math, fused=20)
+        q = got[0][..., :4]
+        assert np.max(np.abs(np.linalg.norm(q, axis=-1) - 1.0)) < 4e-16 * 4  # renormalised every tick
+        assert np.array_equal(got[1], vel)  # free body: velocity is constant, bit for bit
+        lin = pos[..., 4:] + 20 * 1e-3 * vel[..., 3:]
+        assert max_rel(got[0][..., 4:], lin) < 1e-13
+        sl = slice(0, 4096)
+        want = _run_oracle(O, pos[sl], vel[sl], ine[sl], [], 1e-3, 20)
+        if math == "exact":
+            _assert_exact([g[sl] for g in got], want, "full-size slice")
+        else:
+            _assert_close([g[sl] for g in got], want, 20 * FAST_TOL_TICK, "full-size slice fast", check_force=False)
+    # replicated worlds stay replicated (no cross-talk across the batch axis)
+    rep = np.broadcast_to(pos[:1], pos.shape).copy(), np.broadcast_to(vel[:1], vel.shape).copy(), np.broadcast_to(ine[:1], ine.shape).copy()
+    got = _run_gpu(*rep, [el.GravityConst()], {}, 1e-3, 10, "fast")
+    assert np.all(got[0] == got[0][:1]) and np.all(got[1] == got[1][:1])
+
+
+def test_fast_drift_over_1000_ticks(oracle):
+    """FAST vs oracle after 1000 ticks of the rocket-style world (<= 1e-9)."""
+    O = oracle
+    M, N = 256, 1
+    pos, vel, ine = random_world(42, M, N)
+    rng = np.random.default_rng(42)
+    specs = [("gravity", {}), ("thrust", {"thrust": rng.uniform(50, 100, (M, N, 1))}),
+             ("drag", {"wind": rng.normal(0, 1, (M, N, 3)), "cd_rho": 0.6, "area": 0.01}),
+             ("wrench", {"wrench": rng.normal(0, 0.05, (M, N, 6))})]
+    # drag resets torque, so put the wrench after it to keep the attitude dynamics alive
+    oeffs, geffs, cols = [], [], {}
+    for kind, kw in specs:
+        o, g, c = effector_pair(O, kind, **kw)
+        oeffs.append(o); geffs.append(g); cols.update(c)
+    want = _run_oracle(O, pos, vel, ine, oeffs, 0.008333333, 1000)
+    exact = _run_gpu(pos, vel, ine, geffs, cols, 0.008333333, 1000, "exact", fused=50)
+    _assert_exact(exact, want, "1000 ticks exact")
+    fast = _run_gpu(pos, vel, ine, geffs, cols, 0.008333333, 1000, "fast", fused=50)
+    _assert_close(fast, want, FAST_TOL_1000, "1000 ticks fast")
+
+
+# --------------------------------------------------------------------------- the ECS mirror (reads like test_all.py)
+
+
+def test_six_dof_like_reference_test_all():
+    """libs/nox-py/python/tests/test_all.py:67-83 — same script against `el = elodin_b200`."""
+    w = el.World()
+    w.spawn(el.Body(world_pos=el.SpatialTransform(linear=np.array([0.0, 0.0, 0.0])),
+                    world_vel=el.SpatialMotion(linear=np.array([1.0, 0.0, 0.0])),
+                    inertia=el.SpatialInertia(1.0)), "e1")
+    sys = el.six_dof(1.0 / 60.0)
+    exec = w.build(sys)
+    exec.run()
+    df = exec.history("e1.world_pos")
+    x = df["e1.world_pos"][-1]
+    assert np.allclose(x.to_numpy()[:4], np.array([0.0, 0.0, 0.0, 1.0]))
+    assert np.allclose(x.to_numpy()[4:], np.array([0.01666667, 0.0, 0.0]))
+
+
+@pytest.mark.parametrize("omega,want", [
+    ([0.0, 0.0, 1.0], [0.0, 0.0, 0.479425538604203, 0.8775825618903728, 0.0, 0.0, 0.0]),
+    ([0.0, 1.0, 0.0], [0.0, 0.479425538604203, 0.0, 0.8775825618903728, 0.0, 0.0, 0.0]),
+    ([1.0, 1.0, 0.0], [0.45936268493243, 0.45936268493243, 0.0, 0.76024459707606, 0.0, 0.0, 0.0]),
+])
+@pytest.mark.parametrize("math", ["exact", "fast"])
+def test_six_dof_ang_vel_int_like_reference(omega, want, math):
+    """test_all.py:228-291 (Julia/Simulink values, rtol 1e-5)."""
+    w = el.World()
+    w.spawn(el.Body(world_pos=el.SpatialTransform(linear=np.array([0.0, 0.0, 0.0])),
+                    world_vel=el.SpatialMotion(angular=np.array(omega)), inertia=el.SpatialInertia(1.0)), "e1")
+    exec = w.build(el.six_dof(1.0 / 120.0), math=math)
+    exec.run(120)
+    x = exec.history("e1.world_pos")["e1.world_pos"][-1]
+    assert np.isclose(x.to_numpy(), np.array(want), rtol=1e-5).all()
+
+
+def test_six_dof_force_like_reference():
+    """test_all.py:342-366: unit force for 1 s -> x = 0.5."""
+    w = el.World()
+    w.spawn(el.Body(world_pos=el.SpatialTransform(linear=np.array([0.0, 0.0, 0.0])),
+                    world_vel=el.SpatialMotion(angular=np.array([0.0, 0.0, 0.0])), inertia=el.SpatialInertia(1.0)), "e1")
+    constant_force = el.GravityConst((1.0, 0.0, 0.0))  # unit mass: g*m == the reference's constant_force
+    exec = w.build(el.six_dof(1.0 / 120.0, constant_force))
+    exec.run(120)
+    df = exec.history(["e1.world_pos", "e1.world_vel", "e1.world_accel"])
+    assert np.isclose(df["e1.world_pos"][-1].to_numpy(), np.array([0.0, 0.0, 0.0, 1.0, 0.5, 0.0, 0.0]), rtol=1e-5).all()
+    assert np.isclose(df["e1.world_accel"][-1].to_numpy(), [0, 0, 0, 1.0, 0, 0]).all()
+
+
+def test_three_body_example_through_ecs_mirror(golden):
+    """examples/three-body/main.py rebuilt on the mirror: spawn order, entity ids, edges
+    and the 100-tick golden, end to end through World.build / Exec.run / history."""
+    G = 6.6743e-11
+    w = el.World()
+    ics = {"a": ([0.8920281421, 0.0, 0.0], [0.0, 0.9957939373, 0.0]),
+           "b": ([-0.6628498947, 0.0, 0.0], [0.0, -1.6191613336, 0.0]),
+           "c": ([-0.2291782474, 0, 0], [0, 0.6233673964, 0.0])}
+    ids = {}
+    for k, (x, v) in ics.items():
+        ids[k] = w.spawn([el.Body(world_pos=el.WorldPos(linear=np.array(x)),
+                                  world_vel=el.WorldVel(linear=np.array(v)),
+                                  inertia=el.SpatialInertia(1.0 / G))], name=k.upper())
+    assert [int(ids[k]) for k in "abc"] == [1, 2, 3]  # entity 0 = Globals
+    GravityEdge = el.Annotated[el.Edge, el.Component("gravity_edge", el.ComponentType.Edge)]
+
+    @el.dataclass
+    class GravityConstraint(el.Archetype):
+        a: GravityEdge
+
+    for s, d in (("a", "b"), ("b", "a"), ("a", "c"), ("b", "c"), ("c", "a"), ("c", "b")):
+        w.spawn(GravityConstraint(el.Edge(ids[s], ids[d])), name=f"{s.upper()} -> {d.upper()}")
+    assert np.array_equal(w.edge_rows(), THREE_BODY_EDGES)
+    exec = w.build(el.six_dof(sys=el.GravityEdges("newton", G=G)), simulation_rate=120.0)
+    assert exec.sim_time_step == 0.008333333
+    exec.run(100)
+    h = exec.history(["A.world_pos", "B.world_vel", "C.force", "Globals.tick"])
+    assert np.array_equal(h["A.world_pos"], golden["three_body.a.world_pos"])
+    assert np.array_equal(h["B.world_vel"], golden["three_body.b.world_vel"])
+    assert np.array_equal(h["C.force"][1:], golden["three_body.c.force"][1:])
+    assert np.array_equal(h["Globals.tick"], np.arange(101))
