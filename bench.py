@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py — entity-steps/s of the B200 six_dof() RK4 path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--worlds M]
+
+One "step" = one RK4 tick of the hot path over the whole batch of synthetic worlds
+(one body kernel launch, the state streaming HBM -> registers -> HBM).  Workload at
+every N: BASELINE.json configs[1] — the cube-sat single 6DOF body, RK4, dt = 1e-3 —
+batched over the Monte-Carlo world axis (SURVEY §8d C2 "also run M = 2^20.. copies for
+throughput"): 1 body x M worlds per GPU, M = 2^22 (read set 671 MB > 126 MB L2), weak
+scaling (per-GPU work fixed, worlds shard with no data-path collective).  The literal
+configs[1] latency chain (1 body, dependent steps) is reported beside it as
+`single_body`.
+
+value     whole-job entity-steps/s, inputs resident in HBM, CUDA-event timed on the
+          launching stream, max over ranks.
+e2e       the same metric through the reference-shaped C-ABI call
+          b200_sixdof_invoke_batch with pinned HOST buffers: every call uploads all
+          input columns, integrates `e2e_ticks_per_call` ticks, downloads all outputs.
+roofline  algorithmic 264 B/entity-step / mean kernel time vs the measured
+          HBM copy peak (MEASURED_PEAKS.json, else the 6.65 TB/s fallback).
+cpu_baseline / --impl reference
+          the CPU oracle port of the reference arithmetic (oracle/, the reference's
+          Rust+JAX+Cranelift stack cannot be built here) on all host threads, on a
+          bounded sample of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+B_ALG = 264  # algorithmic bytes per entity-step, f64: read pos 56 + vel 48 + inertia 56, write pos 56 + vel 48
+DT = 1.0e-3
+METRIC = "entity-steps/sec (6DOF RK4)"
+UNIT = "entity-steps/s"
+
+
+def synth_world(M: int, seed: int):
+    """cube-sat-like bodies (examples/cube-sat/main.py:14-16: omega = normalize([1,1,1]) * 80 deg/s,
+    m = 2.8252 kg) perturbed per world so that no two worlds are identical (SURVEY §8d synthetic inputs)."""
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=(M, 1, 4))
+    q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    pos = np.concatenate([q, rng.uniform(-1e3, 1e3, (M, 1, 3))], -1)
+    w0 = np.array([1.0, 1.0, 1.0]) / np.sqrt(3.0) * np.radians(80.0)
+    vel = np.concatenate([w0 + rng.normal(0, 0.05, (M, 1, 3)), rng.normal(0, 10, (M, 1, 3))], -1)
+    ine = np.concatenate([rng.uniform(0.01, 0.05, (M, 1, 3)), np.zeros((M, 1, 3)), np.full((M, 1, 1), 2.8252)], -1)
+    return np.ascontiguousarray(pos), np.ascontiguousarray(vel), np.ascontiguousarray(ine)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload_key: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload_key)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(worlds: int, ticks: int, threads: int, seed: int = 1):
+    """entity-steps/s of the CPU oracle port (checker code, timed as the CPU baseline only)."""
+    from oracle import oracle as O
+
+    pos, vel, ine = synth_world(worlds, seed)
+    w = O.World(pos, vel, ine)
+    w.rk4(DT, 1, threads=threads)  # warm
+    t0 = time.perf_counter()
+    w.rk4(DT, ticks, threads=threads)
+    dt = time.perf_counter() - t0
+    return worlds * ticks / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  Its Rust/JAX/Cranelift stack cannot be
+    built in this image, so this arm times the oracle port (oracle/sixdof_oracle.c, validated
+    bit-for-bit against the reference's golden telemetry) with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+
+    O.build()
+    threads = O.max_threads()
+    worlds = 1 << 16  # bounded sample of the M-world workload, per step
+    # calibrate so the K-step run stays within ~minutes
+    for _ in range(max(args.warmup, 1)):
+        cpu_oracle_rate(worlds, 1, threads)
+    pos, vel, ine = synth_world(worlds, 1)
+    w = O.World(pos, vel, ine)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        w.rk4(DT, 1, threads=threads)
+    el_s = time.perf_counter() - t0
+    value = worlds * args.steps / el_s
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": el_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cube-sat 6DOF RK4 dt=1e-3, 1 body x M worlds (configs[1] batched); CPU sample of 65536 worlds per step",
+                   "worlds_per_step": worlds, "dt": DT, "integrator": "rk4"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{worlds} worlds x {args.steps} ticks, oracle/sixdof_oracle.c on {threads} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import elodin_b200 as el
+    from elodin_b200.executor import FORCE, INERTIA, WORLD_ACCEL, WORLD_POS, WORLD_VEL
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: elodin_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    distributed = world_size > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    M = args.worlds
+    K, W = args.steps, max(args.warmup, 3)
+    pos, vel, ine = synth_world(M, 1000 + rank)
+    stream = torch.cuda.Stream()
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if not distributed:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ------------------------------------------------------------------ device-resident throughput
+    ex = el.B200Exec(1, M, DT, None, [], "rk4", "fast", device=local, max_fused_ticks=1)
+    ex.set_stream(stream.cuda_stream)
+    ex.set_state(pos, vel, ine)
+    with torch.cuda.stream(stream):
+        ex.step(W)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = ex.timings()["kernel_launches"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        ex.step(K)
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = ex.timings()["kernel_launches"] - launches0
+        clocks = sampler.stop() if rank == 0 else None
+    value = world_size * M * K / (ms * 1e-3)
+    kernel_ms = ms / K
+    peak, peak_src = measured_peak()
+    achieved = B_ALG * M / (kernel_ms * 1e-3) / 1e9
+
+    if args.kernel_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": W,
+                              "ms_per_step": kernel_ms, "roofline_frac": achieved / peak, "kernel_only": True}))
+        ex.close()
+        if distributed:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------ secondary device numbers (rank 0, N=1 extras)
+    extras = {}
+    with torch.cuda.stream(stream):
+        # fused ticks: state stays in registers across `fuse` ticks (invoke_batch with ticks_per_telemetry > 1)
+        fx = el.B200Exec(1, M, DT, None, [], "rk4", "fast", device=local, max_fused_ticks=args.fuse)
+        fx.set_stream(stream.cuda_stream)
+        fx.set_state(pos, vel, ine)
+        fx.step(args.fuse)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        fx.step(args.fuse * 4)
+        f1.record(stream)
+        barrier()
+        fms = max_over_ranks(f0.elapsed_time(f1))
+        extras["fused"] = {"ticks_per_launch": args.fuse, "value": world_size * M * args.fuse * 4 / (fms * 1e-3),
+                           "unit": UNIT, "note": "FP64-pipe bound: HBM traffic amortised over the fused ticks"}
+        fx.close()
+        if rank == 0:
+            # EXACT arithmetic (bit-identical to the reference-validated oracle)
+            xM = min(M, 1 << 20)
+            xx = el.B200Exec(1, xM, DT, None, [], "rk4", "exact", device=local)
+            xx.set_stream(stream.cuda_stream)
+            xx.set_state(pos[:xM], vel[:xM], ine[:xM])
+            xx.step(3)
+            torch.cuda.synchronize()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record(stream)
+            xx.step(10)
+            x1.record(stream)
+            torch.cuda.synchronize()
+            extras["exact_math"] = {"value": xM * 10 / (x0.elapsed_time(x1) * 1e-3), "unit": UNIT, "worlds": xM}
+            xx.close()
+            # BASELINE configs[1] literally: ONE body, dependent steps (latency chain, one persistent launch per 10^4 ticks)
+            sb = el.B200Exec(1, 1, DT, None, [], "rk4", "fast", device=local, max_fused_ticks=10000)
+            sb.set_stream(stream.cuda_stream)
+            sb.set_state(pos[:1], vel[:1], ine[:1])
+            sb.step(10000)
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_single = 200000
+            s0.record(stream)
+            sb.step(n_single)
+            s1.record(stream)
+            torch.cuda.synchronize()
+            sms = s0.elapsed_time(s1)
+            extras["single_body"] = {"steps": n_single, "ns_per_step": sms * 1e6 / n_single,
+                                     "value": n_single / (sms * 1e-3), "unit": UNIT,
+                                     "note": "configs[1] as written: 1 body, 1e6 dependent steps = %.2f s" % (sms * 1e-3 * 1e6 / n_single)}
+            sb.close()
+
+    # ------------------------------------------------------------------ e2e through the C ABI with host buffers
+    T = args.e2e_ticks
+    eM = args.e2e_worlds
+    epos, evel, eine = synth_world(eM, 2000 + rank)
+    ee = el.B200Exec(1, eM, DT, None, [], "rk4", "fast", device=local, max_fused_ticks=args.fuse)
+    host = {WORLD_POS: epos, WORLD_VEL: evel, INERTIA: eine, WORLD_ACCEL: np.zeros((eM, 1, 6)), FORCE: np.zeros((eM, 1, 6)),
+            el.component_id("tick"): np.zeros(1, dtype=np.uint64), el.component_id("simulation_time_step"): np.array([DT])}
+    pin_in, pin_out = [], []
+    for cid in ee.input_ids:
+        a = el.pinned_empty(host[cid].shape, host[cid].dtype)
+        a[...] = host[cid]
+        pin_in.append(a)
+    for cid in ee.output_ids:
+        pin_out.append(el.pinned_empty(host[cid].shape, host[cid].dtype))
+    in_ptrs = [a.ctypes.data for a in pin_in]
+    out_ptrs = [a.ctypes.data for a in pin_out]
+    h2d = sum(a.nbytes for a in pin_in)
+    d2h = sum(a.nbytes for a in pin_out)
+    ee.invoke_batch_ptrs(in_ptrs, out_ptrs, T)  # warm
+    barrier()
+    calls = args.e2e_calls
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        ee.invoke_batch_ptrs(in_ptrs, out_ptrs, T)  # synchronous: returns with the outputs on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_ms = max_over_ranks(e2e_s * 1e3)
+    e2e_value = world_size * eM * T * calls / (e2e_ms * 1e-3)
+    tm = ee.timings()
+    checksum = float(np.sum(pin_out[ee.output_ids.index(WORLD_POS)][:1024]))  # the host really has the result
+    ee.close()
+
+    # ------------------------------------------------------------------ end-of-run trajectory gather (NCCL, outside the timed region)
+    gather = None
+    if distributed:
+        n_g = min(M, 1 << 16)
+        t_local = torch.empty((n_g, 1, 7), device="cuda", dtype=torch.float64)
+        tmp = torch.empty((M, 1, 7), device="cuda", dtype=torch.float64)
+        ex.download_ptr(WORLD_POS, tmp.data_ptr(), tmp.numel() * 8)
+        t_local.copy_(tmp[:n_g])
+        out = torch.empty((world_size * n_g, 1, 7), device="cuda", dtype=torch.float64)
+        torch.cuda.synchronize()
+        g0 = time.perf_counter()
+        dist.all_gather_into_tensor(out, t_local)
+        torch.cuda.synchronize()
+        gather = {"collective": "nccl all_gather of final WorldPos sample", "bytes": int(out.numel() * 8),
+                  "ms": (time.perf_counter() - g0) * 1e3}
+    ex.close()
+
+    if rank == 0:
+        cpu = None
+        if world_size == 1:
+            from oracle import oracle as O
+
+            O.build()
+            threads = O.max_threads()
+            r1, _ = cpu_oracle_rate(1 << 12, 50, 1)
+            n_ticks = max(20, int(args.cpu_seconds * r1 * min(threads, 8) / (1 << 16)))
+            rate, dt_s = cpu_oracle_rate(1 << 16, n_ticks, threads)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"65536 worlds x {n_ticks} ticks of the same workload in {dt_s:.1f} s (oracle port, {threads} threads); "
+                             f"1 thread: {r1:.3e} entity-steps/s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": W,
+            "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cube-sat 6DOF RK4 dt=1e-3, 1 body x M worlds (BASELINE configs[1] batched over the Monte-Carlo world axis)",
+                       "worlds_per_gpu": M, "bodies_per_world": 1, "dt": DT, "integrator": "rk4", "math": "fast (<=1e-12/tick vs exact)",
+                       "ticks_per_launch": 1, "parallelism": f"worlds sharded x{world_size}, no data-path collective",
+                       "l2_policy": "inputs larger than L2 (read set %.0f MB per tick > 126 MB)" % (160 * M / 1e6),
+                       "e2e_ticks_per_call": T, "e2e_worlds_per_gpu": eM},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic("body_fast_rk4_bytes_per_launch_M%d" % M), "peak_source": peak_src,
+                         "algorithmic_bytes_per_entity_step": B_ALG, "kernel": "body_fast_kernel<RK4>",
+                         "kernel_ms": kernel_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / T, "d2h_bytes_per_step": d2h / T,
+                    "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h, "ticks_per_call": T, "calls": calls,
+                    "ms_per_call": e2e_ms / calls, "phase_ms_last_call": {k: tm[k] for k in ("h2d_upload_ms", "kernel_invoke_ms", "d2h_download_ms")},
+                    "api": "b200_sixdof_invoke_batch (pinned host columns in/out)", "checksum": checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "cpu_baseline": cpu,
+            **extras,
+        }
+        if gather:
+            line["gather"] = gather
+        print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--worlds", type=int, default=1 << 22, help="worlds per GPU (1 body each)")
+    ap.add_argument("--fuse", type=int, default=25, help="ticks per launch of the fused / e2e runs")
+    ap.add_argument("--e2e-ticks", type=int, default=100, help="ticks per invoke_batch call (ticks_per_telemetry)")
+    ap.add_argument("--e2e-worlds", type=int, default=1 << 20)
+    ap.add_argument("--e2e-calls", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--kernel-only", action="store_true", help="profiling aid: only the main timed loop (no e2e / cpu / extras)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -154,7 +154,7 @@ def lib():
     L.b200_sixdof_trajectory_reset.argtypes = [vp]
     L.b200_sixdof_tick_count.argtypes = [vp]
     L.b200_sixdof_tick_count.restype = u64
-    L.b200_sixdof_set_stream.argtypes = [vp, vp]
+    L.b200_sixdof_set_stream.argtypes = [vp, vp, C.c_int]
     L.b200_sixdof_timings.argtypes = [vp, C.POINTER(Timings)]
     L.b200_sixdof_status.argtypes = [vp]
     L.b200_sixdof_device_plane.argtypes = [vp, u64, u32]

@@ -603,12 +603,12 @@ int b200_sixdof_trajectory_reset(b200_sixdof *h)
 
 uint64_t b200_sixdof_tick_count(const b200_sixdof *h) { return h ? h->tick : 0; }
 
-int b200_sixdof_set_stream(b200_sixdof *h, void *cuda_stream)
+int b200_sixdof_set_stream(b200_sixdof *h, void *cuda_stream, int use_own_stream)
 {
     if (!h) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
-    if (cuda_stream) {
+    if (!use_own_stream) {
         if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
         h->stream = (cudaStream_t)cuda_stream;
         h->own_stream = false;

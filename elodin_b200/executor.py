@@ -216,7 +216,12 @@ class B200Exec:
 
     # ---- plumbing ---------------------------------------------------------------
     def set_stream(self, cuda_stream: Optional[int]) -> None:
-        _lib.check(self._L.b200_sixdof_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Run on a caller-owned cudaStream_t (0 = the legacy default stream, which is what
+        torch.cuda.current_stream().cuda_stream returns by default); None = private stream."""
+        if cuda_stream is None:
+            _lib.check(self._L.b200_sixdof_set_stream(self._h, C.c_void_p(0), 1))
+        else:
+            _lib.check(self._L.b200_sixdof_set_stream(self._h, C.c_void_p(int(cuda_stream)), 0))
 
     def timings(self) -> dict:
         t = _lib.Timings()

@@ -410,7 +410,7 @@ class World:
     def finalize(self, n_worlds: int = 1) -> None:
         for col in self.columns.values():
             base = np.stack(col.rows).astype(col.dtype) if col.rows else np.zeros((0, col.width), col.dtype)
-            col.buffer = np.ascontiguousarray(np.broadcast_to(base, (n_worlds,) + base.shape))
+            col.buffer = np.broadcast_to(base, (n_worlds,) + base.shape).copy()
 
     # -- build / run -------------------------------------------------------------
     def build(self, system: System, simulation_rate: float = 120.0, generate_real_time: bool = False,

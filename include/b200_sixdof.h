@@ -216,7 +216,10 @@ int b200_sixdof_trajectory_reset(b200_sixdof *h);
 
 /* plumbing */
 uint64_t b200_sixdof_tick_count(const b200_sixdof *h);
-int b200_sixdof_set_stream(b200_sixdof *h, void *cuda_stream); /* cudaStream_t; NULL = own stream */
+/* Run the handle's work on a caller-owned cudaStream_t (`cuda_stream`, where NULL is
+ * the legacy default stream, e.g. torch.cuda.current_stream().cuda_stream), or, with
+ * use_own_stream != 0, go back to the handle's private non-blocking stream. */
+int b200_sixdof_set_stream(b200_sixdof *h, void *cuda_stream, int use_own_stream);
 int b200_sixdof_timings(const b200_sixdof *h, b200_timings *out);
 int b200_sixdof_status(const b200_sixdof *h);                  /* sticky status of the handle */
 /* raw device plane pointer (plane p of a column), for zero-copy interop (NCCL gather) */
