@@ -382,7 +382,7 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
     h->effectors.assign(d->effectors, d->effectors + d->n_effectors);
     h->desc.effectors = nullptr;
     h->n_bodies = d->n_entities * d->n_worlds;
-    h->ld = round_up(std::max<uint64_t>(h->n_bodies, 1), 32);
+    h->ld = round_up(std::max<uint64_t>(h->n_bodies, 1), 128); // whole 128-body tiles inside every plane
     h->sim_time_step = d->sim_time_step;
 
     int rc = B200_OK;

@@ -14,12 +14,14 @@
 // is x0 (+) (dt*f)*v0 — it never depends on a stage acceleration — so the gravity
 // at all four stages (three distinct positions, f = 0, .5, 1) is a function of
 // the tick's input state alone and needs no grid-wide synchronisation.
+#include <algorithm>
+#include <cstdlib>
+
 #include "sixdof_device.cuh"
 #include "sixdof_internal.h"
 
 namespace b200 {
 
-static constexpr int kBlock = 256;
 
 // ------------------------------------------------------------------ column access
 __device__ __forceinline__ double ldp(const double *base, uint64_t ld, int plane, uint64_t b)
@@ -152,11 +154,11 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
     return F;
 }
 
-template <int INTEG>
-__global__ void __launch_bounds__(kBlock) body_exact_kernel(const __grid_constant__ StepParams P)
+template <int INTEG, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) body_exact_kernel(const __grid_constant__ StepParams P)
 {
     using namespace ex;
-    const uint64_t b = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    const uint64_t b = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (b >= P.n_bodies) return;
 
     Pose x0 = load_pose(P.pos, P.ld, b);
@@ -308,20 +310,16 @@ __device__ __forceinline__ Motion force_out_fast(const Vec3 &a_lin, const Vec3 &
     return F;
 }
 
+// n_ticks ticks of one body, state in registers (shared by the direct and the TMA-pipelined kernel)
 template <int INTEG>
-__global__ void __launch_bounds__(kBlock) body_fast_kernel(const __grid_constant__ StepParams P)
+__device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose &x0, Motion &v0, const Inertia &I,
+                                           Motion &a_last, Motion &f_last)
 {
-    const uint64_t b = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (b >= P.n_bodies) return;
-
-    Pose x0 = load_pose(P.pos, P.ld, b);
-    Motion v0 = load_motion(P.vel, P.ld, b);
-    const Inertia I = load_inertia(P.ine, P.ld, b);
     const Vec3 invI = {1.0 / I.diag.x, 1.0 / I.diag.y, 1.0 / I.diag.z};
     const double inv_m = 1.0 / I.m;
     const Folded f = fold_effectors(P, b, I, invI);
 
-    Motion a_last = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+    a_last = Motion{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
     Quat q_last = x0.q;
     const double dt = P.dt_stage;
 
@@ -382,12 +380,163 @@ __global__ void __launch_bounds__(kBlock) body_fast_kernel(const __grid_constant
         }
         traj_sample(P, b, P.tick0 + t + 1, x0, v0);
     }
+    if (P.write_fa) f_last = force_out_fast(a_last.lin, f.u, q_last, I);
+}
+
+template <int INTEG, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) body_fast_kernel(const __grid_constant__ StepParams P)
+{
+    const uint64_t b = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
+    if (b >= P.n_bodies) return;
+    Pose x0 = load_pose(P.pos, P.ld, b);
+    Motion v0 = load_motion(P.vel, P.ld, b);
+    const Inertia I = load_inertia(P.ine, P.ld, b);
+    Motion a_last, f_last;
+    fast_ticks<INTEG>(P, b, x0, v0, I, a_last, f_last);
     store_pose(P.pos, P.ld, b, x0);
     store_motion(P.vel, P.ld, b, v0);
     if (P.write_fa) {
         store_motion(P.acc, P.ld, b, a_last);
-        store_motion(P.frc, P.ld, b, force_out_fast(a_last.lin, f.u, q_last, I));
+        store_motion(P.frc, P.ld, b, f_last);
     }
+}
+
+// ------------------------------------------------------------------ TMA-pipelined persistent variant
+//
+// One CTA = kPipeTB threads = one tile of kPipeTB bodies at a time, looping over tiles
+// (persistent grid sized to the SM count).  The 17 input planes of the next tiles
+// (pos 7, vel 6, inertia diag 3 + mass) are fetched with cp.async.bulk into a
+// kStages-deep shared-memory ring, completion signalled on mbarriers; the 13 output
+// planes leave through a double-buffered shared-memory tile and cp.async.bulk stores.
+// The FP64 work of tile i therefore overlaps the HBM traffic of tiles i+1.. and i-1,
+// which the direct kernel (1 CTA/SM at 150+ registers) cannot do.
+static constexpr int kPipeTB = 128;
+static constexpr int kPipeIn = 17;
+static constexpr int kPipeOut = 13;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int INTEG, int STAGES, int MINB>
+__global__ void __launch_bounds__(kPipeTB, MINB) body_fast_pipe_kernel(const __grid_constant__ StepParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double(*sin)[kPipeIn][kPipeTB] = reinterpret_cast<double(*)[kPipeIn][kPipeTB]>(smem_raw);
+    double(*sout)[kPipeOut][kPipeTB] =
+        reinterpret_cast<double(*)[kPipeOut][kPipeTB]>(smem_raw + sizeof(double) * STAGES * kPipeIn * kPipeTB);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + sizeof(double) * (STAGES * kPipeIn + 2 * kPipeOut) * kPipeTB);
+
+    const int tid = threadIdx.x;
+    const uint64_t n_tiles = (P.n_bodies + kPipeTB - 1) / kPipeTB;
+    constexpr uint32_t kPlaneBytes = kPipeTB * sizeof(double);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // source plane of input slot k for the tile starting at body b0
+    auto src_plane = [&](int k, uint64_t b0) -> const double * {
+        if (k < 7) return P.pos + (uint64_t)k * P.ld + b0;
+        if (k < 13) return P.vel + (uint64_t)(k - 7) * P.ld + b0;
+        return P.ine + (uint64_t)(k == 16 ? 6 : k - 13) * P.ld + b0;
+    };
+    auto issue_loads = [&](uint64_t tile, int s) { // warp 0
+        if (tid == 0) mbar_expect_tx(&full[s], kPipeIn * kPlaneBytes);
+        __syncwarp();
+        if (tid < kPipeIn) bulk_g2s(&sin[s][tid][0], src_plane(tid, tile * kPipeTB), kPlaneBytes, &full[s]);
+    };
+
+    if (tid < 32)
+        for (int s = 0; s < STAGES; ++s) {
+            const uint64_t tile = blockIdx.x + (uint64_t)s * gridDim.x;
+            if (tile < n_tiles) issue_loads(tile, s);
+        }
+
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        const uint32_t parity = (it / STAGES) & 1u;
+        const uint64_t b = tile * kPipeTB + tid;
+        mbar_wait(&full[s], parity);
+        Pose x0;
+        Motion v0;
+        Inertia I;
+        x0.q = Quat{sin[s][0][tid], sin[s][1][tid], sin[s][2][tid], sin[s][3][tid]};
+        x0.x = Vec3{sin[s][4][tid], sin[s][5][tid], sin[s][6][tid]};
+        v0.ang = Vec3{sin[s][7][tid], sin[s][8][tid], sin[s][9][tid]};
+        v0.lin = Vec3{sin[s][10][tid], sin[s][11][tid], sin[s][12][tid]};
+        I.diag = Vec3{sin[s][13][tid], sin[s][14][tid], sin[s][15][tid]};
+        I.m = sin[s][16][tid];
+        // the output tile about to be written was handed to the async proxy two tiles ago
+        if (tid < kPipeOut) bulk_wait_read<1>();
+        __syncthreads(); // everyone has drained stage s; out[it&1] is free
+        if (tid < 32) {
+            const uint64_t next = tile + (uint64_t)STAGES * gridDim.x;
+            if (next < n_tiles) issue_loads(next, s);
+        }
+        Motion a_last, f_last;
+        const bool live = b < P.n_bodies;
+        if (live) fast_ticks<INTEG>(P, b, x0, v0, I, a_last, f_last);
+        const int ob = it & 1;
+        sout[ob][0][tid] = x0.q.i; sout[ob][1][tid] = x0.q.j; sout[ob][2][tid] = x0.q.k; sout[ob][3][tid] = x0.q.w;
+        sout[ob][4][tid] = x0.x.x; sout[ob][5][tid] = x0.x.y; sout[ob][6][tid] = x0.x.z;
+        sout[ob][7][tid] = v0.ang.x; sout[ob][8][tid] = v0.ang.y; sout[ob][9][tid] = v0.ang.z;
+        sout[ob][10][tid] = v0.lin.x; sout[ob][11][tid] = v0.lin.y; sout[ob][12][tid] = v0.lin.z;
+        if (live && P.write_fa) {
+            store_motion(P.acc, P.ld, b, a_last);
+            store_motion(P.frc, P.ld, b, f_last);
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid < kPipeOut) {
+            double *dst = (tid < 7 ? P.pos + (uint64_t)tid * P.ld : P.vel + (uint64_t)(tid - 7) * P.ld) + tile * kPipeTB;
+            bulk_s2g(dst, &sout[ob][tid][0], kPlaneBytes);
+            bulk_commit();
+        }
+    }
+    if (tid < kPipeOut) bulk_wait_all();
 }
 
 // ================================================================== edge_fold gravity
@@ -595,14 +744,50 @@ __global__ void __launch_bounds__(256) probe_fp64_kernel(double *out, int iters)
 cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode, cudaStream_t s)
 {
     if (P.n_bodies == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((P.n_bodies + kBlock - 1) / kBlock);
     const bool rk4 = integrator == B200_INTEGRATOR_RK4;
     if (math_mode == B200_MATH_EXACT) {
-        if (rk4) body_exact_kernel<B200_INTEGRATOR_RK4><<<grid, kBlock, 0, s>>>(P);
-        else body_exact_kernel<B200_INTEGRATOR_SEMI_IMPLICIT><<<grid, kBlock, 0, s>>>(P);
+        static const int xcfg = [] { const char *e = getenv("B200_EXACT_CFG"); return e ? atoi(e) : 3; }();
+        auto g = [&](int blk) { return (unsigned)((P.n_bodies + blk - 1) / blk); };
+        if (!rk4) body_exact_kernel<B200_INTEGRATOR_SEMI_IMPLICIT, 256, 1><<<g(256), 256, 0, s>>>(P);
+        else switch (xcfg) {
+        case 1: body_exact_kernel<B200_INTEGRATOR_RK4, 256, 2><<<g(256), 256, 0, s>>>(P); break;
+        case 2: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 3><<<g(128), 128, 0, s>>>(P); break;
+        case 0: body_exact_kernel<B200_INTEGRATOR_RK4, 256, 1><<<g(256), 256, 0, s>>>(P); break;
+        default: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 4><<<g(128), 128, 0, s>>>(P); break; // 4.3e9 vs 2.7e9 (256x1)
+        }
     } else {
-        if (rk4) body_fast_kernel<B200_INTEGRATOR_RK4><<<grid, kBlock, 0, s>>>(P);
-        else body_fast_kernel<B200_INTEGRATOR_SEMI_IMPLICIT><<<grid, kBlock, 0, s>>>(P);
+        static const int cfg = [] { const char *e = getenv("B200_BODY_CFG"); return e ? atoi(e) : 3; }();
+        auto g = [&](int blk) { return (unsigned)((P.n_bodies + blk - 1) / blk); };
+        if (!rk4) body_fast_kernel<B200_INTEGRATOR_SEMI_IMPLICIT, 128, 4><<<g(128), 128, 0, s>>>(P);
+        else switch (cfg) {
+        case 1: body_fast_kernel<B200_INTEGRATOR_RK4, 256, 2><<<g(256), 256, 0, s>>>(P); break;
+        case 2: body_fast_kernel<B200_INTEGRATOR_RK4, 128, 3><<<g(128), 128, 0, s>>>(P); break;
+        case 0: body_fast_kernel<B200_INTEGRATOR_RK4, 256, 1><<<g(256), 256, 0, s>>>(P); break;
+        case 4: body_fast_kernel<B200_INTEGRATOR_RK4, 64, 8><<<g(64), 64, 0, s>>>(P); break;
+        case 5: body_fast_kernel<B200_INTEGRATOR_RK4, 128, 5><<<g(128), 128, 0, s>>>(P); break;
+        case 10: case 11: case 12: {
+            // persistent TMA-pipelined kernel; needs plane stride % 128 == 0 (whole tiles inside a plane)
+            const int stages = cfg == 10 ? 2 : (cfg == 11 ? 3 : 4);
+            const size_t smem = sizeof(double) * (stages * kPipeIn + 2 * kPipeOut) * kPipeTB + 8 * stages;
+            auto kern = stages == 2 ? body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 2, 3>
+                                    : (stages == 3 ? body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 3, 2>
+                                                   : body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 4, 2>);
+            static int sm_count = 0, per_sm[5] = {0, 0, 0, 0, 0};
+            if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+            if (!per_sm[stages]) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[stages], kern, kPipeTB, smem);
+                if (per_sm[stages] < 1) per_sm[stages] = 1;
+            }
+            const uint64_t n_tiles = (P.n_bodies + kPipeTB - 1) / kPipeTB;
+            const unsigned grid_p = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)sm_count * per_sm[stages]);
+            kern<<<grid_p, kPipeTB, smem, s>>>(P);
+            break;
+        }
+        // default (cfg 3): 128 threads x 4 CTAs/SM = 16 warps/SM at <= 128 registers — measured 95% of the
+        // HBM copy peak on B200 vs 57% for 256x1 (profiles/r01_tuning.md)
+        default: body_fast_kernel<B200_INTEGRATOR_RK4, 128, 4><<<g(128), 128, 0, s>>>(P); break;
+        }
     }
     return cudaGetLastError();
 }
