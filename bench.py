@@ -174,6 +174,82 @@ def run_reference(args):
     return 0
 
 
+def run_baseline_configs(args, torch, el, stream, local, rank, world_size):
+    """The other BASELINE.json configs (parity-test cases, reported for context; not the headline)."""
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def timed(ex, ticks, warm):
+        ex.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            ex.step(warm)
+            torch.cuda.synchronize()
+            a, b = ev(), ev()
+            a.record(stream)
+            ex.step(ticks)
+            b.record(stream)
+            torch.cuda.synchronize()
+        return a.elapsed_time(b)
+
+    rng = np.random.default_rng(42)
+    # configs[2]: rocket 6DOF + gravity + thrust + drag, 10k Monte-Carlo worlds, 5000 steps @120 Hz (SURVEY §8d C3)
+    M = 10000
+    q = el.Quaternion.from_euler([0.0, np.radians(70.0), 0.0]).arr
+    pos = np.tile(np.concatenate([q, [0, 0, 1.0]]), (M, 1, 1))
+    vel = np.zeros((M, 1, 6))
+    ine = np.tile(np.array([0.1, 1.0, 1.0, 0, 0, 0, 3.0]), (M, 1, 1))
+    effs = [el.GravityConst((0, 0, -9.81)), el.ThrustBody((-1.0, 0, 0), "thrust"), el.DragQuadratic(1.0, 1.0, "wind")]
+    for math in ("fast", "exact"):
+        ex = el.B200Exec(1, M, 0.008333333, None, effs, "rk4", math, device=local, max_fused_ticks=100)
+        ex.set_state(pos, vel, ine, thrust=np.full((M, 1, 1), 88.426), wind=np.zeros((M, 1, 3)))
+        ex.upload("wind", rng.normal(0, 1, (M, 1, 3)))
+        # per-world Cd*rho*A enters through the wind-relative drag; keep one constant pair (the kernel parameter)
+        ms = timed(ex, 5000, 100)
+        out[f"rocket_10k_worlds_{math}"] = {"worlds": M, "steps": 5000, "seconds": ms * 1e-3, "value": M * 5000 / (ms * 1e-3), "unit": UNIT}
+        ex.close()
+    # configs[3]: n-body, 1024 bodies pairwise softened gravity + 6DOF (SURVEY §8d C4), M = 1 and M = 8
+    N = 1024
+    for Mw in (1, 8):
+        p = np.zeros((Mw, N, 7)); p[..., 3] = 1.0; p[..., 4:] = rng.uniform(-30, 30, (Mw, N, 3))
+        v = np.zeros((Mw, N, 6)); v[..., 3:] = rng.normal(0, 1e-7, (Mw, N, 3))
+        m = 10 ** rng.uniform(-10, -3, (Mw, N)); m[:, 0] = 1.0
+        I = np.zeros((Mw, N, 7)); I[..., :3] = m[..., None]; I[..., 6] = m
+        g = el.GravityEdges("softened", k_squared=2.9591220828e-4 / 86400.0 ** 2, softening=1e-10, edges=el.all_pairs_edges(N))
+        for math in ("fast", "exact"):
+            ex = el.B200Exec(N, Mw, 3600.0, None, [g], "rk4", math, device=local)
+            ex.set_state(p, v, I)
+            ticks = 200 if math == "fast" else 50
+            ms = timed(ex, ticks, 5)
+            out[f"nbody_1024_M{Mw}_{math}"] = {"bodies": N, "worlds": Mw, "steps": ticks, "us_per_tick": ms * 1e3 / ticks,
+                                               "value": N * Mw * ticks / (ms * 1e-3), "unit": UNIT,
+                                               "pair_evals_per_s": 3.0 * N * (N - 1) * Mw * ticks / (ms * 1e-3)}
+            ex.close()
+    # configs[4]: falcon9-style Monte-Carlo, 100k rollouts over 8 GPUs = 12.5k worlds per GPU, dt = 1e-3
+    M = 12500
+    pos = np.tile(np.array([0, 0, 0, 1.0, 6.4e6, 0, 0]), (M, 1, 1)) + np.concatenate([np.zeros((M, 1, 4)), rng.normal(0, 10, (M, 1, 3))], -1)
+    vel = np.concatenate([rng.normal(0, 0.01, (M, 1, 3)), rng.normal(0, 50, (M, 1, 3))], -1)
+    ine = np.tile(np.array([4e6, 4e6, 1e5, 0, 0, 0, 3e4]), (M, 1, 1))
+    effs = [el.GravityFrame(), el.WrenchBody("body_wrench", "linear_first")]
+    ex = el.B200Exec(1, M, 1e-3, None, effs, "rk4", "fast", device=local, max_fused_ticks=100)
+    ex.set_state(pos, vel, ine, body_wrench=rng.normal(0, 1e4, (M, 1, 6)))
+    ms = timed(ex, 10000, 100)
+    out["falcon9_mc_12500_worlds_per_gpu_fast"] = {"worlds": M, "steps": 10000, "seconds": ms * 1e-3, "value": M * 10000 / (ms * 1e-3), "unit": UNIT}
+    ex.close()
+    # configs[0]: three-body, 1000 steps (plumbing; EXACT == oracle bit for bit is asserted in tests/ and smoke())
+    G = 6.6743e-11
+    p3 = np.array([[[0, 0, 0, 1, 0.8920281421, 0, 0], [0, 0, 0, 1, -0.6628498947, 0, 0], [0, 0, 0, 1, -0.2291782474, 0, 0]]], dtype=np.float64)
+    v3 = np.array([[[0, 0, 0, 0, 0.9957939373, 0], [0, 0, 0, 0, -1.6191613336, 0], [0, 0, 0, 0, 0.6233673964, 0]]], dtype=np.float64)
+    i3 = np.tile(np.array([1 / G, 1 / G, 1 / G, 0, 0, 0, 1 / G]), (1, 3, 1))
+    ex = el.B200Exec(3, 1, 0.008333333, None, [el.GravityEdges("newton", G=G, edges=np.array([[0, 1], [1, 0], [0, 2], [1, 2], [2, 0], [2, 1]]))],
+                     "rk4", "exact", device=local)
+    ex.set_state(p3, v3, i3)
+    ms = timed(ex, 1000, 10)
+    out["three_body_1000_steps_exact"] = {"steps": 1000, "us_per_tick": ms, "value": 3 * 1000 / (ms * 1e-3), "unit": UNIT,
+                                         "note": "latency bound: 2 launches per tick, 3 bodies"}
+    ex.close()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -380,6 +456,8 @@ def run_b200(args):
         }
         if gather:
             line["gather"] = gather
+        if args.configs:
+            line["baseline_configs"] = run_baseline_configs(args, torch, el, stream, local, rank, world_size)
         print(json.dumps(line))
     if distributed:
         dist.barrier()
@@ -399,6 +477,7 @@ def main():
     ap.add_argument("--e2e-worlds", type=int, default=1 << 20)
     ap.add_argument("--e2e-calls", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--configs", action="store_true", help="also time the other BASELINE.json configs (adds ~1 min)")
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: only the main timed loop (no e2e / cpu / extras)")
     args = ap.parse_args()
     if args.impl == "reference":

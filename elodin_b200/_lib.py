@@ -79,7 +79,7 @@ class Desc(C.Structure):
         ("device", C.c_int32),
         ("max_fused_ticks", C.c_uint32),
         ("trajectory_every", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("invoke_chunk_bodies", C.c_uint32),
         ("trajectory_capacity", C.c_uint64),
     ]
 

@@ -6,9 +6,11 @@
 // fallback anywhere in this file: without a CUDA device every entry point fails
 // with B200_ERR_NO_DEVICE.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -70,6 +72,11 @@ struct b200_sixdof {
     // plumbing
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    // pipelined invoke_batch: copy engines on their own streams, whole-batch AoS staging
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    double *stage_in = nullptr, *stage_out = nullptr;
+    uint64_t stage_in_bytes = 0, stage_out_bytes = 0;
+    std::vector<cudaEvent_t> chunk_in, chunk_out;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int status = B200_OK;
     b200_timings timings{};
@@ -212,38 +219,57 @@ void fill_step_params(b200_sixdof *h, StepParams &P)
     }
 }
 
-int do_step(b200_sixdof *h, uint64_t n_ticks)
+// Integrate n_ticks ticks of the worlds [w0, w0+nw) on `stream`.  Worlds are independent, so a
+// world range can run to completion before the next one starts (used by the pipelined
+// invoke_batch); counters are the caller's business.
+int launch_ticks(b200_sixdof *h, uint64_t w0, uint64_t nw, uint64_t n_ticks, cudaStream_t stream)
 {
-    if (h->status != B200_OK) return fail(h->status, "handle is in a failed state");
-    if (n_ticks == 0 || h->n_bodies == 0) { h->tick += n_ticks; h->ticks_done += n_ticks; return B200_OK; }
+    const uint64_t N = h->desc.n_entities;
+    const uint64_t b0 = w0 * N, nb = nw * N;
+    if (n_ticks == 0 || nb == 0) return B200_OK;
     StepParams P;
     fill_step_params(h, P);
+    // shift every per-body plane base to the range start; rows inside a world keep their index
+    P.pos += b0; P.vel += b0; P.acc += b0; P.frc += b0; P.ine += b0;
+    if (P.gforce) P.gforce += b0;
+    if (P.traj) P.traj += b0;
+    for (uint32_t i = 0; i < P.n_eff; ++i) if (P.eff[i].col) P.eff[i].col += b0;
+    P.n_bodies = nb;
     const bool exact = h->desc.math_mode == B200_MATH_EXACT;
     const bool graph = h->graph_eff >= 0;
     const uint64_t fuse = graph ? 1 : std::max<uint32_t>(1u, h->desc.max_fused_ticks);
-    uint64_t left = n_ticks;
+    uint64_t left = n_ticks, done = 0;
     while (left) {
         const uint64_t n = std::min(left, fuse);
         if (graph) {
             const b200_effector &e = h->effectors[h->graph_eff];
             GraphParams G{};
-            G.pos = P.pos; G.vel = P.vel; G.ine = P.ine; G.gforce = h->gforce;
-            G.ld = h->ld; G.n_entities = P.n_entities; G.n_worlds = (uint32_t)h->desc.n_worlds;
+            G.pos = P.pos; G.vel = P.vel; G.ine = P.ine; G.gforce = h->gforce + b0;
+            G.ld = h->ld; G.n_entities = P.n_entities; G.n_worlds = (uint32_t)nw;
             G.dt_stage = P.dt_stage; G.kind = e.kind; G.integrator = h->desc.integrator;
             G.p0 = e.p[0]; G.p1 = e.p[1]; G.row_ptr = h->row_ptr; G.col_idx = h->col_idx;
-            CU(h, launch_graph_force(G, h->desc.math_mode, h->graph_dense, h->stream));
+            CU(h, launch_graph_force(G, h->desc.math_mode, h->graph_dense, stream));
             h->timings.kernel_launches++;
         }
         P.n_ticks = (uint32_t)n;
-        P.tick0 = h->ticks_done;
+        P.tick0 = h->ticks_done + done;
         P.write_fa = (exact || left == n) ? 1u : 0u; // Force/WorldAccel are only host-visible after the batch
-        CU(h, launch_body_step(P, (int)h->desc.integrator, (int)h->desc.math_mode, h->stream));
+        CU(h, launch_body_step(P, (int)h->desc.integrator, (int)h->desc.math_mode, stream));
         h->timings.kernel_launches++;
-        h->ticks_done += n;
-        h->tick += n;
-        h->timings.ticks += n;
+        done += n;
         left -= n;
     }
+    return B200_OK;
+}
+
+int do_step(b200_sixdof *h, uint64_t n_ticks)
+{
+    if (h->status != B200_OK) return fail(h->status, "handle is in a failed state");
+    int rc = launch_ticks(h, 0, h->desc.n_worlds, n_ticks, h->stream);
+    if (rc) return rc;
+    h->ticks_done += n_ticks;
+    h->tick += n_ticks;
+    h->timings.ticks += n_ticks;
     return B200_OK;
 }
 
@@ -467,7 +493,13 @@ void b200_sixdof_destroy(b200_sixdof *h)
     if (h->has_edge) cudaFree(h->has_edge);
     if (h->gforce) cudaFree(h->gforce);
     if (h->staging) cudaFree(h->staging);
+    if (h->stage_in) cudaFree(h->stage_in);
+    if (h->stage_out) cudaFree(h->stage_out);
     if (h->traj) cudaFree(h->traj);
+    for (auto &e : h->chunk_in) if (e) cudaEventDestroy(e);
+    for (auto &e : h->chunk_out) if (e) cudaEventDestroy(e);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     (void)cudaGetLastError();
@@ -524,31 +556,145 @@ int b200_sixdof_sync(b200_sixdof *h)
     return B200_OK;
 }
 
+// Which input columns really have to cross PCIe: Force is cleared before any effector runs
+// (clear_forces, six_dof.rs:148-150) so its input value is dead; WorldAccel only enters as
+// `0 * a_prev` (rk4.rs:85-104), which FAST math does not evaluate.  EXACT keeps WorldAccel.
+static bool input_is_live(const b200_sixdof *h, uint64_t id)
+{
+    if (id == B200_ID_FORCE) return false;
+    if (id == B200_ID_WORLD_ACCEL) return h->desc.math_mode == B200_MATH_EXACT && h->desc.integrator == B200_INTEGRATOR_RK4;
+    return true;
+}
+
+static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8_t *const *out_cols, uint64_t n_ticks,
+                            uint64_t worlds_per_chunk)
+{
+    const uint64_t N = h->desc.n_entities, M = h->desc.n_worlds;
+    const uint64_t n_chunks = (M + worlds_per_chunk - 1) / worlds_per_chunk;
+    if (!h->copy_in) {
+        CU(h, cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+        CU(h, cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    }
+    while (h->chunk_in.size() < n_chunks) {
+        cudaEvent_t a, b;
+        CU(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->chunk_in.push_back(a);
+        h->chunk_out.push_back(b);
+    }
+    // whole-batch AoS staging: column c of the inputs lives at in_off[c] (doubles)
+    std::vector<uint64_t> in_off(h->input_ids.size(), 0), out_off(h->output_ids.size(), 0);
+    uint64_t in_total = 0, out_total = 0;
+    for (size_t i = 0; i < h->input_ids.size(); ++i) {
+        const Column *c = h->find(h->input_ids[i]);
+        in_off[i] = in_total;
+        if (!c->global && input_is_live(h, c->id)) in_total += h->n_bodies * c->width;
+    }
+    for (size_t i = 0; i < h->output_ids.size(); ++i) {
+        const Column *c = h->find(h->output_ids[i]);
+        out_off[i] = out_total;
+        if (!c->global) out_total += h->n_bodies * c->width;
+    }
+    if (h->stage_in_bytes < in_total * 8) {
+        if (h->stage_in) CU(h, cudaFree(h->stage_in));
+        h->stage_in = nullptr; h->stage_in_bytes = 0;
+        CU(h, cudaMalloc(&h->stage_in, std::max<uint64_t>(in_total * 8, 8)));
+        h->stage_in_bytes = in_total * 8;
+    }
+    if (h->stage_out_bytes < out_total * 8) {
+        if (h->stage_out) CU(h, cudaFree(h->stage_out));
+        h->stage_out = nullptr; h->stage_out_bytes = 0;
+        CU(h, cudaMalloc(&h->stage_out, std::max<uint64_t>(out_total * 8, 8)));
+        h->stage_out_bytes = out_total * 8;
+    }
+    // globals first (host-resident scalars)
+    for (size_t i = 0; i < h->input_ids.size(); ++i) {
+        const Column *c = h->find(h->input_ids[i]);
+        if (c->global) { int rc = do_upload(h, c->id, in_cols[i], 8); if (rc) return rc; }
+    }
+    // the copy streams must not run ahead of work already queued on the compute stream
+    CU(h, cudaEventRecord(h->ev[0], h->stream));
+    CU(h, cudaStreamWaitEvent(h->copy_in, h->ev[0], 0));
+    CU(h, cudaStreamWaitEvent(h->copy_out, h->ev[0], 0));
+
+    for (uint64_t k = 0; k < n_chunks; ++k) {
+        const uint64_t w0 = k * worlds_per_chunk, nw = std::min(worlds_per_chunk, M - w0);
+        const uint64_t b0 = w0 * N, nb = nw * N;
+        // H2D of this world range, every live input column (copy engine 1)
+        for (size_t i = 0; i < h->input_ids.size(); ++i) {
+            const Column *c = h->find(h->input_ids[i]);
+            if (c->global || !input_is_live(h, c->id)) continue;
+            CU(h, cudaMemcpyAsync(h->stage_in + in_off[i] + b0 * c->width, (const double *)in_cols[i] + b0 * c->width,
+                                  nb * c->width * 8, cudaMemcpyDefault, h->copy_in));
+        }
+        CU(h, cudaEventRecord(h->chunk_in[k], h->copy_in));
+        // compute stream: AoS -> SoA, n ticks, SoA -> AoS
+        CU(h, cudaStreamWaitEvent(h->stream, h->chunk_in[k], 0));
+        for (size_t i = 0; i < h->input_ids.size(); ++i) {
+            const Column *c = h->find(h->input_ids[i]);
+            if (c->global || !input_is_live(h, c->id)) continue;
+            CU(h, launch_aos_to_soa(h->stage_in + in_off[i] + b0 * c->width, c->dev + b0, nb, c->width, h->ld, h->stream));
+            h->timings.kernel_launches++;
+        }
+        int rc = launch_ticks(h, w0, nw, n_ticks, h->stream);
+        if (rc) return rc;
+        for (size_t i = 0; i < h->output_ids.size(); ++i) {
+            const Column *c = h->find(h->output_ids[i]);
+            if (c->global) continue;
+            CU(h, launch_soa_to_aos(c->dev + b0, h->stage_out + out_off[i] + b0 * c->width, nb, c->width, h->ld, h->stream));
+            h->timings.kernel_launches++;
+        }
+        CU(h, cudaEventRecord(h->chunk_out[k], h->stream));
+        // D2H of this world range (copy engine 2) overlaps the next range's H2D and ticks
+        CU(h, cudaStreamWaitEvent(h->copy_out, h->chunk_out[k], 0));
+        for (size_t i = 0; i < h->output_ids.size(); ++i) {
+            const Column *c = h->find(h->output_ids[i]);
+            if (c->global) continue;
+            CU(h, cudaMemcpyAsync((double *)out_cols[i] + b0 * c->width, h->stage_out + out_off[i] + b0 * c->width,
+                                  nb * c->width * 8, cudaMemcpyDefault, h->copy_out));
+        }
+    }
+    h->ticks_done += n_ticks;
+    h->tick += n_ticks;
+    h->timings.ticks += n_ticks;
+    for (size_t i = 0; i < h->output_ids.size(); ++i) {
+        const Column *c = h->find(h->output_ids[i]);
+        if (c->global) { int rc = do_download(h, c->id, out_cols[i], 8); if (rc) return rc; }
+    }
+    CU(h, cudaStreamSynchronize(h->copy_out));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return B200_OK;
+}
+
 int b200_sixdof_invoke_batch(b200_sixdof *h, const uint8_t *const *in_cols, uint8_t *const *out_cols, uint64_t n_ticks)
 {
     if (!h) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
     if (!in_cols || !out_cols) return fail(B200_ERR_INVALID_ARGUMENT, "null column tables");
+    if (h->status != B200_OK) return fail(h->status, "handle is in a failed state");
     CU(h, cudaSetDevice(h->device));
-    CU(h, cudaEventRecord(h->ev[0], h->stream));
-    for (size_t i = 0; i < h->input_ids.size(); ++i) {
-        const Column *c = h->find(h->input_ids[i]);
-        int rc = do_upload(h, c->id, in_cols[i], column_bytes(h, *c));
-        if (rc) return rc;
-    }
-    CU(h, cudaEventRecord(h->ev[1], h->stream));
-    int rc = do_step(h, std::max<uint64_t>(n_ticks, 1)); // `n.max(1)`, cranelift_exec.rs:135
+    for (size_t i = 0; i < h->input_ids.size(); ++i)
+        if (!in_cols[i] && column_bytes(h, *h->find(h->input_ids[i]))) return fail(B200_ERR_INVALID_ARGUMENT, "null input column %zu", i);
+    for (size_t i = 0; i < h->output_ids.size(); ++i)
+        if (!out_cols[i] && column_bytes(h, *h->find(h->output_ids[i]))) return fail(B200_ERR_INVALID_ARGUMENT, "null output column %zu", i);
+    n_ticks = std::max<uint64_t>(n_ticks, 1); // `n.max(1)`, cranelift_exec.rs:135
+
+    // World ranges of ~kChunkBodies bodies: range k's PCIe download overlaps range k+1's upload
+    // and ticks (two copy engines + the compute stream).  Small batches run as one range.
+    static const uint64_t kEnvChunk = [] { const char *e = getenv("B200_CHUNK_BODIES"); return e ? (uint64_t)atoll(e) : (uint64_t)0; }();
+    const uint64_t chunk_bodies = h->desc.invoke_chunk_bodies ? h->desc.invoke_chunk_bodies : (kEnvChunk ? kEnvChunk : 131072);
+    const uint64_t N = std::max<uint64_t>(h->desc.n_entities, 1);
+    uint64_t wpc = std::max<uint64_t>(1, chunk_bodies / N);
+    if (N == 1 && wpc >= 128) wpc = wpc / 128 * 128;
+    if (h->n_bodies == 0) wpc = std::max<uint64_t>(h->desc.n_worlds, 1);
+
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = invoke_pipelined(h, in_cols, out_cols, n_ticks, wpc);
     if (rc) return rc;
-    CU(h, cudaEventRecord(h->ev[2], h->stream));
-    for (size_t i = 0; i < h->output_ids.size(); ++i) {
-        const Column *c = h->find(h->output_ids[i]);
-        rc = do_download(h, c->id, out_cols[i], column_bytes(h, *c));
-        if (rc) return rc;
-    }
-    CU(h, cudaEventRecord(h->ev[3], h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    h->timings.h2d_upload_ms = ev_ms(h->ev[0], h->ev[1]);
-    h->timings.kernel_invoke_ms = ev_ms(h->ev[1], h->ev[2]);
-    h->timings.d2h_download_ms = ev_ms(h->ev[2], h->ev[3]);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    // phases overlap in the pipelined path; report the wall time of the call as kernel_invoke
+    h->timings.h2d_upload_ms = 0.0;
+    h->timings.kernel_invoke_ms = ms;
+    h->timings.d2h_download_ms = 0.0;
     return B200_OK;
 }
 

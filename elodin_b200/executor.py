@@ -51,6 +51,7 @@ class B200Exec:
         trajectory_every: int = 0,
         trajectory_capacity: int = 0,
         world=None,
+        invoke_chunk_bodies: int = 0,
     ):
         from .effectors import _flatten
 
@@ -80,6 +81,7 @@ class B200Exec:
         d.max_fused_ticks = int(max_fused_ticks)
         d.trajectory_every = int(trajectory_every)
         d.trajectory_capacity = int(trajectory_capacity)
+        d.invoke_chunk_bodies = int(invoke_chunk_bodies)
         h = C.c_void_p()
         _lib.check(L.b200_sixdof_create(C.byref(d), C.byref(h)))
         self._L, self._h = L, h

@@ -140,7 +140,9 @@ typedef struct b200_sixdof_desc {
     uint32_t max_fused_ticks;  /* ticks one launch may keep in registers (0/1 = one tick per launch);
                                   only used when no effector couples bodies          */
     uint32_t trajectory_every; /* 0 = off; k = record (pos,vel) every k ticks         */
-    uint32_t reserved;
+    uint32_t invoke_chunk_bodies; /* b200_sixdof_invoke_batch splits the world axis into ranges of about
+                                  this many bodies so that range k's download overlaps range k+1's
+                                  upload and ticks; 0 = default (131072)                */
     uint64_t trajectory_capacity; /* samples the device ring can hold                 */
 } b200_sixdof_desc;
 

@@ -328,6 +328,44 @@ def test_abi_errors_match_reference_semantics():
         assert ex.tick == 3
 
 
+@pytest.mark.parametrize("math", ["exact", "fast"])
+def test_invoke_batch_pipelined_world_ranges(oracle, math):
+    """invoke_batch splits the world axis into ranges whose PCIe transfers overlap the ticks of
+    their neighbours; the result must not depend on the split (ragged last range, graph worlds,
+    effector columns, trajectory)."""
+    O = oracle
+    M, N = 37, 5
+    pos, vel, ine = random_world(55, M, N)
+    pos[..., 4:] *= 1e-2
+    rng = np.random.default_rng(5)
+    thrust = rng.uniform(0, 10, (M, N, 1))
+    o1, g1, _ = effector_pair(O, "softened", edges=el.all_pairs_edges(N), k2=0.2, soft=1e-5)
+    o2, g2, _ = effector_pair(O, "thrust", thrust=thrust)
+    acc0 = rng.normal(0, 1, (M, N, 6))
+    want = _run_oracle(O, pos, vel, ine, [o1, o2], 0.01, 6, accel=acc0)
+    outs = {}
+    for chunk in (0, 5 * N, 7 * N, 1000 * N):
+        with el.B200Exec(N, M, 0.01, None, [g1, g2], "rk4", math, invoke_chunk_bodies=chunk, trajectory_every=3,
+                         trajectory_capacity=4) as ex:
+            table = {el.component_id("tick"): np.array([0], dtype=np.uint64), FORCE: rng.normal(size=(M, N, 6)), INERTIA: ine,
+                     WORLD_POS: pos, WORLD_ACCEL: acc0, el.component_id("simulation_time_step"): np.array([0.01]),
+                     WORLD_VEL: vel, el.component_id("thrust"): thrust}
+            o = dict(zip(ex.output_ids, ex.invoke_batch([table[c] for c in ex.input_ids], 6)))
+            traj = ex.trajectory()
+        got = (o[WORLD_POS], o[WORLD_VEL], o[WORLD_ACCEL], o[FORCE])
+        if math == "exact":
+            _assert_exact(got, want, f"chunk={chunk}")
+        else:
+            _assert_close(got, want, 6 * FAST_TOL_TICK, f"chunk={chunk}")
+        assert int(o[el.component_id("tick")][0]) == 6
+        assert np.array_equal(o[INERTIA], ine) and np.array_equal(o[el.component_id("thrust")], thrust)  # pass-through
+        assert np.array_equal(traj[1], np.concatenate([got[0], got[1]], -1))
+        outs[chunk] = got
+    for chunk, got in outs.items():
+        for a, b in zip(got, outs[0]):
+            assert np.array_equal(a, b), chunk  # the split never changes a bit
+
+
 def test_tickfn_shaped_entry():
     pos, vel, ine = random_world(8, 1, 3)
     with el.B200Exec(3, 1, 0.01, None, [], "rk4", "exact") as ex:
