@@ -101,27 +101,37 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples taken while the timed region [t_begin, t_end] ran (under load)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        rows = [r for (t, r) in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.06)]
+        sm = [float(r[1]) for r in rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows_all() if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples_under_load": len(sm), "samples_total": len(self.rows)}
+
+    def rows_all(self):
+        return [r for (_, r) in self.rows]
 
 
 def cpu_oracle_rate(worlds: int, ticks: int, threads: int, seed: int = 1):
@@ -289,22 +299,25 @@ def run_b200(args):
     ex = el.B200Exec(1, M, DT, None, [], "rk4", "fast", device=local, max_fused_ticks=1)
     ex.set_stream(stream.cuda_stream)
     ex.set_state(pos, vel, ine)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first()
     with torch.cuda.stream(stream):
         ex.step(W)
         barrier()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
         launches0 = ex.timings()["kernel_launches"]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        t_begin = time.perf_counter()
         e0.record(stream)
         ex.step(K)
         e1.record(stream)
         barrier()
+        t_end = time.perf_counter()
         ms = max_over_ranks(e0.elapsed_time(e1))
         launches = ex.timings()["kernel_launches"] - launches0
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     value = world_size * M * K / (ms * 1e-3)
     kernel_ms = ms / K
     peak, peak_src = measured_peak()
@@ -468,7 +481,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--worlds", type=int, default=1 << 22, help="worlds per GPU (1 body each)")

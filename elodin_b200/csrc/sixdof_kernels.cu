@@ -553,10 +553,12 @@ __device__ __forceinline__ Vec3 stage_pos(const Vec3 &x, const Vec3 &v, double d
 // kBlockG source bodies of one world, targets streamed through shared memory in
 // tiles; each thread folds its targets sequentially in ascending order, which is
 // the reference's fold order (graph.rs:177-236) — so EXACT stays bit-exact.
-static constexpr int kBlockG = 128;
+static constexpr int kBlockG = 64;
 
+// blockDim = (kBlockG, NS): thread (x, y) folds source x over all targets for stage slot y,
+// so the three stage positions of a tick proceed in parallel while every fold stays sequential.
 template <bool EXACT, bool RK4>
-__global__ void __launch_bounds__(kBlockG) graph_dense_kernel(const __grid_constant__ GraphParams G)
+__global__ void __launch_bounds__(kBlockG * 3) graph_dense_kernel(const __grid_constant__ GraphParams G)
 {
     constexpr int NS = RK4 ? 3 : 1;
     __shared__ double sx[NS][3][kBlockG];
@@ -566,19 +568,95 @@ __global__ void __launch_bounds__(kBlockG) graph_dense_kernel(const __grid_const
     const uint32_t tiles = (N + kBlockG - 1) / kBlockG;
     const uint32_t world = blockIdx.x / tiles;
     const uint32_t tile = blockIdx.x % tiles;
-    const uint32_t i = tile * kBlockG + threadIdx.x;
+    const uint32_t tx = threadIdx.x, sl = threadIdx.y; // sl = stage slot
+    const uint32_t i = tile * kBlockG + tx;
     const uint64_t wbase = (uint64_t)world * N;
     const bool active = i < N;
     const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
 
-    double dtf[3];
-    dtf[0] = EXACT ? ex::mul(G.dt_stage, 0.0) : 0.0;
-    dtf[1] = EXACT ? ex::mul(G.dt_stage, 0.5) : 0.5 * G.dt_stage;
-    dtf[2] = EXACT ? ex::mul(G.dt_stage, 1.0) : G.dt_stage;
+    const double fac = sl == 0 ? 0.0 : (sl == 1 ? 0.5 : 1.0);
+    const double dtf = EXACT ? ex::mul(G.dt_stage, fac) : fac * G.dt_stage;
 
-    Vec3 xi[NS];
+    Vec3 xi = {0, 0, 0}, acc = {0, 0, 0};
     double mi = 0.0;
-    Vec3 acc[NS];
+    if (active) {
+        const uint64_t b = wbase + i;
+        const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+        const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+        mi = ldp(G.ine, G.ld, 6, b);
+        xi = RK4 ? stage_pos<EXACT>(x, v, dtf) : x;
+    }
+
+    for (uint32_t j0 = 0; j0 < N; j0 += kBlockG) {
+        const uint32_t j = j0 + tx;
+        __syncthreads();
+        if (j < N) {
+            const uint64_t b = wbase + j;
+            const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+            const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+            const Vec3 p = RK4 ? stage_pos<EXACT>(x, v, dtf) : x;
+            sx[sl][0][tx] = p.x; sx[sl][1][tx] = p.y; sx[sl][2][tx] = p.z;
+            if (sl == 0) sm[tx] = ldp(G.ine, G.ld, 6, b);
+        }
+        __syncthreads();
+        const uint32_t jn = min((uint32_t)kBlockG, N - j0);
+        if (active) {
+            for (uint32_t jj = 0; jj < jn; ++jj) {
+                if (j0 + jj == i) continue;
+                const double mj = sm[jj];
+                const Vec3 xj = {sx[sl][0][jj], sx[sl][1][jj], sx[sl][2][jj]};
+                if (EXACT) {
+                    if (newton) ex::fold_newton(G.p0, xi, mi, xj, mj, acc);
+                    else ex::fold_softened(G.p0, G.p1, xi, mi, xj, mj, acc);
+                } else {
+                    // common factor (G|K^2)*m_i applied after the loop
+                    const Vec3 r = {xj.x - xi.x, xj.y - xi.y, xj.z - xi.z};
+                    const double d2 = r.x * r.x + r.y * r.y + r.z * r.z + (newton ? 0.0 : G.p1);
+                    const double inv = rsqrt(d2);
+                    const double w = mj * inv * inv * inv;
+                    acc.x = fma(w, r.x, acc.x); acc.y = fma(w, r.y, acc.y); acc.z = fma(w, r.z, acc.z);
+                }
+            }
+        }
+    }
+    if (active) {
+        const uint64_t b = wbase + i;
+        const double k = EXACT ? 1.0 : G.p0 * mi;
+        stp(G.gforce, G.ld, sl * 3 + 0, b, EXACT ? acc.x : k * acc.x);
+        stp(G.gforce, G.ld, sl * 3 + 1, b, EXACT ? acc.y : k * acc.y);
+        stp(G.gforce, G.ld, sl * 3 + 2, b, EXACT ? acc.z : k * acc.z);
+    }
+}
+
+// FAST all-pairs: one warp per source body, lanes stride over the targets of a tile and
+// keep private partial sums; a fixed xor-butterfly of warp shuffles combines them (the
+// summation order differs from the reference's sequential fold -> tolerance, not bit
+// parity; EXACT uses graph_dense_kernel).  8 warps = 8 sources of one world per CTA share
+// the shared-memory tile of stage positions, so N = 1024, M = 1 still fills 128 SMs.
+static constexpr int kFastWarps = 8;
+static constexpr int kFastTJ = 256;
+
+template <bool RK4>
+__global__ void __launch_bounds__(kFastWarps * 32) graph_dense_fast_kernel(const __grid_constant__ GraphParams G)
+{
+    constexpr int NS = RK4 ? 3 : 1;
+    __shared__ double sx[NS][3][kFastTJ];
+    __shared__ double sm[kFastTJ];
+
+    const uint32_t N = G.n_entities;
+    const uint32_t groups = (N + kFastWarps - 1) / kFastWarps;
+    const uint32_t world = blockIdx.x / groups;
+    const uint32_t grp = blockIdx.x % groups;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t i = grp * kFastWarps + warp;
+    const uint64_t wbase = (uint64_t)world * N;
+    const bool active = i < N;
+    const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
+    const double soft = newton ? 0.0 : G.p1;
+    const double dtf[3] = {0.0, 0.5 * G.dt_stage, G.dt_stage};
+
+    Vec3 xi[NS], acc[NS];
+    double mi = 0.0;
 #pragma unroll
     for (int s = 0; s < NS; ++s) { xi[s] = Vec3{0, 0, 0}; acc[s] = Vec3{0, 0, 0}; }
     if (active) {
@@ -587,10 +665,9 @@ __global__ void __launch_bounds__(kBlockG) graph_dense_kernel(const __grid_const
         const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
         mi = ldp(G.ine, G.ld, 6, b);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) xi[s] = RK4 ? stage_pos<EXACT>(x, v, dtf[s]) : x;
+        for (int s = 0; s < NS; ++s) xi[s] = RK4 ? stage_pos<false>(x, v, dtf[s]) : x;
     }
-
-    for (uint32_t j0 = 0; j0 < N; j0 += kBlockG) {
+    for (uint32_t j0 = 0; j0 < N; j0 += kFastTJ) {
         const uint32_t j = j0 + threadIdx.x;
         __syncthreads();
         if (j < N) {
@@ -599,43 +676,46 @@ __global__ void __launch_bounds__(kBlockG) graph_dense_kernel(const __grid_const
             const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                const Vec3 p = RK4 ? stage_pos<EXACT>(x, v, dtf[s]) : x;
+                const Vec3 p = RK4 ? stage_pos<false>(x, v, dtf[s]) : x;
                 sx[s][0][threadIdx.x] = p.x; sx[s][1][threadIdx.x] = p.y; sx[s][2][threadIdx.x] = p.z;
             }
             sm[threadIdx.x] = ldp(G.ine, G.ld, 6, b);
         }
         __syncthreads();
-        const uint32_t jn = min((uint32_t)kBlockG, N - j0);
+        const uint32_t jn = min((uint32_t)kFastTJ, N - j0);
         if (active) {
-            for (uint32_t jj = 0; jj < jn; ++jj) {
+#pragma unroll 2
+            for (uint32_t jj = lane; jj < jn; jj += 32) {
                 if (j0 + jj == i) continue;
                 const double mj = sm[jj];
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
-                    const Vec3 xj = {sx[s][0][jj], sx[s][1][jj], sx[s][2][jj]};
-                    if (EXACT) {
-                        if (newton) ex::fold_newton(G.p0, xi[s], mi, xj, mj, acc[s]);
-                        else ex::fold_softened(G.p0, G.p1, xi[s], mi, xj, mj, acc[s]);
-                    } else {
-                        // common factor (G|K^2)*m_i applied after the loop; sign folded in below
-                        const Vec3 r = {xj.x - xi[s].x, xj.y - xi[s].y, xj.z - xi[s].z};
-                        const double d2 = r.x * r.x + r.y * r.y + r.z * r.z + (newton ? 0.0 : G.p1);
-                        const double inv = rsqrt(d2);
-                        const double w = mj * inv * inv * inv;
-                        acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
-                    }
+                    const Vec3 r = {sx[s][0][jj] - xi[s].x, sx[s][1][jj] - xi[s].y, sx[s][2][jj] - xi[s].z};
+                    const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, soft)));
+                    const double inv = rsqrt(d2);
+                    const double w = mj * inv * inv * inv;
+                    acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
                 }
             }
         }
     }
-    if (active) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            acc[s].x += __shfl_xor_sync(0xffffffffu, acc[s].x, off);
+            acc[s].y += __shfl_xor_sync(0xffffffffu, acc[s].y, off);
+            acc[s].z += __shfl_xor_sync(0xffffffffu, acc[s].z, off);
+        }
+    }
+    if (active && lane == 0) {
         const uint64_t b = wbase + i;
-        const double k = EXACT ? 1.0 : G.p0 * mi;
+        const double k = G.p0 * mi;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-            stp(G.gforce, G.ld, s * 3 + 0, b, EXACT ? acc[s].x : k * acc[s].x);
-            stp(G.gforce, G.ld, s * 3 + 1, b, EXACT ? acc[s].y : k * acc[s].y);
-            stp(G.gforce, G.ld, s * 3 + 2, b, EXACT ? acc[s].z : k * acc[s].z);
+            stp(G.gforce, G.ld, s * 3 + 0, b, k * acc[s].x);
+            stp(G.gforce, G.ld, s * 3 + 1, b, k * acc[s].y);
+            stp(G.gforce, G.ld, s * 3 + 2, b, k * acc[s].z);
         }
     }
 }
@@ -800,8 +880,15 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
     if (dense) {
         const unsigned tiles = (G.n_entities + kBlockG - 1) / kBlockG;
         const unsigned grid = tiles * G.n_worlds;
-        if (exact) { if (rk4) graph_dense_kernel<true, true><<<grid, kBlockG, 0, s>>>(G); else graph_dense_kernel<true, false><<<grid, kBlockG, 0, s>>>(G); }
-        else { if (rk4) graph_dense_kernel<false, true><<<grid, kBlockG, 0, s>>>(G); else graph_dense_kernel<false, false><<<grid, kBlockG, 0, s>>>(G); }
+        static const int gcfg = [] { const char *e = getenv("B200_GRAPH_CFG"); return e ? atoi(e) : 1; }();
+        const dim3 blk3(kBlockG, 3), blk1(kBlockG, 1);
+        if (exact) { if (rk4) graph_dense_kernel<true, true><<<grid, blk3, 0, s>>>(G); else graph_dense_kernel<true, false><<<grid, blk1, 0, s>>>(G); }
+        else if (gcfg == 0) { if (rk4) graph_dense_kernel<false, true><<<grid, blk3, 0, s>>>(G); else graph_dense_kernel<false, false><<<grid, blk1, 0, s>>>(G); }
+        else {
+            const unsigned gridf = ((G.n_entities + kFastWarps - 1) / kFastWarps) * G.n_worlds;
+            if (rk4) graph_dense_fast_kernel<true><<<gridf, kFastWarps * 32, 0, s>>>(G);
+            else graph_dense_fast_kernel<false><<<gridf, kFastWarps * 32, 0, s>>>(G);
+        }
     } else {
         const uint64_t total = (uint64_t)G.n_entities * G.n_worlds;
         const unsigned grid = (unsigned)((total + kBlockG - 1) / kBlockG);
