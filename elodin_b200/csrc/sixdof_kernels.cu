@@ -322,20 +322,26 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
     a_last = Motion{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
     Quat q_last = x0.q;
     const double dt = P.dt_stage;
+    const bool has_u = (f.u.x != 0.0) | (f.u.y != 0.0) | (f.u.z != 0.0);
+    const bool has_fb = (f.fb.x != 0.0) | (f.fb.y != 0.0) | (f.fb.z != 0.0);
 
     for (uint32_t t = 0; t < P.n_ticks; ++t) {
         if (INTEG == B200_INTEGRATOR_RK4) {
             const Vec3 w0 = v0.ang, u0 = v0.lin;
             // the three distinct stage poses depend on (x0, v0) only (rk4.rs:85-111)
-            const Quat q1 = fa::advance(x0.q, Vec3{0.0, 0.0, 0.0});
+            const Quat q1 = fa::normalize(x0.q); // x0 (+) 0*v0 still renormalises (spatial.rs:540-545)
             const double h2 = 0.25 * dt, h4 = 0.5 * dt;
             const Quat q2 = fa::advance(x0.q, Vec3{h2 * w0.x, h2 * w0.y, h2 * w0.z});
             const Quat q4 = fa::advance(x0.q, Vec3{h4 * w0.x, h4 * w0.y, h4 * w0.z});
             const Vec3 x2 = {fma(h4, u0.x, x0.x.x), fma(h4, u0.y, x0.x.y), fma(h4, u0.z, x0.x.z)};
             const Vec3 x4 = {fma(dt, u0.x, x0.x.x), fma(dt, u0.y, x0.x.y), fma(dt, u0.z, x0.x.z)};
             // angular acceleration R(q) u and rotated body force, once per distinct attitude
-            const Vec3 aa1 = fa::rot(q1, f.u), aa2 = fa::rot(q2, f.u), aa4 = fa::rot(q4, f.u);
-            const Vec3 fb1 = fa::rot(q1, f.fb), fb2 = fa::rot(q2, f.fb), fb4 = fa::rot(q4, f.fb);
+            // (rotating an all-zero body torque / force is skipped: most bodies of a world carry
+            // no body-frame wrench; NaNs compare unequal to zero and still take the full path)
+            const Vec3 zero3 = {0.0, 0.0, 0.0};
+            Vec3 aa1 = zero3, aa2 = zero3, aa4 = zero3, fb1 = zero3, fb2 = zero3, fb4 = zero3;
+            if (has_u) { aa1 = fa::rot(q1, f.u); aa2 = fa::rot(q2, f.u); aa4 = fa::rot(q4, f.u); }
+            if (has_fb) { fb1 = fa::rot(q1, f.fb); fb2 = fa::rot(q2, f.fb); fb4 = fa::rot(q4, f.fb); }
             // stage 1: v = v0
             const Vec3 al1 = lin_accel_fast(P, f, b, 0, fb1, x0.x, u0, I.m, inv_m);
             // stage 2: v = v0 + dt/2 a1
@@ -367,8 +373,8 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
             const double n2 = x0.q.i * x0.q.i + x0.q.j * x0.q.j + x0.q.k * x0.q.k + x0.q.w * x0.q.w;
             const double rn = rsqrt(n2);
             const Quat qn = {x0.q.i * rn, x0.q.j * rn, x0.q.k * rn, x0.q.w * rn};
-            const Vec3 aa = fa::rot(qn, f.u);
-            const Vec3 fbw = fa::rot(qn, f.fb);
+            const Vec3 aa = has_u ? fa::rot(qn, f.u) : Vec3{0.0, 0.0, 0.0};
+            const Vec3 fbw = has_fb ? fa::rot(qn, f.fb) : Vec3{0.0, 0.0, 0.0};
             const Vec3 al = lin_accel_fast(P, f, b, 0, fbw, x0.x, v0.lin, I.m, inv_m);
             const double d = P.dt_final;
             v0.ang = Vec3{fma(d, aa.x, v0.ang.x), fma(d, aa.y, v0.ang.y), fma(d, aa.z, v0.ang.z)};
