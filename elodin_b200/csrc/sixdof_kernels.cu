@@ -634,95 +634,90 @@ __global__ void __launch_bounds__(kBlockG * 3) graph_dense_kernel(const __grid_c
     }
 }
 
-// FAST all-pairs: one warp per source body, lanes stride over the targets of a tile and
-// keep private partial sums; a fixed xor-butterfly of warp shuffles combines them (the
-// summation order differs from the reference's sequential fold -> tolerance, not bit
-// parity; EXACT uses graph_dense_kernel).  8 warps = 8 sources of one world per CTA share
-// the shared-memory tile of stage positions, so N = 1024, M = 1 still fills 128 SMs.
-static constexpr int kFastWarps = 8;
+// FAST all-pairs: one warp per (source body, stage slot); lanes stride over the targets of a
+// tile and keep private partial sums, a fixed xor-butterfly of warp shuffles combines them
+// (summation order differs from the reference's sequential fold -> tolerance, not bit
+// parity; EXACT uses graph_dense_kernel).  blockDim = (32, kFastSrc, NS): the 8 sources x 3
+// slots of a CTA share one shared-memory tile of stage positions, and N = 1024, M = 1 still
+// spreads over 128 CTAs x 24 warps.
+static constexpr int kFastSrc = 8;
 static constexpr int kFastTJ = 256;
 
 template <bool RK4>
-__global__ void __launch_bounds__(kFastWarps * 32) graph_dense_fast_kernel(const __grid_constant__ GraphParams G)
+__global__ void __launch_bounds__(32 * kFastSrc * (RK4 ? 3 : 1)) graph_dense_fast_kernel(const __grid_constant__ GraphParams G)
 {
     constexpr int NS = RK4 ? 3 : 1;
+    constexpr int NT = 32 * kFastSrc * NS;
     __shared__ double sx[NS][3][kFastTJ];
     __shared__ double sm[kFastTJ];
 
     const uint32_t N = G.n_entities;
-    const uint32_t groups = (N + kFastWarps - 1) / kFastWarps;
+    const uint32_t groups = (N + kFastSrc - 1) / kFastSrc;
     const uint32_t world = blockIdx.x / groups;
     const uint32_t grp = blockIdx.x % groups;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t i = grp * kFastWarps + warp;
+    const uint32_t lane = threadIdx.x, src = threadIdx.y, sl = threadIdx.z;
+    const uint32_t flat = (sl * kFastSrc + src) * 32 + lane;
+    const uint32_t i = grp * kFastSrc + src;
     const uint64_t wbase = (uint64_t)world * N;
     const bool active = i < N;
     const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
     const double soft = newton ? 0.0 : G.p1;
-    const double dtf[3] = {0.0, 0.5 * G.dt_stage, G.dt_stage};
+    const double dtf = sl == 0 ? 0.0 : (sl == 1 ? 0.5 * G.dt_stage : G.dt_stage);
 
-    Vec3 xi[NS], acc[NS];
+    Vec3 xi = {0, 0, 0}, acc = {0, 0, 0};
     double mi = 0.0;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) { xi[s] = Vec3{0, 0, 0}; acc[s] = Vec3{0, 0, 0}; }
     if (active) {
         const uint64_t b = wbase + i;
         const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
         const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
         mi = ldp(G.ine, G.ld, 6, b);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) xi[s] = RK4 ? stage_pos<false>(x, v, dtf[s]) : x;
+        xi = RK4 ? stage_pos<false>(x, v, dtf) : x;
     }
     for (uint32_t j0 = 0; j0 < N; j0 += kFastTJ) {
-        const uint32_t j = j0 + threadIdx.x;
         __syncthreads();
-        if (j < N) {
-            const uint64_t b = wbase + j;
-            const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
-            const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const Vec3 p = RK4 ? stage_pos<false>(x, v, dtf[s]) : x;
-                sx[s][0][threadIdx.x] = p.x; sx[s][1][threadIdx.x] = p.y; sx[s][2][threadIdx.x] = p.z;
+        // NT threads fill the (kFastTJ x NS) tile: thread t -> target t % TJ, slot t / TJ
+        for (uint32_t t = flat; t < kFastTJ * NS; t += NT) {
+            const uint32_t jt = t % kFastTJ, st = t / kFastTJ;
+            const uint32_t j = j0 + jt;
+            if (j < N) {
+                const uint64_t b = wbase + j;
+                const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+                const double f = st == 0 ? 0.0 : (st == 1 ? 0.5 * G.dt_stage : G.dt_stage);
+                Vec3 pnt = x;
+                if (RK4) {
+                    const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+                    pnt = stage_pos<false>(x, v, f);
+                }
+                sx[st][0][jt] = pnt.x; sx[st][1][jt] = pnt.y; sx[st][2][jt] = pnt.z;
+                if (st == 0) sm[jt] = ldp(G.ine, G.ld, 6, b);
             }
-            sm[threadIdx.x] = ldp(G.ine, G.ld, 6, b);
         }
         __syncthreads();
         const uint32_t jn = min((uint32_t)kFastTJ, N - j0);
         if (active) {
-#pragma unroll 2
+#pragma unroll 4
             for (uint32_t jj = lane; jj < jn; jj += 32) {
-                if (j0 + jj == i) continue;
-                const double mj = sm[jj];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const Vec3 r = {sx[s][0][jj] - xi[s].x, sx[s][1][jj] - xi[s].y, sx[s][2][jj] - xi[s].z};
-                    const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, soft)));
-                    const double inv = rsqrt(d2);
-                    const double w = mj * inv * inv * inv;
-                    acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
-                }
+                const Vec3 r = {sx[sl][0][jj] - xi.x, sx[sl][1][jj] - xi.y, sx[sl][2][jj] - xi.z};
+                const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, soft)));
+                // the self pair contributes exactly nothing (and would be 0 * inf for Newton)
+                const double inv = rsqrt(d2);
+                const double w = (j0 + jj == i) ? 0.0 : sm[jj] * inv * inv * inv;
+                acc.x = fma(w, r.x, acc.x); acc.y = fma(w, r.y, acc.y); acc.z = fma(w, r.z, acc.z);
             }
         }
     }
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            acc[s].x += __shfl_xor_sync(0xffffffffu, acc[s].x, off);
-            acc[s].y += __shfl_xor_sync(0xffffffffu, acc[s].y, off);
-            acc[s].z += __shfl_xor_sync(0xffffffffu, acc[s].z, off);
-        }
+    for (int off = 16; off > 0; off >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
     }
     if (active && lane == 0) {
         const uint64_t b = wbase + i;
         const double k = G.p0 * mi;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            stp(G.gforce, G.ld, s * 3 + 0, b, k * acc[s].x);
-            stp(G.gforce, G.ld, s * 3 + 1, b, k * acc[s].y);
-            stp(G.gforce, G.ld, s * 3 + 2, b, k * acc[s].z);
-        }
+        stp(G.gforce, G.ld, sl * 3 + 0, b, k * acc.x);
+        stp(G.gforce, G.ld, sl * 3 + 1, b, k * acc.y);
+        stp(G.gforce, G.ld, sl * 3 + 2, b, k * acc.z);
     }
 }
 
@@ -891,9 +886,9 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
         if (exact) { if (rk4) graph_dense_kernel<true, true><<<grid, blk3, 0, s>>>(G); else graph_dense_kernel<true, false><<<grid, blk1, 0, s>>>(G); }
         else if (gcfg == 0) { if (rk4) graph_dense_kernel<false, true><<<grid, blk3, 0, s>>>(G); else graph_dense_kernel<false, false><<<grid, blk1, 0, s>>>(G); }
         else {
-            const unsigned gridf = ((G.n_entities + kFastWarps - 1) / kFastWarps) * G.n_worlds;
-            if (rk4) graph_dense_fast_kernel<true><<<gridf, kFastWarps * 32, 0, s>>>(G);
-            else graph_dense_fast_kernel<false><<<gridf, kFastWarps * 32, 0, s>>>(G);
+            const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
+            if (rk4) graph_dense_fast_kernel<true><<<gridf, dim3(32, kFastSrc, 3), 0, s>>>(G);
+            else graph_dense_fast_kernel<false><<<gridf, dim3(32, kFastSrc, 1), 0, s>>>(G);
         }
     } else {
         const uint64_t total = (uint64_t)G.n_entities * G.n_worlds;
