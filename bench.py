@@ -274,6 +274,8 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: elodin_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     distributed = world_size > 1
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

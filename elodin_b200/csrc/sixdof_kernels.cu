@@ -643,11 +643,14 @@ __global__ void __launch_bounds__(kBlockG * 3) graph_dense_kernel(const __grid_c
 static constexpr int kFastSrc = 8;
 static constexpr int kFastTJ = 256;
 
-template <bool RK4>
-__global__ void __launch_bounds__(32 * kFastSrc * (RK4 ? 3 : 1)) graph_dense_fast_kernel(const __grid_constant__ GraphParams G)
+// SPLIT = true : blockDim (32, kFastSrc, NS), one warp per (source, slot)  — small batches
+// SPLIT = false: blockDim (32, kFastSrc, 1),  one warp per source, NS slots — large batches
+template <bool RK4, bool SPLIT>
+__global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) graph_dense_fast_kernel(const __grid_constant__ GraphParams G)
 {
-    constexpr int NS = RK4 ? 3 : 1;
-    constexpr int NT = 32 * kFastSrc * NS;
+    constexpr int NS = RK4 ? 3 : 1;       // stage slots of a tick
+    constexpr int NW = SPLIT ? 1 : NS;    // slots folded by one warp
+    constexpr int NT = 32 * kFastSrc * (SPLIT ? NS : 1);
     __shared__ double sx[NS][3][kFastTJ];
     __shared__ double sm[kFastTJ];
 
@@ -655,38 +658,40 @@ __global__ void __launch_bounds__(32 * kFastSrc * (RK4 ? 3 : 1)) graph_dense_fas
     const uint32_t groups = (N + kFastSrc - 1) / kFastSrc;
     const uint32_t world = blockIdx.x / groups;
     const uint32_t grp = blockIdx.x % groups;
-    const uint32_t lane = threadIdx.x, src = threadIdx.y, sl = threadIdx.z;
-    const uint32_t flat = (sl * kFastSrc + src) * 32 + lane;
+    const uint32_t lane = threadIdx.x, src = threadIdx.y, sl0 = SPLIT ? threadIdx.z : 0;
+    const uint32_t flat = (threadIdx.z * kFastSrc + src) * 32 + lane;
     const uint32_t i = grp * kFastSrc + src;
     const uint64_t wbase = (uint64_t)world * N;
     const bool active = i < N;
     const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
     const double soft = newton ? 0.0 : G.p1;
-    const double dtf = sl == 0 ? 0.0 : (sl == 1 ? 0.5 * G.dt_stage : G.dt_stage);
+    auto dtf_of = [&](uint32_t sl) { return sl == 0 ? 0.0 : (sl == 1 ? 0.5 * G.dt_stage : G.dt_stage); };
 
-    Vec3 xi = {0, 0, 0}, acc = {0, 0, 0};
+    Vec3 xi[NW], acc[NW];
     double mi = 0.0;
+#pragma unroll
+    for (int s = 0; s < NW; ++s) { xi[s] = Vec3{0, 0, 0}; acc[s] = Vec3{0, 0, 0}; }
     if (active) {
         const uint64_t b = wbase + i;
         const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
         const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
         mi = ldp(G.ine, G.ld, 6, b);
-        xi = RK4 ? stage_pos<false>(x, v, dtf) : x;
+#pragma unroll
+        for (int s = 0; s < NW; ++s) xi[s] = RK4 ? stage_pos<false>(x, v, dtf_of(sl0 + s)) : x;
     }
     for (uint32_t j0 = 0; j0 < N; j0 += kFastTJ) {
         __syncthreads();
-        // NT threads fill the (kFastTJ x NS) tile: thread t -> target t % TJ, slot t / TJ
+        // NT threads fill the (kFastTJ x NS) tile: element t -> target t % TJ, slot t / TJ
         for (uint32_t t = flat; t < kFastTJ * NS; t += NT) {
             const uint32_t jt = t % kFastTJ, st = t / kFastTJ;
             const uint32_t j = j0 + jt;
             if (j < N) {
                 const uint64_t b = wbase + j;
                 const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
-                const double f = st == 0 ? 0.0 : (st == 1 ? 0.5 * G.dt_stage : G.dt_stage);
                 Vec3 pnt = x;
                 if (RK4) {
                     const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
-                    pnt = stage_pos<false>(x, v, f);
+                    pnt = stage_pos<false>(x, v, dtf_of(st));
                 }
                 sx[st][0][jt] = pnt.x; sx[st][1][jt] = pnt.y; sx[st][2][jt] = pnt.z;
                 if (st == 0) sm[jt] = ldp(G.ine, G.ld, 6, b);
@@ -695,29 +700,40 @@ __global__ void __launch_bounds__(32 * kFastSrc * (RK4 ? 3 : 1)) graph_dense_fas
         __syncthreads();
         const uint32_t jn = min((uint32_t)kFastTJ, N - j0);
         if (active) {
-#pragma unroll 4
+#pragma unroll 2
             for (uint32_t jj = lane; jj < jn; jj += 32) {
-                const Vec3 r = {sx[sl][0][jj] - xi.x, sx[sl][1][jj] - xi.y, sx[sl][2][jj] - xi.z};
-                const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, soft)));
                 // the self pair contributes exactly nothing (and would be 0 * inf for Newton)
-                const double inv = rsqrt(d2);
-                const double w = (j0 + jj == i) ? 0.0 : sm[jj] * inv * inv * inv;
-                acc.x = fma(w, r.x, acc.x); acc.y = fma(w, r.y, acc.y); acc.z = fma(w, r.z, acc.z);
+                const double mj = (j0 + jj == i) ? 0.0 : sm[jj];
+                const bool self = j0 + jj == i;
+#pragma unroll
+                for (int s = 0; s < NW; ++s) {
+                    const Vec3 r = {sx[sl0 + s][0][jj] - xi[s].x, sx[sl0 + s][1][jj] - xi[s].y, sx[sl0 + s][2][jj] - xi[s].z};
+                    const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, soft)));
+                    const double inv = rsqrt(d2);
+                    const double w = self ? 0.0 : mj * inv * inv * inv;
+                    acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
+                }
             }
         }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+    for (int s = 0; s < NW; ++s) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            acc[s].x += __shfl_xor_sync(0xffffffffu, acc[s].x, off);
+            acc[s].y += __shfl_xor_sync(0xffffffffu, acc[s].y, off);
+            acc[s].z += __shfl_xor_sync(0xffffffffu, acc[s].z, off);
+        }
     }
     if (active && lane == 0) {
         const uint64_t b = wbase + i;
         const double k = G.p0 * mi;
-        stp(G.gforce, G.ld, sl * 3 + 0, b, k * acc.x);
-        stp(G.gforce, G.ld, sl * 3 + 1, b, k * acc.y);
-        stp(G.gforce, G.ld, sl * 3 + 2, b, k * acc.z);
+#pragma unroll
+        for (int s = 0; s < NW; ++s) {
+            stp(G.gforce, G.ld, (sl0 + s) * 3 + 0, b, k * acc[s].x);
+            stp(G.gforce, G.ld, (sl0 + s) * 3 + 1, b, k * acc[s].y);
+            stp(G.gforce, G.ld, (sl0 + s) * 3 + 2, b, k * acc[s].z);
+        }
     }
 }
 
@@ -887,8 +903,12 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
         else if (gcfg == 0) { if (rk4) graph_dense_kernel<false, true><<<grid, blk3, 0, s>>>(G); else graph_dense_kernel<false, false><<<grid, blk1, 0, s>>>(G); }
         else {
             const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
-            if (rk4) graph_dense_fast_kernel<true><<<gridf, dim3(32, kFastSrc, 3), 0, s>>>(G);
-            else graph_dense_fast_kernel<false><<<gridf, dim3(32, kFastSrc, 1), 0, s>>>(G);
+            // few CTAs: split the stage slots over warps to fill the machine; many CTAs: keep
+            // 3 slots per warp (more ILP per lane, 3 CTAs/SM) — measured on N = 1024, M = 1 / 8
+            const bool split = gcfg == 2 || (gcfg == 1 && gridf < 3u * 148u);
+            if (!rk4) graph_dense_fast_kernel<false, false><<<gridf, dim3(32, kFastSrc, 1), 0, s>>>(G);
+            else if (split) graph_dense_fast_kernel<true, true><<<gridf, dim3(32, kFastSrc, 3), 0, s>>>(G);
+            else graph_dense_fast_kernel<true, false><<<gridf, dim3(32, kFastSrc, 1), 0, s>>>(G);
         }
     } else {
         const uint64_t total = (uint64_t)G.n_entities * G.n_worlds;

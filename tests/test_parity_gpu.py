@@ -509,3 +509,41 @@ def test_three_body_example_through_ecs_mirror(golden):
     assert np.array_equal(h["B.world_vel"], golden["three_body.b.world_vel"])
     assert np.array_equal(h["C.force"][1:], golden["three_body.c.force"][1:])
     assert np.array_equal(h["Globals.tick"], np.arange(101))
+
+
+def test_monte_carlo_campaign_is_one_executor(oracle):
+    """Plan -> per-world parameter columns -> one executor == one run per plan row
+    (the reference's process-per-world model, libs/monte-carlo/src/lib.rs:2083)."""
+    from elodin_b200 import monte_carlo as mc
+
+    O = oracle
+    spec = {"monte_carlo": {"n_samples": 12, "seed": 42, "method": "lhs", "variables": {
+        "thrust_gain": {"dist": "uniform", "min": 0.8, "max": 1.2}, "mass": {"dist": "uniform", "min": 2.5, "max": 3.5}}}}
+    rows = mc.materialize(spec)
+    Thrust = el.Annotated[np.ndarray, el.Component("thrust", el.ComponentType.F64)]
+
+    @el.dataclass
+    class Motor(el.Archetype):
+        thrust: Thrust
+
+    def world():
+        w = el.World()
+        w.spawn([el.Body(world_pos=el.SpatialTransform(angular=el.Quaternion.from_euler([0.0, np.radians(70.0), 0.0])),
+                         inertia=el.SpatialInertia(3.0, np.array([0.1, 1.0, 1.0]))), Motor(np.array([88.426]))], name="rocket")
+        return w
+
+    system = lambda: el.six_dof(sys=el.GravityConst((0.0, 0.0, -9.81)) | el.ThrustBody((-1.0, 0.0, 0.0), "thrust"))
+    cols = mc.world_params(rows, 1, {"thrust": lambda p: [88.426 * p["thrust_gain"]],
+                                     "inertia": lambda p: [0.1, 1.0, 1.0, 0, 0, 0, p["mass"]]})
+    campaign = world().build(system(), n_worlds=12, world_params=cols, telemetry_rate=12.0)
+    campaign.run(30)
+    batch = campaign.history_worlds("rocket.world_pos")
+    assert batch.shape == (4, 12, 7)  # initial row + 3 telemetry cycles of 10 ticks
+    for k in (0, 5, 11):
+        single = world().build(system(), world_params={name: a[k:k + 1] for name, a in cols.items()}, telemetry_rate=12.0)
+        single.run(30)
+        assert np.array_equal(single.history_worlds("rocket.world_pos")[:, 0], batch[:, k])
+        w0 = O.World(campaign._history[el.component_id("world_pos")][0][k:k + 1], np.zeros((1, 1, 6)), cols["inertia"][k:k + 1])
+        w0.rk4(campaign.sim_time_step, 30, [O.Effector(O.EFF_GRAVITY_CONST, p=(0, 0, -9.81)),
+                                           O.Effector(O.EFF_THRUST_BODY, p=(-1.0, 0, 0), column=cols["thrust"][k:k + 1])])
+        assert np.array_equal(w0.pos[0, 0], batch[-1, k])
