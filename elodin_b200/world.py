@@ -487,8 +487,9 @@ class Exec:
             col = world.columns.get(component_id(cname))
             if col is None or col.entity_ids != bodies:
                 raise _lib.B200ValueError(_lib.ERR_COMPONENT_NOT_FOUND, f"component not found: {cname}")
+        # ticks of one invoke_batch stay in registers up to 32 at a time (no effect on results)
         self.backend = B200Exec(len(bodies), self.n_worlds, self.sim_time_step, self.six.time_step, self.six.effectors,
-                                self.six.integrator.value, math, device, world=world)
+                                self.six.integrator.value, math, device, max_fused_ticks=32, world=world)
         for e in self.six.effectors:
             cname = e.column_name()
             if cname:
