@@ -389,11 +389,27 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
     if (P.write_fa) f_last = force_out_fast(a_last.lin, f.u, q_last, I);
 }
 
+// Effector columns are consumed inside the (uniform) effector switch, i.e. after the state
+// loads and the reciprocal prologue; prefetching them first puts their HBM latency under the
+// state loads instead of behind them.
+__device__ __forceinline__ void prefetch_effector_columns(const StepParams &P, uint64_t b)
+{
+    for (uint32_t e = 0; e < P.n_eff; ++e) {
+        const double *col = P.eff[e].col;
+        if (!col) continue;
+        const uint32_t w = P.eff[e].kind == B200_EFF_WRENCH_BODY ? 6u : (P.eff[e].kind == B200_EFF_DRAG_QUADRATIC ? 3u : 1u);
+        for (uint32_t k = 0; k < w; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(col + (uint64_t)k * P.ld + b));
+    }
+    if (P.gforce)
+        for (uint32_t k = 0; k < 9; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.gforce + (uint64_t)k * P.ld + b));
+}
+
 template <int INTEG, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) body_fast_kernel(const __grid_constant__ StepParams P)
 {
     const uint64_t b = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (b >= P.n_bodies) return;
+    prefetch_effector_columns(P, b);
     Pose x0 = load_pose(P.pos, P.ld, b);
     Motion v0 = load_motion(P.vel, P.ld, b);
     const Inertia I = load_inertia(P.ine, P.ld, b);

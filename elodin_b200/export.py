@@ -1,0 +1,75 @@
+"""CSV telemetry export in the layout of `elodin-db export --format csv --flatten`.
+
+The reference's CI regression gate (scripts/ci/regress.sh) exports every (entity, component)
+time series to `<entity>.<component>.csv` and diffs the directory against
+scripts/ci/baseline/<example>-csv with scripts/ci/compare_baseline_csv.py (same file set, same
+headers ignoring `time`, same row count, values within tolerances.json).  `export_csv` writes a
+B200 run in that layout so the same gate — and anything else that consumes those exports —
+works on GPU runs unchanged.
+
+Naming (observed in scripts/ci/baseline/three-body-csv): entity names are lower-cased with
+spaces -> "_" ("A -> B" -> "a_>_b"); columns are `<entity>.<component>` for scalars and
+`<entity>.<component>_<element>` otherwise, with the component's `element_names` metadata
+(python/elodin/__init__.py:594-625) or 0..n-1; file names are made Windows-safe exactly like
+scripts/ci/windows_paths.py:21-22 ("_>_" -> "_to_", ">" -> "to").
+"""
+
+from __future__ import annotations
+
+import datetime as _dt
+import os
+from typing import List, Optional
+
+import numpy as np
+
+from ._lib import component_id
+
+
+def _entity_key(name: str) -> str:
+    return name.lower().replace(" ", "_")
+
+
+def _safe_file(name: str) -> str:
+    return name.replace("_>_", "_to_").replace(">", "to")
+
+
+def _fmt(v) -> str:
+    if isinstance(v, (np.integer, int)):
+        return str(int(v))
+    return repr(float(v))
+
+
+def export_csv(exec_, out_dir: str, start_timestamp: Optional[_dt.datetime] = None, world: int = 0) -> List[str]:
+    """Write one CSV per (entity, component) of `exec_`'s recorded history (world `world`)."""
+    os.makedirs(out_dir, exist_ok=True)
+    w = exec_.world
+    t0 = start_timestamp or _dt.datetime(2026, 1, 1)
+    n_rows = len(exec_._globals_hist)
+    dt_row = exec_.sim_time_step * exec_.ticks_per_telemetry
+    times = [(t0 + _dt.timedelta(seconds=dt_row * i)).isoformat() for i in range(n_rows)]
+    written = []
+
+    def write(stem: str, header: List[str], rows) -> None:
+        path = os.path.join(out_dir, _safe_file(stem) + ".csv")
+        with open(path, "w", newline="") as f:
+            f.write(",".join(["time"] + header) + "\n")
+            for t, r in zip(times, rows):
+                f.write(",".join([t] + [_fmt(x) for x in np.atleast_1d(r)]) + "\n")
+        written.append(path)
+
+    write("globals.tick", ["globals.tick"], [g[0] for g in exec_._globals_hist])
+    write("globals.simulation_time_step", ["globals.simulation_time_step"], [g[1] for g in exec_._globals_hist])
+    for cid, col in w.columns.items():
+        comp = col.component
+        names = comp.metadata.get("element_names")
+        elems = names.split(",") if names else [str(i) for i in range(col.width)]
+        for row, ent in enumerate(col.entity_ids):
+            ename = w.entity_names.get(ent)
+            if ename is None:
+                continue
+            key = _entity_key(ename)
+            base = f"{key}.{comp.name}"
+            header = [base] if (col.width == 1 and not names) else [f"{base}_{e}" for e in elems]
+            series = [h[world, row] for h in exec_._history[cid]]
+            write(base, header, series)
+    return written

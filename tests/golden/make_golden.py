@@ -49,6 +49,18 @@ def main() -> int:
     for comp in ("world_pos", "world_vel", "world_accel", "force", "inertia", "wind"):
         out[f"ball.{comp}"] = read("ball", f"ball.{comp}")
     out["ball.simulation_time_step"] = read("ball", "globals.simulation_time_step")
+    # layout of the exported directory (file stems + header rows), for the CSV-export parity test
+    layout = {}
+    d = os.path.join(BASE, "three-body-csv")
+    for fn in sorted(os.listdir(d)):
+        if fn.endswith(".csv"):
+            with open(os.path.join(d, fn), newline="") as f:
+                layout[fn] = next(csv.reader(f))
+            if "gravity_edge" in fn:
+                out[f"three_body.file.{fn}"] = read("three-body", fn[:-4])
+    import json
+    with open(os.path.join(os.path.dirname(OUT), "three_body_csv_layout.json"), "w") as f:
+        json.dump(layout, f, indent=0, ensure_ascii=False)
     np.savez_compressed(OUT, **out)
     print(f"wrote {OUT}: {len(out)} arrays, {os.path.getsize(OUT)} bytes")
     return 0

@@ -547,3 +547,57 @@ def test_monte_carlo_campaign_is_one_executor(oracle):
         w0.rk4(campaign.sim_time_step, 30, [O.Effector(O.EFF_GRAVITY_CONST, p=(0, 0, -9.81)),
                                            O.Effector(O.EFF_THRUST_BODY, p=(-1.0, 0, 0), column=cols["thrust"][k:k + 1])])
         assert np.array_equal(w0.pos[0, 0], batch[-1, k])
+
+
+def test_three_body_csv_export_passes_the_reference_regression_gate(golden, tmp_path):
+    """World.run -> export_csv writes the directory `elodin-db export --format csv --flatten`
+    would, and it satisfies scripts/ci/compare_baseline_csv.py's checks against the reference's
+    own three-body baseline: same file set, same headers (time ignored), same row count, every
+    numeric cell within tolerances.json (1e-4) — here in fact bit-identical."""
+    import csv
+    import json
+    import math
+    import os
+
+    from elodin_b200.export import export_csv
+
+    G = 6.6743e-11
+    w = el.World()
+    ids = {}
+    for k, x, v in (("A", [0.8920281421, 0.0, 0.0], [0.0, 0.9957939373, 0.0]), ("B", [-0.6628498947, 0.0, 0.0], [0.0, -1.6191613336, 0.0]),
+                    ("C", [-0.2291782474, 0, 0], [0, 0.6233673964, 0.0])):
+        ids[k] = w.spawn([el.Body(world_pos=el.WorldPos(linear=np.array(x)), world_vel=el.WorldVel(linear=np.array(v)),
+                                  inertia=el.Inertia(1.0 / G))], name=k)
+    GravityEdge = el.Annotated[el.Edge, el.Component("gravity_edge", el.ComponentType.Edge)]
+
+    @el.dataclass
+    class GravityConstraint(el.Archetype):
+        a: GravityEdge
+
+    for s_, d in (("A", "B"), ("B", "A"), ("A", "C"), ("B", "C"), ("C", "A"), ("C", "B")):
+        w.spawn(GravityConstraint(el.Edge(ids[s_], ids[d])), name=f"{s_} -> {d}")
+    ex = w.run(el.six_dof(sys=el.GravityEdges("newton", G=G)), simulation_rate=120.0, max_ticks=100)
+    out = os.environ.get("B200_EXPORT_DIR") or str(tmp_path / "three-body-csv")
+    export_csv(ex, out)
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "three_body_csv_layout.json")) as f:
+        layout = json.load(f)
+    got_files = sorted(fn for fn in os.listdir(out) if fn.endswith(".csv"))
+    assert got_files == sorted(layout)  # same file set (incl. a_to_b.gravity_edge.csv, globals.*.csv)
+    for fn, want_header in layout.items():
+        with open(os.path.join(out, fn), newline="") as f:
+            rows = list(csv.reader(f))
+        assert rows[0] == want_header, fn  # identical header incl. the greek element names
+        assert len(rows) - 1 == 101, fn
+        stem = fn[:-4]
+        if stem.startswith("globals."):
+            ref = golden["three_body." + stem.split(".", 1)[1]]
+        elif "gravity_edge" in stem:
+            ref = golden[f"three_body.file.{fn}"]
+        else:
+            ref = golden[f"three_body.{stem}"]
+        for r, want in zip(rows[1:], ref):
+            for cell, b in zip(r[1:], np.atleast_1d(want)):
+                a = float(cell)
+                assert math.isclose(a, float(b), rel_tol=1e-4, abs_tol=1e-4)  # the reference gate
+                assert a == float(b), (fn, cell, b)                          # and in fact exact
