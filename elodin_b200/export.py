@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import datetime as _dt
 import os
+import re
 from typing import List, Optional
 
 import numpy as np
@@ -25,8 +26,19 @@ import numpy as np
 from ._lib import component_id
 
 
+_WORD_SPLIT = re.compile(r"[ \-_]+")
+_CASE_SPLIT = re.compile(r"(?<=[a-z])(?=[A-Z])|(?<=[A-Z])(?=[A-Z][a-z])")
+
+
 def _entity_key(name: str) -> str:
-    return name.lower().replace(" ", "_")
+    """Entity name -> id, as WorldBuilder derives it (libs/nox-py/src/world_builder.rs:281-285):
+    `name.without_boundaries(digits).to_case(Case::Snake)` of the convert_case crate — words split
+    at spaces / hyphens / underscores and lower->Upper or ACRONYMWord boundaries (not at digits),
+    lower-cased and joined with "_".  "A -> B" -> "a_>_b", "fooBar" -> "foo_bar", "e1" -> "e1"."""
+    words = []
+    for tok in _WORD_SPLIT.split(name):
+        words += [w for w in _CASE_SPLIT.split(tok) if w]
+    return "_".join(w.lower() for w in words)
 
 
 def _safe_file(name: str) -> str:
