@@ -89,3 +89,15 @@ def test_product_never_imports_the_oracle():
     # and the shared library does not depend on it
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_header_is_plain_c_and_usable_from_c(built_lib, tmp_path):
+    """include/b200_sixdof.h compiles as C99 and a C program links against the library (the
+    cgo / FFI view of the boundary).  Without a GPU the program checks the loud failure."""
+    exe = tmp_path / "abi_smoke"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", os.path.join(ROOT, "tests", "c", "abi_smoke.c"),
+                    "-I", os.path.join(ROOT, "include"), "-L", os.path.join(ROOT, "elodin_b200"), "-lb200_sixdof",
+                    "-Wl,-rpath," + os.path.join(ROOT, "elodin_b200"), "-lm", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ok" in out.stdout or "failed loudly" in out.stdout
