@@ -14,6 +14,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sixdof_internal.h"
@@ -566,6 +567,16 @@ static bool input_is_live(const b200_sixdof *h, uint64_t id)
     return true;
 }
 
+// Output columns the kernels never write (Inertia, effector input columns) are pass-through
+// variables of the reference system (`builder.to_compiled_system()` returns every var): their
+// output buffer is the input buffer's content, so it is filled host-to-host on worker threads
+// while the PCIe link carries the columns that did change.
+static bool output_is_pass_through(uint64_t id)
+{
+    return id != B200_ID_WORLD_POS && id != B200_ID_WORLD_VEL && id != B200_ID_WORLD_ACCEL && id != B200_ID_FORCE &&
+           id != B200_ID_TICK && id != B200_ID_SIMULATION_TIME_STEP;
+}
+
 static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8_t *const *out_cols, uint64_t n_ticks,
                             uint64_t worlds_per_chunk)
 {
@@ -593,7 +604,32 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
     for (size_t i = 0; i < h->output_ids.size(); ++i) {
         const Column *c = h->find(h->output_ids[i]);
         out_off[i] = out_total;
-        if (!c->global) out_total += h->n_bodies * c->width;
+        if (!c->global && !output_is_pass_through(c->id)) out_total += h->n_bodies * c->width;
+    }
+    // host-to-host fill of the pass-through outputs, split over a few worker threads
+    std::vector<std::thread> fillers;
+    struct Joiner { std::vector<std::thread> &v; ~Joiner() { for (auto &t : v) if (t.joinable()) t.join(); } } joiner{fillers};
+    for (size_t i = 0; i < h->output_ids.size(); ++i) {
+        const Column *c = h->find(h->output_ids[i]);
+        if (c->global || !output_is_pass_through(c->id)) continue;
+        const uint8_t *src = nullptr;
+        for (size_t k = 0; k < h->input_ids.size(); ++k) if (h->input_ids[k] == c->id) src = in_cols[k];
+        if (!src || src == out_cols[i]) continue;
+        cudaPointerAttributes a_in{}, a_out{};
+        const bool dev_in = cudaPointerGetAttributes(&a_in, src) == cudaSuccess && a_in.type == cudaMemoryTypeDevice;
+        const bool dev_out = cudaPointerGetAttributes(&a_out, out_cols[i]) == cudaSuccess && a_out.type == cudaMemoryTypeDevice;
+        (void)cudaGetLastError();
+        const uint64_t bytes = h->n_bodies * c->width * 8ull;
+        if (dev_in || dev_out) { // device-resident caller buffers: let the copy engine do it
+            CU(h, cudaMemcpyAsync(out_cols[i], src, bytes, cudaMemcpyDefault, h->copy_out));
+            continue;
+        }
+        const unsigned parts = bytes >= (8u << 20) ? 4u : 1u;
+        for (unsigned t = 0; t < parts; ++t) {
+            const uint64_t o0 = bytes * t / parts, o1 = bytes * (t + 1) / parts;
+            uint8_t *dst = out_cols[i];
+            fillers.emplace_back([dst, src, o0, o1] { std::memcpy(dst + o0, src + o0, o1 - o0); });
+        }
     }
     if (h->stage_in_bytes < in_total * 8) {
         if (h->stage_in) CU(h, cudaFree(h->stage_in));
@@ -640,7 +676,7 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
         if (rc) return rc;
         for (size_t i = 0; i < h->output_ids.size(); ++i) {
             const Column *c = h->find(h->output_ids[i]);
-            if (c->global) continue;
+            if (c->global || output_is_pass_through(c->id)) continue;
             CU(h, launch_soa_to_aos(c->dev + b0, h->stage_out + out_off[i] + b0 * c->width, nb, c->width, h->ld, h->stream));
             h->timings.kernel_launches++;
         }
@@ -649,7 +685,7 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
         CU(h, cudaStreamWaitEvent(h->copy_out, h->chunk_out[k], 0));
         for (size_t i = 0; i < h->output_ids.size(); ++i) {
             const Column *c = h->find(h->output_ids[i]);
-            if (c->global) continue;
+            if (c->global || output_is_pass_through(c->id)) continue;
             CU(h, cudaMemcpyAsync((double *)out_cols[i] + b0 * c->width, h->stage_out + out_off[i] + b0 * c->width,
                                   nb * c->width * 8, cudaMemcpyDefault, h->copy_out));
         }
