@@ -601,3 +601,96 @@ def test_three_body_csv_export_passes_the_reference_regression_gate(golden, tmp_
                 a = float(cell)
                 assert math.isclose(a, float(b), rel_tol=1e-4, abs_tol=1e-4)  # the reference gate
                 assert a == float(b), (fn, cell, b)                          # and in fact exact
+
+
+# --------------------------------------------------------------------------- BASELINE.json configs at full size
+
+
+def test_config_nbody_1024_full_size(oracle):
+    """configs[3]: 1024 bodies, all-pairs softened gravity + 6DOF (SURVEY §8d C4 inputs).  EXACT is
+    bit-identical to the oracle at full N (the tiled kernel keeps the sequential fold order); FAST is
+    within tolerance; and the size-independent property holds: total linear momentum is conserved
+    (pairwise forces cancel) to rounding."""
+    O = oracle
+    N = 1024
+    rng = np.random.default_rng(7)
+    pos = np.zeros((1, N, 7)); pos[..., 3] = 1.0; pos[..., 4:] = rng.uniform(-30, 30, (1, N, 3))
+    vel = np.zeros((1, N, 6)); vel[..., 3:] = rng.normal(0, 1e-7, (1, N, 3))
+    m = 10 ** rng.uniform(-10, -3, (1, N)); m[:, 0] = 1.0
+    ine = np.zeros((1, N, 7)); ine[..., :3] = m[..., None]; ine[..., 6] = m
+    k2 = 2.9591220828e-4 / 86400.0 ** 2
+    edges = el.all_pairs_edges(N)
+    o, g, _ = effector_pair(O, "softened", edges=edges, k2=k2, soft=1e-10)
+    dt = 3600.0
+    want = _run_oracle(O, pos, vel, ine, [o], dt, 2)
+    got = _run_gpu(pos, vel, ine, [g], {}, dt, 2, "exact")
+    _assert_exact(got, want, "n-body 1024 exact")
+    fast = _run_gpu(pos, vel, ine, [g], {}, dt, 2, "fast")
+    _assert_close(fast, want, 1e-10, "n-body 1024 fast")
+    p0 = np.sum(m[0, :, None] * vel[0, :, 3:], axis=0)
+    for name, res in (("exact", got), ("fast", _run_gpu(pos, vel, ine, [g], {}, dt, 50, "fast"))):
+        p1 = np.sum(m[0, :, None] * res[1][0, :, 3:], axis=0)
+        scale = np.sum(m[0, :, None] * np.abs(res[1][0, :, 3:]))
+        assert np.max(np.abs(p1 - p0)) <= 1e-12 * scale, name
+
+
+def test_config_rocket_10k_worlds_full_size(oracle):
+    """configs[2]: 10 000 Monte-Carlo worlds of the rocket (const-g + body thrust + quadratic drag),
+    q = euler(0, 70 deg, 0), m = 3, I = [0.1, 1, 1], 120 Hz.  A strided sample of worlds is checked
+    against the oracle (EXACT bit-exact, FAST <= 1e-9 after 1000 ticks); worlds with identical
+    parameters must produce identical bits wherever they sit in the batch."""
+    O = oracle
+    M = 10000
+    rng = np.random.default_rng(42)
+    q = el.Quaternion.from_euler([0.0, np.radians(70.0), 0.0]).arr
+    pos = np.tile(np.concatenate([q, [0, 0, 1.0]]), (M, 1, 1))
+    vel = np.zeros((M, 1, 6)); vel[..., 3:] = rng.normal(0, 0.1, (M, 1, 3))
+    ine = np.tile(np.array([0.1, 1.0, 1.0, 0, 0, 0, 3.0]), (M, 1, 1))
+    thrust = 88.426 * rng.uniform(0.8, 1.2, (M, 1, 1))
+    wind = rng.normal(0, 2.0, (M, 1, 3))
+    # duplicate world 17 at the far end of the batch
+    for a in (pos, vel, ine, thrust, wind):
+        a[M - 3] = a[17]
+    specs = [("gravity", {}), ("thrust", {"thrust": thrust}), ("drag", {"wind": wind, "cd_rho": 0.6125, "area": 0.0025})]
+    oeffs, geffs, cols = [], [], {}
+    for kind, kw in specs:
+        o, g, c = effector_pair(O, kind, **kw)
+        oeffs.append(o); geffs.append(g); cols.update(c)
+    dt = 0.008333333
+    idx = np.arange(0, M, 157)
+    sub = lambda a: np.ascontiguousarray(a[idx])
+    sub_effs = [O.Effector(O.EFF_GRAVITY_CONST, p=(0, 0, -9.81)), O.Effector(O.EFF_THRUST_BODY, p=(-1.0, 0, 0), column=sub(thrust)),
+                O.Effector(O.EFF_DRAG_QUADRATIC, p=(0.6125, 0.0025), column=sub(wind))]
+    want = _run_oracle(O, sub(pos), sub(vel), sub(ine), sub_effs, dt, 1000)
+    exact = _run_gpu(pos, vel, ine, geffs, cols, dt, 1000, "exact", fused=100)
+    _assert_exact([a[idx] for a in exact], want, "rocket 10k exact sample")
+    fast = _run_gpu(pos, vel, ine, geffs, cols, dt, 1000, "fast", fused=100)
+    _assert_close([a[idx] for a in fast], want, FAST_TOL_1000, "rocket 10k fast sample")
+    for res in (exact, fast):
+        for a in res:
+            assert np.array_equal(a[M - 3], a[17])
+        assert np.all(np.isfinite(res[0])) and np.all(np.isfinite(res[1]))
+        assert np.max(np.abs(np.linalg.norm(res[0][..., :4], axis=-1) - 1.0)) < 1e-15 * 8
+
+
+def test_config_falcon9_style_worlds(oracle):
+    """configs[4] per-GPU shard: 12 500 worlds, dt = 1e-3, rotating-frame gravity + body wrench
+    ([f, tau] layout); strided sample vs the oracle."""
+    O = oracle
+    M = 12500
+    rng = np.random.default_rng(20170814)
+    pos = np.tile(np.array([0, 0, 0, 1.0, 6.4e6, 0, 0]), (M, 1, 1))
+    pos[..., 4:] += rng.normal(0, 10, (M, 1, 3))
+    vel = np.concatenate([rng.normal(0, 0.01, (M, 1, 3)), rng.normal(0, 50, (M, 1, 3))], -1)
+    ine = np.tile(np.array([4e6, 4e6, 1e5, 0, 0, 0, 3e4]), (M, 1, 1))
+    wrench = rng.normal(0, 1e4, (M, 1, 6))
+    idx = np.arange(0, M, 211)
+    sub = lambda a: np.ascontiguousarray(a[idx])
+    of, gf, _ = effector_pair(O, "frame")
+    ow = O.Effector(O.EFF_WRENCH_BODY, flags=O.FLAG_WRENCH_LINEAR_FIRST, column=sub(wrench))
+    gw = el.WrenchBody("aero_force", "linear_first")
+    want = _run_oracle(O, sub(pos), sub(vel), sub(ine), [of, ow], 1e-3, 500)
+    exact = _run_gpu(pos, vel, ine, [gf, gw], {"aero_force": wrench}, 1e-3, 500, "exact", fused=100)
+    _assert_exact([a[idx] for a in exact], want, "falcon9 exact sample")
+    fast = _run_gpu(pos, vel, ine, [gf, gw], {"aero_force": wrench}, 1e-3, 500, "fast", fused=100)
+    _assert_close([a[idx] for a in fast], want, FAST_TOL_1000, "falcon9 fast sample")
