@@ -694,3 +694,36 @@ def test_config_falcon9_style_worlds(oracle):
     _assert_exact([a[idx] for a in exact], want, "falcon9 exact sample")
     fast = _run_gpu(pos, vel, ine, [gf, gw], {"aero_force": wrench}, 1e-3, 500, "fast", fused=100)
     _assert_close([a[idx] for a in fast], want, FAST_TOL_1000, "falcon9 fast sample")
+
+
+def test_host_system_feeds_per_tick_inputs(oracle):
+    """`non_effectors | six_dof(...)` (examples/rocket/main.py:560-576): a per-tick host system
+    (here a thrust curve indexed by tick, like rocket/main.py:416-426) updates an effector input
+    column between GPU ticks; the result equals the oracle stepped tick by tick with the same values."""
+    O = oracle
+    Thrust = el.Annotated[np.ndarray, el.Component("thrust", el.ComponentType.F64)]
+
+    @el.dataclass
+    class Motor(el.Archetype):
+        thrust: Thrust
+
+    w = el.World()
+    q = el.Quaternion.from_euler([0.0, np.radians(70.0), 0.0])
+    w.spawn([el.Body(world_pos=el.SpatialTransform(angular=q, linear=np.array([0.0, 0.0, 1.0])),
+                     inertia=el.SpatialInertia(3.0, np.array([0.1, 1.0, 1.0]))), Motor(np.array([0.0]))], name="rocket")
+    curve = lambda tick: 300.0 * np.exp(-0.05 * tick)
+
+    @el.host_system
+    def thrust(ctx):
+        ctx.column("thrust")[...] = curve(ctx.tick)
+
+    effectors = el.GravityConst((0.0, 0.0, -9.81)) | el.ThrustBody((-1.0, 0.0, 0.0), "thrust")
+    ex = w.build(thrust | el.six_dof(sys=effectors, integrator=el.Integrator.Rk4), simulation_rate=120.0)
+    ex.run(25)
+    ow = O.World(np.concatenate([q.arr, [0, 0, 1.0]])[None, None], np.zeros((1, 1, 6)), np.array([[[0.1, 1.0, 1.0, 0, 0, 0, 3.0]]]))
+    for t in range(25):
+        ow.rk4(ex.sim_time_step, 1, [O.Effector(O.EFF_GRAVITY_CONST, p=(0, 0, -9.81)),
+                                     O.Effector(O.EFF_THRUST_BODY, p=(-1.0, 0, 0), column=np.array([[[curve(t)]]]))])
+    h = ex.history(["rocket.world_pos", "rocket.world_vel", "rocket.thrust", "Globals.tick"])
+    assert np.array_equal(h["rocket.world_pos"][-1], ow.pos[0, 0]) and np.array_equal(h["rocket.world_vel"][-1], ow.vel[0, 0])
+    assert h["rocket.thrust"][-1][0] == curve(24) and int(h["Globals.tick"][-1]) == 25
