@@ -445,18 +445,28 @@ def run_b200(args):
     # ------------------------------------------------------------------ end-of-run trajectory gather (NCCL, outside the timed region)
     gather = None
     if distributed:
-        n_g = min(M, 1 << 16)
-        t_local = torch.empty((n_g, 1, 7), device="cuda", dtype=torch.float64)
-        tmp = torch.empty((M, 1, 7), device="cuda", dtype=torch.float64)
-        ex.download_ptr(WORLD_POS, tmp.data_ptr(), tmp.numel() * 8)
-        t_local.copy_(tmp[:n_g])
-        out = torch.empty((world_size * n_g, 1, 7), device="cuda", dtype=torch.float64)
+        from elodin_b200.sharding import gather_worlds
+
+        gM, g_ticks, g_every = 1 << 16, 50, 10
+        gpos, gvel, gine = synth_world(gM, 3000 + rank)
+        gx = el.B200Exec(1, gM, DT, None, [], "rk4", "fast", device=local, max_fused_ticks=10, trajectory_every=g_every,
+                         trajectory_capacity=g_ticks // g_every)
+        gx.set_state(gpos, gvel, gine)
+        gx.step(g_ticks, sync=True)
+        n_s = gx.trajectory_len()
+        traj = torch.empty((n_s, gM, 1, 13), device="cuda", dtype=torch.float64)
+        gx.trajectory_to_ptr(traj.data_ptr(), traj.numel() * 8)  # device -> device, [samples][worlds][entities][13]
+        local_traj = traj.permute(1, 0, 2, 3).contiguous()      # world-major for the world-axis gather
         torch.cuda.synchronize()
+        dist.barrier()
         g0 = time.perf_counter()
-        dist.all_gather_into_tensor(out, t_local)
+        full = gather_worlds(local_traj, gM * world_size)
         torch.cuda.synchronize()
-        gather = {"collective": "nccl all_gather of final WorldPos sample", "bytes": int(out.numel() * 8),
-                  "ms": (time.perf_counter() - g0) * 1e3}
+        g_ms = (time.perf_counter() - g0) * 1e3
+        gather = {"collective": "nccl all_gather of the trajectory ring (pos+vel samples), world-sharded",
+                  "samples": int(n_s), "worlds_total": int(full.shape[0]), "bytes_gathered": int(full.numel() * 8),
+                  "ms": g_ms, "gbps": full.numel() * 8 / (g_ms * 1e-3) / 1e9}
+        gx.close()
     ex.close()
 
     if rank == 0:
