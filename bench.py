@@ -457,6 +457,7 @@ def run_b200(args):
         traj = torch.empty((n_s, gM, 1, 13), device="cuda", dtype=torch.float64)
         gx.trajectory_to_ptr(traj.data_ptr(), traj.numel() * 8)  # device -> device, [samples][worlds][entities][13]
         local_traj = traj.permute(1, 0, 2, 3).contiguous()      # world-major for the world-axis gather
+        gather_worlds(local_traj[:128], 128 * world_size)  # warm the communicator
         torch.cuda.synchronize()
         dist.barrier()
         g0 = time.perf_counter()
