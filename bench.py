@@ -229,12 +229,13 @@ def run_baseline_configs(args, torch, el, stream, local, rank, world_size):
     pos = np.tile(np.concatenate([q, [0, 0, 1.0]]), (M, 1, 1))
     vel = np.zeros((M, 1, 6))
     ine = np.tile(np.array([0.1, 1.0, 1.0, 0, 0, 0, 3.0]), (M, 1, 1))
-    effs = [el.GravityConst((0, 0, -9.81)), el.ThrustBody((-1.0, 0, 0), "thrust"), el.DragQuadratic(1.0, 1.0, "wind")]
+    effs = [el.GravityConst((0, 0, -9.81)), el.ThrustBody((-1.0, 0, 0), "thrust"),
+            el.DragQuadratic(column="wind", per_body_params=True)]
+    # per-world drag: wind ~ N(0,1), Cd*rho ~ U(0.3, 0.9), A ~ U(1e-3, 1e-2)  (per-world Cd*rho*A)
+    drag_col = np.concatenate([rng.normal(0, 1, (M, 1, 3)), rng.uniform(0.3, 0.9, (M, 1, 1)), rng.uniform(1e-3, 1e-2, (M, 1, 1))], -1)
     for math in ("fast", "exact"):
         ex = el.B200Exec(1, M, 0.008333333, None, effs, "rk4", math, device=local, max_fused_ticks=100)
-        ex.set_state(pos, vel, ine, thrust=np.full((M, 1, 1), 88.426), wind=np.zeros((M, 1, 3)))
-        ex.upload("wind", rng.normal(0, 1, (M, 1, 3)))
-        # per-world Cd*rho*A enters through the wind-relative drag; keep one constant pair (the kernel parameter)
+        ex.set_state(pos, vel, ine, thrust=np.full((M, 1, 1), 88.426), wind=drag_col)
         ms = timed(ex, 5000, 100)
         out[f"rocket_10k_worlds_{math}"] = {"worlds": M, "steps": 5000, "seconds": ms * 1e-3, "value": M * 5000 / (ms * 1e-3), "unit": UNIT}
         ex.close()

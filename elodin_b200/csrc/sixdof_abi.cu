@@ -217,6 +217,7 @@ void fill_step_params(b200_sixdof *h, StepParams &P)
         std::memcpy(P.eff[i].p, e.p, sizeof e.p);
         const Column *c = e.column_id ? h->find(e.column_id) : nullptr;
         P.eff[i].col = c ? c->dev : nullptr;
+        P.eff[i].col_width = c ? c->width : 0;
     }
 }
 
@@ -442,7 +443,7 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
         }
         if (e.kind == B200_EFF_GRAVITY_FRAME) ++n_frame;
         if (e.column_id) {
-            if (e.column_width != want_w)
+            if (e.column_width != want_w && !(e.kind == B200_EFF_DRAG_QUADRATIC && e.column_width == 5))
                 return bail(fail(B200_ERR_VALUE_SIZE_MISMATCH, "effector %zu: column width %u, kind %u needs %u", i, e.column_width, e.kind, want_w));
         } else if (e.kind == B200_EFF_THRUST_BODY || e.kind == B200_EFF_WRENCH_BODY) {
             return bail(fail(B200_ERR_INVALID_ARGUMENT, "effector %zu (kind %u) needs an input column", i, e.kind));

@@ -15,6 +15,8 @@ struct EffDev {
     uint32_t flags;
     double p[8];
     const double *col;
+    uint32_t col_width;
+    uint32_t pad;
 };
 
 // Launch parameters of the per-body integrator kernels.  All columns are SoA:

@@ -98,7 +98,9 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
             if (E.col) { w0 = ldp(E.col, P.ld, 0, b); w1 = ldp(E.col, P.ld, 1, b); w2 = ldp(E.col, P.ld, 2, b); }
             const Vec3 fl = {sub(w0, sv.lin.x), sub(w1, sv.lin.y), sub(w2, sv.lin.z)};
             const double speed = sqr(dot3(fl));
-            const double drag = mul(0.5, mul(mul(E.p[0], mul(speed, speed)), E.p[1]));
+            const double cd_rho = E.col_width == 5 ? ldp(E.col, P.ld, 3, b) : E.p[0];
+            const double area = E.col_width == 5 ? ldp(E.col, P.ld, 4, b) : E.p[1];
+            const double drag = mul(0.5, mul(mul(cd_rho, mul(speed, speed)), area));
             F.ang = Vec3{0.0, 0.0, 0.0};
             F.lin = Vec3{add(F.lin.x, mul(drag, div(fl.x, speed))), add(F.lin.y, mul(drag, div(fl.y, speed))),
                          add(F.lin.z, mul(drag, div(fl.z, speed)))};
@@ -235,7 +237,7 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
             break;
         case B200_EFF_DRAG_QUADRATIC:
             f.drag = true;
-            f.kd = 0.5 * E.p[0] * E.p[1];
+            f.kd = E.col_width == 5 ? 0.5 * ldp(E.col, P.ld, 3, b) * ldp(E.col, P.ld, 4, b) : 0.5 * E.p[0] * E.p[1];
             if (E.col) f.wind = Vec3{ldp(E.col, P.ld, 0, b), ldp(E.col, P.ld, 1, b), ldp(E.col, P.ld, 2, b)};
             tb = Vec3{0.0, 0.0, 0.0}; // the reference's apply_drag returns SpatialForce(linear=...): torque reset
             break;
@@ -397,7 +399,7 @@ __device__ __forceinline__ void prefetch_effector_columns(const StepParams &P, u
     for (uint32_t e = 0; e < P.n_eff; ++e) {
         const double *col = P.eff[e].col;
         if (!col) continue;
-        const uint32_t w = P.eff[e].kind == B200_EFF_WRENCH_BODY ? 6u : (P.eff[e].kind == B200_EFF_DRAG_QUADRATIC ? 3u : 1u);
+        const uint32_t w = P.eff[e].col_width;
         for (uint32_t k = 0; k < w; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(col + (uint64_t)k * P.ld + b));
     }
     if (P.gforce)

@@ -89,9 +89,11 @@ class DragQuadratic(Effector):
     cd_rho: float = 0.5 * 1.225
     area: float = 2 * 3.1415 * 0.2 ** 2
     column: Optional[str] = "wind"
+    per_body_params: bool = False  # column is [wind(3), Cd*rho, area] (per-world drag in Monte-Carlo batches)
 
     def lower(self, world):
-        return _base(_lib.EFF_DRAG_QUADRATIC, (self.cd_rho, self.area), column=self.column, width=3)
+        return _base(_lib.EFF_DRAG_QUADRATIC, (self.cd_rho, self.area), column=self.column,
+                     width=5 if self.per_body_params else 3)
 
 
 @dataclass

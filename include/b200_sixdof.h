@@ -86,7 +86,8 @@ enum {
      * p[0..2] = g */
     B200_EFF_GRAVITY_CONST = 1,
     /* quadratic drag on the stage velocity, examples/ball/sim.py:99-116
-     * p[0] = Cd*rho, p[1] = area; column (optional, width 3) = wind;
+     * p[0] = Cd*rho, p[1] = area; column (optional) = wind (width 3), or wind + per-body
+     * [Cd*rho, area] (width 5: Monte-Carlo worlds with their own drag parameters);
      * NOTE (reference behaviour): result torque is reset to 0. */
     B200_EFF_DRAG_QUADRATIC = 2,
     /* F.lin += (q @ axis) * thrust      examples/rocket/main.py:429-431

@@ -165,7 +165,10 @@ static void eff_drag_quadratic(const orc_effector *e, const double *wind, const 
     const double w0 = wind ? wind[0] : 0.0, w1 = wind ? wind[1] : 0.0, w2 = wind ? wind[2] : 0.0;
     fl[0] = w0 - vel[3]; fl[1] = w1 - vel[4]; fl[2] = w2 - vel[5];
     const double speed = sqrt(dot3(fl, fl));
-    const double drag = 0.5 * ((e->p[0] * (speed * speed)) * e->p[1]);
+    /* width-5 column: [wind(3), Cd*rho, area] per body (Monte-Carlo worlds with their own drag) */
+    const double cd_rho = (wind && e->column_width == 5) ? wind[3] : e->p[0];
+    const double area = (wind && e->column_width == 5) ? wind[4] : e->p[1];
+    const double drag = 0.5 * ((cd_rho * (speed * speed)) * area);
     const double d0 = fl[0] / speed, d1 = fl[1] / speed, d2 = fl[2] / speed;
     F[0] = 0.0; F[1] = 0.0; F[2] = 0.0;
     F[3] = F[3] + drag * d0;

@@ -727,3 +727,24 @@ def test_host_system_feeds_per_tick_inputs(oracle):
     h = ex.history(["rocket.world_pos", "rocket.world_vel", "rocket.thrust", "Globals.tick"])
     assert np.array_equal(h["rocket.world_pos"][-1], ow.pos[0, 0]) and np.array_equal(h["rocket.world_vel"][-1], ow.vel[0, 0])
     assert h["rocket.thrust"][-1][0] == curve(24) and int(h["Globals.tick"][-1]) == 25
+
+
+def test_per_world_drag_parameters(oracle):
+    """quadratic drag with per-world Cd*rho*A — the drag column carries
+    [wind(3), Cd*rho, area] per body."""
+    O = oracle
+    M, N = 40, 2
+    pos, vel, ine = random_world(91, M, N)
+    rng = np.random.default_rng(2)
+    col = np.concatenate([rng.normal(0, 1, (M, N, 3)), rng.uniform(0.3, 0.9, (M, N, 1)), rng.uniform(0.001, 0.01, (M, N, 1))], -1)
+    og = O.Effector(O.EFF_GRAVITY_CONST, p=(0, 0, -9.81))
+    od = O.Effector(O.EFF_DRAG_QUADRATIC, p=(9e9, 9e9), column=col)  # constants must be ignored
+    want = _run_oracle(O, pos, vel, ine, [og, od], 0.01, 8)
+    effs = [el.GravityConst(), el.DragQuadratic(9e9, 9e9, "wind", per_body_params=True)]
+    got = _run_gpu(pos, vel, ine, effs, {"wind": col}, 0.01, 8, "exact")
+    _assert_exact(got, want, "per-world drag")
+    fast = _run_gpu(pos, vel, ine, effs, {"wind": col}, 0.01, 8, "fast")
+    _assert_close(fast, want, 8 * FAST_TOL_TICK, "per-world drag fast")
+    # and it differs from constant parameters (the column values are really used)
+    other = _run_gpu(pos, vel, ine, [el.GravityConst(), el.DragQuadratic(0.6, 0.005, "wind")], {"wind": col[..., :3]}, 0.01, 8, "exact")
+    assert not np.array_equal(other[1], got[1])
