@@ -499,7 +499,7 @@ def run_b200(args):
                          "kernel_ms": kernel_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / T, "d2h_bytes_per_step": d2h / T,
                     "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h, "ticks_per_call": T, "calls": calls,
-                    "ms_per_call": e2e_ms / calls, "phase_ms_last_call": {k: tm[k] for k in ("h2d_upload_ms", "kernel_invoke_ms", "d2h_download_ms")},
+                    "ms_per_call": e2e_ms / calls, "engine_busy_ms_last_call": {k: tm[k] for k in ("h2d_upload_ms", "kernel_invoke_ms", "d2h_download_ms", "invoke_wall_ms")},
                     "api": "b200_sixdof_invoke_batch (pinned host columns in/out)", "checksum": checksum,
                     "host_cpus_bound": numa_cpus},
             "gpu_launches": int(launches),

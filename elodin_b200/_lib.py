@@ -89,6 +89,7 @@ class Timings(C.Structure):
         ("h2d_upload_ms", C.c_double),
         ("kernel_invoke_ms", C.c_double),
         ("d2h_download_ms", C.c_double),
+        ("invoke_wall_ms", C.c_double),
         ("kernel_launches", C.c_uint64),
         ("ticks", C.c_uint64),
     ]

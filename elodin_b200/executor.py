@@ -229,7 +229,8 @@ class B200Exec:
         t = _lib.Timings()
         _lib.check(self._L.b200_sixdof_timings(self._h, C.byref(t)))
         return {"h2d_upload_ms": t.h2d_upload_ms, "kernel_invoke_ms": t.kernel_invoke_ms,
-                "d2h_download_ms": t.d2h_download_ms, "kernel_launches": int(t.kernel_launches),
+                "d2h_download_ms": t.d2h_download_ms, "invoke_wall_ms": t.invoke_wall_ms,
+                "kernel_launches": int(t.kernel_launches),
                 "ticks": int(t.ticks)}
 
     def device_plane(self, cid, plane: int) -> int:

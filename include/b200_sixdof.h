@@ -147,10 +147,13 @@ typedef struct b200_sixdof_desc {
     uint64_t trajectory_capacity; /* samples the device ring can hold                 */
 } b200_sixdof_desc;
 
-typedef struct b200_timings {  /* TickTimings analogue, libs/nox-py/src/profile.rs */
+typedef struct b200_timings {  /* TickTimings analogue, libs/nox-py/src/profile.rs — of the last
+                                  invoke_batch: busy spans of the upload copy engine, the compute stream
+                                  and the download copy engine (they overlap) and the call's wall time */
     double h2d_upload_ms;
     double kernel_invoke_ms;
     double d2h_download_ms;
+    double invoke_wall_ms;
     uint64_t kernel_launches;  /* launches of this library's kernels since create   */
     uint64_t ticks;            /* ticks integrated since create                      */
 } b200_timings;
