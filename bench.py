@@ -158,7 +158,7 @@ def run_reference(args):
 
     O.build()
     threads = O.max_threads()
-    worlds = 1 << 16  # bounded sample of the M-world workload, per step
+    worlds = 1 << 18  # bounded sample of the M-world workload, per step (enough work per thread to amortise the fork/join)
     # calibrate so the K-step run stays within ~minutes
     for _ in range(max(args.warmup, 1)):
         cpu_oracle_rate(worlds, 1, threads)
@@ -173,7 +173,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": el_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cube-sat 6DOF RK4 dt=1e-3, 1 body x M worlds (configs[1] batched); CPU sample of 65536 worlds per step",
+        "config": {"workload": "cube-sat 6DOF RK4 dt=1e-3, 1 body x M worlds (configs[1] batched); CPU sample of 262144 worlds per step",
                    "worlds_per_step": worlds, "dt": DT, "integrator": "rk4"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{worlds} worlds x {args.steps} ticks, oracle/sixdof_oracle.c on {threads} threads"},
