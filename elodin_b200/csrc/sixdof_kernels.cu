@@ -284,7 +284,7 @@ __device__ __forceinline__ Vec3 lin_accel_fast(const StepParams &P, const Folded
     }
     if (f.frame) {
         const double r2 = x.x * x.x + x.y * x.y + x.z * x.z;
-        const double ir = rsqrt(r2);
+        const double ir = fa::rsqrt_nr(r2);
         const double g = -f.mu * ir * ir * ir;
         const Vec3 c = fa::cross(f.om, v);
         const Vec3 c2 = fa::cross(f.om, fa::cross(f.om, x));
@@ -317,8 +317,8 @@ template <int INTEG>
 __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose &x0, Motion &v0, const Inertia &I,
                                            Motion &a_last, Motion &f_last)
 {
-    const Vec3 invI = {1.0 / I.diag.x, 1.0 / I.diag.y, 1.0 / I.diag.z};
-    const double inv_m = 1.0 / I.m;
+    const Vec3 invI = {fa::rcp_nr(I.diag.x), fa::rcp_nr(I.diag.y), fa::rcp_nr(I.diag.z)};
+    const double inv_m = fa::rcp_nr(I.m);
     const Folded f = fold_effectors(P, b, I, invI);
 
     a_last = Motion{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
@@ -373,7 +373,7 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
         } else {
             // semi_implicit.rs:42-62; calc_accel rotates by q/|q| whatever |q| is
             const double n2 = x0.q.i * x0.q.i + x0.q.j * x0.q.j + x0.q.k * x0.q.k + x0.q.w * x0.q.w;
-            const double rn = rsqrt(n2);
+            const double rn = fa::rsqrt_nr(n2);
             const Quat qn = {x0.q.i * rn, x0.q.j * rn, x0.q.k * rn, x0.q.w * rn};
             const Vec3 aa = has_u ? fa::rot(qn, f.u) : Vec3{0.0, 0.0, 0.0};
             const Vec3 fbw = has_fb ? fa::rot(qn, f.fb) : Vec3{0.0, 0.0, 0.0};
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(kBlockG * 3) graph_dense_kernel(const __grid_c
                     // common factor (G|K^2)*m_i applied after the loop
                     const Vec3 r = {xj.x - xi.x, xj.y - xi.y, xj.z - xi.z};
                     const double d2 = r.x * r.x + r.y * r.y + r.z * r.z + (newton ? 0.0 : G.p1);
-                    const double inv = rsqrt(d2);
+                    const double inv = fa::rsqrt_nr(d2);
                     const double w = mj * inv * inv * inv;
                     acc.x = fma(w, r.x, acc.x); acc.y = fma(w, r.y, acc.y); acc.z = fma(w, r.z, acc.z);
                 }
@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) grap
         __syncthreads();
         const uint32_t jn = min((uint32_t)kFastTJ, N - j0);
         if (active) {
-#pragma unroll 2
+#pragma unroll 4
             for (uint32_t jj = lane; jj < jn; jj += 32) {
                 // the self pair contributes exactly nothing (and would be 0 * inf for Newton)
                 const double mj = (j0 + jj == i) ? 0.0 : sm[jj];
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) grap
                 for (int s = 0; s < NW; ++s) {
                     const Vec3 r = {sx[sl0 + s][0][jj] - xi[s].x, sx[sl0 + s][1][jj] - xi[s].y, sx[sl0 + s][2][jj] - xi[s].z};
                     const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, soft)));
-                    const double inv = rsqrt(d2);
+                    const double inv = fa::rsqrt_nr(d2);
                     const double w = self ? 0.0 : mj * inv * inv * inv;
                     acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
                 }
@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(kBlockG) graph_csr_kernel(const __grid_constan
             } else {
                 const Vec3 r = {xj.x - xi[s].x, xj.y - xi[s].y, xj.z - xi[s].z};
                 const double d2 = r.x * r.x + r.y * r.y + r.z * r.z + (newton ? 0.0 : G.p1);
-                const double inv = rsqrt(d2);
+                const double inv = fa::rsqrt_nr(d2);
                 const double w = mj * inv * inv * inv;
                 acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
             }
