@@ -101,3 +101,15 @@ def test_header_is_plain_c_and_usable_from_c(built_lib, tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "ok" in out.stdout or "failed loudly" in out.stdout
+
+
+def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
+    """No CUDA extension => the product raises; it never substitutes a CPU path."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libb200_sixdof.so"))
+    with pytest.raises(el.B200Error, match="no CPU fallback"):
+        el.B200Exec(1, 1, 0.01)
+    w = el.World()
+    w.spawn(el.Body(), name="e1")
+    with pytest.raises(el.B200Error):
+        w.build(el.six_dof())
