@@ -18,6 +18,8 @@ from __future__ import annotations
 import dataclasses
 import enum
 import re
+import sys
+import time
 import typing
 from typing import Any, Callable, Dict, List, Optional, Sequence, Union
 
@@ -432,7 +434,32 @@ class World:
             post_step=None, db_path: Optional[str] = None, interactive: bool = True, start_timestamp=None,
             log_level=None, backend: str = "b200", math: str = "exact", n_worlds: int = 1) -> "Exec":
         """Headless `World.run` (python/elodin/__init__.py:673-718): runs to max_ticks.  The
-        DB server / editor / CLI layers of the reference are out of scope."""
+        DB server / editor layers of the reference are out of scope.  Like the reference's
+        WorldBuilder::run it looks at sys.argv: `python sim.py bench --ticks N [--detail]`
+        builds, runs N ticks and prints the reference's bench lines (world_builder.rs:868-909),
+        which examples/n-body/benchmark_backends.py parses."""
+        argv = sys.argv[1:]
+        if argv[:1] == ["bench"]:
+            ticks = int(argv[argv.index("--ticks") + 1]) if "--ticks" in argv else 1000
+            t0 = time.perf_counter()
+            ex = self.build(system, simulation_rate, generate_real_time, telemetry_rate, default_playback_speed,
+                            max_ticks, optimize, db_path, backend, math, n_worlds)
+            ex.build_ms = (time.perf_counter() - t0) * 1e3
+            ex.run(ticks, show_progress=False)
+            prof = ex.profile()
+            tpt = int(prof["ticks_per_telemetry"])
+            print(f"= tick time:          {prof['tick']:.3f} ms (batch of {tpt} ticks)")
+            print(f"build time:           {prof['build']:.3f} ms")
+            print(f"real_time_factor:     {prof['real_time_factor']:.3f}")
+            if "--detail" in argv:
+                print(f"copy_to_client time:  {prof['copy_to_client']:.3f} ms")
+                print(f"execute_buffers time: {prof['execute_buffers']:.3f} ms")
+                print(f"copy_to_host time:    {prof['copy_to_host']:.3f} ms")
+                print(f"h2d_upload time:      {prof['h2d_upload']:.3f} ms")
+                print(f"kernel_invoke time:   {prof['kernel_invoke']:.3f} ms ({tpt} invocations)")
+                print(f"d2h_download time:    {prof['d2h_download']:.3f} ms")
+                print(f"add_to_history time:  {prof['add_to_history']:.3f} ms")
+            return ex
         if max_ticks is None:
             raise ValueError("elodin_b200.World.run is headless: pass max_ticks")
         ex = self.build(system, simulation_rate, generate_real_time, telemetry_rate, default_playback_speed,
@@ -497,6 +524,8 @@ class Exec:
                 if col is None or col.entity_ids != bodies:
                     raise _lib.B200ValueError(_lib.ERR_COMPONENT_NOT_FOUND, f"component not found: {cname}")
         self.tick = 0
+        self.build_ms = 0.0
+        self._prof = {"execute_buffers": [], "add_to_history": [], "h2d_upload": [], "kernel_invoke": [], "d2h_download": []}
         self.dirty: set = set()
         self._history: Dict[int, List[np.ndarray]] = {cid: [] for cid in self.world.columns}
         self._globals_hist: List[tuple] = []
@@ -548,13 +577,20 @@ class Exec:
                     pre_step(self.tick, ctx)
                 for s in self.pre_systems:
                     s.fn(ctx)
+                t_inv = time.perf_counter()
                 self._invoke(per_call)
+                self._prof["execute_buffers"].append((time.perf_counter() - t_inv) * 1e3 * (n / per_call))
+                tm = self.backend.timings()
+                for k_src, k_dst in (("h2d_upload_ms", "h2d_upload"), ("kernel_invoke_ms", "kernel_invoke"), ("d2h_download_ms", "d2h_download")):
+                    self._prof[k_dst].append(tm[k_src])
                 for s in self.post_systems:
                     s.fn(ctx)
                 if post_step:
                     post_step(self.tick, ctx)
                 done += per_call
+            t_hist = time.perf_counter()
             self._record()
+            self._prof["add_to_history"].append((time.perf_counter() - t_hist) * 1e3)
             remaining -= n
         return self
 
@@ -589,4 +625,16 @@ class Exec:
         return self.world.columns[cid].buffer[0]
 
     def profile(self) -> dict:
-        return self.backend.timings()
+        """Profiler::profile (libs/nox-py/src/profile.rs:28-56): mean ms per telemetry cycle and
+        real_time_factor = time_step * ticks_per_telemetry / tick (history/DB commit included
+        the way the reference includes add_to_history)."""
+        mean = lambda k: float(np.mean(self._prof[k])) if self._prof[k] else 0.0
+        tick = mean("execute_buffers") + mean("add_to_history")
+        batch_ms = self.sim_time_step * 1e3 * max(self.ticks_per_telemetry, 1)
+        out = {"build": self.build_ms, "copy_to_client": 0.0, "execute_buffers": mean("execute_buffers"), "copy_to_host": 0.0,
+               "h2d_upload": mean("h2d_upload"), "kernel_invoke": mean("kernel_invoke"), "d2h_download": mean("d2h_download"),
+               "add_to_history": mean("add_to_history"), "tick": tick, "time_step": self.sim_time_step * 1e3,
+               "ticks_per_telemetry": float(self.ticks_per_telemetry),
+               "real_time_factor": (batch_ms / tick) if tick > 0 else float("inf")}
+        out.update({"backend": self.backend.timings()})
+        return out

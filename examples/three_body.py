@@ -1,6 +1,7 @@
 """examples/three-body/main.py of the reference, on the B200 backend.
 
     python examples/three_body.py [ticks]
+    python examples/three_body.py bench --ticks 1000 [--detail]      # the reference's bench CLI
 
 Same script shape as the reference (spawn three bodies, six gravity edges, el.six_dof(sys=gravity),
 run); the only changes are the import and that `gravity` is the built-in edge_fold effector
@@ -45,8 +46,10 @@ w.spawn(GravityConstraint(c, b), name="C -> B")
 
 gravity = el.GravityEdges("newton", G=G)  # edge_fold over the spawned GravityEdge components
 sys_ = el.six_dof(sys=gravity)
-ticks = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-sim = w.run(sys_, simulation_rate=1.0 / SIM_TIME_STEP, max_ticks=ticks)
+ticks = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1000
+sim = w.run(sys_, simulation_rate=1.0 / SIM_TIME_STEP, max_ticks=ticks)  # `python three_body.py bench --ticks N` also works
+if sys.argv[1:2] == ["bench"]:
+    raise SystemExit(0)
 h = sim.history(["A.world_pos", "B.world_pos", "C.world_pos"])
 for k, v in h.items():
     print(k, "after", ticks, "ticks:", v[-1][4:])
