@@ -65,6 +65,8 @@ struct b200_sixdof {
     uint32_t *row_ptr = nullptr, *col_idx = nullptr;
     uint8_t *has_edge = nullptr;
     double *gforce = nullptr;
+    double *pos_alt = nullptr, *vel_alt = nullptr; // ping-pong planes of the one-launch n-body tick
+    bool nbody_fused = false;                       // decided once per handle (whole-batch grid size)
     // staging for AoS <-> SoA
     double *staging = nullptr;
     uint64_t staging_bytes = 0;
@@ -186,6 +188,12 @@ int build_graph(b200_sixdof *h, const b200_effector &e)
     CU(h, cudaMemcpy(h->has_edge, has.data(), has.size(), cudaMemcpyHostToDevice));
     CU(h, cudaMalloc(&h->gforce, 9ull * h->ld * 8ull));
     CU(h, cudaMemset(h->gforce, 0, 9ull * h->ld * 8ull));
+    if (h->desc.math_mode == B200_MATH_FAST && dense) {
+        CU(h, cudaMalloc(&h->pos_alt, 7ull * h->ld * 8ull));
+        CU(h, cudaMalloc(&h->vel_alt, 6ull * h->ld * 8ull));
+        CU(h, cudaMemset(h->pos_alt, 0, 7ull * h->ld * 8ull));
+        CU(h, cudaMemset(h->vel_alt, 0, 6ull * h->ld * 8ull));
+    }
     return B200_OK;
 }
 
@@ -239,6 +247,7 @@ int launch_ticks(b200_sixdof *h, uint64_t w0, uint64_t nw, uint64_t n_ticks, cud
     const bool graph = h->graph_eff >= 0;
     const uint64_t fuse = graph ? 1 : std::max<uint32_t>(1u, h->desc.max_fused_ticks);
     uint64_t left = n_ticks, done = 0;
+    double *pos_next = h->pos_alt ? h->pos_alt + b0 : nullptr, *vel_next = h->vel_alt ? h->vel_alt + b0 : nullptr;
     while (left) {
         const uint64_t n = std::min(left, fuse);
         if (graph) {
@@ -248,6 +257,19 @@ int launch_ticks(b200_sixdof *h, uint64_t w0, uint64_t nw, uint64_t n_ticks, cud
             G.ld = h->ld; G.n_entities = P.n_entities; G.n_worlds = (uint32_t)nw;
             G.dt_stage = P.dt_stage; G.kind = e.kind; G.integrator = h->desc.integrator;
             G.p0 = e.p[0]; G.p1 = e.p[1]; G.row_ptr = h->row_ptr; G.col_idx = h->col_idx;
+            if (h->nbody_fused) {
+                // gravity + integration in one launch; the new state lands in the other plane set
+                P.n_ticks = 1;
+                P.tick0 = h->ticks_done + done;
+                P.write_fa = (left == 1) ? 1u : 0u;
+                CU(h, launch_nbody_tick_fused(G, P, pos_next, vel_next, stream));
+                h->timings.kernel_launches++;
+                std::swap(P.pos, pos_next);
+                std::swap(P.vel, vel_next);
+                done += 1;
+                left -= 1;
+                continue;
+            }
             CU(h, launch_graph_force(G, h->desc.math_mode, h->graph_dense, stream));
             h->timings.kernel_launches++;
         }
@@ -262,11 +284,21 @@ int launch_ticks(b200_sixdof *h, uint64_t w0, uint64_t nw, uint64_t n_ticks, cud
     return B200_OK;
 }
 
+// After every world range has advanced n_ticks through the one-launch n-body tick, the live pose /
+// velocity planes are the "other" set when n_ticks is odd: make them the columns' planes.
+void commit_ping_pong(b200_sixdof *h, uint64_t n_ticks)
+{
+    if (!h->nbody_fused || !(n_ticks & 1) || h->n_bodies == 0) return;
+    std::swap(h->find(B200_ID_WORLD_POS)->dev, h->pos_alt);
+    std::swap(h->find(B200_ID_WORLD_VEL)->dev, h->vel_alt);
+}
+
 int do_step(b200_sixdof *h, uint64_t n_ticks)
 {
     if (h->status != B200_OK) return fail(h->status, "handle is in a failed state");
     int rc = launch_ticks(h, 0, h->desc.n_worlds, n_ticks, h->stream);
     if (rc) return rc;
+    commit_ping_pong(h, n_ticks);
     h->ticks_done += n_ticks;
     h->tick += n_ticks;
     h->timings.ticks += n_ticks;
@@ -470,6 +502,11 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
     if (h->graph_eff >= 0) {
         // copy the edge arrays' content now: the caller's pointers are only valid for this call
         if ((rc = build_graph(h, h->effectors[h->graph_eff]))) return bail(rc);
+        {
+            GraphParams G{};
+            G.n_entities = (uint32_t)d->n_entities; G.n_worlds = (uint32_t)d->n_worlds; G.integrator = d->integrator;
+            h->nbody_fused = h->pos_alt && nbody_fused_applicable(G, (int)d->math_mode, h->graph_dense);
+        }
         h->effectors[h->graph_eff].edge_from = h->effectors[h->graph_eff].edge_to = nullptr;
     }
     if (d->trajectory_every && d->trajectory_capacity) {
@@ -492,6 +529,8 @@ void b200_sixdof_destroy(b200_sixdof *h)
     if (h->col_idx) cudaFree(h->col_idx);
     if (h->has_edge) cudaFree(h->has_edge);
     if (h->gforce) cudaFree(h->gforce);
+    if (h->pos_alt) cudaFree(h->pos_alt);
+    if (h->vel_alt) cudaFree(h->vel_alt);
     if (h->staging) cudaFree(h->staging);
     if (h->stage_in) cudaFree(h->stage_in);
     if (h->stage_out) cudaFree(h->stage_out);
@@ -675,10 +714,14 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
         }
         int rc = launch_ticks(h, w0, nw, n_ticks, h->stream);
         if (rc) return rc;
+        const bool flipped = h->nbody_fused && (n_ticks & 1); // live pose / velocity sit in the other plane set
         for (size_t i = 0; i < h->output_ids.size(); ++i) {
             const Column *c = h->find(h->output_ids[i]);
             if (c->global || output_is_pass_through(c->id)) continue;
-            CU(h, launch_soa_to_aos(c->dev + b0, h->stage_out + out_off[i] + b0 * c->width, nb, c->width, h->ld, h->stream));
+            const double *live = c->dev;
+            if (flipped && c->id == B200_ID_WORLD_POS) live = h->pos_alt;
+            if (flipped && c->id == B200_ID_WORLD_VEL) live = h->vel_alt;
+            CU(h, launch_soa_to_aos(live + b0, h->stage_out + out_off[i] + b0 * c->width, nb, c->width, h->ld, h->stream));
             h->timings.kernel_launches++;
         }
         CU(h, cudaEventRecord(h->chunk_out[k], h->stream));
@@ -693,6 +736,7 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
                                   nb * c->width * 8, cudaMemcpyDefault, h->copy_out));
         }
     }
+    commit_ping_pong(h, n_ticks);
     h->ticks_done += n_ticks;
     h->tick += n_ticks;
     h->timings.ticks += n_ticks;

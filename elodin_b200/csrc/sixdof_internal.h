@@ -64,6 +64,9 @@ struct GraphParams {
 // kernel launchers (sixdof_kernels.cu); every one returns the launch status
 cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode, cudaStream_t s);
 cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, cudaStream_t s);
+// one-launch n-body tick (gravity + integration) for small grids; new pose / velocity go to *_out
+bool nbody_fused_applicable(const GraphParams &G, int math_mode, bool dense);
+cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, double *pos_out, double *vel_out, cudaStream_t s);
 cudaError_t launch_aos_to_soa(const double *aos, double *soa, uint64_t n_bodies, uint32_t width, uint64_t ld,
                               cudaStream_t s);
 cudaError_t launch_soa_to_aos(const double *soa, double *aos, uint64_t n_bodies, uint32_t width, uint64_t ld,

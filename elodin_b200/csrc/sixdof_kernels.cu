@@ -659,18 +659,21 @@ __global__ void __launch_bounds__(kBlockG * 3) graph_dense_kernel(const __grid_c
 // slots of a CTA share one shared-memory tile of stage positions, and N = 1024, M = 1 still
 // spreads over 128 CTAs x 24 warps.
 static constexpr int kFastSrc = 8;
-static constexpr int kFastTJ = 256;
 
 // SPLIT = true : blockDim (32, kFastSrc, NS), one warp per (source, slot)  — small batches
 // SPLIT = false: blockDim (32, kFastSrc, 1),  one warp per source, NS slots — large batches
-template <bool RK4, bool SPLIT>
+// TJ = targets per shared-memory tile: 256 (3 CTAs/SM) for big grids; 1024 for small grids, where
+// the whole world of an N <= 1024 system is staged in ONE load phase instead of four dependent ones.
+template <bool RK4, bool SPLIT, int TJ>
 __global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) graph_dense_fast_kernel(const __grid_constant__ GraphParams G)
 {
     constexpr int NS = RK4 ? 3 : 1;       // stage slots of a tick
     constexpr int NW = SPLIT ? 1 : NS;    // slots folded by one warp
     constexpr int NT = 32 * kFastSrc * (SPLIT ? NS : 1);
-    __shared__ double sx[NS][3][kFastTJ];
-    __shared__ double sm[kFastTJ];
+    constexpr int kFastTJ = TJ;
+    extern __shared__ double dsm[];
+    double(*sx)[3][TJ] = reinterpret_cast<double(*)[3][TJ]>(dsm);
+    double *sm = dsm + NS * 3 * TJ;
 
     const uint32_t N = G.n_entities;
     const uint32_t groups = (N + kFastSrc - 1) / kFastSrc;
@@ -751,6 +754,103 @@ __global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) grap
             stp(G.gforce, G.ld, (sl0 + s) * 3 + 0, b, k * acc[s].x);
             stp(G.gforce, G.ld, (sl0 + s) * 3 + 1, b, k * acc[s].y);
             stp(G.gforce, G.ld, (sl0 + s) * 3 + 2, b, k * acc[s].z);
+        }
+    }
+}
+
+// Small grids (one or a few worlds): gravity AND the body tick in ONE launch.  The CTA computes the
+// three stage-slot forces of its 8 sources exactly like graph_dense_fast_kernel<RK4, SPLIT>, then 8 of
+// its threads integrate those sources.  Other CTAs are still reading this tick's positions, so the
+// new pose / velocity go to a second set of planes (ping-pong, swapped by the host after the launch).
+// Saves the dependent second launch (~7 us of pure latency per tick at N = 1024, M = 1).
+template <int TJ>
+__global__ void __launch_bounds__(32 * kFastSrc * 3) nbody_tick_fused_kernel(const __grid_constant__ GraphParams G,
+                                                                              const __grid_constant__ StepParams P,
+                                                                              double *__restrict__ pos_out,
+                                                                              double *__restrict__ vel_out)
+{
+    constexpr int NS = 3;
+    constexpr int NT = 32 * kFastSrc * NS;
+    extern __shared__ double dsm[];
+    double(*sx)[3][TJ] = reinterpret_cast<double(*)[3][TJ]>(dsm);
+    double *sm = dsm + NS * 3 * TJ;
+
+    const uint32_t N = G.n_entities;
+    const uint32_t groups = (N + kFastSrc - 1) / kFastSrc;
+    const uint32_t world = blockIdx.x / groups;
+    const uint32_t grp = blockIdx.x % groups;
+    const uint32_t lane = threadIdx.x, src = threadIdx.y, sl = threadIdx.z;
+    const uint32_t flat = (sl * kFastSrc + src) * 32 + lane;
+    const uint32_t i = grp * kFastSrc + src;
+    const uint64_t wbase = (uint64_t)world * N;
+    const bool active = i < N;
+    const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
+    const double soft = newton ? 0.0 : G.p1;
+    auto dtf_of = [&](uint32_t k) { return k == 0 ? 0.0 : (k == 1 ? 0.5 * G.dt_stage : G.dt_stage); };
+
+    Vec3 xi = {0, 0, 0}, acc = {0, 0, 0};
+    double mi = 0.0;
+    if (active) {
+        const uint64_t b = wbase + i;
+        const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+        const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+        mi = ldp(G.ine, G.ld, 6, b);
+        xi = stage_pos<false>(x, v, dtf_of(sl));
+    }
+    for (uint32_t j0 = 0; j0 < N; j0 += TJ) {
+        __syncthreads();
+        for (uint32_t t = flat; t < TJ * NS; t += NT) {
+            const uint32_t jt = t % TJ, st = t / TJ;
+            const uint32_t j = j0 + jt;
+            if (j < N) {
+                const uint64_t b = wbase + j;
+                const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+                const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+                const Vec3 pnt = stage_pos<false>(x, v, dtf_of(st));
+                sx[st][0][jt] = pnt.x; sx[st][1][jt] = pnt.y; sx[st][2][jt] = pnt.z;
+                if (st == 0) sm[jt] = ldp(G.ine, G.ld, 6, b);
+            }
+        }
+        __syncthreads();
+        const uint32_t jn = min((uint32_t)TJ, N - j0);
+        if (active) {
+#pragma unroll 4
+            for (uint32_t jj = lane; jj < jn; jj += 32) {
+                const bool self = j0 + jj == i;
+                const Vec3 r = {sx[sl][0][jj] - xi.x, sx[sl][1][jj] - xi.y, sx[sl][2][jj] - xi.z};
+                const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, soft)));
+                const double inv = fa::rsqrt_nr(d2);
+                const double w = self ? 0.0 : sm[jj] * inv * inv * inv;
+                acc.x = fma(w, r.x, acc.x); acc.y = fma(w, r.y, acc.y); acc.z = fma(w, r.z, acc.z);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+    }
+    if (active && lane == 0) {
+        const uint64_t b = wbase + i;
+        const double k = G.p0 * mi;
+        stp(G.gforce, G.ld, sl * 3 + 0, b, k * acc.x);
+        stp(G.gforce, G.ld, sl * 3 + 1, b, k * acc.y);
+        stp(G.gforce, G.ld, sl * 3 + 2, b, k * acc.z);
+    }
+    __syncthreads(); // the CTA's gforce entries are visible to its integrating threads
+    if (active && lane == 0 && sl == 0) {
+        const uint64_t b = wbase + i;
+        Pose x0 = load_pose(P.pos, P.ld, b);
+        Motion v0 = load_motion(P.vel, P.ld, b);
+        const Inertia I = load_inertia(P.ine, P.ld, b);
+        Motion a_last, f_last;
+        fast_ticks<B200_INTEGRATOR_RK4>(P, b, x0, v0, I, a_last, f_last);
+        store_pose(pos_out, P.ld, b, x0);
+        store_motion(vel_out, P.ld, b, v0);
+        if (P.write_fa) {
+            store_motion(P.acc, P.ld, b, a_last);
+            store_motion(P.frc, P.ld, b, f_last);
         }
     }
 }
@@ -924,9 +1024,16 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
             // few CTAs: split the stage slots over warps to fill the machine; many CTAs: keep
             // 3 slots per warp (more ILP per lane, 3 CTAs/SM) — measured on N = 1024, M = 1 / 8
             const bool split = gcfg == 2 || (gcfg == 1 && gridf < 3u * 148u);
-            if (!rk4) graph_dense_fast_kernel<false, false><<<gridf, dim3(32, kFastSrc, 1), 0, s>>>(G);
-            else if (split) graph_dense_fast_kernel<true, true><<<gridf, dim3(32, kFastSrc, 3), 0, s>>>(G);
-            else graph_dense_fast_kernel<true, false><<<gridf, dim3(32, kFastSrc, 1), 0, s>>>(G);
+            constexpr size_t smem256 = (3 * 3 + 1) * 256 * sizeof(double), smem1024 = (3 * 3 + 1) * 1024 * sizeof(double);
+            if (!rk4) graph_dense_fast_kernel<false, false, 256><<<gridf, dim3(32, kFastSrc, 1), smem256, s>>>(G);
+            else if (split) {
+                static bool attr_set = false;
+                if (!attr_set) {
+                    cudaFuncSetAttribute(graph_dense_fast_kernel<true, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1024);
+                    attr_set = true;
+                }
+                graph_dense_fast_kernel<true, true, 1024><<<gridf, dim3(32, kFastSrc, 3), smem1024, s>>>(G);
+            } else graph_dense_fast_kernel<true, false, 256><<<gridf, dim3(32, kFastSrc, 1), smem256, s>>>(G);
         }
     } else {
         const uint64_t total = (uint64_t)G.n_entities * G.n_worlds;
@@ -934,6 +1041,27 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
         if (exact) { if (rk4) graph_csr_kernel<true, true><<<grid, kBlockG, 0, s>>>(G); else graph_csr_kernel<true, false><<<grid, kBlockG, 0, s>>>(G); }
         else { if (rk4) graph_csr_kernel<false, true><<<grid, kBlockG, 0, s>>>(G); else graph_csr_kernel<false, false><<<grid, kBlockG, 0, s>>>(G); }
     }
+    return cudaGetLastError();
+}
+
+bool nbody_fused_applicable(const GraphParams &G, int math_mode, bool dense)
+{
+    if (math_mode != B200_MATH_FAST || !dense || G.integrator != B200_INTEGRATOR_RK4) return false;
+    static const int fcfg = [] { const char *e = getenv("B200_NBODY_FUSED"); return e ? atoi(e) : 1; }();
+    const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
+    return fcfg != 0 && gridf < 3u * 148u; // the same "small grid" rule as the split gravity kernel
+}
+
+cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, double *pos_out, double *vel_out, cudaStream_t s)
+{
+    constexpr size_t smem = (3 * 3 + 1) * 1024 * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(nbody_tick_fused_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
+    nbody_tick_fused_kernel<1024><<<gridf, dim3(32, kFastSrc, 3), smem, s>>>(G, P, pos_out, vel_out);
     return cudaGetLastError();
 }
 

@@ -748,3 +748,28 @@ def test_per_world_drag_parameters(oracle):
     # and it differs from constant parameters (the column values are really used)
     other = _run_gpu(pos, vel, ine, [el.GravityConst(), el.DragQuadratic(0.6, 0.005, "wind")], {"wind": col[..., :3]}, 0.01, 8, "exact")
     assert not np.array_equal(other[1], got[1])
+
+
+@pytest.mark.parametrize("n_ticks", [1, 5, 6])
+def test_fused_nbody_tick_ping_pong(oracle, n_ticks):
+    """Small-grid FAST n-body runs gravity + integration in one launch with ping-pong pose/velocity
+    planes: odd and even tick counts, step() and chunked invoke_batch, repeated calls."""
+    O = oracle
+    M, N = 9, 70
+    pos, vel, ine = random_world(61, M, N)
+    pos[..., 4:] *= 1e-2
+    o, g, _ = effector_pair(O, "softened", edges=el.all_pairs_edges(N), k2=0.3, soft=1e-5)
+    want = _run_oracle(O, pos, vel, ine, [o], 0.01, 2 * n_ticks)
+    with el.B200Exec(N, M, 0.01, None, [g], "rk4", "fast", invoke_chunk_bodies=4 * N) as ex:
+        ex.set_state(pos, vel, ine)
+        ex.step(n_ticks, sync=True)                      # first half through step()
+        mid = (ex.download(WORLD_POS), ex.download(WORLD_VEL))
+        table = {el.component_id("tick"): np.array([n_ticks], dtype=np.uint64), FORCE: np.zeros((M, N, 6)), INERTIA: ine,
+                 WORLD_POS: mid[0], WORLD_ACCEL: np.zeros((M, N, 6)), el.component_id("simulation_time_step"): np.array([0.01]),
+                 WORLD_VEL: mid[1]}
+        out = dict(zip(ex.output_ids, ex.invoke_batch([table[c] for c in ex.input_ids], n_ticks)))  # second half, chunked
+        got = (out[WORLD_POS], out[WORLD_VEL], out[WORLD_ACCEL], out[FORCE])
+        _assert_close(got, want, 1e-11, f"fused n-body {n_ticks}")
+        # the device-resident state agrees with what invoke_batch returned
+        assert np.array_equal(ex.download(WORLD_POS), out[WORLD_POS]) and np.array_equal(ex.download(WORLD_VEL), out[WORLD_VEL])
+        assert int(out[el.component_id("tick")][0]) == 2 * n_ticks
