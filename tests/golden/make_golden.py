@@ -4,7 +4,7 @@ Run in the build container (where /root/reference is mounted):
 
     python tests/golden/make_golden.py
 
-Reads  /root/reference/scripts/ci/baseline/{three-body,rocket,ball}-csv/*.csv
+Reads  /root/reference/scripts/ci/baseline/{three-body,rocket,ball,cube-sat}-csv/*.csv
        (101 rows each, written by the reference's `bench --ticks 100` +
         `elodin-db export --format csv --flatten`, scripts/ci/regress.sh)
 Writes tests/golden/elodin_ci_baseline.npz   (f64 arrays, bit-exact copies of
@@ -49,6 +49,11 @@ def main() -> int:
     for comp in ("world_pos", "world_vel", "world_accel", "force", "inertia", "wind"):
         out[f"ball.{comp}"] = read("ball", f"ball.{comp}")
     out["ball.simulation_time_step"] = read("ball", "globals.simulation_time_step")
+    # cube-sat runs Integrator.SemiImplicit (examples/cube-sat/main.py:710); its `earth` entity is a free
+    # spinning body (zero force), which pins semi_implicit.rs:42-62 without needing the EGM08 / reaction-wheel models
+    for comp in ("world_pos", "world_vel", "world_accel", "force", "inertia"):
+        out[f"cube_sat.earth.{comp}"] = read("cube-sat", f"earth.{comp}")
+    out["cube_sat.simulation_time_step"] = read("cube-sat", "globals.simulation_time_step")
     # layout of the exported directory (file stems + header rows), for the CSV-export parity test
     layout = {}
     d = os.path.join(BASE, "three-body-csv")

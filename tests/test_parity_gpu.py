@@ -773,3 +773,22 @@ def test_fused_nbody_tick_ping_pong(oracle, n_ticks):
         # the device-resident state agrees with what invoke_batch returned
         assert np.array_equal(ex.download(WORLD_POS), out[WORLD_POS]) and np.array_equal(ex.download(WORLD_VEL), out[WORLD_VEL])
         assert int(out[el.component_id("tick")][0]) == 2 * n_ticks
+
+
+def test_cube_sat_earth_semi_implicit_golden(golden):
+    """SemiImplicit on the GPU vs the reference's cube-sat golden (`earth` entity, 100 rows):
+    EXACT bit for bit through the trajectory ring, FAST within tolerance."""
+    g = golden
+    dt = float(g["cube_sat.simulation_time_step"][0, 0])
+    p0, v0, i0 = (g[f"cube_sat.earth.{c}"][0][None, None] for c in ("world_pos", "world_vel", "inertia"))
+    with el.B200Exec(1, 1, dt, None, [], "semi_implicit", "exact", max_fused_ticks=10, trajectory_every=1,
+                     trajectory_capacity=100) as ex:
+        ex.set_state(p0, v0, i0)
+        ex.step(100, sync=True)
+        traj = ex.trajectory()
+        acc = ex.download(WORLD_ACCEL)
+    assert np.array_equal(traj[:, 0, 0, :7], g["cube_sat.earth.world_pos"][1:])
+    assert np.array_equal(traj[:, 0, 0, 7:], g["cube_sat.earth.world_vel"][1:])
+    assert np.array_equal(acc[0, 0], g["cube_sat.earth.world_accel"][100])
+    fast = _run_gpu(p0, v0, i0, [], {}, dt, 100, "fast", "semi_implicit")
+    assert max_rel(fast[0][0], g["cube_sat.earth.world_pos"][100][None]) < 1e-13
