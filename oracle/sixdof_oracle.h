@@ -7,8 +7,9 @@
  * product (elodin_b200/csrc) never links or calls it.
  *
  * Parity status: PINNED against the reference's own golden telemetry
- * (scripts/ci/baseline/{three-body,rocket,ball}-csv, repacked under
- * tests/golden/ by tests/golden/make_golden.py) and its known-answer tests
+ * (scripts/ci/baseline/{three-body,rocket,ball}-csv for RK4 and the `earth`
+ * entity of cube-sat-csv for SemiImplicit, repacked under tests/golden/ by
+ * tests/golden/make_golden.py) and its known-answer tests
  * (libs/nox/src/spatial.rs:630-676, libs/nox/src/quaternion.rs:352-388,
  * libs/nox-py/python/tests/test_all.py:67-83,228-291,342-366).
  * UNPINNED (no golden in the reference): softened n-body gravity at N>3 and the
