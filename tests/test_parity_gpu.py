@@ -792,3 +792,88 @@ def test_cube_sat_earth_semi_implicit_golden(golden):
     assert np.array_equal(acc[0, 0], g["cube_sat.earth.world_accel"][100])
     fast = _run_gpu(p0, v0, i0, [], {}, dt, 100, "fast", "semi_implicit")
     assert max_rel(fast[0][0], g["cube_sat.earth.world_pos"][100][None]) < 1e-13
+
+
+# --------------------------------------------------------------------------- fuzz + edge cases
+
+
+def _random_program(rng, M, N):
+    """A random ordered effector list (kinds may repeat in EXACT) with its columns."""
+    kinds = ["gravity", "thrust", "wrench", "drag", "frame", "wrench_lin"]
+    n = int(rng.integers(0, 6))
+    specs, have_cols = [], set()
+    for k in rng.choice(kinds, size=n, replace=True):
+        if k == "gravity":
+            specs.append(("gravity", {"g": tuple(rng.normal(0, 5, 3))}))
+        elif k == "thrust" and "thrust" not in have_cols:
+            have_cols.add("thrust")
+            specs.append(("thrust", {"thrust": rng.uniform(-50, 300, (M, N, 1)), "axis": tuple(rng.normal(0, 1, 3))}))
+        elif k in ("wrench", "wrench_lin") and "aero_force" not in have_cols:
+            have_cols.add("aero_force")
+            specs.append(("wrench", {"wrench": rng.normal(0, 4, (M, N, 6)), "linear_first": k == "wrench_lin"}))
+        elif k == "drag" and "wind" not in have_cols:
+            have_cols.add("wind")
+            specs.append(("drag", {"wind": rng.normal(0, 2, (M, N, 3)), "cd_rho": float(rng.uniform(0.1, 1)), "area": float(rng.uniform(0.001, 0.1))}))
+        elif k == "frame" and "frame" not in have_cols:
+            have_cols.add("frame")
+            specs.append(("frame", {"mu": float(rng.uniform(1e3, 1e5)), "omega": tuple(rng.normal(0, 1e-2, 3))}))
+    return specs
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_fuzz_random_effector_programs(oracle, case):
+    """Random ordered effector programs x sizes x integrator x tick fusion x invoke chunking:
+    EXACT == oracle bit for bit; FAST within tolerance."""
+    O = oracle
+    rng = np.random.default_rng(9000 + case)
+    M, N = int(rng.integers(1, 40)), int(rng.integers(1, 9))
+    ticks = int(rng.integers(1, 9))
+    integrator = "rk4" if rng.random() < 0.7 else "semi_implicit"
+    time_step = None if rng.random() < 0.6 else float(rng.uniform(0.002, 0.02))
+    fused = int(rng.choice([1, 2, 7, 64]))
+    pos, vel, ine = random_world(7000 + case, M, N, unit_q=rng.random() < 0.8)
+    pos[..., 4:] = pos[..., 4:] * 0.1 + 50.0  # keep |r| away from 0 for the frame effector
+    specs = _random_program(rng, M, N)
+    oeffs, geffs, cols = [], [], {}
+    for kind, kw in specs:
+        o, g, c = effector_pair(O, kind, **kw)
+        oeffs.append(o); geffs.append(g); cols.update(c)
+    acc0 = rng.normal(0, 1, (M, N, 6))
+    dt = float(rng.uniform(1e-3, 1e-2))
+    want = _run_oracle(O, pos, vel, ine, oeffs, dt, ticks, integrator, time_step, accel=acc0)
+    got = _run_gpu(pos, vel, ine, geffs, cols, dt, ticks, "exact", integrator, time_step, fused, accel=acc0)
+    _assert_exact(got, want, f"fuzz {case} {[k for k, _ in specs]} M={M} N={N} {integrator}")
+    fast = _run_gpu(pos, vel, ine, geffs, cols, dt, ticks, "fast", integrator, time_step, fused, accel=acc0)
+    _assert_close(fast, want, ticks * 2e-12, f"fuzz fast {case}")
+
+
+def test_edge_cases_nan_inf_zero(oracle):
+    """Degenerate inputs behave like the reference arithmetic: zero quaternion (0/0), zero mass and
+    zero inertia (x/0), zero relative wind in the drag (0/0), huge and denormal values.  EXACT must
+    agree with the oracle including where the NaNs / infs land."""
+    O = oracle
+    M, N = 1, 8
+    pos, vel, ine = random_world(3, M, N)
+    pos[0, 0, :4] = 0.0                      # zero quaternion -> NaN attitude
+    ine[0, 1, 6] = 0.0                       # zero mass -> inf / NaN linear accel
+    ine[0, 2, 0] = 0.0                       # zero Ixx
+    vel[0, 3, 3:] = [1.0, 2.0, 3.0]          # wind == velocity -> drag direction 0/0
+    pos[0, 4, 4:] = 1e300                    # huge
+    vel[0, 5, :] = 5e-324                    # denormal
+    pos[0, 6, 4:] = -0.0                     # signed zeros
+    vel[0, 6, 3:] = -0.0
+    wind = np.zeros((M, N, 3)); wind[0, 3] = [1.0, 2.0, 3.0]; wind[0, [0, 1, 2, 4, 5, 6, 7]] = 0.5
+    og, gg, _ = effector_pair(O, "gravity")
+    od, gd, c1 = effector_pair(O, "drag", wind=wind, cd_rho=0.6, area=0.01)
+    ow, gw, c2 = effector_pair(O, "wrench", wrench=np.full((M, N, 6), 0.25))
+    want = _run_oracle(O, pos, vel, ine, [og, od, ow], 0.01, 3)
+    got = _run_gpu(pos, vel, ine, [gg, gd, gw], {**c1, **c2}, 0.01, 3, "exact")
+    for name, a, b in zip(("pos", "vel", "accel", "force"), got, want):
+        assert np.array_equal(a, b, equal_nan=True), name
+        assert np.array_equal(np.signbit(a[np.isfinite(b)]), np.signbit(b[np.isfinite(b)])), name  # signed zeros too
+    assert np.isnan(got[0][0, 0]).any() and np.isnan(got[1][0, 3, 3:]).all()  # the degenerate bodies really are degenerate
+    assert np.isfinite(got[0][0, 7]).all()                                      # and they do not contaminate a healthy one
+    fast = _run_gpu(pos, vel, ine, [gg, gd, gw], {**c1, **c2}, 0.01, 3, "fast")
+    assert np.isnan(fast[1][0, 3, 3:]).all() and np.isnan(fast[0][0, 0, :4]).all()  # FAST keeps the 0/0 semantics
+    ok = [6, 7]
+    _assert_close([a[:, ok] for a in fast], [b[:, ok] for b in want], 3 * FAST_TOL_TICK, "healthy bodies, fast")
