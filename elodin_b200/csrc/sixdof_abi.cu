@@ -314,14 +314,9 @@ int do_upload(b200_sixdof *h, uint64_t id, const void *src, uint64_t bytes)
                     (unsigned long long)id, (unsigned long long)column_bytes(h, *c), (unsigned long long)bytes);
     if (!src) return fail(B200_ERR_INVALID_ARGUMENT, "null source buffer");
     if (c->global) {
+        // the two globals are 8-byte host scalars (Globals entity, world.rs:174-191)
         uint64_t raw;
-        cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
-            CU(h, cudaMemcpy(&raw, src, 8, cudaMemcpyDeviceToHost));
-        } else {
-            (void)cudaGetLastError();
-            std::memcpy(&raw, src, 8);
-        }
+        std::memcpy(&raw, src, 8);
         if (id == B200_ID_TICK) h->tick = raw;
         else std::memcpy(&h->sim_time_step, &raw, 8);
         return B200_OK;
@@ -347,13 +342,7 @@ int do_download(b200_sixdof *h, uint64_t id, void *dst, uint64_t bytes)
         uint64_t raw;
         if (id == B200_ID_TICK) raw = h->tick;
         else std::memcpy(&raw, &h->sim_time_step, 8);
-        cudaPointerAttributes at{};
-        if (cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
-            CU(h, cudaMemcpy(dst, &raw, 8, cudaMemcpyHostToDevice));
-        } else {
-            (void)cudaGetLastError();
-            std::memcpy(dst, &raw, 8);
-        }
+        std::memcpy(dst, &raw, 8);
         return B200_OK;
     }
     if (bytes == 0) return B200_OK;

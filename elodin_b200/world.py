@@ -545,19 +545,47 @@ class Exec:
             self._history[cid].append(col.buffer.copy())
         self._globals_hist.append((self.tick, self.sim_time_step))
 
+    def _bind_buffers(self) -> None:
+        """Pointer tables for invoke_batch, built once: inputs are the world's own column buffers
+        (updated in place, so the addresses are stable), outputs are executor-owned buffers that never
+        alias an input (cranelift_exec.rs:101-107,138-154)."""
+        be = self.backend
+        self._tick_in = np.zeros(1, dtype=np.uint64)
+        self._dt_in = np.array([self.sim_time_step])
+        self._ins, self._outs = [], []
+        for cid in be.input_ids:
+            if cid == component_id("tick"):
+                self._ins.append(self._tick_in)
+            elif cid == component_id("simulation_time_step"):
+                self._ins.append(self._dt_in)
+            else:
+                buf = self.world.columns[cid].buffer
+                assert buf.flags.c_contiguous and buf.nbytes == be.column_bytes(cid)
+                self._ins.append(buf)
+        for cid in be.output_ids:
+            if cid in (component_id("tick"), component_id("simulation_time_step")):
+                self._outs.append(np.zeros(1, dtype=np.uint64 if cid == component_id("tick") else np.float64))
+            else:
+                self._outs.append(np.empty_like(self.world.columns[cid].buffer))
+        self._in_ptrs = [a.ctypes.data for a in self._ins]
+        self._out_ptrs = [a.ctypes.data for a in self._outs]
+
     def _invoke(self, n: int) -> None:
         """WorldExec::run -> invoke_batch (cranelift_exec.rs:284-303,129-195)."""
         be = self.backend
-        ins = [self._host_col(cid) for cid in be.input_ids]
-        outs = be.invoke_batch(ins, n)
-        for cid, buf in zip(be.output_ids, outs):
+        if not hasattr(self, "_in_ptrs"):
+            self._bind_buffers()
+        self._tick_in[0] = self.tick
+        self._dt_in[0] = self.sim_time_step
+        be.invoke_batch_ptrs(self._in_ptrs, self._out_ptrs, n)
+        for cid, buf in zip(be.output_ids, self._outs):
             if cid == component_id("tick"):
                 self.tick = int(buf[0])  # world.advance_tick() x n
             elif cid != component_id("simulation_time_step"):
                 col = self.world.columns[cid]
                 if col.buffer.nbytes != buf.nbytes:
                     raise _lib.B200ValueError(_lib.ERR_VALUE_SIZE_MISMATCH, "value size mismatch")
-                col.buffer[...] = buf.reshape(col.buffer.shape)
+                np.copyto(col.buffer, buf)
 
     # -- public API ------------------------------------------------------------------
     def run(self, ticks: int = 1, show_progress: bool = True, is_canceled=None, pre_step=None, post_step=None):
