@@ -80,6 +80,9 @@ struct b200_sixdof {
     double *stage_in = nullptr, *stage_out = nullptr;
     uint64_t stage_in_bytes = 0, stage_out_bytes = 0;
     std::vector<cudaEvent_t> chunk_in, chunk_out;
+    // small batches: packed pinned host staging (one PCIe transfer per direction)
+    uint8_t *host_pack = nullptr;
+    uint64_t host_pack_bytes = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [0,1] H2D span, [2,3] compute span, [4,5] D2H span
     int status = B200_OK;
     b200_timings timings{};
@@ -526,6 +529,7 @@ void b200_sixdof_destroy(b200_sixdof *h)
     if (h->traj) cudaFree(h->traj);
     for (auto &e : h->chunk_in) if (e) cudaEventDestroy(e);
     for (auto &e : h->chunk_out) if (e) cudaEventDestroy(e);
+    if (h->host_pack) cudaFreeHost(h->host_pack);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -602,6 +606,76 @@ static bool output_is_pass_through(uint64_t id)
 {
     return id != B200_ID_WORLD_POS && id != B200_ID_WORLD_VEL && id != B200_ID_WORLD_ACCEL && id != B200_ID_FORCE &&
            id != B200_ID_TICK && id != B200_ID_SIMULATION_TIME_STEP;
+}
+
+// Small batches (interactive single-vehicle sims: the reference's everyday case) are bound by the
+// number of driver calls, not by bytes: pack every live input column into one pinned block, ONE
+// host->device copy, ONE layout launch for all columns, the ticks, ONE layout launch, ONE copy back.
+static int invoke_small(b200_sixdof *h, const uint8_t *const *in_cols, uint8_t *const *out_cols, uint64_t n_ticks)
+{
+    MultiColumns mi{}, mo{};
+    uint64_t in_total = 0, out_total = 0;
+    std::vector<std::pair<size_t, uint64_t>> in_map, out_map; // (column index, byte offset in the packed block)
+    for (size_t i = 0; i < h->input_ids.size(); ++i) {
+        Column *c = h->find(h->input_ids[i]);
+        if (c->global) { int rc = do_upload(h, c->id, in_cols[i], 8); if (rc) return rc; continue; }
+        if (!input_is_live(h, c->id)) continue;
+        mi.col[mi.n++] = {in_total, c->dev, c->width, 0};
+        in_map.push_back({i, in_total * 8});
+        in_total += h->n_bodies * c->width;
+    }
+    for (size_t i = 0; i < h->output_ids.size(); ++i) {
+        Column *c = h->find(h->output_ids[i]);
+        if (c->global || output_is_pass_through(c->id)) continue;
+        mo.col[mo.n++] = {out_total, c->dev, c->width, 0};
+        out_map.push_back({i, out_total * 8});
+        out_total += h->n_bodies * c->width;
+    }
+    const uint64_t need = std::max(in_total, out_total) * 8;
+    if (h->host_pack_bytes < need) {
+        if (h->host_pack) cudaFreeHost(h->host_pack);
+        h->host_pack = nullptr; h->host_pack_bytes = 0;
+        CU(h, cudaHostAlloc((void **)&h->host_pack, std::max<uint64_t>(need, 4096), cudaHostAllocDefault));
+        h->host_pack_bytes = std::max<uint64_t>(need, 4096);
+    }
+    int rc = ensure_staging(h, std::max<uint64_t>(need, 8));
+    if (rc) return rc;
+    for (auto &m : in_map) {
+        const Column *c = h->find(h->input_ids[m.first]);
+        std::memcpy(h->host_pack + m.second, in_cols[m.first], h->n_bodies * c->width * 8);
+    }
+    mi.packed = mo.packed = h->staging;
+    if (in_total) {
+        CU(h, cudaMemcpyAsync(h->staging, h->host_pack, in_total * 8, cudaMemcpyHostToDevice, h->stream));
+        CU(h, launch_multi_transpose(mi, h->n_bodies, h->ld, true, h->stream));
+        h->timings.kernel_launches++;
+    }
+    rc = launch_ticks(h, 0, h->desc.n_worlds, n_ticks, h->stream);
+    if (rc) return rc;
+    commit_ping_pong(h, n_ticks);
+    for (uint32_t k = 0; k < mo.n; ++k) mo.col[k].soa = h->find(h->output_ids[out_map[k].first])->dev; // after a ping-pong swap
+    h->ticks_done += n_ticks;
+    h->tick += n_ticks;
+    h->timings.ticks += n_ticks;
+    if (out_total) {
+        CU(h, launch_multi_transpose(mo, h->n_bodies, h->ld, false, h->stream));
+        h->timings.kernel_launches++;
+        CU(h, cudaMemcpyAsync(h->host_pack, h->staging, out_total * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (auto &m : out_map) {
+        const Column *c = h->find(h->output_ids[m.first]);
+        std::memcpy(out_cols[m.first], h->host_pack + m.second, h->n_bodies * c->width * 8);
+    }
+    for (size_t i = 0; i < h->output_ids.size(); ++i) {
+        const Column *c = h->find(h->output_ids[i]);
+        if (c->global) { rc = do_download(h, c->id, out_cols[i], 8); if (rc) return rc; continue; }
+        if (!output_is_pass_through(c->id)) continue;
+        for (size_t k = 0; k < h->input_ids.size(); ++k)
+            if (h->input_ids[k] == c->id && in_cols[k] != out_cols[i]) std::memcpy(out_cols[i], in_cols[k], h->n_bodies * c->width * 8);
+    }
+    h->timings.h2d_upload_ms = h->timings.kernel_invoke_ms = h->timings.d2h_download_ms = 0.0; // not separable here
+    return B200_OK;
 }
 
 static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8_t *const *out_cols, uint64_t n_ticks,
@@ -766,7 +840,25 @@ int b200_sixdof_invoke_batch(b200_sixdof *h, const uint8_t *const *in_cols, uint
     if (h->n_bodies == 0) wpc = std::max<uint64_t>(h->desc.n_worlds, 1);
 
     auto t0 = std::chrono::steady_clock::now();
-    int rc = invoke_pipelined(h, in_cols, out_cols, n_ticks, wpc);
+    // host pointers only on the small path (it packs with memcpy); device-resident callers use the pipeline
+    bool small = h->n_bodies > 0 && h->n_bodies * 32ull * 8ull <= (256ull << 10) && h->input_ids.size() <= 16 &&
+                 !h->desc.invoke_chunk_bodies;
+    if (small) { // the packed path memcpy()s: only for host-resident caller buffers
+        for (size_t i = 0; i < h->input_ids.size() && small; ++i) {
+            if (h->find(h->input_ids[i])->global) continue;
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, in_cols[i]) == cudaSuccess && at.type == cudaMemoryTypeDevice) small = false;
+            break;
+        }
+        for (size_t i = 0; i < h->output_ids.size() && small; ++i) {
+            if (h->find(h->output_ids[i])->global) continue;
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, out_cols[i]) == cudaSuccess && at.type == cudaMemoryTypeDevice) small = false;
+            break;
+        }
+        (void)cudaGetLastError();
+    }
+    int rc = small ? invoke_small(h, in_cols, out_cols, n_ticks) : invoke_pipelined(h, in_cols, out_cols, n_ticks, wpc);
     if (rc) return rc;
     h->timings.invoke_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return B200_OK;

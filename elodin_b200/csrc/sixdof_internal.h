@@ -61,6 +61,20 @@ struct GraphParams {
     const uint32_t *col_idx;
 };
 
+// Column table of the one-launch layout kernel used by small batches
+struct MultiColumns {
+    struct Col {
+        uint64_t aos_offset; // doubles from `packed`
+        double *soa;         // plane 0 of the device column
+        uint32_t width;
+        uint32_t pad;
+    };
+    double *packed;          // packed AoS staging (device)
+    uint32_t n;
+    uint32_t pad;
+    Col col[16];
+};
+
 // kernel launchers (sixdof_kernels.cu); every one returns the launch status
 cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode, cudaStream_t s);
 cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, cudaStream_t s);
@@ -73,6 +87,7 @@ cudaError_t launch_soa_to_aos(const double *soa, double *aos, uint64_t n_bodies,
                               cudaStream_t s);
 cudaError_t launch_traj_to_aos(const double *traj, double *aos, uint64_t n_samples, uint64_t n_bodies, uint64_t ld,
                                cudaStream_t s);
+cudaError_t launch_multi_transpose(const MultiColumns &mc, uint64_t n_bodies, uint64_t ld, bool to_soa, cudaStream_t s);
 cudaError_t launch_probe_fp64(double *out, int iters, int blocks, cudaStream_t s);
 
 } // namespace b200

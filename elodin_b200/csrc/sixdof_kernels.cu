@@ -942,6 +942,31 @@ __global__ void __launch_bounds__(kTile) soa_to_aos_kernel(const double *__restr
     for (uint32_t i = threadIdx.x; i < nb * width; i += kTile) dst[i] = tile[(i / width) * pitch + (i % width)];
 }
 
+// All columns of a small batch in one launch: blockIdx.y selects the column, the AoS side of every
+// column lives in one packed staging buffer (one PCIe transfer per direction per invoke_batch).
+__global__ void __launch_bounds__(kTile) multi_transpose_kernel(const __grid_constant__ MultiColumns mc, uint64_t n_bodies, uint64_t ld,
+                                                                int to_soa)
+{
+    extern __shared__ double tile[];
+    const MultiColumns::Col c = mc.col[blockIdx.y];
+    const uint32_t width = c.width, pitch = width | 1u;
+    const uint64_t base = (uint64_t)blockIdx.x * kTile;
+    if (base >= n_bodies) return;
+    const uint32_t nb = (uint32_t)min((uint64_t)kTile, n_bodies - base);
+    double *aos = mc.packed + c.aos_offset + base * width;
+    if (to_soa) {
+        for (uint32_t i = threadIdx.x; i < nb * width; i += kTile) tile[(i / width) * pitch + (i % width)] = aos[i];
+        __syncthreads();
+        if (threadIdx.x < nb)
+            for (uint32_t k = 0; k < width; ++k) c.soa[(uint64_t)k * ld + base + threadIdx.x] = tile[threadIdx.x * pitch + k];
+    } else {
+        if (threadIdx.x < nb)
+            for (uint32_t k = 0; k < width; ++k) tile[threadIdx.x * pitch + k] = c.soa[(uint64_t)k * ld + base + threadIdx.x];
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nb * width; i += kTile) aos[i] = tile[(i / width) * pitch + (i % width)];
+    }
+}
+
 // FP64 FMA throughput probe: 8 independent chains per thread
 __global__ void __launch_bounds__(256) probe_fp64_kernel(double *out, int iters)
 {
@@ -1090,6 +1115,16 @@ cudaError_t launch_traj_to_aos(const double *traj, double *aos, uint64_t n_sampl
         soa_to_aos_kernel<<<grid, kTile, kTile * 13 * sizeof(double), s>>>(traj + s0 * 13 * ld, aos + s0 * n_bodies * 13,
                                                                           n_bodies, 13, ld);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_multi_transpose(const MultiColumns &mc, uint64_t n_bodies, uint64_t ld, bool to_soa, cudaStream_t s)
+{
+    if (n_bodies == 0 || mc.n == 0) return cudaSuccess;
+    uint32_t wmax = 1;
+    for (uint32_t i = 0; i < mc.n; ++i) wmax = std::max(wmax, mc.col[i].width);
+    const dim3 grid((unsigned)((n_bodies + kTile - 1) / kTile), mc.n);
+    multi_transpose_kernel<<<grid, kTile, kTile * (wmax | 1u) * sizeof(double), s>>>(mc, n_bodies, ld, to_soa ? 1 : 0);
     return cudaGetLastError();
 }
 
