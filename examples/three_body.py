@@ -16,15 +16,13 @@ SIM_TIME_STEP = 1.0 / 120.0
 G = 6.6743e-11
 
 w = el.World()
-a = w.spawn([el.Body(world_pos=el.WorldPos(linear=np.array([0.8920281421, 0.0, 0.0])),
-                     world_vel=el.WorldVel(linear=np.array([0.0, 0.9957939373, 0.0])),
-                     inertia=el.Inertia(1.0 / G))], name="A")
-b = w.spawn([el.Body(world_pos=el.WorldPos(linear=np.array([-0.6628498947, 0.0, 0.0])),
-                     world_vel=el.WorldVel(linear=np.array([0.0, -1.6191613336, 0.0])),
-                     inertia=el.Inertia(1.0 / G))], name="B")
-c = w.spawn([el.Body(world_pos=el.WorldPos(linear=np.array([-0.2291782474, 0, 0])),
-                     world_vel=el.WorldVel(linear=np.array([0, 0.6233673964, 0.0])),
-                     inertia=el.Inertia(1.0 / G))], name="C")
+# figure-eight-like initial conditions of the reference example (positions on the x axis, velocities along y)
+INITIAL = {"A": (0.8920281421, 0.9957939373), "B": (-0.6628498947, -1.6191613336), "C": (-0.2291782474, 0.6233673964)}
+body = {name: w.spawn([el.Body(world_pos=el.WorldPos(linear=np.array([x, 0.0, 0.0])),
+                               world_vel=el.WorldVel(linear=np.array([0.0, vy, 0.0])),
+                               inertia=el.Inertia(1.0 / G))], name=name)
+        for name, (x, vy) in INITIAL.items()}
+a, b, c = body["A"], body["B"], body["C"]
 
 GravityEdge = el.Annotated[el.Edge, el.Component("gravity_edge", el.ComponentType.Edge)]
 
@@ -37,12 +35,9 @@ class GravityConstraint(el.Archetype):
         self.a = el.Edge(a, b)
 
 
-w.spawn(GravityConstraint(a, b), name="A -> B")
-w.spawn(GravityConstraint(b, a), name="B -> A")
-w.spawn(GravityConstraint(a, c), name="A -> C")
-w.spawn(GravityConstraint(b, c), name="B -> C")
-w.spawn(GravityConstraint(c, a), name="C -> A")
-w.spawn(GravityConstraint(c, b), name="C -> B")
+# directed gravity edges in the reference's spawn order (it fixes the edge_fold order per source body)
+for src, dst in (("A", "B"), ("B", "A"), ("A", "C"), ("B", "C"), ("C", "A"), ("C", "B")):
+    w.spawn(GravityConstraint(body[src], body[dst]), name=f"{src} -> {dst}")
 
 gravity = el.GravityEdges("newton", G=G)  # edge_fold over the spawned GravityEdge components
 sys_ = el.six_dof(sys=gravity)
