@@ -62,6 +62,7 @@ class Effector(C.Structure):
         ("n_edges", C.c_uint64),
         ("edge_from", C.c_void_p),
         ("edge_to", C.c_void_p),
+        ("entity_mask", C.c_void_p),
     ]
 
 

@@ -51,6 +51,7 @@ uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 struct b200_sixdof {
     b200_sixdof_desc desc{};
     std::vector<b200_effector> effectors;
+    std::vector<uint8_t *> eff_masks; // device copies of the per-effector entity masks (nullptr = all)
     int device = 0;
     uint64_t n_bodies = 0;
     uint64_t ld = 0;
@@ -227,6 +228,7 @@ void fill_step_params(b200_sixdof *h, StepParams &P)
         const Column *c = e.column_id ? h->find(e.column_id) : nullptr;
         P.eff[i].col = c ? c->dev : nullptr;
         P.eff[i].col_width = c ? c->width : 0;
+        P.eff[i].mask = i < h->eff_masks.size() ? h->eff_masks[i] : nullptr;
     }
 }
 
@@ -490,6 +492,18 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
             if ((rc = add_column(h, e.column_id, e.column_width, false))) return bail(rc);
         }
     build_id_tables(h);
+    // per-effector entity masks: copy now, the caller's arrays are only valid for this call
+    h->eff_masks.assign(h->effectors.size(), nullptr);
+    for (size_t i = 0; i < h->effectors.size(); ++i) {
+        b200_effector &e = h->effectors[i];
+        if (e.entity_mask && d->n_entities) {
+            if (cudaMalloc(&h->eff_masks[i], d->n_entities) != cudaSuccess)
+                return bail(cuda_fail(nullptr, cudaGetLastError(), "cudaMalloc(entity mask)"));
+            if (cudaMemcpy(h->eff_masks[i], e.entity_mask, d->n_entities, cudaMemcpyHostToDevice) != cudaSuccess)
+                return bail(cuda_fail(nullptr, cudaGetLastError(), "cudaMemcpy(entity mask)"));
+        }
+        e.entity_mask = nullptr;
+    }
 
     if (h->graph_eff >= 0) {
         // copy the edge arrays' content now: the caller's pointers are only valid for this call
@@ -517,6 +531,7 @@ void b200_sixdof_destroy(b200_sixdof *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &c : h->cols) if (c.dev) cudaFree(c.dev);
+    for (auto m : h->eff_masks) if (m) cudaFree(m);
     if (h->row_ptr) cudaFree(h->row_ptr);
     if (h->col_idx) cudaFree(h->col_idx);
     if (h->has_edge) cudaFree(h->has_edge);

@@ -17,6 +17,7 @@ struct EffDev {
     const double *col;
     uint32_t col_width;
     uint32_t pad;
+    const uint8_t *mask; // [n_entities] or nullptr (query-join membership)
 };
 
 // Launch parameters of the per-body integrator kernels.  All columns are SoA:

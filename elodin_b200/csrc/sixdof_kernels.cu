@@ -86,6 +86,7 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
     Motion F = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
     for (uint32_t e = 0; e < P.n_eff; ++e) {
         const EffDev &E = P.eff[e];
+        if (E.mask && !E.mask[b % P.n_entities]) continue; // entity does not own the effector's components (query join)
         switch (E.kind) {
         case B200_EFF_GRAVITY_CONST: { // ball/sim.py:56-58: f + SpatialForce(linear=g*m)
             F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
@@ -231,6 +232,7 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
     Vec3 tb = {0.0, 0.0, 0.0};
     for (uint32_t e = 0; e < P.n_eff; ++e) {
         const EffDev &E = P.eff[e];
+        if (E.mask && !E.mask[b % P.n_entities]) continue; // query join: not a member
         switch (E.kind) {
         case B200_EFF_GRAVITY_CONST:
             f.fw.x = fma(E.p[0], I.m, f.fw.x); f.fw.y = fma(E.p[1], I.m, f.fw.y); f.fw.z = fma(E.p[2], I.m, f.fw.z);

@@ -57,6 +57,19 @@ class Effector(System):
     def column_name(self) -> Optional[str]:
         return getattr(self, "column", None)
 
+    def with_mask(self, mask) -> "Effector":
+        """Restrict the effector to the entity rows where `mask` is true — the query-join rule of
+        the reference (query.rs:672-710): an @el.map effector only runs on entities that own every
+        component it reads.  `World.build` sets this automatically from component membership."""
+        self._mask = None if mask is None else np.ascontiguousarray(np.asarray(mask, dtype=np.uint8))
+        return self
+
+    def _attach_mask(self, e: "_lib.Effector") -> "_lib.Effector":
+        m = getattr(self, "_mask", None)
+        if m is not None:
+            e.entity_mask = m.ctypes.data
+        return e
+
 
 def _base(kind, p=(), flags=0, column: Optional[str] = None, width=0) -> _lib.Effector:
     e = _lib.Effector()
@@ -77,7 +90,7 @@ class GravityConst(Effector):
     g: Sequence[float] = (0.0, 0.0, -9.81)
 
     def lower(self, world):
-        return _base(_lib.EFF_GRAVITY_CONST, self.g)
+        return self._attach_mask(_base(_lib.EFF_GRAVITY_CONST, self.g))
 
 
 @dataclass
@@ -92,8 +105,8 @@ class DragQuadratic(Effector):
     per_body_params: bool = False  # column is [wind(3), Cd*rho, area] (per-world drag in Monte-Carlo batches)
 
     def lower(self, world):
-        return _base(_lib.EFF_DRAG_QUADRATIC, (self.cd_rho, self.area), column=self.column,
-                     width=5 if self.per_body_params else 3)
+        return self._attach_mask(_base(_lib.EFF_DRAG_QUADRATIC, (self.cd_rho, self.area), column=self.column,
+                                       width=5 if self.per_body_params else 3))
 
 
 @dataclass
@@ -104,7 +117,7 @@ class ThrustBody(Effector):
     column: str = "thrust"
 
     def lower(self, world):
-        return _base(_lib.EFF_THRUST_BODY, self.axis, column=self.column, width=1)
+        return self._attach_mask(_base(_lib.EFF_THRUST_BODY, self.axis, column=self.column, width=1))
 
 
 @dataclass
@@ -120,7 +133,7 @@ class WrenchBody(Effector):
         if self.layout not in ("torque_first", "linear_first"):
             raise ValueError(f"unknown wrench layout {self.layout!r}")
         flags = _lib.EFF_FLAG_WRENCH_LINEAR_FIRST if self.layout == "linear_first" else 0
-        return _base(_lib.EFF_WRENCH_BODY, flags=flags, column=self.column, width=6)
+        return self._attach_mask(_base(_lib.EFF_WRENCH_BODY, flags=flags, column=self.column, width=6))
 
 
 @dataclass
@@ -132,7 +145,7 @@ class GravityFrame(Effector):
     omega: Sequence[float] = (0.0, 0.0, 7.292115e-5)
 
     def lower(self, world):
-        return _base(_lib.EFF_GRAVITY_FRAME, (self.mu, *self.omega))
+        return self._attach_mask(_base(_lib.EFF_GRAVITY_FRAME, (self.mu, *self.omega)))
 
 
 @dataclass

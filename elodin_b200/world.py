@@ -514,15 +514,29 @@ class Exec:
             col = world.columns.get(component_id(cname))
             if col is None or col.entity_ids != bodies:
                 raise _lib.B200ValueError(_lib.ERR_COMPONENT_NOT_FOUND, f"component not found: {cname}")
+        # Query join (query.rs:672-710): an effector only runs on the entities that own its input
+        # component.  Full membership -> no mask; partial (order-preserving) membership -> entity mask +
+        # a body-row-expanded copy of the column for the device; no members / foreign order -> error.
+        self._partial: Dict[int, tuple] = {}
+        for e in self.six.effectors:
+            cname = e.column_name()
+            if not cname:
+                continue
+            col = world.columns.get(component_id(cname))
+            if col is None or not col.entity_ids:
+                raise _lib.B200ValueError(_lib.ERR_COMPONENT_NOT_FOUND, f"component not found: {cname}")
+            if col.entity_ids == bodies:
+                continue
+            rows = [bodies.index(ent) for ent in col.entity_ids if ent in bodies]
+            if len(rows) != len(col.entity_ids) or rows != sorted(rows):
+                raise _lib.B200ValueError(_lib.ERR_COMPONENT_NOT_FOUND, f"component not found: {cname} (owners are not Body entities)")
+            mask = np.zeros(len(bodies), dtype=np.uint8)
+            mask[rows] = 1
+            e.with_mask(mask)
+            self._partial[component_id(cname)] = (np.asarray(rows), np.zeros((self.n_worlds, len(bodies), col.width)))
         # ticks of one invoke_batch stay in registers up to 32 at a time (no effect on results)
         self.backend = B200Exec(len(bodies), self.n_worlds, self.sim_time_step, self.six.time_step, self.six.effectors,
                                 self.six.integrator.value, math, device, max_fused_ticks=32, world=world)
-        for e in self.six.effectors:
-            cname = e.column_name()
-            if cname:
-                col = world.columns.get(component_id(cname))
-                if col is None or col.entity_ids != bodies:
-                    raise _lib.B200ValueError(_lib.ERR_COMPONENT_NOT_FOUND, f"component not found: {cname}")
         self.tick = 0
         self.build_ms = 0.0
         self._prof = {"execute_buffers": [], "add_to_history": [], "h2d_upload": [], "kernel_invoke": [], "d2h_download": []}
@@ -558,6 +572,8 @@ class Exec:
                 self._ins.append(self._tick_in)
             elif cid == component_id("simulation_time_step"):
                 self._ins.append(self._dt_in)
+            elif cid in self._partial:
+                self._ins.append(self._partial[cid][1])  # body-row-expanded copy, refreshed before every invoke
             else:
                 buf = self.world.columns[cid].buffer
                 assert buf.flags.c_contiguous and buf.nbytes == be.column_bytes(cid)
@@ -565,6 +581,8 @@ class Exec:
         for cid in be.output_ids:
             if cid in (component_id("tick"), component_id("simulation_time_step")):
                 self._outs.append(np.zeros(1, dtype=np.uint64 if cid == component_id("tick") else np.float64))
+            elif cid in self._partial:
+                self._outs.append(np.empty_like(self._partial[cid][1]))
             else:
                 self._outs.append(np.empty_like(self.world.columns[cid].buffer))
         self._in_ptrs = [a.ctypes.data for a in self._ins]
@@ -577,11 +595,13 @@ class Exec:
             self._bind_buffers()
         self._tick_in[0] = self.tick
         self._dt_in[0] = self.sim_time_step
+        for cid, (rows, expanded) in self._partial.items():
+            expanded[:, rows, :] = self.world.columns[cid].buffer
         be.invoke_batch_ptrs(self._in_ptrs, self._out_ptrs, n)
         for cid, buf in zip(be.output_ids, self._outs):
             if cid == component_id("tick"):
                 self.tick = int(buf[0])  # world.advance_tick() x n
-            elif cid != component_id("simulation_time_step"):
+            elif cid != component_id("simulation_time_step") and cid not in self._partial:
                 col = self.world.columns[cid]
                 if col.buffer.nbytes != buf.nbytes:
                     raise _lib.B200ValueError(_lib.ERR_VALUE_SIZE_MISMATCH, "value size mismatch")

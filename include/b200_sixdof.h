@@ -124,6 +124,10 @@ typedef struct b200_effector {
     uint64_t n_edges;       /* GRAVITY_EDGES_*: directed edges, spawn order         */
     const uint32_t *edge_from; /* entity row index within a world                   */
     const uint32_t *edge_to;
+    const uint8_t *entity_mask; /* [n_entities] or NULL: 1 = the effector applies to that entity row.
+                                   Mirrors the reference's query join (query.rs:672-710): an @el.map
+                                   effector only runs on entities that own every component it reads
+                                   (e.g. drag only on bodies with a `wind` component).  Copied at create. */
 } b200_effector;
 
 typedef struct b200_sixdof_desc {

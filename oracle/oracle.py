@@ -38,6 +38,7 @@ class _Effector(C.Structure):
         ("n_edges", C.c_uint64),
         ("edge_from", C.c_void_p),
         ("edge_to", C.c_void_p),
+        ("entity_mask", C.c_void_p),
     ]
 
 
@@ -128,6 +129,7 @@ class Effector:
     flags: int = 0
     column: np.ndarray | None = None  # [M, N, width]
     edges: np.ndarray | None = None  # [E, 2] (from, to) entity rows
+    mask: np.ndarray | None = None  # [N] bool: entity rows the effector applies to (query join)
 
     _keep: list = field(default_factory=list, repr=False)
 
@@ -150,6 +152,10 @@ class Effector:
             e.n_edges = len(f)
             e.edge_from = f.ctypes.data
             e.edge_to = t.ctypes.data
+        if self.mask is not None:
+            m = np.ascontiguousarray(np.asarray(self.mask, dtype=np.uint8))
+            self._keep.append(m)
+            e.entity_mask = m.ctypes.data
         return e
 
 

@@ -298,6 +298,7 @@ static void eval_pipe(uint64_t n, uint64_t world, const double *inertia, uint32_
             continue;
         }
         for (uint64_t i = 0; i < n; ++i) {
+            if (e->entity_mask && !e->entity_mask[i]) continue; /* entity lacks one of the effector's components */
             const double *col = e->column ? e->column + (world * n + i) * e->column_width : 0;
             switch (e->kind) {
             case ORC_EFF_GRAVITY_CONST: eff_gravity_const(e, inertia + 7 * i, F + 6 * i); break;

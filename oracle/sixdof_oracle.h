@@ -48,6 +48,7 @@ typedef struct orc_effector {
     uint64_t n_edges;
     const uint32_t *edge_from;
     const uint32_t *edge_to;
+    const uint8_t *entity_mask; /* [n] or NULL: query-join membership (query.rs:672-710) */
 } orc_effector;
 
 /* AoS columns [n_worlds][n][width], exactly the host layout of the C ABI */

@@ -54,7 +54,7 @@ def test_component_id_matches_reference_table(built_lib):
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.Effector) == 4 + 4 + 64 + 8 + 4 + 4 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.Effector) == 4 + 4 + 64 + 8 + 4 + 4 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.Desc) == 16 + 16 + 16 + 8 + 4 + 4 + 4 + 4 + 8
     assert ctypes.sizeof(_lib.Timings) == 48
 

@@ -260,3 +260,19 @@ def test_oracle_world_axis_and_threads(oracle):
               O.Effector(O.EFF_THRUST_BODY, p=(-1.0, 0, 0), column=thrust[m:m + 1])]
         c = O.World(pos[m], vel[m], ine[m]).rk4(0.01, 7, e1)
         assert np.array_equal(c.pos[0], a.pos[m]) and np.array_equal(c.vel[0], a.vel[m])
+
+
+def test_oracle_entity_masks(oracle):
+    """An effector with an entity mask equals the unmasked effector on members and no effector on the rest."""
+    O = oracle
+    rng = np.random.default_rng(4)
+    q = rng.normal(size=(1, 3, 4)); q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    pos = np.concatenate([q, rng.normal(size=(1, 3, 3))], -1)
+    vel = rng.normal(size=(1, 3, 6))
+    ine = np.concatenate([rng.uniform(1, 2, (1, 3, 3)), np.zeros((1, 3, 3)), rng.uniform(1, 2, (1, 3, 1))], -1)
+    thrust = rng.uniform(1, 5, (1, 3, 1))
+    masked = O.World(pos, vel, ine).rk4(0.01, 3, [O.Effector(O.EFF_THRUST_BODY, p=(1.0, 0, 0), column=thrust, mask=[1, 0, 1])])
+    full = O.World(pos, vel, ine).rk4(0.01, 3, [O.Effector(O.EFF_THRUST_BODY, p=(1.0, 0, 0), column=thrust)])
+    free = O.World(pos, vel, ine).rk4(0.01, 3)
+    assert np.array_equal(masked.pos[0, [0, 2]], full.pos[0, [0, 2]]) and np.array_equal(masked.vel[0, 1], free.vel[0, 1])
+    assert not np.array_equal(masked.vel[0, 1], full.vel[0, 1])

@@ -877,3 +877,54 @@ def test_edge_cases_nan_inf_zero(oracle):
     assert np.isnan(fast[1][0, 3, 3:]).all() and np.isnan(fast[0][0, 0, :4]).all()  # FAST keeps the 0/0 semantics
     ok = [6, 7]
     _assert_close([a[:, ok] for a in fast], [b[:, ok] for b in want], 3 * FAST_TOL_TICK, "healthy bodies, fast")
+
+
+def test_effectors_follow_the_query_join(oracle):
+    """Heterogeneous world, like the reference's mixed archetypes (ball: only the ball owns `wind`;
+    cube-sat: earth / satellite / wheels): an effector runs only on entities that own its input
+    component (query.rs:672-710).  ECS mirror -> entity masks -> kernels == oracle with the same masks."""
+    O = oracle
+    Wind = el.Annotated[np.ndarray, el.Component("wind", el.ComponentType(el.PrimitiveType.F64, (3,)))]
+    Thrust = el.Annotated[np.ndarray, el.Component("thrust", el.ComponentType.F64)]
+
+    @el.dataclass
+    class WindData(el.Archetype):
+        wind: Wind
+
+    @el.dataclass
+    class Motor(el.Archetype):
+        thrust: Thrust
+
+    rng = np.random.default_rng(12)
+    w = el.World()
+    pos, vel, ine = random_world(12, 1, 4)
+    arch = lambda i: el.Body(world_pos=el.SpatialTransform(arr=pos[0, i]), world_vel=el.SpatialMotion(angular=vel[0, i, :3], linear=vel[0, i, 3:]),
+                             inertia=el.SpatialInertia(ine[0, i, 6], ine[0, i, :3]))
+    w.spawn([arch(0)], name="plain")                                        # neither wind nor thrust
+    w.spawn([arch(1), WindData(np.array([1.0, -2.0, 0.5]))], name="ball")   # drag only
+    w.spawn([arch(2), Motor(np.array([40.0]))], name="rocket")              # thrust only
+    w.spawn([arch(3), WindData(np.array([0.0, 3.0, 0.0])), Motor(np.array([15.0]))], name="both")
+    system = el.six_dof(sys=el.GravityConst((0.0, 0.0, -9.81)) | el.ThrustBody((-1.0, 0.0, 0.0), "thrust") | el.DragQuadratic(0.6, 0.05, "wind"))
+    wind = np.zeros((1, 4, 3)); wind[0, 1] = [1.0, -2.0, 0.5]; wind[0, 3] = [0.0, 3.0, 0.0]
+    thrust = np.zeros((1, 4, 1)); thrust[0, 2] = 40.0; thrust[0, 3] = 15.0
+    oeffs = [O.Effector(O.EFF_GRAVITY_CONST, p=(0, 0, -9.81)),
+             O.Effector(O.EFF_THRUST_BODY, p=(-1.0, 0, 0), column=thrust, mask=[0, 0, 1, 1]),
+             O.Effector(O.EFF_DRAG_QUADRATIC, p=(0.6, 0.05), column=wind, mask=[0, 1, 0, 1])]
+    for math in ("exact", "fast"):
+        ex = w.build(system, simulation_rate=120.0, math=math)
+        ex.run(12)
+        ow = O.World(pos, vel, ine).rk4(ex.sim_time_step, 12, oeffs)
+        for i, name in enumerate(("plain", "ball", "rocket", "both")):
+            h = ex.history([f"{name}.world_pos", f"{name}.world_vel", f"{name}.force"])
+            got = (h[f"{name}.world_pos"][-1], h[f"{name}.world_vel"][-1], h[f"{name}.force"][-1])
+            want = (ow.pos[0, i], ow.vel[0, i], ow.force[0, i])
+            for a, b in zip(got, want):
+                if math == "exact":
+                    assert np.array_equal(a, b), (name, math)
+                else:
+                    assert np.max(np.abs(a - b)) <= 12 * FAST_TOL_TICK * max(np.max(np.abs(b)), 1e-300), (name, math)
+        # the plain body saw gravity only: its force is exactly m*g with zero torque
+        f_plain = ex.history("plain.force")["plain.force"][-1]
+        assert np.array_equal(f_plain[:3], [0, 0, 0]) and f_plain[5] == -9.81 * ine[0, 0, 6]
+        # the drag quirk (torque reset) only hits members: "rocket" keeps no torque anyway, "both" is zeroed by drag
+        assert ex.history("ball.wind")["ball.wind"].shape == (13, 3)
