@@ -544,16 +544,8 @@ class Exec:
         self._history: Dict[int, List[np.ndarray]] = {cid: [] for cid in self.world.columns}
         self._globals_hist: List[tuple] = []
         self._record()
-        self._uploaded = False
 
     # -- data plumbing -------------------------------------------------------------
-    def _host_col(self, cid: int) -> np.ndarray:
-        if cid == component_id("tick"):
-            return np.array([self.tick], dtype=np.uint64)
-        if cid == component_id("simulation_time_step"):
-            return np.array([self.sim_time_step])
-        return self.world.columns[cid].buffer
-
     def _record(self) -> None:
         for cid, col in self.world.columns.items():
             self._history[cid].append(col.buffer.copy())
