@@ -80,7 +80,7 @@ __device__ __forceinline__ void traj_sample(const StepParams &P, uint64_t b, uin
 
 // clear_forces | effectors (array order) on the stage state; six_dof.rs:148-150,195
 __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t b, int slot, const Pose &sx,
-                                                  const Motion &sv, const Inertia &I)
+                                                  const ex::PoseInv &pi, const Motion &sv, const Inertia &I)
 {
     using namespace ex;
     Motion F = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
@@ -109,7 +109,7 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
         }
         case B200_EFF_THRUST_BODY: { // rocket/main.py:429-431
             const double t = E.col ? ldp(E.col, P.ld, 0, b) : 0.0;
-            const Vec3 d = qrot(sx.q, Vec3{E.p[0], E.p[1], E.p[2]});
+            const Vec3 d = qrot_with(sx.q, pi.qi, Vec3{E.p[0], E.p[1], E.p[2]});
             F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
             F.lin = Vec3{add(F.lin.x, mul(d.x, t)), add(F.lin.y, mul(d.y, t)), add(F.lin.z, mul(d.z, t))};
             break;
@@ -121,8 +121,8 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
                 c = Vec3{ldp(E.col, P.ld, 3, b), ldp(E.col, P.ld, 4, b), ldp(E.col, P.ld, 5, b)};
             }
             const bool lin_first = (E.flags & B200_EFF_FLAG_WRENCH_LINEAR_FIRST) != 0;
-            const Vec3 tw = qrot(sx.q, lin_first ? c : a);
-            const Vec3 fw = qrot(sx.q, lin_first ? a : c);
+            const Vec3 tw = qrot_with(sx.q, pi.qi, lin_first ? c : a);
+            const Vec3 fw = qrot_with(sx.q, pi.qi, lin_first ? a : c);
             F.ang = Vec3{add(F.ang.x, tw.x), add(F.ang.y, tw.y), add(F.ang.z, tw.z)};
             F.lin = Vec3{add(F.lin.x, fw.x), add(F.lin.y, fw.y), add(F.lin.z, fw.z)};
             break;
@@ -175,18 +175,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_exact_kernel(const __grid_co
             // rk4.rs:85-123 (see the header comment of oracle/sixdof_oracle.c for the derivation)
             Motion sa = a_out; // du.a before stage 1 is the WorldAccel column
             Motion kv, ka;
+            // three distinct stage poses (f = 0, .5, 1), functions of (x0, v0) only; stages 2 and 3 share
+            // the f = .5 pose and its inverses — identical inputs, identical bits — so each is built once
 #pragma unroll 1
-            for (int s = 0; s < 4; ++s) {
-                const double fac = (s == 0) ? 0.0 : ((s == 3) ? 1.0 : 0.5);
-                const double dtf = mul(P.dt_stage, fac);
+            for (int k = 0; k < 3; ++k) {
+                const double dtf = mul(P.dt_stage, k == 0 ? 0.0 : (k == 1 ? 0.5 : 1.0));
                 const Pose sx = tadd(x0, scale(dtf, v0));
-                const Motion sv = madd(v0, scale(dtf, sa));
-                const int slot = (s == 0) ? 0 : ((s == 3) ? 2 : 1);
-                f_out = effectors_exact(P, b, slot, sx, sv, I);
-                sa = calc_accel(sx, f_out, I);
-                if (s == 0) { kv = sv; ka = sa; }
-                else if (s == 3) { kv = madd(kv, sv); ka = madd(ka, sa); }
-                else { kv = madd(kv, scale(2.0, sv)); ka = madd(ka, scale(2.0, sa)); }
+                const PoseInv pi = pose_inverses(sx.q);
+                const int n_stages = (k == 1) ? 2 : 1;
+#pragma unroll 1
+                for (int j = 0; j < n_stages; ++j) {
+                    const int s = (k == 0) ? 0 : (k == 1 ? 1 + j : 3);
+                    const Motion sv = madd(v0, scale(dtf, sa));
+                    f_out = effectors_exact(P, b, k, sx, pi, sv, I);
+                    sa = calc_accel_with(sx, pi, f_out, I);
+                    if (s == 0) { kv = sv; ka = sa; }
+                    else if (s == 3) { kv = madd(kv, sv); ka = madd(ka, sa); }
+                    else { kv = madd(kv, scale(2.0, sv)); ka = madd(ka, scale(2.0, sa)); }
+                }
             }
             const double c = mul(P.dt_final, 1.0 / 6.0);
             x0 = tadd(x0, scale(c, kv));
@@ -194,8 +200,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_exact_kernel(const __grid_co
             a_out = sa;
         } else {
             // semi_implicit.rs:42-62
-            f_out = effectors_exact(P, b, 0, x0, v0, I);
-            a_out = calc_accel(x0, f_out, I);
+            const PoseInv pi = pose_inverses(x0.q);
+            f_out = effectors_exact(P, b, 0, x0, pi, v0, I);
+            a_out = calc_accel_with(x0, pi, f_out, I);
             v0 = madd(v0, scale(P.dt_final, a_out));
             x0 = tadd(x0, scale(P.dt_final, v0));
         }
