@@ -15,6 +15,7 @@
 // at all four stages (three distinct positions, f = 0, .5, 1) is a function of
 // the tick's input state alone and needs no grid-wide synchronisation.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "sixdof_device.cuh"
@@ -990,6 +991,21 @@ __global__ void __launch_bounds__(256) probe_fp64_kernel(double *out, int iters)
 
 // ================================================================== launchers
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember per (kernel, device) whether it
+// has been raised (a process may hold handles on several GPUs).
+template <typename K>
+static cudaError_t ensure_dynamic_smem(K kernel, size_t bytes)
+{
+    static std::atomic<uint64_t> done{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_relaxed) & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_relaxed);
+    return e;
+}
+
 cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode, cudaStream_t s)
 {
     if (P.n_bodies == 0) return cudaSuccess;
@@ -1021,15 +1037,15 @@ cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode,
             auto kern = stages == 2 ? body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 2, 3>
                                     : (stages == 3 ? body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 3, 2>
                                                    : body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 4, 2>);
-            static int sm_count = 0, per_sm[5] = {0, 0, 0, 0, 0};
-            if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
-            if (!per_sm[stages]) {
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[stages], kern, kPipeTB, smem);
-                if (per_sm[stages] < 1) per_sm[stages] = 1;
-            }
+            // opt-in tuning variant: attributes are (re)set on every launch, cheap next to a >100 us kernel
+            int dev = 0, sm_count = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPipeTB, smem);
+            if (per_sm < 1) per_sm = 1;
             const uint64_t n_tiles = (P.n_bodies + kPipeTB - 1) / kPipeTB;
-            const unsigned grid_p = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)sm_count * per_sm[stages]);
+            const unsigned grid_p = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)sm_count * per_sm);
             kern<<<grid_p, kPipeTB, smem, s>>>(P);
             break;
         }
@@ -1061,11 +1077,8 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
             constexpr size_t smem256 = (3 * 3 + 1) * 256 * sizeof(double), smem1024 = (3 * 3 + 1) * 1024 * sizeof(double);
             if (!rk4) graph_dense_fast_kernel<false, false, 256><<<gridf, dim3(32, kFastSrc, 1), smem256, s>>>(G);
             else if (split) {
-                static bool attr_set = false;
-                if (!attr_set) {
-                    cudaFuncSetAttribute(graph_dense_fast_kernel<true, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1024);
-                    attr_set = true;
-                }
+                const cudaError_t e = ensure_dynamic_smem(graph_dense_fast_kernel<true, true, 1024>, smem1024);
+                if (e != cudaSuccess) return e;
                 graph_dense_fast_kernel<true, true, 1024><<<gridf, dim3(32, kFastSrc, 3), smem1024, s>>>(G);
             } else graph_dense_fast_kernel<true, false, 256><<<gridf, dim3(32, kFastSrc, 1), smem256, s>>>(G);
         }
@@ -1089,11 +1102,8 @@ bool nbody_fused_applicable(const GraphParams &G, int math_mode, bool dense)
 cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, double *pos_out, double *vel_out, cudaStream_t s)
 {
     constexpr size_t smem = (3 * 3 + 1) * 1024 * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(nbody_tick_fused_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    const cudaError_t e = ensure_dynamic_smem(nbody_tick_fused_kernel<1024>, smem);
+    if (e != cudaSuccess) return e;
     const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
     nbody_tick_fused_kernel<1024><<<gridf, dim3(32, kFastSrc, 3), smem, s>>>(G, P, pos_out, vel_out);
     return cudaGetLastError();
