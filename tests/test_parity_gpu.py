@@ -930,3 +930,25 @@ def test_effectors_follow_the_query_join(oracle):
             assert f_plain[5] == -9.81 * ine[0, 0, 6]
         # the drag quirk (torque reset) only hits members: "rocket" keeps no torque anyway, "both" is zeroed by drag
         assert ex.history("ball.wind")["ball.wind"].shape == (13, 3)
+
+
+def test_two_devices_in_one_process():
+    """One handle per GPU inside a single process (the C ABI selects the device per call): both
+    produce the bits of a single-GPU run, including the >48 KB dynamic-shared-memory kernels."""
+    if el.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    M, N = 2, 96
+    pos, vel, ine = random_world(71, M, N)
+    pos[..., 4:] *= 1e-2
+    mk = lambda dev, math: el.B200Exec(N, M, 0.01, None, [el.GravityEdges("softened", k_squared=0.2, softening=1e-5,
+                                                                           edges=el.all_pairs_edges(N))], "rk4", math, device=dev)
+    for math in ("exact", "fast"):
+        a, b = mk(0, math), mk(1, math)
+        for ex in (a, b):
+            ex.set_state(pos, vel, ine)
+        for _ in range(3):  # interleave the two devices
+            a.step(2); b.step(2)
+        a.sync(); b.sync()
+        ra, rb = (a.download(WORLD_POS), a.download(WORLD_VEL)), (b.download(WORLD_POS), b.download(WORLD_VEL))
+        a.close(); b.close()
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), math
