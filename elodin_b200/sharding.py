@@ -36,6 +36,11 @@ def gather_worlds(local, n_worlds: int, group=None):
     ws = dist.get_world_size(group)
     sizes = shard_sizes(n_worlds, ws)
     mx = max(sizes)
+    if min(sizes) == mx and local.shape[0] == mx:
+        # equal shards: one flat all-gather straight into the result (no per-rank staging tensors)
+        out = torch.empty((ws * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     out = [torch.empty_like(pad) for _ in range(ws)]

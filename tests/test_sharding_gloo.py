@@ -46,8 +46,9 @@ def _worker(rank, ws, port, n_worlds, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_gather_and_counters():
-    n_worlds, ws = 11, 2  # ragged: 6 + 5
+@pytest.mark.parametrize("n_worlds", [11, 12])  # ragged (6 + 5) and equal shards (flat all-gather path)
+def test_two_rank_gather_and_counters(n_worlds):
+    ws = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
