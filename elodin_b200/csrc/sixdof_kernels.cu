@@ -491,14 +491,18 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int INTEG, int STAGES, int MINB>
+// DIRECT_OUT: results leave with plain coalesced stores (no output tiles), which shrinks the CTA to
+// STAGES x 17 KB of shared memory so that 4 CTAs/SM fit at 128 registers — the input ring then keeps
+// ~17 KB per CTA in flight at all times, independent of how long the FP64 phase of a tile takes.
+template <int INTEG, int STAGES, int MINB, bool DIRECT_OUT>
 __global__ void __launch_bounds__(kPipeTB, MINB) body_fast_pipe_kernel(const __grid_constant__ StepParams P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kOutTiles = DIRECT_OUT ? 0 : 2;
     double(*sin)[kPipeIn][kPipeTB] = reinterpret_cast<double(*)[kPipeIn][kPipeTB]>(smem_raw);
     double(*sout)[kPipeOut][kPipeTB] =
         reinterpret_cast<double(*)[kPipeOut][kPipeTB]>(smem_raw + sizeof(double) * STAGES * kPipeIn * kPipeTB);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + sizeof(double) * (STAGES * kPipeIn + 2 * kPipeOut) * kPipeTB);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + sizeof(double) * (STAGES * kPipeIn + kOutTiles * kPipeOut) * kPipeTB);
 
     const int tid = threadIdx.x;
     const uint64_t n_tiles = (P.n_bodies + kPipeTB - 1) / kPipeTB;
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__(kPipeTB, MINB) body_fast_pipe_kernel(const __g
         I.diag = Vec3{sin[s][13][tid], sin[s][14][tid], sin[s][15][tid]};
         I.m = sin[s][16][tid];
         // the output tile about to be written was handed to the async proxy two tiles ago
-        if (tid < kPipeOut) bulk_wait_read<1>();
+        if (!DIRECT_OUT && tid < kPipeOut) bulk_wait_read<1>();
         __syncthreads(); // everyone has drained stage s; out[it&1] is free
         if (tid < 32) {
             const uint64_t next = tile + (uint64_t)STAGES * gridDim.x;
@@ -553,6 +557,17 @@ __global__ void __launch_bounds__(kPipeTB, MINB) body_fast_pipe_kernel(const __g
         Motion a_last, f_last;
         const bool live = b < P.n_bodies;
         if (live) fast_ticks<INTEG>(P, b, x0, v0, I, a_last, f_last);
+        if (DIRECT_OUT) {
+            if (live) {
+                store_pose(P.pos, P.ld, b, x0);
+                store_motion(P.vel, P.ld, b, v0);
+                if (P.write_fa) {
+                    store_motion(P.acc, P.ld, b, a_last);
+                    store_motion(P.frc, P.ld, b, f_last);
+                }
+            }
+            continue;
+        }
         const int ob = it & 1;
         sout[ob][0][tid] = x0.q.i; sout[ob][1][tid] = x0.q.j; sout[ob][2][tid] = x0.q.k; sout[ob][3][tid] = x0.q.w;
         sout[ob][4][tid] = x0.x.x; sout[ob][5][tid] = x0.x.y; sout[ob][6][tid] = x0.x.z;
@@ -570,7 +585,7 @@ __global__ void __launch_bounds__(kPipeTB, MINB) body_fast_pipe_kernel(const __g
             bulk_commit();
         }
     }
-    if (tid < kPipeOut) bulk_wait_all();
+    if (!DIRECT_OUT && tid < kPipeOut) bulk_wait_all();
 }
 
 // ================================================================== edge_fold gravity
@@ -1030,13 +1045,16 @@ cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode,
         case 0: body_fast_kernel<B200_INTEGRATOR_RK4, 256, 1><<<g(256), 256, 0, s>>>(P); break;
         case 4: body_fast_kernel<B200_INTEGRATOR_RK4, 64, 8><<<g(64), 64, 0, s>>>(P); break;
         case 5: body_fast_kernel<B200_INTEGRATOR_RK4, 128, 5><<<g(128), 128, 0, s>>>(P); break;
-        case 10: case 11: case 12: {
+        case 10: case 11: case 12: case 13: case 14: {
             // persistent TMA-pipelined kernel; needs plane stride % 128 == 0 (whole tiles inside a plane)
-            const int stages = cfg == 10 ? 2 : (cfg == 11 ? 3 : 4);
-            const size_t smem = sizeof(double) * (stages * kPipeIn + 2 * kPipeOut) * kPipeTB + 8 * stages;
-            auto kern = stages == 2 ? body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 2, 3>
-                                    : (stages == 3 ? body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 3, 2>
-                                                   : body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 4, 2>);
+            const bool direct = cfg >= 13;
+            const int stages = cfg == 10 ? 2 : (cfg == 11 ? 3 : (cfg == 12 ? 4 : (cfg == 13 ? 2 : 3)));
+            const size_t smem = sizeof(double) * (stages * kPipeIn + (direct ? 0 : 2) * kPipeOut) * kPipeTB + 8 * stages;
+            auto kern = cfg == 10 ? body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 2, 3, false>
+                      : cfg == 11 ? body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 3, 2, false>
+                      : cfg == 12 ? body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 4, 2, false>
+                      : cfg == 13 ? body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 2, 4, true>
+                                  : body_fast_pipe_kernel<B200_INTEGRATOR_RK4, 3, 4, true>;
             // opt-in tuning variant: attributes are (re)set on every launch, cheap next to a >100 us kernel
             int dev = 0, sm_count = 0, per_sm = 0;
             cudaGetDevice(&dev);
