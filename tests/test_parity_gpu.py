@@ -952,3 +952,24 @@ def test_two_devices_in_one_process():
         ra, rb = (a.download(WORLD_POS), a.download(WORLD_VEL)), (b.download(WORLD_POS), b.download(WORLD_VEL))
         a.close(); b.close()
         assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]), math
+
+
+def test_fast_math_is_run_to_run_deterministic():
+    """FAST changes the summation order of the gravity fold (warp-shuffle butterfly) but the order is
+    fixed: two executors fed the same inputs return the same bits, whatever the tick fusion or the
+    invoke range size."""
+    M, N = 5, 150
+    pos, vel, ine = random_world(81, M, N)
+    pos[..., 4:] *= 1e-2
+    rng = np.random.default_rng(8)
+    thrust = rng.uniform(0, 3, (M, N, 1))
+    effs = lambda: [el.GravityEdges("softened", k_squared=0.2, softening=1e-5, edges=el.all_pairs_edges(N)),
+                    el.ThrustBody((0.0, 1.0, 0.0), "thrust")]
+    runs = []
+    for chunk in (0, 2 * N):
+        with el.B200Exec(N, M, 0.01, None, effs(), "rk4", "fast", invoke_chunk_bodies=chunk) as ex:
+            ex.set_state(pos, vel, ine, thrust=thrust)
+            ex.step(7, sync=True)
+            runs.append((ex.download(WORLD_POS), ex.download(WORLD_VEL), ex.download(FORCE)))
+    for a, b in zip(*runs):
+        assert np.array_equal(a, b)
