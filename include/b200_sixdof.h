@@ -72,9 +72,12 @@ enum {
     /* literal operation order of libs/nox/src/{spatial,quaternion}.rs, no FMA
      * contraction, IEEE div/sqrt: bit-identical to oracle/sixdof_oracle.c */
     B200_MATH_EXACT = 0,
-    /* FMA contraction + hoisted reciprocals + rotation-matrix form of the
-     * inertia apply; agrees with EXACT to <= 1e-12 relative per tick
-     * (tests/test_parity_gpu.py states and checks the tolerance) */
+    /* FMA contraction, hoisted reciprocals (hardware seed + 2 Newton steps), cross-product
+     * rotations, R^-1/R cancelled around the mass divide, effectors folded once per launch;
+     * agrees with EXACT to <= 1e-12 relative per tick (tests/test_parity_gpu.py states and
+     * checks the tolerance).  Documented deviations from the literal arithmetic: the stage-1
+     * term `0 * WorldAccel` (rk4.rs:85-104) is not evaluated, so a non-finite WorldAccel input
+     * does not poison the step; denormal inputs to 1/x and 1/sqrt(x) flush to zero. */
     B200_MATH_FAST = 1
 };
 
