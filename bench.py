@@ -402,6 +402,36 @@ def run_b200(args):
             torch.cuda.synchronize()
             extras["exact_math"] = {"value": xM * 10 / (x0.elapsed_time(x1) * 1e-3), "unit": UNIT, "worlds": xM}
             xx.close()
+            # the same kernel with effector sets loaded (every stage rotates body-frame forces / torques):
+            # rocket = const-g + body thrust + quadratic drag; falcon9 = rotating-frame gravity + body wrench
+            rng = np.random.default_rng(5)
+            sets = {
+                "rocket": ([el.GravityConst(), el.ThrustBody((-1.0, 0.0, 0.0), "thrust"), el.DragQuadratic(0.6, 0.01, "wind")],
+                           {"thrust": rng.uniform(50, 100, (M, 1, 1)), "wind": rng.normal(0, 1, (M, 1, 3))}, 264 + 8 * 4),
+                "falcon9": ([el.GravityFrame(), el.WrenchBody("body_wrench", "linear_first")],
+                            {"body_wrench": rng.normal(0, 1e3, (M, 1, 6))}, 264 + 8 * 6),
+            }
+            eff_out = {}
+            for name, (effs, cols, bytes_per) in sets.items():
+                p2 = pos.copy()
+                if name == "falcon9":
+                    p2[..., 4:] += np.array([6.4e6, 0.0, 0.0])
+                sx = el.B200Exec(1, M, DT, None, effs, "rk4", "fast", device=local)
+                sx.set_stream(stream.cuda_stream)
+                sx.set_state(p2, vel, ine, **cols)
+                sx.step(5)
+                torch.cuda.synchronize()
+                q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                q0.record(stream)
+                sx.step(100)
+                q1.record(stream)
+                torch.cuda.synchronize()
+                t_ms = q0.elapsed_time(q1) / 100
+                eff_out[name] = {"value": M / (t_ms * 1e-3), "unit": UNIT, "bytes_per_entity_step": bytes_per,
+                                 "achieved_GBps": bytes_per * M / (t_ms * 1e-3) / 1e9, "frac": bytes_per * M / (t_ms * 1e-3) / 1e9 / peak}
+                sx.close()
+                del p2, cols
+            extras["effector_sets"] = eff_out
             # BASELINE configs[1] literally: ONE body, dependent steps (latency chain, one persistent launch per 10^4 ticks)
             sb = el.B200Exec(1, 1, DT, None, [], "rk4", "fast", device=local, max_fused_ticks=10000)
             sb.set_stream(stream.cuda_stream)

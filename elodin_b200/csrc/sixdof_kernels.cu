@@ -341,10 +341,14 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
         if (INTEG == B200_INTEGRATOR_RK4) {
             const Vec3 w0 = v0.ang, u0 = v0.lin;
             // the three distinct stage poses depend on (x0, v0) only (rk4.rs:85-111)
-            const Quat q1 = fa::normalize(x0.q); // x0 (+) 0*v0 still renormalises (spatial.rs:540-545)
+            // (the stage attitudes only matter to bodies that carry a body-frame force or torque)
             const double h2 = 0.25 * dt, h4 = 0.5 * dt;
-            const Quat q2 = fa::advance(x0.q, Vec3{h2 * w0.x, h2 * w0.y, h2 * w0.z});
-            const Quat q4 = fa::advance(x0.q, Vec3{h4 * w0.x, h4 * w0.y, h4 * w0.z});
+            Quat q1 = x0.q, q2 = x0.q, q4 = x0.q;
+            if (has_u | has_fb) {
+                q1 = fa::normalize(x0.q); // x0 (+) 0*v0 still renormalises (spatial.rs:540-545)
+                q2 = fa::advance(x0.q, Vec3{h2 * w0.x, h2 * w0.y, h2 * w0.z});
+                q4 = fa::advance(x0.q, Vec3{h4 * w0.x, h4 * w0.y, h4 * w0.z});
+            }
             const Vec3 x2 = {fma(h4, u0.x, x0.x.x), fma(h4, u0.y, x0.x.y), fma(h4, u0.z, x0.x.z)};
             const Vec3 x4 = {fma(dt, u0.x, x0.x.x), fma(dt, u0.y, x0.x.y), fma(dt, u0.z, x0.x.z)};
             // angular acceleration R(q) u and rotated body force, once per distinct attitude
