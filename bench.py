@@ -282,7 +282,18 @@ def run_baseline_configs(args, torch, el, stream, local, rank, world_size):
     return out
 
 
+def ensure_built():
+    """Harness step: (re)build the in-tree CUDA library if its sources are newer (make is a no-op otherwise)."""
+    try:
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "elodin_b200", "csrc")], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        pass  # the import below fails loudly if the library is really missing
+
+
 def run_b200(args):
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        ensure_built()
     import torch
     import torch.distributed as dist
 
