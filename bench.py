@@ -284,16 +284,19 @@ def run_baseline_configs(args, torch, el, stream, local, rank, world_size):
 
 def ensure_built():
     """Harness step: (re)build the in-tree CUDA library if its sources are newer (make is a no-op otherwise)."""
+    import fcntl
+
     try:
-        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "elodin_b200", "csrc")], check=True,
-                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        with open(os.path.join(ROOT, "elodin_b200", "csrc", ".build.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)  # ranks of one node take turns; all but the first find it up to date
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "elodin_b200", "csrc")], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     except Exception:
         pass  # the import below fails loudly if the library is really missing
 
 
 def run_b200(args):
-    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
-        ensure_built()
+    ensure_built()
     import torch
     import torch.distributed as dist
 
