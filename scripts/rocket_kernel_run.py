@@ -1,0 +1,20 @@
+"""FAST body kernel with the rocket effector set at 2^21 worlds (ncu target)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import elodin_b200 as el, bench
+M = 1 << 21
+pos, vel, ine = bench.synth_world(M, 1)
+rng = np.random.default_rng(0)
+which = sys.argv[1] if len(sys.argv) > 1 else "rocket"
+if which == "rocket":
+    effs = [el.GravityConst(), el.ThrustBody((-1.0, 0, 0), "thrust"), el.DragQuadratic(0.6, 0.01, "wind")]
+    cols = {"thrust": rng.uniform(50, 100, (M, 1, 1)), "wind": rng.normal(0, 1, (M, 1, 3))}
+else:
+    pos[..., 4:] += np.array([6.4e6, 0, 0])
+    effs = [el.GravityFrame(), el.WrenchBody("body_wrench", "linear_first")]
+    cols = {"body_wrench": rng.normal(0, 1e3, (M, 1, 6))}
+ex = el.B200Exec(1, M, 1e-3, None, effs, "rk4", "fast")
+ex.set_state(pos, vel, ine, **cols)
+ex.step(8, sync=True)
+print("done")
