@@ -369,6 +369,12 @@ def run_b200(args):
         clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
         if clocks is not None:
             clocks["window"] = window
+    # integrity sample: the state the TIMED executor ended in, for a strided set of worlds (checked against
+    # the CPU oracle below, rank 0 / N = 1 only) — shows the timed launches really integrated every tick
+    ticks_total = ex.tick
+    vidx = np.arange(0, M, max(M // 256, 1))[:256]
+    final_pos = ex.download(WORLD_POS)[vidx]
+    final_vel = ex.download(WORLD_VEL)[vidx]
     value = world_size * M * K / (ms * 1e-3)
     kernel_ms = ms / K
     peak, peak_src = measured_peak()
@@ -529,6 +535,7 @@ def run_b200(args):
 
     if rank == 0:
         cpu = None
+        verified = None
         traffic = ncu_traffic("body_fast_rk4_bytes_per_launch_M%d" % M)
         if world_size == 1:
             from oracle import oracle as O
@@ -538,6 +545,12 @@ def run_b200(args):
             r1, _ = cpu_oracle_rate(1 << 12, 50, 1)
             n_ticks = max(20, int(args.cpu_seconds * r1 * min(threads, 8) / (1 << 16)))
             rate, dt_s = cpu_oracle_rate(1 << 16, n_ticks, threads)
+            chk = O.World(pos[vidx], vel[vidx], ine[vidx]).rk4(DT, ticks_total, threads=min(threads, 64))
+            scale = lambda a: max(float(np.max(np.abs(a))), 1e-300)
+            verified = {"worlds_checked": int(len(vidx)), "ticks": int(ticks_total), "against": "CPU oracle (exact arithmetic)",
+                        "max_rel_err_q": float(np.max(np.abs(final_pos[..., :4] - chk.pos[..., :4])) / scale(chk.pos[..., :4])),
+                        "max_rel_err_x": float(np.max(np.abs(final_pos[..., 4:] - chk.pos[..., 4:])) / scale(chk.pos[..., 4:])),
+                        "max_rel_err_vel": float(np.max(np.abs(final_vel - chk.vel)) / scale(chk.vel))}
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"65536 worlds x {n_ticks} ticks of the same workload in {dt_s:.1f} s (oracle port, {threads} threads); "
                              f"1 thread: {r1:.3e} entity-steps/s"}
@@ -564,6 +577,7 @@ def run_b200(args):
                     "api": "b200_sixdof_invoke_batch (pinned host columns in/out)", "checksum": checksum,
                     "host_cpus_bound": numa_cpus},
             "gpu_launches": int(launches),
+            "verified": verified,
             "clocks": clocks,
             "cpu_baseline": cpu,
             **extras,
