@@ -17,6 +17,8 @@ value     whole-job entity-steps/s, inputs resident in HBM, CUDA-event timed on 
 e2e       the same metric through the reference-shaped C-ABI call
           b200_sixdof_invoke_batch with pinned HOST buffers: every call uploads all
           input columns, integrates `e2e_ticks_per_call` ticks, downloads all outputs.
+verified  the timed executor's final state (256 strided worlds) against the CPU oracle advanced the
+          same number of ticks: the timed launches did the work.
 roofline  algorithmic 264 B/entity-step / mean kernel time vs the measured
           HBM copy peak (MEASURED_PEAKS.json, else the 6.65 TB/s fallback).
 cpu_baseline / --impl reference
