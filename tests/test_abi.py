@@ -113,3 +113,16 @@ def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
     w.spawn(el.Body(), name="e1")
     with pytest.raises(el.B200Error):
         w.build(el.six_dof())
+
+
+def test_cpp_host_mirror_compiles_and_runs(built_lib, tmp_path):
+    """include/b200_world.hpp (World / Exec / WorldExec, the compiled-language mirror of the Rust
+    executor seam) builds with g++ -std=c++17 and runs the reference's checks through the C ABI; without
+    a GPU the program verifies the loud NO_DEVICE failure."""
+    exe = tmp_path / "world_exec_test"
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "tests", "cpp", "world_exec_test.cpp"),
+                    "-I", os.path.join(ROOT, "include"), "-L", os.path.join(ROOT, "elodin_b200"), "-lb200_sixdof",
+                    "-Wl,-rpath," + os.path.join(ROOT, "elodin_b200"), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "ok" in out.stdout or "failed loudly" in out.stdout
