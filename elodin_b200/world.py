@@ -654,6 +654,15 @@ class Exec:
             out[pair] = np.stack([h[0, row] for h in self._history[cid]]).view(_Series)
         return out
 
+    def write_db(self, path: str, start_timestamp_us: Optional[int] = None, world: int = 0):
+        """Write the recorded telemetry as an elodin-db directory (`elodin_b200.db_sink`): what the
+        reference's `init_db` + `commit_world_head_unified` leave on disk for `elodin-db export` / the editor."""
+        from . import db_sink
+
+        if start_timestamp_us is None:
+            return db_sink.write_db(self, path, world=world)
+        return db_sink.write_db(self, path, start_timestamp_us, world)
+
     def history_worlds(self, pair: str) -> np.ndarray:
         ent, comp = pair.rsplit(".", 1)
         col = self.world.columns[component_id(comp)]

@@ -602,6 +602,22 @@ def test_three_body_csv_export_passes_the_reference_regression_gate(golden, tmp_
                 assert math.isclose(a, float(b), rel_tol=1e-4, abs_tol=1e-4)  # the reference gate
                 assert a == float(b), (fn, cell, b)                          # and in fact exact
 
+    # the same run through the elodin-db directory format: GPU history -> db -> `export`
+    from elodin_b200 import db_sink
+
+    db = str(tmp_path / "three-body-db")
+    ex.write_db(db)
+    _, series, _ = db_sink.read_db(db)
+    assert sorted(db_sink._safe_name(n) + ".csv" for n in series) == got_files
+    assert np.array_equal(series["b.world_vel"].values, golden["three_body.b.world_vel"])
+    assert series["a.world_pos"].timestamps[:3].tolist() == [s0 := int(series["a.world_pos"].timestamps[0]), s0, s0 + 8333]
+    out2 = str(tmp_path / "three-body-csv-from-db")
+    db_sink.export_db_csv(db, out2)
+    for fn in got_files:
+        a = [r.split(",")[1:] for r in open(os.path.join(out, fn)).read().splitlines()]
+        b = [r.split(",")[1:] for r in open(os.path.join(out2, fn)).read().splitlines()]
+        assert a == b, fn                                                    # identical apart from `time`
+
 
 # --------------------------------------------------------------------------- BASELINE.json configs at full size
 
