@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200_sixdof.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_EFFECTORS = 8
 
 OK = 0
@@ -38,6 +38,7 @@ EFF_GRAVITY_FRAME = 5
 EFF_GRAVITY_EDGES_NEWTON = 6
 EFF_GRAVITY_EDGES_SOFTENED = 7
 EFF_FLAG_WRENCH_LINEAR_FIRST = 1
+TRAJ_FULL = 1
 
 # every symbol include/b200_sixdof.h declares (tests/test_abi.py checks the export table against it)
 SYMBOLS = [
@@ -45,7 +46,8 @@ SYMBOLS = [
     "b200_sixdof_create", "b200_sixdof_destroy", "b200_sixdof_input_ids", "b200_sixdof_output_ids",
     "b200_sixdof_column_bytes", "b200_sixdof_upload", "b200_sixdof_download", "b200_sixdof_step",
     "b200_sixdof_sync", "b200_sixdof_invoke_batch", "b200_sixdof_bind_tick", "b200_sixdof_tick",
-    "b200_sixdof_trajectory_len", "b200_sixdof_trajectory_download", "b200_sixdof_trajectory_reset",
+    "b200_sixdof_trajectory_len", "b200_sixdof_trajectory_width", "b200_sixdof_trajectory_download",
+    "b200_sixdof_trajectory_reset",
     "b200_sixdof_tick_count", "b200_sixdof_set_stream", "b200_sixdof_timings", "b200_sixdof_status",
     "b200_sixdof_device_plane", "b200_sixdof_plane_stride", "b200_probe_copy_gbs", "b200_probe_fp64_gflops",
 ]
@@ -82,6 +84,8 @@ class Desc(C.Structure):
         ("trajectory_every", C.c_uint32),
         ("invoke_chunk_bodies", C.c_uint32),
         ("trajectory_capacity", C.c_uint64),
+        ("trajectory_flags", C.c_uint32),
+        ("reserved0", C.c_uint32),
     ]
 
 
@@ -152,6 +156,8 @@ def lib():
     L.b200_sixdof_tick.restype = None
     L.b200_sixdof_trajectory_len.argtypes = [vp]
     L.b200_sixdof_trajectory_len.restype = u64
+    L.b200_sixdof_trajectory_width.argtypes = [vp]
+    L.b200_sixdof_trajectory_width.restype = C.c_uint32
     L.b200_sixdof_trajectory_download.argtypes = [vp, vp, u64]
     L.b200_sixdof_trajectory_reset.argtypes = [vp]
     L.b200_sixdof_tick_count.argtypes = [vp]

@@ -73,6 +73,7 @@ struct b200_sixdof {
     uint64_t staging_bytes = 0;
     // trajectory
     double *traj = nullptr;
+    uint32_t traj_planes = 13;   // 25 with B200_TRAJ_FULL
     // plumbing
     cudaStream_t stream = nullptr;
     bool own_stream = true;
@@ -220,6 +221,7 @@ void fill_step_params(b200_sixdof *h, StepParams &P)
     P.traj = h->traj;
     P.traj_capacity = h->desc.trajectory_capacity;
     P.traj_every = h->traj ? h->desc.trajectory_every : 0;
+    P.traj_planes = h->traj_planes;
     for (size_t i = 0; i < h->effectors.size(); ++i) {
         const b200_effector &e = h->effectors[i];
         P.eff[i].kind = e.kind;
@@ -418,6 +420,8 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
     if (d->n_effectors && !d->effectors) return fail(B200_ERR_INVALID_ARGUMENT, "n_effectors > 0 but effectors is null");
     if (d->n_worlds == 0) return fail(B200_ERR_INVALID_ARGUMENT, "n_worlds must be >= 1");
     if (d->n_entities > 0xffffffffull || d->n_worlds > 0xffffffffull) return fail(B200_ERR_UNSUPPORTED, "n_entities / n_worlds exceed 2^32-1");
+    if ((d->trajectory_flags & ~(uint32_t)B200_TRAJ_FULL) || d->reserved0)
+        return fail(B200_ERR_INVALID_ARGUMENT, "unknown trajectory_flags 0x%x / non-zero reserved field", d->trajectory_flags);
     if (!(d->sim_time_step > 0.0) || !std::isfinite(d->sim_time_step))
         return fail(B200_ERR_INVALID_ARGUMENT, "invalid time step: %g", d->sim_time_step); // Error::InvalidTimeStep
 
@@ -516,7 +520,8 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
         h->effectors[h->graph_eff].edge_from = h->effectors[h->graph_eff].edge_to = nullptr;
     }
     if (d->trajectory_every && d->trajectory_capacity) {
-        if (cudaMalloc(&h->traj, d->trajectory_capacity * 13ull * h->ld * 8ull) != cudaSuccess)
+        h->traj_planes = (d->trajectory_flags & B200_TRAJ_FULL) ? 25u : 13u;
+        if (cudaMalloc(&h->traj, d->trajectory_capacity * (uint64_t)h->traj_planes * h->ld * 8ull) != cudaSuccess)
             return bail(cuda_fail(nullptr, cudaGetLastError(), "cudaMalloc(trajectory)"));
     }
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(cuda_fail(nullptr, cudaGetLastError(), "create sync"));
@@ -874,7 +879,14 @@ int b200_sixdof_invoke_batch(b200_sixdof *h, const uint8_t *const *in_cols, uint
         (void)cudaGetLastError();
     }
     int rc = small ? invoke_small(h, in_cols, out_cols, n_ticks) : invoke_pipelined(h, in_cols, out_cols, n_ticks, wpc);
-    if (rc) return rc;
+    if (rc) {
+        // copies into the caller's buffers may still be queued: they must not outlive this call
+        (void)cudaStreamSynchronize(h->stream);
+        if (h->copy_in) (void)cudaStreamSynchronize(h->copy_in);
+        if (h->copy_out) (void)cudaStreamSynchronize(h->copy_out);
+        (void)cudaGetLastError();
+        return rc;
+    }
     h->timings.invoke_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return B200_OK;
 }
@@ -903,23 +915,26 @@ int b200_sixdof_trajectory_download(b200_sixdof *h, void *dst, uint64_t bytes)
     if (!h) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
     CU(h, cudaSetDevice(h->device));
     const uint64_t n = b200_sixdof_trajectory_len(h);
-    const uint64_t want = n * h->n_bodies * 13ull * 8ull;
+    const uint64_t W = h->traj_planes;
+    const uint64_t want = n * h->n_bodies * W * 8ull;
     if (bytes != want) return fail(B200_ERR_VALUE_SIZE_MISMATCH, "trajectory is %llu bytes, got %llu", (unsigned long long)want, (unsigned long long)bytes);
     if (want == 0) return B200_OK;
     // convert in chunks through the staging buffer
-    const uint64_t per_sample = h->n_bodies * 13ull * 8ull;
+    const uint64_t per_sample = h->n_bodies * W * 8ull;
     const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (256ull << 20) / per_sample));
     int rc = ensure_staging(h, chunk * per_sample);
     if (rc) return rc;
     for (uint64_t s0 = 0; s0 < n; s0 += chunk) {
         const uint64_t ns = std::min(chunk, n - s0);
-        CU(h, launch_traj_to_aos(h->traj + s0 * 13ull * h->ld, h->staging, ns, h->n_bodies, h->ld, h->stream));
+        CU(h, launch_traj_to_aos(h->traj + s0 * W * h->ld, h->staging, ns, h->n_bodies, h->ld, (uint32_t)W, h->stream));
         h->timings.kernel_launches++;
         CU(h, cudaMemcpyAsync((char *)dst + s0 * per_sample, h->staging, ns * per_sample, cudaMemcpyDefault, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
     }
     return B200_OK;
 }
+
+uint32_t b200_sixdof_trajectory_width(const b200_sixdof *h) { return (h && h->traj) ? h->traj_planes : 0; }
 
 int b200_sixdof_trajectory_reset(b200_sixdof *h)
 {

@@ -38,11 +38,11 @@ struct StepParams {
     double dt_final;    // six_dof(time_step=) or dt_stage (rk4.rs:83,119)
     uint32_t n_ticks;   // ticks integrated by this launch (state stays in registers)
     uint32_t write_fa;  // materialise Force / WorldAccel at the end of the launch
-    // trajectory ring: sample s, plane p at traj + (s*13 + p)*ld
+    // trajectory ring: sample s, plane p at traj + (s*traj_planes + p)*ld
     double *traj;
     uint64_t traj_capacity;
-    uint32_t traj_every; // 0 = off
-    uint32_t pad;
+    uint32_t traj_every;  // 0 = off
+    uint32_t traj_planes; // 13 (pos, vel) or 25 (+ accel, force)
     uint64_t tick0;     // global tick count before this launch
     EffDev eff[B200_MAX_EFFECTORS];
 };
@@ -87,7 +87,7 @@ cudaError_t launch_aos_to_soa(const double *aos, double *soa, uint64_t n_bodies,
 cudaError_t launch_soa_to_aos(const double *soa, double *aos, uint64_t n_bodies, uint32_t width, uint64_t ld,
                               cudaStream_t s);
 cudaError_t launch_traj_to_aos(const double *traj, double *aos, uint64_t n_samples, uint64_t n_bodies, uint64_t ld,
-                               cudaStream_t s);
+                               uint32_t width, cudaStream_t s);
 cudaError_t launch_multi_transpose(const MultiColumns &mc, uint64_t n_bodies, uint64_t ld, bool to_soa, cudaStream_t s);
 cudaError_t launch_probe_fp64(double *out, int iters, int blocks, cudaStream_t s);
 

@@ -15,7 +15,9 @@
 // at all four stages (three distinct positions, f = 0, .5, 1) is a function of
 // the tick's input state alone and needs no grid-wide synchronisation.
 #include <algorithm>
-#include <atomic>
+#include <mutex>
+#include <utility>
+#include <vector>
 #include <cstdlib>
 
 #include "sixdof_device.cuh"
@@ -66,15 +68,25 @@ __device__ __forceinline__ void store_motion(double *p, uint64_t ld, uint64_t b,
     stp(p, ld, 3, b, m.lin.x); stp(p, ld, 4, b, m.lin.y); stp(p, ld, 5, b, m.lin.z);
 }
 
-__device__ __forceinline__ void traj_sample(const StepParams &P, uint64_t b, uint64_t tick_after, const Pose &x,
-                                            const Motion &v)
+// slot of the telemetry sample due after `tick_after` ticks, if any
+__device__ __forceinline__ bool traj_due(const StepParams &P, uint64_t tick_after, uint64_t &slot)
 {
-    if (P.traj_every == 0 || (tick_after % P.traj_every) != 0) return;
-    const uint64_t s = tick_after / P.traj_every - 1;
-    if (s >= P.traj_capacity) return;
-    double *t = P.traj + s * 13ull * P.ld;
+    if (P.traj_every == 0 || (tick_after % P.traj_every) != 0) return false;
+    slot = tick_after / P.traj_every - 1;
+    return slot < P.traj_capacity;
+}
+__device__ __forceinline__ void traj_store_state(const StepParams &P, uint64_t b, uint64_t slot, const Pose &x, const Motion &v)
+{
+    double *t = P.traj + slot * (uint64_t)P.traj_planes * P.ld;
     store_pose(t, P.ld, b, x);
     store_motion(t + 7ull * P.ld, P.ld, b, v);
+}
+// B200_TRAJ_FULL: WorldAccel and Force as the tick leaves them in the ECS columns
+__device__ __forceinline__ void traj_store_af(const StepParams &P, uint64_t b, uint64_t slot, const Motion &a, const Motion &f)
+{
+    double *t = P.traj + (slot * (uint64_t)P.traj_planes + 13ull) * P.ld;
+    store_motion(t, P.ld, b, a);
+    store_motion(t + 6ull * P.ld, P.ld, b, f);
 }
 
 // ================================================================== EXACT body kernel
@@ -207,7 +219,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_exact_kernel(const __grid_co
             v0 = madd(v0, scale(P.dt_final, a_out));
             x0 = tadd(x0, scale(P.dt_final, v0));
         }
-        traj_sample(P, b, P.tick0 + t + 1, x0, v0);
+        uint64_t slot;
+        if (traj_due(P, P.tick0 + t + 1, slot)) {
+            traj_store_state(P, b, slot, x0, v0);
+            if (P.traj_planes == 25) traj_store_af(P, b, slot, a_out, f_out);
+        }
     }
     store_pose(P.pos, P.ld, b, x0);
     store_motion(P.vel, P.ld, b, v0);
@@ -323,7 +339,7 @@ __device__ __forceinline__ Motion force_out_fast(const Vec3 &a_lin, const Vec3 &
 }
 
 // n_ticks ticks of one body, state in registers (shared by the direct and the TMA-pipelined kernel)
-template <int INTEG>
+template <int INTEG, bool TRAJ>
 __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose &x0, Motion &v0, const Inertia &I,
                                            Motion &a_last, Motion &f_last)
 {
@@ -400,7 +416,13 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
             x0.x = Vec3{fma(d, v0.lin.x, x0.x.x), fma(d, v0.lin.y, x0.x.y), fma(d, v0.lin.z, x0.x.z)};
             a_last.ang = aa; a_last.lin = al; q_last = qn;
         }
-        traj_sample(P, b, P.tick0 + t + 1, x0, v0);
+        if (TRAJ) { // compiled out of the launches that record nothing (the roofline case)
+            uint64_t slot;
+            if (traj_due(P, P.tick0 + t + 1, slot)) {
+                traj_store_state(P, b, slot, x0, v0);
+                if (P.traj_planes == 25) traj_store_af(P, b, slot, a_last, force_out_fast(a_last.lin, f.u, q_last, I));
+            }
+        }
     }
     if (P.write_fa) f_last = force_out_fast(a_last.lin, f.u, q_last, I);
 }
@@ -420,7 +442,7 @@ __device__ __forceinline__ void prefetch_effector_columns(const StepParams &P, u
         for (uint32_t k = 0; k < 9; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.gforce + (uint64_t)k * P.ld + b));
 }
 
-template <int INTEG, int BLOCK, int MINB>
+template <int INTEG, int BLOCK, int MINB, bool TRAJ>
 __global__ void __launch_bounds__(BLOCK, MINB) body_fast_kernel(const __grid_constant__ StepParams P)
 {
     const uint64_t b = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -430,7 +452,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_fast_kernel(const __grid_con
     Motion v0 = load_motion(P.vel, P.ld, b);
     const Inertia I = load_inertia(P.ine, P.ld, b);
     Motion a_last, f_last;
-    fast_ticks<INTEG>(P, b, x0, v0, I, a_last, f_last);
+    fast_ticks<INTEG, TRAJ>(P, b, x0, v0, I, a_last, f_last);
     store_pose(P.pos, P.ld, b, x0);
     store_motion(P.vel, P.ld, b, v0);
     if (P.write_fa) {
@@ -560,7 +582,7 @@ __global__ void __launch_bounds__(kPipeTB, MINB) body_fast_pipe_kernel(const __g
         }
         Motion a_last, f_last;
         const bool live = b < P.n_bodies;
-        if (live) fast_ticks<INTEG>(P, b, x0, v0, I, a_last, f_last);
+        if (live) fast_ticks<INTEG, true>(P, b, x0, v0, I, a_last, f_last);
         if (DIRECT_OUT) {
             if (live) {
                 store_pose(P.pos, P.ld, b, x0);
@@ -874,7 +896,7 @@ __global__ void __launch_bounds__(32 * kFastSrc * 3) nbody_tick_fused_kernel(con
         Motion v0 = load_motion(P.vel, P.ld, b);
         const Inertia I = load_inertia(P.ine, P.ld, b);
         Motion a_last, f_last;
-        fast_ticks<B200_INTEGRATOR_RK4>(P, b, x0, v0, I, a_last, f_last);
+        fast_ticks<B200_INTEGRATOR_RK4, true>(P, b, x0, v0, I, a_last, f_last);
         store_pose(pos_out, P.ld, b, x0);
         store_motion(vel_out, P.ld, b, v0);
         if (P.write_fa) {
@@ -1010,20 +1032,36 @@ __global__ void __launch_bounds__(256) probe_fp64_kernel(double *out, int iters)
 
 // ================================================================== launchers
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember per (kernel, device) whether it
-// has been raised (a process may hold handles on several GPUs).
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (kernel, device): remember which pairs have been
+// raised (a process may hold handles on several GPUs; several kernels share a function-pointer type).
 template <typename K>
 static cudaError_t ensure_dynamic_smem(K kernel, size_t bytes)
 {
-    static std::atomic<uint64_t> done{0};
+    static std::mutex mu;
+    static std::vector<std::pair<const void *, uint64_t>> done; // (kernel, device bitmask)
     int dev = 0;
     cudaGetDevice(&dev);
     const uint64_t bit = 1ull << (dev & 63);
-    if (done.load(std::memory_order_relaxed) & bit) return cudaSuccess;
+    const void *key = reinterpret_cast<const void *>(kernel);
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &d : done)
+        if (d.first == key) {
+            if (d.second & bit) return cudaSuccess;
+            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (e == cudaSuccess) d.second |= bit;
+            return e;
+        }
     const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_relaxed);
+    if (e == cudaSuccess) done.emplace_back(key, bit);
     return e;
 }
+
+// the instantiation without trajectory code for launches that record nothing, the generic one otherwise
+#define BODY_FAST(INTEG, BLOCK, MINB)                                                        \
+    do {                                                                                     \
+        if (P.traj_every) body_fast_kernel<INTEG, BLOCK, MINB, true><<<g(BLOCK), BLOCK, 0, s>>>(P);  \
+        else body_fast_kernel<INTEG, BLOCK, MINB, false><<<g(BLOCK), BLOCK, 0, s>>>(P);      \
+    } while (0)
 
 cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode, cudaStream_t s)
 {
@@ -1042,13 +1080,13 @@ cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode,
     } else {
         static const int cfg = [] { const char *e = getenv("B200_BODY_CFG"); return e ? atoi(e) : 3; }();
         auto g = [&](int blk) { return (unsigned)((P.n_bodies + blk - 1) / blk); };
-        if (!rk4) body_fast_kernel<B200_INTEGRATOR_SEMI_IMPLICIT, 128, 4><<<g(128), 128, 0, s>>>(P);
+        if (!rk4) BODY_FAST(B200_INTEGRATOR_SEMI_IMPLICIT, 128, 4);
         else switch (cfg) {
-        case 1: body_fast_kernel<B200_INTEGRATOR_RK4, 256, 2><<<g(256), 256, 0, s>>>(P); break;
-        case 2: body_fast_kernel<B200_INTEGRATOR_RK4, 128, 3><<<g(128), 128, 0, s>>>(P); break;
-        case 0: body_fast_kernel<B200_INTEGRATOR_RK4, 256, 1><<<g(256), 256, 0, s>>>(P); break;
-        case 4: body_fast_kernel<B200_INTEGRATOR_RK4, 64, 8><<<g(64), 64, 0, s>>>(P); break;
-        case 5: body_fast_kernel<B200_INTEGRATOR_RK4, 128, 5><<<g(128), 128, 0, s>>>(P); break;
+        case 1: BODY_FAST(B200_INTEGRATOR_RK4, 256, 2); break;
+        case 2: BODY_FAST(B200_INTEGRATOR_RK4, 128, 3); break;
+        case 0: BODY_FAST(B200_INTEGRATOR_RK4, 256, 1); break;
+        case 4: BODY_FAST(B200_INTEGRATOR_RK4, 64, 8); break;
+        case 5: BODY_FAST(B200_INTEGRATOR_RK4, 128, 5); break;
         case 10: case 11: case 12: case 13: case 14: {
             // persistent TMA-pipelined kernel; needs plane stride % 128 == 0 (whole tiles inside a plane)
             const bool direct = cfg >= 13;
@@ -1073,7 +1111,7 @@ cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode,
         }
         // default (cfg 3): 128 threads x 4 CTAs/SM = 16 warps/SM at <= 128 registers — measured 95% of the
         // HBM copy peak on B200 vs 57% for 256x1 (profiles/r01_tuning.md)
-        default: body_fast_kernel<B200_INTEGRATOR_RK4, 128, 4><<<g(128), 128, 0, s>>>(P); break;
+        default: BODY_FAST(B200_INTEGRATOR_RK4, 128, 4); break;
         }
     }
     return cudaGetLastError();
@@ -1147,14 +1185,17 @@ cudaError_t launch_soa_to_aos(const double *soa, double *aos, uint64_t n_bodies,
     return cudaGetLastError();
 }
 
-cudaError_t launch_traj_to_aos(const double *traj, double *aos, uint64_t n_samples, uint64_t n_bodies, uint64_t ld, cudaStream_t s)
+cudaError_t launch_traj_to_aos(const double *traj, double *aos, uint64_t n_samples, uint64_t n_bodies, uint64_t ld,
+                               uint32_t width, cudaStream_t s)
 {
     if (n_bodies == 0 || n_samples == 0) return cudaSuccess;
+    const size_t smem = (size_t)kTile * (width | 1u) * sizeof(double); // 25 planes: 52 KB, above the 48 KB default
+    cudaError_t e = ensure_dynamic_smem(soa_to_aos_kernel, smem);
+    if (e != cudaSuccess) return e;
     for (uint64_t s0 = 0; s0 < n_samples; s0 += 32768) {
         const unsigned ny = (unsigned)min((uint64_t)32768, n_samples - s0);
         const dim3 grid((unsigned)((n_bodies + kTile - 1) / kTile), ny);
-        soa_to_aos_kernel<<<grid, kTile, kTile * 13 * sizeof(double), s>>>(traj + s0 * 13 * ld, aos + s0 * n_bodies * 13,
-                                                                          n_bodies, 13, ld);
+        soa_to_aos_kernel<<<grid, kTile, smem, s>>>(traj + s0 * width * ld, aos + s0 * n_bodies * width, n_bodies, width, ld);
     }
     return cudaGetLastError();
 }

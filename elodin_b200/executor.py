@@ -52,6 +52,7 @@ class B200Exec:
         trajectory_capacity: int = 0,
         world=None,
         invoke_chunk_bodies: int = 0,
+        trajectory_full: bool = False,
     ):
         from .effectors import _flatten
 
@@ -82,6 +83,7 @@ class B200Exec:
         d.trajectory_every = int(trajectory_every)
         d.trajectory_capacity = int(trajectory_capacity)
         d.invoke_chunk_bodies = int(invoke_chunk_bodies)
+        d.trajectory_flags = _lib.TRAJ_FULL if trajectory_full else 0
         h = C.c_void_p()
         _lib.check(L.b200_sixdof_create(C.byref(d), C.byref(h)))
         self._L, self._h = L, h
@@ -202,11 +204,15 @@ class B200Exec:
     def trajectory_len(self) -> int:
         return int(self._L.b200_sixdof_trajectory_len(self._h))
 
+    def trajectory_width(self) -> int:
+        """13 = (world_pos[7], world_vel[6]); 25 with trajectory_full: + (world_accel[6], force[6])."""
+        return int(self._L.b200_sixdof_trajectory_width(self._h))
+
     def trajectory(self) -> np.ndarray:
-        """[samples, n_worlds, n_entities, 13] = (world_pos[7], world_vel[6]) per sample."""
+        """[samples, n_worlds, n_entities, width] — see trajectory_width()."""
         self.sync()
         n = self.trajectory_len()
-        out = np.empty((n, self.n_worlds, self.n_entities, 13))
+        out = np.empty((n, self.n_worlds, self.n_entities, max(self.trajectory_width(), 13)))
         _lib.check(self._L.b200_sixdof_trajectory_download(self._h, out.ctypes.data, out.nbytes))
         return out
 

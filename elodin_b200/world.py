@@ -18,6 +18,7 @@ from __future__ import annotations
 import dataclasses
 import enum
 import re
+import os
 import sys
 import time
 import typing
@@ -419,14 +420,14 @@ class World:
               telemetry_rate: Optional[float] = None, default_playback_speed: float = 1.0,
               max_ticks: Optional[int] = None, optimize: bool = False, db_path: Optional[str] = None,
               backend: str = "b200", math: str = "exact", n_worlds: int = 1, device: int = -1,
-              world_params: Optional[Dict[str, np.ndarray]] = None) -> "Exec":
+              world_params: Optional[Dict[str, np.ndarray]] = None, resident: Optional[bool] = None) -> "Exec":
         if backend not in ("b200", "b200-exact", "b200-fast"):
             raise _lib.B200Error(
                 _lib.ERR_UNSUPPORTED,
                 f"unknown backend '{backend}': this package only provides 'b200' (no cranelift / jax fallback)")
         if backend == "b200-fast":
             math = "fast"
-        return Exec(self, system, simulation_rate, telemetry_rate, max_ticks, math, n_worlds, device, world_params)
+        return Exec(self, system, simulation_rate, telemetry_rate, max_ticks, math, n_worlds, device, world_params, resident)
 
     def run(self, system: System, simulation_rate: float = 120.0, generate_real_time: bool = False,
             telemetry_rate: Optional[float] = None, default_playback_speed: float = 1.0,
@@ -486,7 +487,7 @@ class Exec:
 
     def __init__(self, world: World, system: System, simulation_rate: float, telemetry_rate: Optional[float],
                  max_ticks: Optional[int], math: str, n_worlds: int, device: int,
-                 world_params: Optional[Dict[str, np.ndarray]]):
+                 world_params: Optional[Dict[str, np.ndarray]], resident: Optional[bool] = None):
         systems = _flatten(system)
         six = [s for s in systems if isinstance(s, SixDof)]
         if len(six) != 1:
@@ -534,9 +535,22 @@ class Exec:
             mask[rows] = 1
             e.with_mask(mask)
             self._partial[component_id(cname)] = (np.asarray(rows), np.zeros((self.n_worlds, len(bodies), col.width)))
+        # Device-resident telemetry cycles (small interactive worlds): the state stays on the GPU for a whole
+        # run() and every telemetry sample — all five Body columns — is recorded into the device trajectory
+        # ring, read back in one transfer per `_ring_cap` cycles instead of one PCIe round trip per cycle.
+        # Results are identical to the invoke_batch path (same kernels, same tick boundaries).
+        n_bodies = len(bodies) * self.n_worlds
+        if resident is None:
+            resident = os.environ.get("B200_RESIDENT", "1") != "0" and 0 < n_bodies <= 65536
+        self._ring_cap = 0
+        if resident and n_bodies:
+            ld = (n_bodies + 127) // 128 * 128
+            self._ring_cap = int(max(1, min(4096, (64 << 20) // (25 * ld * 8))))
         # ticks of one invoke_batch stay in registers up to 32 at a time (no effect on results)
         self.backend = B200Exec(len(bodies), self.n_worlds, self.sim_time_step, self.six.time_step, self.six.effectors,
-                                self.six.integrator.value, math, device, max_fused_ticks=32, world=world)
+                                self.six.integrator.value, math, device, max_fused_ticks=32, world=world,
+                                trajectory_every=self.ticks_per_telemetry if self._ring_cap else 0,
+                                trajectory_capacity=self._ring_cap, trajectory_full=bool(self._ring_cap))
         self.tick = 0
         self.build_ms = 0.0
         self._prof = {"execute_buffers": [], "add_to_history": [], "h2d_upload": [], "kernel_invoke": [], "d2h_download": []}
@@ -599,12 +613,65 @@ class Exec:
                     raise _lib.B200ValueError(_lib.ERR_VALUE_SIZE_MISMATCH, "value size mismatch")
                 np.copyto(col.buffer, buf)
 
+    def _run_resident(self, cycles: int) -> None:
+        """`cycles` whole telemetry cycles without leaving the device: upload the host columns once, step,
+        read the recorded samples back per ring-full, leave the final state in the host columns."""
+        be = self.backend
+        tpt = self.ticks_per_telemetry
+        tick_id, dt_id = component_id("tick"), component_id("simulation_time_step")
+        t0 = time.perf_counter()
+        for cid in be.input_ids:
+            if cid == tick_id:
+                be.upload(cid, np.array([self.tick], dtype=np.uint64))
+            elif cid == dt_id:
+                be.upload(cid, np.array([self.sim_time_step]))
+            elif cid in self._partial:
+                rows, expanded = self._partial[cid]
+                expanded[:, rows, :] = self.world.columns[cid].buffer
+                be.upload(cid, expanded)
+            else:
+                be.upload(cid, self.world.columns[cid].buffer)
+        upload_ms = (time.perf_counter() - t0) * 1e3
+        body_cols = [(component_id("world_pos"), 0, 7), (component_id("world_vel"), 7, 13),
+                     (component_id("world_accel"), 13, 19), (component_id("force"), 19, 25)]
+        sampled = {cid for cid, _, _ in body_cols}
+        while cycles > 0:
+            c = min(cycles, self._ring_cap)
+            t0 = time.perf_counter()
+            be.trajectory_reset()
+            be.step(c * tpt)
+            traj = be.trajectory()                                   # [c, n_worlds, n_bodies, 25]
+            run_ms = (time.perf_counter() - t0) * 1e3 + upload_ms
+            upload_ms = 0.0
+            t_hist = time.perf_counter()
+            for k in range(c):
+                self.tick += tpt
+                for cid, lo, hi in body_cols:
+                    self._history[cid].append(np.ascontiguousarray(traj[k, :, :, lo:hi]))
+                for cid, col in self.world.columns.items():
+                    if cid not in sampled:
+                        self._history[cid].append(col.buffer.copy())  # not written by six_dof(): pass-through
+                self._globals_hist.append((self.tick, self.sim_time_step))
+            for cid, lo, hi in body_cols:
+                np.copyto(self.world.columns[cid].buffer, traj[-1, :, :, lo:hi])
+            hist_ms = (time.perf_counter() - t_hist) * 1e3
+            self._prof["execute_buffers"] += [run_ms / c] * c
+            self._prof["add_to_history"] += [hist_ms / c] * c
+            for k_dst in ("h2d_upload", "kernel_invoke", "d2h_download"):
+                self._prof[k_dst] += [0.0] * c                        # not separable on this path
+            cycles -= c
+
     # -- public API ------------------------------------------------------------------
     def run(self, ticks: int = 1, show_progress: bool = True, is_canceled=None, pre_step=None, post_step=None):
         """exec.rs:111-173: `while remaining > 0 { exec.run(); commit_world_head }` — one
-        invoke_batch of ticks_per_telemetry ticks per cycle, a history row per cycle."""
+        invoke_batch of ticks_per_telemetry ticks per cycle, a history row per cycle.  Runs without host
+        callbacks take the device-resident route for their whole cycles (same rows, one transfer)."""
         remaining = int(ticks)
         host_cb = bool(self.pre_systems or self.post_systems or pre_step or post_step)
+        if self._ring_cap and not host_cb and is_canceled is None and remaining >= self.ticks_per_telemetry:
+            whole = remaining // self.ticks_per_telemetry
+            self._run_resident(whole)
+            remaining -= whole * self.ticks_per_telemetry
         while remaining > 0:
             if is_canceled is not None and is_canceled():
                 break

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200_SIXDOF_ABI_VERSION 1u
+#define B200_SIXDOF_ABI_VERSION 2u
 
 /* ---- status codes (0 = ok).  Names follow libs/nox-py/src/error.rs:7-44 ---- */
 enum {
@@ -79,6 +79,14 @@ enum {
      * term `0 * WorldAccel` (rk4.rs:85-104) is not evaluated, so a non-finite WorldAccel input
      * does not poison the step; denormal inputs to 1/x and 1/sqrt(x) flush to zero. */
     B200_MATH_FAST = 1
+};
+
+/* ---- trajectory ring contents (b200_sixdof_desc.trajectory_flags) ---- */
+enum {
+    /* a sample also carries WorldAccel[6] and Force[6] (the stage-4 values the tick leaves in the
+     * ECS columns): 25 f64 per body instead of 13, i.e. every column `commit_world_head_unified`
+     * (impeller2_server.rs:390-438) would have written for that telemetry tick */
+    B200_TRAJ_FULL = 1
 };
 
 /* ---- built-in effectors.  Evaluated in array order
@@ -152,6 +160,8 @@ typedef struct b200_sixdof_desc {
                                   this many bodies so that range k's download overlaps range k+1's
                                   upload and ticks; 0 = default (131072)                */
     uint64_t trajectory_capacity; /* samples the device ring can hold                 */
+    uint32_t trajectory_flags; /* B200_TRAJ_*                                        */
+    uint32_t reserved0;        /* must be 0                                          */
 } b200_sixdof_desc;
 
 typedef struct b200_timings {  /* TickTimings analogue, libs/nox-py/src/profile.rs — of the last
@@ -221,9 +231,13 @@ int b200_sixdof_invoke_batch(b200_sixdof *h, const uint8_t *const *in_cols,
 int b200_sixdof_bind_tick(b200_sixdof *h);
 void b200_sixdof_tick(const uint8_t *const *in_cols, uint8_t **out_cols);
 
-/* Trajectory ring: samples of (world_pos[7], world_vel[6]) taken every
- * `trajectory_every` ticks.  Download layout [samples][n_worlds][n_entities][13]. */
+/* Trajectory ring: samples of (world_pos[7], world_vel[6]) — with B200_TRAJ_FULL also
+ * (world_accel[6], force[6]) — taken every `trajectory_every` ticks.  Download layout
+ * [samples][n_worlds][n_entities][width], width = b200_sixdof_trajectory_width() = 13 | 25.
+ * The ring lets a telemetry_rate < simulation_rate run stay device-resident between samples:
+ * upload once, step, read the samples back in one transfer. */
 uint64_t b200_sixdof_trajectory_len(const b200_sixdof *h);
+uint32_t b200_sixdof_trajectory_width(const b200_sixdof *h);
 int b200_sixdof_trajectory_download(b200_sixdof *h, void *dst, uint64_t bytes);
 int b200_sixdof_trajectory_reset(b200_sixdof *h);
 

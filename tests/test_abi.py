@@ -53,10 +53,29 @@ def test_component_id_matches_reference_table(built_lib):
     assert el.component_id("a.b") == built_lib.b200_component_id(b"a.b")
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
     assert ctypes.sizeof(_lib.Effector) == 4 + 4 + 64 + 8 + 4 + 4 + 8 + 8 + 8 + 8
-    assert ctypes.sizeof(_lib.Desc) == 16 + 16 + 16 + 8 + 4 + 4 + 4 + 4 + 8
+    assert ctypes.sizeof(_lib.Desc) == 16 + 16 + 16 + 8 + 4 + 4 + 4 + 4 + 8 + 4 + 4
     assert ctypes.sizeof(_lib.Timings) == 48
+    # and against the C compiler's view of include/b200_sixdof.h: sizes, every field offset, the ABI version
+    fields = {"b200_effector": _lib.Effector, "b200_sixdof_desc": _lib.Desc, "b200_timings": _lib.Timings}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200_sixdof.h"', 'int main(void) {',
+           'printf("abi %u\\n", B200_SIXDOF_ABI_VERSION);']
+    for cname, st in fields.items():
+        src.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in st._fields_:
+            src.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src += ["return 0; }"]
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", str(c), "-I", os.path.join(ROOT, "include"), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(got["abi"]) == _lib.ABI_VERSION
+    for cname, st in fields.items():
+        assert int(got[cname]) == ctypes.sizeof(st), cname
+        for fname, _ in st._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(st, fname).offset, (cname, fname)
 
 
 def test_no_gpu_means_loud_failure_not_cpu_fallback(built_lib):

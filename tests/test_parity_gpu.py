@@ -285,6 +285,61 @@ def test_trajectory_ring_matches_states():
         assert ex.tick == 60
 
 
+@pytest.mark.parametrize("math", ["exact", "fast"])
+@pytest.mark.parametrize("case", ["effectors", "nbody", "semi_implicit"])
+def test_full_trajectory_ring_carries_accel_and_force(math, case):
+    """B200_TRAJ_FULL: a sample holds all five Body columns' worth of telemetry — (pos, vel, accel, force)
+    exactly as a download after that tick returns them — whatever the launch fusing, for free bodies with
+    effectors, for the n-body tick (one-launch variant in FAST) and for the semi-implicit integrator."""
+    integ = "semi_implicit" if case == "semi_implicit" else "rk4"
+    if case == "nbody":
+        M, N = 2, 24
+        pos, vel, ine = random_world(11, M, N)
+        effs, cols = [el.GravityEdges("softened", k_squared=1e-3, softening=1e-6, edges=el.all_pairs_edges(N))], {}
+    else:
+        M, N = 5, 3
+        pos, vel, ine = random_world(12, M, N)
+        rng = np.random.default_rng(5)
+        effs = [el.GravityConst(), el.ThrustBody(), el.WrenchBody()]
+        cols = {"thrust": rng.uniform(1, 5, (M, N, 1)), "aero_force": rng.normal(0, 1, (M, N, 6))}
+    every, n_cycles = 3, 7
+    def snapshots(full, fused):
+        with el.B200Exec(N, M, 0.01, None, effs, integ, math, max_fused_ticks=fused, trajectory_every=every,
+                         trajectory_capacity=n_cycles, trajectory_full=full) as ex:
+            ex.set_state(pos, vel, ine, **cols)
+            assert ex.trajectory_width() == (25 if full else 13)
+            snaps = []
+            for _ in range(n_cycles):
+                ex.step(every, sync=True)
+                snaps.append(np.concatenate([ex.download(c) for c in (WORLD_POS, WORLD_VEL, WORLD_ACCEL, FORCE)], -1))
+            return np.stack(snaps), ex.trajectory()
+    snaps, traj = snapshots(True, 1)
+    assert traj.shape == (n_cycles, M, N, 25)
+    assert np.array_equal(traj, snaps)
+    # one launch for the whole run (ticks fused in registers where the path allows it): same samples
+    with el.B200Exec(N, M, 0.01, None, effs, integ, math, max_fused_ticks=32, trajectory_every=every,
+                     trajectory_capacity=n_cycles, trajectory_full=True) as ex:
+        ex.set_state(pos, vel, ine, **cols)
+        ex.step(every * n_cycles, sync=True)
+        assert np.array_equal(ex.trajectory(), snaps)
+    # and the 13-wide ring is the same run's (pos, vel)
+    _, traj13 = snapshots(False, 8)
+    assert np.array_equal(traj13, snaps[..., :13])
+
+
+def test_unknown_trajectory_flags_are_rejected():
+    from elodin_b200 import _lib
+    import ctypes as C
+
+    d = _lib.Desc()
+    d.abi_version, d.n_entities, d.n_worlds, d.sim_time_step, d.time_step, d.device = _lib.ABI_VERSION, 1, 1, 0.01, float("nan"), -1
+    d.trajectory_flags = 2
+    h = C.c_void_p()
+    assert _lib.lib().b200_sixdof_create(C.byref(d), C.byref(h)) == _lib.ERR_INVALID_ARGUMENT
+    d.trajectory_flags, d.abi_version = 0, 1
+    assert _lib.lib().b200_sixdof_create(C.byref(d), C.byref(h)) == _lib.ERR_INVALID_ARGUMENT  # ABI v1 callers are refused
+
+
 @pytest.mark.parametrize("B", [1, 31, 32, 33, 255, 257, 1000, 4097])
 def test_layout_roundtrip_ragged(B):
     """K6 aos<->soa: upload then download returns the same bytes for ragged sizes."""
@@ -946,6 +1001,58 @@ def test_effectors_follow_the_query_join(oracle):
             assert f_plain[5] == -9.81 * ine[0, 0, 6]
         # the drag quirk (torque reset) only hits members: "rocket" keeps no torque anyway, "both" is zeroed by drag
         assert ex.history("ball.wind")["ball.wind"].shape == (13, 3)
+
+
+@pytest.mark.parametrize("math", ["exact", "fast"])
+@pytest.mark.parametrize("telemetry_rate", [None, 24.0])
+def test_resident_run_equals_invoke_batch_run(math, telemetry_rate):
+    """Exec.run without host callbacks keeps the state on the device and reads all telemetry back from the
+    full trajectory ring; the rows it records — every component, every cycle, plus a ragged tail that goes
+    through invoke_batch — are the rows the one-invoke-per-cycle route records, bit for bit (heterogeneous
+    world with a partial-membership effector column, and an n-body world)."""
+    Thrust = el.Annotated[np.ndarray, el.Component("thrust", el.ComponentType.F64)]
+
+    @el.dataclass
+    class Motor(el.Archetype):
+        thrust: Thrust
+
+    pos, vel, ine = random_world(21, 1, 5)
+    arch = lambda i: el.Body(world_pos=el.SpatialTransform(arr=pos[0, i]), world_vel=el.SpatialMotion(angular=vel[0, i, :3], linear=vel[0, i, 3:]),
+                             inertia=el.SpatialInertia(ine[0, i, 6], ine[0, i, :3]))
+
+    def mixed():
+        w = el.World()
+        w.spawn([arch(0)], name="plain")
+        w.spawn([arch(1), Motor(np.array([40.0]))], name="rocket")
+        w.spawn([arch(2)], name="third")
+        return w, el.six_dof(sys=el.GravityConst((0.0, 0.0, -9.81)) | el.ThrustBody((-1.0, 0.0, 0.0), "thrust")), ("plain", "rocket", "third")
+
+    def nbody():
+        w = el.World()
+        for i in range(5):
+            w.spawn([arch(i)], name=f"p{i}")
+        return w, el.six_dof(sys=el.GravityEdges("softened", k_squared=1e-2, softening=1e-6, edges=el.all_pairs_edges(5))), tuple(f"p{i}" for i in range(5))
+
+    for make in (mixed, nbody):
+        runs = []
+        for resident in (True, False):
+            w, system, names = make()
+            ex = w.build(system, simulation_rate=120.0, telemetry_rate=telemetry_rate, math=math, n_worlds=3, resident=resident)
+            assert bool(ex._ring_cap) == resident
+            ex.run(23)            # telemetry_rate 24 -> 5 ticks per cycle: 4 resident cycles + a 3-tick tail
+            ex.run(10)            # a second run() re-uploads the host columns and carries on
+            runs.append((ex, names))
+        (a, names), (b, _) = runs
+        assert a.tick == b.tick == 33
+        if telemetry_rate is None:  # one cycle per tick: the resident route has no per-cycle layout launches
+            assert a.backend.timings()["kernel_launches"] < b.backend.timings()["kernel_launches"]
+        for name in names:
+            for comp in ("world_pos", "world_vel", "world_accel", "force", "inertia"):
+                ha, hb = a.history_worlds(f"{name}.{comp}"), b.history_worlds(f"{name}.{comp}")
+                assert ha.shape == hb.shape and np.array_equal(ha, hb), (make.__name__, name, comp)
+        assert np.array_equal(a.history("globals.tick")["globals.tick"], b.history("globals.tick")["globals.tick"])
+        for cid, col in a.world.columns.items():
+            assert np.array_equal(col.buffer, b.world.columns[cid].buffer)
 
 
 def test_two_devices_in_one_process():
