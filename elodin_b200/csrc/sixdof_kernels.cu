@@ -1032,28 +1032,26 @@ __global__ void __launch_bounds__(256) probe_fp64_kernel(double *out, int iters)
 
 // ================================================================== launchers
 
-// cudaFuncAttributeMaxDynamicSharedMemorySize is per (kernel, device): remember which pairs have been
-// raised (a process may hold handles on several GPUs; several kernels share a function-pointer type).
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (kernel, device): remember the size each pair has been
+// raised to (a process may hold handles on several GPUs; several kernels share a function-pointer type;
+// one kernel may be launched with several tile sizes).
 template <typename K>
 static cudaError_t ensure_dynamic_smem(K kernel, size_t bytes)
 {
+    struct Entry { const void *kernel; int device; size_t bytes; };
     static std::mutex mu;
-    static std::vector<std::pair<const void *, uint64_t>> done; // (kernel, device bitmask)
+    static std::vector<Entry> done;
     int dev = 0;
     cudaGetDevice(&dev);
-    const uint64_t bit = 1ull << (dev & 63);
     const void *key = reinterpret_cast<const void *>(kernel);
     std::lock_guard<std::mutex> lock(mu);
-    for (auto &d : done)
-        if (d.first == key) {
-            if (d.second & bit) return cudaSuccess;
-            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-            if (e == cudaSuccess) d.second |= bit;
-            return e;
-        }
+    Entry *hit = nullptr;
+    for (auto &d : done) if (d.kernel == key && d.device == dev) hit = &d;
+    if (hit && hit->bytes >= bytes) return cudaSuccess;
     const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e == cudaSuccess) done.emplace_back(key, bit);
-    return e;
+    if (e != cudaSuccess) return e;
+    if (hit) hit->bytes = bytes; else done.push_back(Entry{key, dev, bytes});
+    return cudaSuccess;
 }
 
 // the instantiation without trajectory code for launches that record nothing, the generic one otherwise
