@@ -68,6 +68,8 @@ struct b200_sixdof {
     double *gforce = nullptr;
     double *pos_alt = nullptr, *vel_alt = nullptr; // ping-pong planes of the one-launch n-body tick
     bool nbody_fused = false;                       // decided once per handle (whole-batch grid size)
+    bool small_world = false;                       // <= 32 bodies per world: whole ticks in one warp, n ticks per launch
+    uint32_t max_deg = 0;
     // staging for AoS <-> SoA
     double *staging = nullptr;
     uint64_t staging_bytes = 0;
@@ -185,6 +187,7 @@ int build_graph(b200_sixdof *h, const b200_effector &e)
         }
     }
     h->graph_dense = dense;
+    for (uint32_t i = 0; i < N; ++i) h->max_deg = std::max<uint32_t>(h->max_deg, (uint32_t)adj[i].size());
     CU(h, cudaMalloc(&h->row_ptr, (N + 1) * sizeof(uint32_t)));
     CU(h, cudaMalloc(&h->col_idx, std::max<size_t>(col.size(), 1) * sizeof(uint32_t)));
     CU(h, cudaMalloc(&h->has_edge, has.size()));
@@ -252,7 +255,7 @@ int launch_ticks(b200_sixdof *h, uint64_t w0, uint64_t nw, uint64_t n_ticks, cud
     P.n_bodies = nb;
     const bool exact = h->desc.math_mode == B200_MATH_EXACT;
     const bool graph = h->graph_eff >= 0;
-    const uint64_t fuse = graph ? 1 : std::max<uint32_t>(1u, h->desc.max_fused_ticks);
+    const uint64_t fuse = (graph && !h->small_world) ? 1 : std::max<uint32_t>(1u, h->desc.max_fused_ticks);
     uint64_t left = n_ticks, done = 0;
     double *pos_next = h->pos_alt ? h->pos_alt + b0 : nullptr, *vel_next = h->vel_alt ? h->vel_alt + b0 : nullptr;
     while (left) {
@@ -263,7 +266,18 @@ int launch_ticks(b200_sixdof *h, uint64_t w0, uint64_t nw, uint64_t n_ticks, cud
             G.pos = P.pos; G.vel = P.vel; G.ine = P.ine; G.gforce = h->gforce + b0;
             G.ld = h->ld; G.n_entities = P.n_entities; G.n_worlds = (uint32_t)nw;
             G.dt_stage = P.dt_stage; G.kind = e.kind; G.integrator = h->desc.integrator;
-            G.p0 = e.p[0]; G.p1 = e.p[1]; G.row_ptr = h->row_ptr; G.col_idx = h->col_idx;
+            G.p0 = e.p[0]; G.p1 = e.p[1]; G.row_ptr = h->row_ptr; G.col_idx = h->col_idx; G.max_deg = h->max_deg;
+            if (h->small_world) {
+                // gravity through warp shuffles + integration, n ticks in one launch, state in registers
+                P.n_ticks = (uint32_t)n;
+                P.tick0 = h->ticks_done + done;
+                P.write_fa = (exact || left == n) ? 1u : 0u;
+                CU(h, launch_small_world(G, P, (int)h->desc.math_mode, stream));
+                h->timings.kernel_launches++;
+                done += n;
+                left -= n;
+                continue;
+            }
             if (h->nbody_fused) {
                 // gravity + integration in one launch; the new state lands in the other plane set
                 P.n_ticks = 1;
@@ -515,7 +529,8 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
         {
             GraphParams G{};
             G.n_entities = (uint32_t)d->n_entities; G.n_worlds = (uint32_t)d->n_worlds; G.integrator = d->integrator;
-            h->nbody_fused = h->pos_alt && nbody_fused_applicable(G, (int)d->math_mode, h->graph_dense);
+            h->small_world = small_world_applicable(G);
+            h->nbody_fused = !h->small_world && h->pos_alt && nbody_fused_applicable(G, (int)d->math_mode, h->graph_dense);
         }
         h->effectors[h->graph_eff].edge_from = h->effectors[h->graph_eff].edge_to = nullptr;
     }

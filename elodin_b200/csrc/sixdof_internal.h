@@ -60,6 +60,8 @@ struct GraphParams {
     double p0, p1;           // G | K^2, softening
     const uint32_t *row_ptr; // CSR over sources (n_entities+1), spawn order kept inside a row
     const uint32_t *col_idx;
+    uint32_t max_deg;        // largest out-degree (uniform trip count of small_world_kernel's shuffle loop)
+    uint32_t pad;
 };
 
 // Column table of the one-launch layout kernel used by small batches
@@ -82,6 +84,9 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
 // one-launch n-body tick (gravity + integration) for small grids; new pose / velocity go to *_out
 bool nbody_fused_applicable(const GraphParams &G, int math_mode, bool dense);
 cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, double *pos_out, double *vel_out, cudaStream_t s);
+// worlds of <= 32 bodies: gravity + integration of n_ticks ticks in one launch, one warp per floor(32/N) worlds
+bool small_world_applicable(const GraphParams &G);
+cudaError_t launch_small_world(const GraphParams &G, const StepParams &P, int math_mode, cudaStream_t s);
 cudaError_t launch_aos_to_soa(const double *aos, double *soa, uint64_t n_bodies, uint32_t width, uint64_t ld,
                               cudaStream_t s);
 cudaError_t launch_soa_to_aos(const double *soa, double *aos, uint64_t n_bodies, uint32_t width, uint64_t ld,

@@ -91,9 +91,19 @@ __device__ __forceinline__ void traj_store_af(const StepParams &P, uint64_t b, u
 
 // ================================================================== EXACT body kernel
 
+// edge_fold gravity of one body at the three stage positions, held in registers by the kernels that
+// compute it themselves (small_world_kernel) instead of reading the gforce planes
+struct GravReg {
+    Vec3 g0, g1, g2;
+    bool has; // the body owns >= 1 out-edge
+};
+__device__ __forceinline__ Vec3 grav_slot(const GravReg &g, int slot) { return slot == 0 ? g.g0 : (slot == 1 ? g.g1 : g.g2); }
+
 // clear_forces | effectors (array order) on the stage state; six_dof.rs:148-150,195
+template <bool GREG>
 __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t b, int slot, const Pose &sx,
-                                                  const ex::PoseInv &pi, const Motion &sv, const Inertia &I)
+                                                  const ex::PoseInv &pi, const Motion &sv, const Inertia &I,
+                                                  const GravReg &greg)
 {
     using namespace ex;
     Motion F = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
@@ -157,7 +167,9 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
         }
         case B200_EFF_GRAVITY_EDGES_NEWTON:
         case B200_EFF_GRAVITY_EDGES_SOFTENED: { // Force := edge_fold(init 0) for bodies that own an edge
-            if (P.gforce && P.has_edge && P.has_edge[b % P.n_entities]) {
+            if (GREG) {
+                if (greg.has) { F.ang = Vec3{0.0, 0.0, 0.0}; F.lin = grav_slot(greg, slot); }
+            } else if (P.gforce && P.has_edge && P.has_edge[b % P.n_entities]) {
                 F.ang = Vec3{0.0, 0.0, 0.0};
                 F.lin = Vec3{ldp(P.gforce, P.ld, slot * 3 + 0, b), ldp(P.gforce, P.ld, slot * 3 + 1, b),
                              ldp(P.gforce, P.ld, slot * 3 + 2, b)};
@@ -170,10 +182,52 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
     return F;
 }
 
+// one tick of one body in EXACT arithmetic (state in registers)
+template <int INTEG, bool GREG>
+__device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose &x0, Motion &v0, Motion &a_out,
+                                           Motion &f_out, const Inertia &I, const GravReg &greg)
+{
+    using namespace ex;
+    if (INTEG == B200_INTEGRATOR_RK4) {
+        // rk4.rs:85-123 (see the header comment of oracle/sixdof_oracle.c for the derivation)
+        Motion sa = a_out; // du.a before stage 1 is the WorldAccel column
+        Motion kv, ka;
+        // three distinct stage poses (f = 0, .5, 1), functions of (x0, v0) only; stages 2 and 3 share
+        // the f = .5 pose and its inverses — identical inputs, identical bits — so each is built once
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+            const double dtf = mul(P.dt_stage, k == 0 ? 0.0 : (k == 1 ? 0.5 : 1.0));
+            const Pose sx = tadd(x0, scale(dtf, v0));
+            const PoseInv pi = pose_inverses(sx.q);
+            const int n_stages = (k == 1) ? 2 : 1;
+#pragma unroll 1
+            for (int j = 0; j < n_stages; ++j) {
+                const int s = (k == 0) ? 0 : (k == 1 ? 1 + j : 3);
+                const Motion sv = madd(v0, scale(dtf, sa));
+                f_out = effectors_exact<GREG>(P, b, k, sx, pi, sv, I, greg);
+                sa = calc_accel_with(sx, pi, f_out, I);
+                if (s == 0) { kv = sv; ka = sa; }
+                else if (s == 3) { kv = madd(kv, sv); ka = madd(ka, sa); }
+                else { kv = madd(kv, scale(2.0, sv)); ka = madd(ka, scale(2.0, sa)); }
+            }
+        }
+        const double c = mul(P.dt_final, 1.0 / 6.0);
+        x0 = tadd(x0, scale(c, kv));
+        v0 = madd(v0, scale(c, ka));
+        a_out = sa;
+    } else {
+        // semi_implicit.rs:42-62
+        const PoseInv pi = pose_inverses(x0.q);
+        f_out = effectors_exact<GREG>(P, b, 0, x0, pi, v0, I, greg);
+        a_out = calc_accel_with(x0, pi, f_out, I);
+        v0 = madd(v0, scale(P.dt_final, a_out));
+        x0 = tadd(x0, scale(P.dt_final, v0));
+    }
+}
+
 template <int INTEG, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) body_exact_kernel(const __grid_constant__ StepParams P)
 {
-    using namespace ex;
     const uint64_t b = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
     if (b >= P.n_bodies) return;
 
@@ -182,43 +236,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_exact_kernel(const __grid_co
     Motion a_out = load_motion(P.acc, P.ld, b);
     Motion f_out = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
     const Inertia I = load_inertia(P.ine, P.ld, b);
+    const GravReg no_greg{};
 
     for (uint32_t t = 0; t < P.n_ticks; ++t) {
-        if (INTEG == B200_INTEGRATOR_RK4) {
-            // rk4.rs:85-123 (see the header comment of oracle/sixdof_oracle.c for the derivation)
-            Motion sa = a_out; // du.a before stage 1 is the WorldAccel column
-            Motion kv, ka;
-            // three distinct stage poses (f = 0, .5, 1), functions of (x0, v0) only; stages 2 and 3 share
-            // the f = .5 pose and its inverses — identical inputs, identical bits — so each is built once
-#pragma unroll 1
-            for (int k = 0; k < 3; ++k) {
-                const double dtf = mul(P.dt_stage, k == 0 ? 0.0 : (k == 1 ? 0.5 : 1.0));
-                const Pose sx = tadd(x0, scale(dtf, v0));
-                const PoseInv pi = pose_inverses(sx.q);
-                const int n_stages = (k == 1) ? 2 : 1;
-#pragma unroll 1
-                for (int j = 0; j < n_stages; ++j) {
-                    const int s = (k == 0) ? 0 : (k == 1 ? 1 + j : 3);
-                    const Motion sv = madd(v0, scale(dtf, sa));
-                    f_out = effectors_exact(P, b, k, sx, pi, sv, I);
-                    sa = calc_accel_with(sx, pi, f_out, I);
-                    if (s == 0) { kv = sv; ka = sa; }
-                    else if (s == 3) { kv = madd(kv, sv); ka = madd(ka, sa); }
-                    else { kv = madd(kv, scale(2.0, sv)); ka = madd(ka, scale(2.0, sa)); }
-                }
-            }
-            const double c = mul(P.dt_final, 1.0 / 6.0);
-            x0 = tadd(x0, scale(c, kv));
-            v0 = madd(v0, scale(c, ka));
-            a_out = sa;
-        } else {
-            // semi_implicit.rs:42-62
-            const PoseInv pi = pose_inverses(x0.q);
-            f_out = effectors_exact(P, b, 0, x0, pi, v0, I);
-            a_out = calc_accel_with(x0, pi, f_out, I);
-            v0 = madd(v0, scale(P.dt_final, a_out));
-            x0 = tadd(x0, scale(P.dt_final, v0));
-        }
+        exact_tick<INTEG, false>(P, b, x0, v0, a_out, f_out, I, no_greg);
         uint64_t slot;
         if (traj_due(P, P.tick0 + t + 1, slot)) {
             traj_store_state(P, b, slot, x0, v0);
@@ -247,7 +268,9 @@ struct Folded {
     bool drag, frame, graph;
 };
 
-__device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b, const Inertia &I, const Vec3 &invI)
+template <bool GREG>
+__device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b, const Inertia &I, const Vec3 &invI,
+                                                 const GravReg &greg)
 {
     Folded f;
     f.fw = f.fb = f.u = f.wind = f.om = Vec3{0.0, 0.0, 0.0};
@@ -287,7 +310,7 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
             break;
         case B200_EFF_GRAVITY_EDGES_NEWTON:
         case B200_EFF_GRAVITY_EDGES_SOFTENED: // host guarantees this is effector 0 in FAST mode
-            f.graph = P.gforce && P.has_edge && P.has_edge[b % P.n_entities];
+            f.graph = GREG ? greg.has : (P.gforce && P.has_edge && P.has_edge[b % P.n_entities]);
             break;
         default: break;
         }
@@ -297,8 +320,10 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
 }
 
 // linear acceleration of one stage: everything that depends on (q, x, v)
+template <bool GREG>
 __device__ __forceinline__ Vec3 lin_accel_fast(const StepParams &P, const Folded &f, uint64_t b, int slot,
-                                               const Vec3 &fbw, const Vec3 &x, const Vec3 &v, double m, double inv_m)
+                                               const Vec3 &fbw, const Vec3 &x, const Vec3 &v, double m, double inv_m,
+                                               const GravReg &greg)
 {
     Vec3 F = {f.fw.x + fbw.x, f.fw.y + fbw.y, f.fw.z + fbw.z};
     if (f.drag) {
@@ -319,9 +344,14 @@ __device__ __forceinline__ Vec3 lin_accel_fast(const StepParams &P, const Folded
         F.z = fma(fma(g, x.z, -2.0 * c.z - c2.z), m, F.z);
     }
     if (f.graph) {
-        F.x += ldp(P.gforce, P.ld, slot * 3 + 0, b);
-        F.y += ldp(P.gforce, P.ld, slot * 3 + 1, b);
-        F.z += ldp(P.gforce, P.ld, slot * 3 + 2, b);
+        if (GREG) {
+            const Vec3 g = grav_slot(greg, slot);
+            F.x += g.x; F.y += g.y; F.z += g.z;
+        } else {
+            F.x += ldp(P.gforce, P.ld, slot * 3 + 0, b);
+            F.y += ldp(P.gforce, P.ld, slot * 3 + 1, b);
+            F.z += ldp(P.gforce, P.ld, slot * 3 + 2, b);
+        }
     }
     return Vec3{F.x * inv_m, F.y * inv_m, F.z * inv_m};
 }
@@ -339,13 +369,16 @@ __device__ __forceinline__ Motion force_out_fast(const Vec3 &a_lin, const Vec3 &
 }
 
 // n_ticks ticks of one body, state in registers (shared by the direct and the TMA-pipelined kernel)
-template <int INTEG, bool TRAJ>
+// (n_ticks, tick0, want_f) are P.n_ticks, P.tick0, P.write_fa for the kernels that integrate a launch's ticks
+// in one call; small_world_kernel calls it once per tick with that tick's gravity in `greg`
+template <int INTEG, bool TRAJ, bool GREG = false>
 __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose &x0, Motion &v0, const Inertia &I,
-                                           Motion &a_last, Motion &f_last)
+                                           Motion &a_last, Motion &f_last, uint32_t n_ticks, uint64_t tick0, bool want_f,
+                                           const GravReg &greg)
 {
     const Vec3 invI = {fa::rcp_nr(I.diag.x), fa::rcp_nr(I.diag.y), fa::rcp_nr(I.diag.z)};
     const double inv_m = fa::rcp_nr(I.m);
-    const Folded f = fold_effectors(P, b, I, invI);
+    const Folded f = fold_effectors<GREG>(P, b, I, invI, greg);
 
     a_last = Motion{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
     Quat q_last = x0.q;
@@ -353,7 +386,7 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
     const bool has_u = (f.u.x != 0.0) | (f.u.y != 0.0) | (f.u.z != 0.0);
     const bool has_fb = (f.fb.x != 0.0) | (f.fb.y != 0.0) | (f.fb.z != 0.0);
 
-    for (uint32_t t = 0; t < P.n_ticks; ++t) {
+    for (uint32_t t = 0; t < n_ticks; ++t) {
         if (INTEG == B200_INTEGRATOR_RK4) {
             const Vec3 w0 = v0.ang, u0 = v0.lin;
             // the three distinct stage poses depend on (x0, v0) only (rk4.rs:85-111)
@@ -375,16 +408,16 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
             if (has_u) { aa1 = fa::rot(q1, f.u); aa2 = fa::rot(q2, f.u); aa4 = fa::rot(q4, f.u); }
             if (has_fb) { fb1 = fa::rot(q1, f.fb); fb2 = fa::rot(q2, f.fb); fb4 = fa::rot(q4, f.fb); }
             // stage 1: v = v0
-            const Vec3 al1 = lin_accel_fast(P, f, b, 0, fb1, x0.x, u0, I.m, inv_m);
+            const Vec3 al1 = lin_accel_fast<GREG>(P, f, b, 0, fb1, x0.x, u0, I.m, inv_m, greg);
             // stage 2: v = v0 + dt/2 a1
             const Vec3 u2 = {fma(h4, al1.x, u0.x), fma(h4, al1.y, u0.y), fma(h4, al1.z, u0.z)};
-            const Vec3 al2 = lin_accel_fast(P, f, b, 1, fb2, x2, u2, I.m, inv_m);
+            const Vec3 al2 = lin_accel_fast<GREG>(P, f, b, 1, fb2, x2, u2, I.m, inv_m, greg);
             // stage 3: same pose as stage 2, v = v0 + dt/2 a2
             const Vec3 u3 = {fma(h4, al2.x, u0.x), fma(h4, al2.y, u0.y), fma(h4, al2.z, u0.z)};
-            const Vec3 al3 = lin_accel_fast(P, f, b, 1, fb2, x2, u3, I.m, inv_m);
+            const Vec3 al3 = lin_accel_fast<GREG>(P, f, b, 1, fb2, x2, u3, I.m, inv_m, greg);
             // stage 4: v = v0 + dt a3
             const Vec3 u4 = {fma(dt, al3.x, u0.x), fma(dt, al3.y, u0.y), fma(dt, al3.z, u0.z)};
-            const Vec3 al4 = lin_accel_fast(P, f, b, 2, fb4, x4, u4, I.m, inv_m);
+            const Vec3 al4 = lin_accel_fast<GREG>(P, f, b, 2, fb4, x4, u4, I.m, inv_m, greg);
             // k.v sum = 6 v0 + dt (a1 + a2 + a3);  k.a sum = a1 + 2 a2 + 2 a3 + a4   (a3.ang == a2.ang)
             const double c = P.dt_final * (1.0 / 6.0);
             const Vec3 kw = {fma(dt, aa1.x + 2.0 * aa2.x, 6.0 * w0.x), fma(dt, aa1.y + 2.0 * aa2.y, 6.0 * w0.y),
@@ -407,7 +440,7 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
             const Quat qn = {x0.q.i * rn, x0.q.j * rn, x0.q.k * rn, x0.q.w * rn};
             const Vec3 aa = has_u ? fa::rot(qn, f.u) : Vec3{0.0, 0.0, 0.0};
             const Vec3 fbw = has_fb ? fa::rot(qn, f.fb) : Vec3{0.0, 0.0, 0.0};
-            const Vec3 al = lin_accel_fast(P, f, b, 0, fbw, x0.x, v0.lin, I.m, inv_m);
+            const Vec3 al = lin_accel_fast<GREG>(P, f, b, 0, fbw, x0.x, v0.lin, I.m, inv_m, greg);
             const double d = P.dt_final;
             v0.ang = Vec3{fma(d, aa.x, v0.ang.x), fma(d, aa.y, v0.ang.y), fma(d, aa.z, v0.ang.z)};
             v0.lin = Vec3{fma(d, al.x, v0.lin.x), fma(d, al.y, v0.lin.y), fma(d, al.z, v0.lin.z)};
@@ -418,13 +451,13 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
         }
         if (TRAJ) { // compiled out of the launches that record nothing (the roofline case)
             uint64_t slot;
-            if (traj_due(P, P.tick0 + t + 1, slot)) {
+            if (traj_due(P, tick0 + t + 1, slot)) {
                 traj_store_state(P, b, slot, x0, v0);
                 if (P.traj_planes == 25) traj_store_af(P, b, slot, a_last, force_out_fast(a_last.lin, f.u, q_last, I));
             }
         }
     }
-    if (P.write_fa) f_last = force_out_fast(a_last.lin, f.u, q_last, I);
+    if (want_f) f_last = force_out_fast(a_last.lin, f.u, q_last, I);
 }
 
 // Effector columns are consumed inside the (uniform) effector switch, i.e. after the state
@@ -452,7 +485,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_fast_kernel(const __grid_con
     Motion v0 = load_motion(P.vel, P.ld, b);
     const Inertia I = load_inertia(P.ine, P.ld, b);
     Motion a_last, f_last;
-    fast_ticks<INTEG, TRAJ>(P, b, x0, v0, I, a_last, f_last);
+    fast_ticks<INTEG, TRAJ>(P, b, x0, v0, I, a_last, f_last, P.n_ticks, P.tick0, P.write_fa != 0, GravReg{});
     store_pose(P.pos, P.ld, b, x0);
     store_motion(P.vel, P.ld, b, v0);
     if (P.write_fa) {
@@ -582,7 +615,7 @@ __global__ void __launch_bounds__(kPipeTB, MINB) body_fast_pipe_kernel(const __g
         }
         Motion a_last, f_last;
         const bool live = b < P.n_bodies;
-        if (live) fast_ticks<INTEG, true>(P, b, x0, v0, I, a_last, f_last);
+        if (live) fast_ticks<INTEG, true>(P, b, x0, v0, I, a_last, f_last, P.n_ticks, P.tick0, P.write_fa != 0, GravReg{});
         if (DIRECT_OUT) {
             if (live) {
                 store_pose(P.pos, P.ld, b, x0);
@@ -896,7 +929,7 @@ __global__ void __launch_bounds__(32 * kFastSrc * 3) nbody_tick_fused_kernel(con
         Motion v0 = load_motion(P.vel, P.ld, b);
         const Inertia I = load_inertia(P.ine, P.ld, b);
         Motion a_last, f_last;
-        fast_ticks<B200_INTEGRATOR_RK4, true>(P, b, x0, v0, I, a_last, f_last);
+        fast_ticks<B200_INTEGRATOR_RK4, true>(P, b, x0, v0, I, a_last, f_last, P.n_ticks, P.tick0, P.write_fa != 0, GravReg{});
         store_pose(pos_out, P.ld, b, x0);
         store_motion(vel_out, P.ld, b, v0);
         if (P.write_fa) {
@@ -956,6 +989,106 @@ __global__ void __launch_bounds__(kBlockG) graph_csr_kernel(const __grid_constan
         stp(G.gforce, G.ld, s * 3 + 0, t, EXACT ? acc[s].x : k * acc[s].x);
         stp(G.gforce, G.ld, s * 3 + 1, t, EXACT ? acc[s].y : k * acc[s].y);
         stp(G.gforce, G.ld, s * 3 + 2, t, EXACT ? acc[s].z : k * acc[s].z);
+    }
+}
+
+// ================================================================== small graph worlds: whole ticks in one warp
+//
+// A world of N <= 32 bodies fits in a warp: lane = body, floor(32/N) whole worlds per warp.  The edge_fold
+// gravity of a tick needs the other bodies' three stage positions — functions of (x0, v0) only — which the
+// lanes exchange with warp shuffles, so the state never leaves registers between ticks: one launch integrates
+// n_ticks ticks (the generic route is two launches and a round trip of the 9 gravity planes through HBM per
+// tick).  Every lane folds its out-edges sequentially in CSR (= spawn) order with the same ex:: functions as
+// graph_dense_kernel / graph_csr_kernel, then runs the same tick function as body_exact_kernel — EXACT stays
+// bit-identical to the oracle.  FAST folds sequentially too (no tree), with the FAST kernels' arithmetic.
+template <bool EXACT, int INTEG>
+__global__ void __launch_bounds__(128) small_world_kernel(const __grid_constant__ GraphParams G,
+                                                          const __grid_constant__ StepParams P)
+{
+    constexpr bool RK4 = INTEG == B200_INTEGRATOR_RK4;
+    constexpr int NS = RK4 ? 3 : 1;
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t N = G.n_entities;
+    const uint32_t wpw = 32u / N; // worlds per warp
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t wl = lane / N, ent = lane - wl * N;
+    const uint64_t world = warp * wpw + wl;
+    const bool live = wl < wpw && world < G.n_worlds;
+    const uint64_t b = live ? world * N + ent : 0;
+    const uint32_t lane0 = lane - ent; // first lane of this lane's world
+    const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
+
+    Pose x0 = {{0.0, 0.0, 0.0, 1.0}, {0.0, 0.0, 0.0}};
+    Motion v0 = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}}, a_out = v0, f_out = v0;
+    Inertia I = {{1.0, 1.0, 1.0}, 1.0};
+    uint32_t e0 = 0, deg = 0;
+    if (live) {
+        x0 = load_pose(P.pos, P.ld, b);
+        v0 = load_motion(P.vel, P.ld, b);
+        if (EXACT) a_out = load_motion(P.acc, P.ld, b);
+        I = load_inertia(P.ine, P.ld, b);
+        e0 = G.row_ptr[ent];
+        deg = G.row_ptr[ent + 1] - e0;
+    }
+    GravReg g;
+    g.g0 = g.g1 = g.g2 = Vec3{0.0, 0.0, 0.0};
+    g.has = deg != 0;
+
+    for (uint32_t t = 0; t < P.n_ticks; ++t) {
+        // stage positions of this body and the running folds, one per distinct stage position
+        Vec3 p[NS], acc[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const double fac = s == 0 ? 0.0 : (s == 1 ? 0.5 : 1.0);
+            const double dtf = EXACT ? ex::mul(G.dt_stage, fac) : fac * G.dt_stage;
+            p[s] = RK4 ? stage_pos<EXACT>(x0.x, v0.lin, dtf) : x0.x;
+            acc[s] = Vec3{0.0, 0.0, 0.0};
+        }
+        for (uint32_t k = 0; k < G.max_deg; ++k) { // warp-uniform trip count: every lane takes part in the shuffles
+            const bool on = k < deg;
+            const uint32_t src = lane0 + (on ? G.col_idx[e0 + k] : ent);
+            const double mj = __shfl_sync(FULL, I.m, src);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const Vec3 xj = {__shfl_sync(FULL, p[s].x, src), __shfl_sync(FULL, p[s].y, src), __shfl_sync(FULL, p[s].z, src)};
+                if (!on) continue;
+                if (EXACT) {
+                    if (newton) ex::fold_newton(G.p0, p[s], I.m, xj, mj, acc[s]);
+                    else ex::fold_softened(G.p0, G.p1, p[s], I.m, xj, mj, acc[s]);
+                } else {
+                    const Vec3 r = {xj.x - p[s].x, xj.y - p[s].y, xj.z - p[s].z};
+                    const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, newton ? 0.0 : G.p1)));
+                    const double inv = fa::rsqrt_nr(d2);
+                    const double w = mj * inv * inv * inv;
+                    acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
+                }
+            }
+        }
+        const double kf = EXACT ? 1.0 : G.p0 * I.m; // FAST: common factor (G | K^2) * m_i applied once
+        g.g0 = EXACT ? acc[0] : Vec3{kf * acc[0].x, kf * acc[0].y, kf * acc[0].z};
+        if (RK4) {
+            g.g1 = EXACT ? acc[NS - 2] : Vec3{kf * acc[NS - 2].x, kf * acc[NS - 2].y, kf * acc[NS - 2].z};
+            g.g2 = EXACT ? acc[NS - 1] : Vec3{kf * acc[NS - 1].x, kf * acc[NS - 1].y, kf * acc[NS - 1].z};
+        }
+        if (!live) continue;
+        if (EXACT) {
+            exact_tick<INTEG, true>(P, b, x0, v0, a_out, f_out, I, g);
+            uint64_t slot;
+            if (traj_due(P, P.tick0 + t + 1, slot)) {
+                traj_store_state(P, b, slot, x0, v0);
+                if (P.traj_planes == 25) traj_store_af(P, b, slot, a_out, f_out);
+            }
+        } else {
+            fast_ticks<INTEG, true, true>(P, b, x0, v0, I, a_out, f_out, 1u, P.tick0 + t, P.write_fa && t + 1 == P.n_ticks, g);
+        }
+    }
+    if (!live) return;
+    store_pose(P.pos, P.ld, b, x0);
+    store_motion(P.vel, P.ld, b, v0);
+    if (P.write_fa) {
+        store_motion(P.acc, P.ld, b, a_out);
+        store_motion(P.frc, P.ld, b, f_out);
     }
 }
 
@@ -1164,6 +1297,29 @@ cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, d
     if (e != cudaSuccess) return e;
     const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
     nbody_tick_fused_kernel<1024><<<gridf, dim3(32, kFastSrc, 3), smem, s>>>(G, P, pos_out, vel_out);
+    return cudaGetLastError();
+}
+
+bool small_world_applicable(const GraphParams &G)
+{
+    static const int cfg = [] { const char *e = getenv("B200_SMALL_WORLD"); return e ? atoi(e) : 1; }();
+    return cfg != 0 && G.n_entities >= 1 && G.n_entities <= 32;
+}
+
+cudaError_t launch_small_world(const GraphParams &G, const StepParams &P, int math_mode, cudaStream_t s)
+{
+    if (G.n_entities == 0 || G.n_worlds == 0) return cudaSuccess;
+    const uint32_t wpw = 32u / G.n_entities;
+    const uint64_t warps = ((uint64_t)G.n_worlds + wpw - 1) / wpw;
+    const unsigned grid = (unsigned)((warps + 3) / 4); // 4 warps per CTA
+    const bool rk4 = G.integrator == B200_INTEGRATOR_RK4;
+    if (math_mode == B200_MATH_EXACT) {
+        if (rk4) small_world_kernel<true, B200_INTEGRATOR_RK4><<<grid, 128, 0, s>>>(G, P);
+        else small_world_kernel<true, B200_INTEGRATOR_SEMI_IMPLICIT><<<grid, 128, 0, s>>>(G, P);
+    } else {
+        if (rk4) small_world_kernel<false, B200_INTEGRATOR_RK4><<<grid, 128, 0, s>>>(G, P);
+        else small_world_kernel<false, B200_INTEGRATOR_SEMI_IMPLICIT><<<grid, 128, 0, s>>>(G, P);
+    }
     return cudaGetLastError();
 }
 
