@@ -529,7 +529,7 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
         {
             GraphParams G{};
             G.n_entities = (uint32_t)d->n_entities; G.n_worlds = (uint32_t)d->n_worlds; G.integrator = d->integrator;
-            h->small_world = small_world_applicable(G);
+            h->small_world = small_world_applicable(G, (int)d->math_mode);
             h->nbody_fused = !h->small_world && h->pos_alt && nbody_fused_applicable(G, (int)d->math_mode, h->graph_dense);
         }
         h->effectors[h->graph_eff].edge_from = h->effectors[h->graph_eff].edge_to = nullptr;

@@ -85,7 +85,7 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
 bool nbody_fused_applicable(const GraphParams &G, int math_mode, bool dense);
 cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, double *pos_out, double *vel_out, cudaStream_t s);
 // worlds of <= 32 bodies: gravity + integration of n_ticks ticks in one launch, one warp per floor(32/N) worlds
-bool small_world_applicable(const GraphParams &G);
+bool small_world_applicable(const GraphParams &G, int math_mode);
 cudaError_t launch_small_world(const GraphParams &G, const StepParams &P, int math_mode, cudaStream_t s);
 cudaError_t launch_aos_to_soa(const double *aos, double *soa, uint64_t n_bodies, uint32_t width, uint64_t ld,
                               cudaStream_t s);

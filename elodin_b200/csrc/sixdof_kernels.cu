@@ -1300,10 +1300,13 @@ cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, d
     return cudaGetLastError();
 }
 
-bool small_world_applicable(const GraphParams &G)
+bool small_world_applicable(const GraphParams &G, int math_mode)
 {
+    // measured (profiles/r01_small_world.md): FAST wins up to the full warp (N = 32: 2.6x the two-launch route,
+    // N = 3: 37x); EXACT folds its 3 stage slots one after the other per lane and breaks even near N = 32
     static const int cfg = [] { const char *e = getenv("B200_SMALL_WORLD"); return e ? atoi(e) : 1; }();
-    return cfg != 0 && G.n_entities >= 1 && G.n_entities <= 32;
+    const uint32_t limit = math_mode == B200_MATH_EXACT ? 16u : 32u;
+    return cfg != 0 && G.n_entities >= 1 && G.n_entities <= (cfg == 2 ? 32u : limit);
 }
 
 cudaError_t launch_small_world(const GraphParams &G, const StepParams &P, int math_mode, cudaStream_t s)

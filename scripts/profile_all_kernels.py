@@ -34,4 +34,17 @@ p = np.zeros((64, 512, 7)); p[..., 3] = 1.0; p[..., 4:] = rng.uniform(-30, 30, (
 I = np.ones((64, 512, 7))
 with el.B200Exec(512, 64, 0.01, None, [el.GravityEdges("softened", k_squared=1e-3, softening=1e-6, edges=edges)], "rk4", "fast") as ex:
     ex.set_state(p, np.zeros((64, 512, 6)), I); ex.step(3, sync=True)
+# small graph worlds: small_world_kernel (one warp per floor(32/N) worlds, 16 ticks per launch), FAST and EXACT
+for Nw, Mw in ((3, 1 << 18), (8, 1 << 16)):
+    p = np.zeros((Mw, Nw, 7)); p[..., 3] = 1.0; p[..., 4:] = rng.uniform(-30, 30, (Mw, Nw, 3))
+    v = np.zeros((Mw, Nw, 6)); v[..., 3:] = rng.normal(0, 1e-3, (Mw, Nw, 3))
+    m = 10 ** rng.uniform(-3, 0, (Mw, Nw)); I = np.zeros((Mw, Nw, 7)); I[..., :3] = m[..., None]; I[..., 6] = m
+    g = el.GravityEdges("softened", k_squared=1e-3, softening=1e-6, edges=el.all_pairs_edges(Nw))
+    for math in ("fast", "exact"):
+        with el.B200Exec(Nw, Mw, 0.01, None, [g], "rk4", math, max_fused_ticks=16) as ex:
+            ex.set_state(p, v, I); ex.step(32, sync=True)
+# full-telemetry trajectory ring: body_fast_kernel<.., TRAJ = true> recording 25 planes every 4th tick + its read-back
+with el.B200Exec(1, M, 1e-3, None, [], "rk4", "fast", max_fused_ticks=16, trajectory_every=4, trajectory_capacity=4,
+                 trajectory_full=True) as ex:
+    ex.set_state(pos, vel, ine); ex.step(16, sync=True); ex.trajectory()
 print("done")
