@@ -1001,8 +1001,8 @@ __global__ void __launch_bounds__(kBlockG) graph_csr_kernel(const __grid_constan
 // tick).  Every lane folds its out-edges sequentially in CSR (= spawn) order with the same ex:: functions as
 // graph_dense_kernel / graph_csr_kernel, then runs the same tick function as body_exact_kernel — EXACT stays
 // bit-identical to the oracle.  FAST folds sequentially too (no tree), with the FAST kernels' arithmetic.
-template <bool EXACT, int INTEG>
-__global__ void __launch_bounds__(128) small_world_kernel(const __grid_constant__ GraphParams G,
+template <bool EXACT, int INTEG, int MINB>
+__global__ void __launch_bounds__(128, MINB) small_world_kernel(const __grid_constant__ GraphParams G,
                                                           const __grid_constant__ StepParams P)
 {
     constexpr bool RK4 = INTEG == B200_INTEGRATOR_RK4;
@@ -1302,11 +1302,24 @@ cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, d
 
 bool small_world_applicable(const GraphParams &G, int math_mode)
 {
-    // measured (profiles/r01_small_world.md): FAST wins up to the full warp (N = 32: 2.6x the two-launch route,
-    // N = 3: 37x); EXACT folds its 3 stage slots one after the other per lane and breaks even near N = 32
+    // measured (profiles/r01_small_world.md): faster than the two-launch route over the whole range a warp can
+    // hold, in both arithmetic modes (N = 3: 53x FAST / 4.4x EXACT; N = 32: 3.6x / 1.35x)
+    (void)math_mode;
     static const int cfg = [] { const char *e = getenv("B200_SMALL_WORLD"); return e ? atoi(e) : 1; }();
-    const uint32_t limit = math_mode == B200_MATH_EXACT ? 16u : 32u;
-    return cfg != 0 && G.n_entities >= 1 && G.n_entities <= (cfg == 2 ? 32u : limit);
+    return cfg != 0 && G.n_entities >= 1 && G.n_entities <= 32;
+}
+
+template <int MINB>
+static void launch_small_world_cfg(const GraphParams &G, const StepParams &P, int math_mode, unsigned grid, cudaStream_t s)
+{
+    const bool rk4 = G.integrator == B200_INTEGRATOR_RK4;
+    if (math_mode == B200_MATH_EXACT) {
+        if (rk4) small_world_kernel<true, B200_INTEGRATOR_RK4, MINB><<<grid, 128, 0, s>>>(G, P);
+        else small_world_kernel<true, B200_INTEGRATOR_SEMI_IMPLICIT, MINB><<<grid, 128, 0, s>>>(G, P);
+    } else {
+        if (rk4) small_world_kernel<false, B200_INTEGRATOR_RK4, MINB><<<grid, 128, 0, s>>>(G, P);
+        else small_world_kernel<false, B200_INTEGRATOR_SEMI_IMPLICIT, MINB><<<grid, 128, 0, s>>>(G, P);
+    }
 }
 
 cudaError_t launch_small_world(const GraphParams &G, const StepParams &P, int math_mode, cudaStream_t s)
@@ -1315,13 +1328,13 @@ cudaError_t launch_small_world(const GraphParams &G, const StepParams &P, int ma
     const uint32_t wpw = 32u / G.n_entities;
     const uint64_t warps = ((uint64_t)G.n_worlds + wpw - 1) / wpw;
     const unsigned grid = (unsigned)((warps + 3) / 4); // 4 warps per CTA
-    const bool rk4 = G.integrator == B200_INTEGRATOR_RK4;
-    if (math_mode == B200_MATH_EXACT) {
-        if (rk4) small_world_kernel<true, B200_INTEGRATOR_RK4><<<grid, 128, 0, s>>>(G, P);
-        else small_world_kernel<true, B200_INTEGRATOR_SEMI_IMPLICIT><<<grid, 128, 0, s>>>(G, P);
-    } else {
-        if (rk4) small_world_kernel<false, B200_INTEGRATOR_RK4><<<grid, 128, 0, s>>>(G, P);
-        else small_world_kernel<false, B200_INTEGRATOR_SEMI_IMPLICIT><<<grid, 128, 0, s>>>(G, P);
+    // resident CTAs per SM the register allocation is bounded for (B200_SMALL_WORLD_CFG = 2 | 3 | 4): the kernel
+    // is latency-bound, 16 warps/SM at 128 registers (a few spilled doubles) beat 8 warps at 196 by 1.3-1.45x
+    static const int cfg = [] { const char *e = getenv("B200_SMALL_WORLD_CFG"); return e ? atoi(e) : 4; }();
+    switch (cfg) {
+    case 2: launch_small_world_cfg<2>(G, P, math_mode, grid, s); break;
+    case 3: launch_small_world_cfg<3>(G, P, math_mode, grid, s); break;
+    default: launch_small_world_cfg<4>(G, P, math_mode, grid, s); break;
     }
     return cudaGetLastError();
 }

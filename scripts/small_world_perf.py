@@ -6,8 +6,10 @@ import numpy as np, torch
 import elodin_b200 as el
 
 cases = [(3, 1, 2000), (3, 1 << 18, 64), (8, 1 << 16, 64), (16, 1 << 14, 64), (32, 1 << 13, 32)]
+if os.environ.get("SW_QUICK"):
+    cases = [(3, 1 << 18, 64), (8, 1 << 16, 64), (32, 1 << 13, 32)]
 rng = np.random.default_rng(3)
-tag = "small_world=" + os.environ.get("B200_SMALL_WORLD", "1")
+tag = "small_world=" + os.environ.get("B200_SMALL_WORLD", "1") + " cfg=" + os.environ.get("B200_SMALL_WORLD_CFG", "2")
 for math in ("fast", "exact"):
     for N, M, T in cases:
         p = np.zeros((M, N, 7)); p[..., 3] = 1.0; p[..., 4:] = rng.uniform(-30, 30, (M, N, 3))
