@@ -644,14 +644,13 @@ class Exec:
             run_ms = (time.perf_counter() - t0) * 1e3 + upload_ms
             upload_ms = 0.0
             t_hist = time.perf_counter()
-            for k in range(c):
-                self.tick += tpt
-                for cid, lo, hi in body_cols:
-                    self._history[cid].append(np.ascontiguousarray(traj[k, :, :, lo:hi]))
-                for cid, col in self.world.columns.items():
-                    if cid not in sampled:
-                        self._history[cid].append(col.buffer.copy())  # not written by six_dof(): pass-through
-                self._globals_hist.append((self.tick, self.sim_time_step))
+            for cid, lo, hi in body_cols:                            # one contiguous block per column, rows are views
+                self._history[cid].extend(np.ascontiguousarray(traj[:, :, :, lo:hi]))
+            for cid, col in self.world.columns.items():
+                if cid not in sampled:                               # not written by six_dof(): pass-through
+                    self._history[cid].extend([col.buffer.copy()] * c)
+            self._globals_hist.extend((self.tick + (k + 1) * tpt, self.sim_time_step) for k in range(c))
+            self.tick += c * tpt
             for cid, lo, hi in body_cols:
                 np.copyto(self.world.columns[cid].buffer, traj[-1, :, :, lo:hi])
             hist_ms = (time.perf_counter() - t_hist) * 1e3
