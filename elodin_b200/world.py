@@ -466,6 +466,13 @@ class World:
         ex = self.build(system, simulation_rate, generate_real_time, telemetry_rate, default_playback_speed,
                         max_ticks, optimize, db_path, backend, math, n_worlds)
         ex.run(max_ticks, show_progress=False, is_canceled=is_canceled, pre_step=pre_step, post_step=post_step)
+        if db_path:
+            # the reference's `World.run(db_path=...)` leaves an elodin-db directory behind (impeller2_server.rs:
+            # 229-309, 390-438); here it is written from the recorded telemetry once the run is over
+            ts = None
+            if start_timestamp is not None:
+                ts = int(start_timestamp.timestamp() * 1e6) if hasattr(start_timestamp, "timestamp") else int(start_timestamp)
+            ex.write_db(db_path, ts)
         return ex
 
 

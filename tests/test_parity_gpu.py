@@ -238,6 +238,45 @@ def test_sparse_graph_csr_and_order(oracle):
         _run_gpu(pos, vel, ine, [gg, g], {}, 0.01, 1, "fast")
 
 
+@pytest.mark.parametrize("N", [1, 2, 3, 7, 16, 31, 32])
+@pytest.mark.parametrize("integrator", ["rk4", "semi_implicit"])
+def test_small_world_kernel_sparse_and_dense(oracle, N, integrator):
+    """Worlds of <= 32 bodies run whole ticks inside one warp (small_world_kernel): gravity through warp
+    shuffles in CSR = spawn order, several ticks per launch, ragged worlds per warp (32 % N != 0), bodies
+    without out-edges keeping the other effectors' force, a thrust column next to the graph effector.
+    EXACT stays bit-identical to the oracle; FAST within tolerance."""
+    O = oracle
+    M = 41
+    pos, vel, ine = random_world(100 + N, M, N)
+    rng = np.random.default_rng(N)
+    pos[..., 4:] = rng.uniform(-5, 5, (M, N, 3))
+    thrust = rng.uniform(0, 3, (M, N, 1))
+    graphs = {"dense": el.all_pairs_edges(N)}
+    if N >= 3:
+        e = np.array([(i, j) for i in range(0, N, 2) for j in rng.permutation(N)[:5] if i != j])
+        rng.shuffle(e)
+        graphs["sparse"] = e
+    for name, edges in graphs.items():
+        if len(edges) == 0:
+            continue
+        og, gg, _ = effector_pair(O, "gravity")
+        ot, gt, cols = effector_pair(O, "thrust", thrust=thrust)
+        o, g, _ = effector_pair(O, "softened", edges=edges, k2=0.3, soft=1e-6)
+        # EXACT keeps array order (gravity first: bodies without edges keep it); FAST needs the graph effector first
+        want = _run_oracle(O, pos, vel, ine, [og, o, ot], 0.01, 7, integrator)
+        with el.B200Exec(N, M, 0.01, None, [gg, g, gt], integrator, "exact", max_fused_ticks=3) as ex:
+            ex.set_state(pos, vel, ine, **cols)
+            ex.step(7, sync=True)  # 3 + 3 + 1 ticks per launch
+            got = (ex.download(WORLD_POS), ex.download(WORLD_VEL), ex.download(WORLD_ACCEL), ex.download(FORCE))
+        _assert_exact(got, want, f"small world N={N} {name} {integrator}")
+        want2 = _run_oracle(O, pos, vel, ine, [o, og, ot], 0.01, 7, integrator)
+        with el.B200Exec(N, M, 0.01, None, [g, gg, gt], integrator, "fast", max_fused_ticks=4) as ex:
+            ex.set_state(pos, vel, ine, **cols)
+            ex.step(7, sync=True)
+            fast = (ex.download(WORLD_POS), ex.download(WORLD_VEL), ex.download(WORLD_ACCEL), ex.download(FORCE))
+        _assert_close(fast, want2, 7 * 1e-11, f"small world fast N={N} {name} {integrator}")
+
+
 def test_semi_implicit_nbody(oracle):
     O = oracle
     M, N = 2, 33
@@ -662,6 +701,8 @@ def test_three_body_csv_export_passes_the_reference_regression_gate(golden, tmp_
 
     db = str(tmp_path / "three-body-db")
     ex.write_db(db)
+    with pytest.raises(FileExistsError):
+        ex.write_db(db)  # create_new semantics: never overwrites a database
     _, series, _ = db_sink.read_db(db)
     assert sorted(db_sink._safe_name(n) + ".csv" for n in series) == got_files
     assert np.array_equal(series["b.world_vel"].values, golden["three_body.b.world_vel"])
