@@ -274,13 +274,27 @@ def run_baseline_configs(args, torch, el, stream, local, rank, world_size):
     p3 = np.array([[[0, 0, 0, 1, 0.8920281421, 0, 0], [0, 0, 0, 1, -0.6628498947, 0, 0], [0, 0, 0, 1, -0.2291782474, 0, 0]]], dtype=np.float64)
     v3 = np.array([[[0, 0, 0, 0, 0.9957939373, 0], [0, 0, 0, 0, -1.6191613336, 0], [0, 0, 0, 0, 0.6233673964, 0]]], dtype=np.float64)
     i3 = np.tile(np.array([1 / G, 1 / G, 1 / G, 0, 0, 0, 1 / G]), (1, 3, 1))
-    ex = el.B200Exec(3, 1, 0.008333333, None, [el.GravityEdges("newton", G=G, edges=np.array([[0, 1], [1, 0], [0, 2], [1, 2], [2, 0], [2, 1]]))],
-                     "rk4", "exact", device=local)
-    ex.set_state(p3, v3, i3)
-    ms = timed(ex, 1000, 10)
-    out["three_body_1000_steps_exact"] = {"steps": 1000, "us_per_tick": ms, "value": 3 * 1000 / (ms * 1e-3), "unit": UNIT,
-                                         "note": "latency bound: 2 launches per tick, 3 bodies"}
-    ex.close()
+    edges3 = np.array([[0, 1], [1, 0], [0, 2], [1, 2], [2, 0], [2, 1]])
+    for math in ("exact", "fast"):
+        ex = el.B200Exec(3, 1, 0.008333333, None, [el.GravityEdges("newton", G=G, edges=edges3)], "rk4", math, device=local,
+                         max_fused_ticks=32)
+        ex.set_state(p3, v3, i3)
+        ms = timed(ex, 1000, 32)
+        out[f"three_body_1000_steps_{math}"] = {"steps": 1000, "us_per_tick": ms, "value": 3 * 1000 / (ms * 1e-3), "unit": UNIT,
+                                               "note": "one world in one warp (small_world_kernel), 32 ticks per launch: a dependent "
+                                                       "latency chain, no roofline"}
+        ex.close()
+    # the same system as a Monte-Carlo batch: 2^18 perturbed three-body worlds
+    Mw = 1 << 18
+    pM = np.tile(p3, (Mw, 1, 1)); pM[..., 4:] += rng.normal(0, 1e-3, (Mw, 3, 3))
+    for math in ("exact", "fast"):
+        ex = el.B200Exec(3, Mw, 0.008333333, None, [el.GravityEdges("newton", G=G, edges=edges3)], "rk4", math, device=local,
+                         max_fused_ticks=32)
+        ex.set_state(pM, np.tile(v3, (Mw, 1, 1)), np.tile(i3, (Mw, 1, 1)))
+        ms = timed(ex, 64, 32)
+        out[f"three_body_{Mw}_worlds_{math}"] = {"worlds": Mw, "steps": 64, "us_per_tick": ms * 1e3 / 64,
+                                                 "value": 3 * Mw * 64 / (ms * 1e-3), "unit": UNIT}
+        ex.close()
     return out
 
 
