@@ -23,7 +23,6 @@ from typing import List, Optional
 
 import numpy as np
 
-from ._lib import component_id
 
 
 _WORD_SPLIT = re.compile(r"[ \-_]+")

@@ -10,7 +10,6 @@ from __future__ import annotations
 
 from typing import List, Tuple
 
-import numpy as np
 
 
 def shard_worlds(n_worlds: int, rank: int, world_size: int) -> Tuple[int, int]:

@@ -22,13 +22,13 @@ import os
 import sys
 import time
 import typing
-from typing import Any, Callable, Dict, List, Optional, Sequence, Union
+from typing import Callable, Dict, List, Optional, Sequence, Union
 
 import numpy as np
 
 from . import _lib
 from ._lib import component_id
-from .effectors import Pipe, System, _flatten
+from .effectors import System, _flatten
 from .executor import B200Exec
 
 # --------------------------------------------------------------------------- value types
