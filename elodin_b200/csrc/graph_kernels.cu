@@ -1,0 +1,554 @@
+// sm_100a kernels of GraphQuery.edge_fold gravity (K3 of SURVEY §2.4) and the kernels that fuse it with the
+// body tick (nbody_tick_fused_kernel, small_world_kernel).
+//
+// Why one launch per tick suffices even with body-body coupling: in the reference's RK4
+// (libs/nox-py/src/integrator/rk4.rs:85-111) every stage position is x0 (+) (dt*f)*v0 — it never
+// depends on a stage acceleration — so the gravity at all four stages (three distinct positions,
+// f = 0, .5, 1) is a function of the tick's input state alone and needs no grid-wide synchronisation.
+#include <algorithm>
+
+#include "sixdof_tick.cuh"
+#include "sixdof_launch.h"
+
+namespace b200 {
+
+// ================================================================== edge_fold gravity
+
+// stage position of a body for slot 0/1/2 (f = 0, .5, 1): x (+) (dt*f)*v, linear part
+template <bool EXACT>
+__device__ __forceinline__ Vec3 stage_pos(const Vec3 &x, const Vec3 &v, double dtf)
+{
+    if (EXACT) return Vec3{ex::add(x.x, ex::mul(dtf, v.x)), ex::add(x.y, ex::mul(dtf, v.y)), ex::add(x.z, ex::mul(dtf, v.z))};
+    return Vec3{fma(dtf, v.x, x.x), fma(dtf, v.y, x.y), fma(dtf, v.z, x.z)};
+}
+
+// Dense all-pairs (every body's out-edges are all other bodies, ascending): block =
+// kBlockG source bodies of one world, targets streamed through shared memory in
+// tiles; each thread folds its targets sequentially in ascending order, which is
+// the reference's fold order (graph.rs:177-236) — so EXACT stays bit-exact.
+static constexpr int kBlockG = 64;
+
+// blockDim = (kBlockG, NS): thread (x, y) folds source x over all targets for stage slot y,
+// so the three stage positions of a tick proceed in parallel while every fold stays sequential.
+template <bool EXACT, bool RK4>
+__global__ void __launch_bounds__(kBlockG * 3) graph_dense_kernel(const __grid_constant__ GraphParams G)
+{
+    constexpr int NS = RK4 ? 3 : 1;
+    __shared__ double sx[NS][3][kBlockG];
+    __shared__ double sm[kBlockG];
+
+    const uint32_t N = G.n_entities;
+    const uint32_t tiles = (N + kBlockG - 1) / kBlockG;
+    const uint32_t world = blockIdx.x / tiles;
+    const uint32_t tile = blockIdx.x % tiles;
+    const uint32_t tx = threadIdx.x, sl = threadIdx.y; // sl = stage slot
+    const uint32_t i = tile * kBlockG + tx;
+    const uint64_t wbase = (uint64_t)world * N;
+    const bool active = i < N;
+    const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
+
+    const double fac = sl == 0 ? 0.0 : (sl == 1 ? 0.5 : 1.0);
+    const double dtf = EXACT ? ex::mul(G.dt_stage, fac) : fac * G.dt_stage;
+
+    Vec3 xi = {0, 0, 0}, acc = {0, 0, 0};
+    double mi = 0.0;
+    if (active) {
+        const uint64_t b = wbase + i;
+        const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+        const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+        mi = ldp(G.ine, G.ld, 6, b);
+        xi = RK4 ? stage_pos<EXACT>(x, v, dtf) : x;
+    }
+
+    for (uint32_t j0 = 0; j0 < N; j0 += kBlockG) {
+        const uint32_t j = j0 + tx;
+        __syncthreads();
+        if (j < N) {
+            const uint64_t b = wbase + j;
+            const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+            const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+            const Vec3 p = RK4 ? stage_pos<EXACT>(x, v, dtf) : x;
+            sx[sl][0][tx] = p.x; sx[sl][1][tx] = p.y; sx[sl][2][tx] = p.z;
+            if (sl == 0) sm[tx] = ldp(G.ine, G.ld, 6, b);
+        }
+        __syncthreads();
+        const uint32_t jn = min((uint32_t)kBlockG, N - j0);
+        if (active) {
+            for (uint32_t jj = 0; jj < jn; ++jj) {
+                if (j0 + jj == i) continue;
+                const double mj = sm[jj];
+                const Vec3 xj = {sx[sl][0][jj], sx[sl][1][jj], sx[sl][2][jj]};
+                if (EXACT) {
+                    if (newton) ex::fold_newton(G.p0, xi, mi, xj, mj, acc);
+                    else ex::fold_softened(G.p0, G.p1, xi, mi, xj, mj, acc);
+                } else {
+                    // common factor (G|K^2)*m_i applied after the loop
+                    const Vec3 r = {xj.x - xi.x, xj.y - xi.y, xj.z - xi.z};
+                    const double d2 = r.x * r.x + r.y * r.y + r.z * r.z + (newton ? 0.0 : G.p1);
+                    const double inv = fa::rsqrt_nr(d2);
+                    const double w = mj * inv * inv * inv;
+                    acc.x = fma(w, r.x, acc.x); acc.y = fma(w, r.y, acc.y); acc.z = fma(w, r.z, acc.z);
+                }
+            }
+        }
+    }
+    if (active) {
+        const uint64_t b = wbase + i;
+        const double k = EXACT ? 1.0 : G.p0 * mi;
+        stp(G.gforce, G.ld, sl * 3 + 0, b, EXACT ? acc.x : k * acc.x);
+        stp(G.gforce, G.ld, sl * 3 + 1, b, EXACT ? acc.y : k * acc.y);
+        stp(G.gforce, G.ld, sl * 3 + 2, b, EXACT ? acc.z : k * acc.z);
+    }
+}
+
+// FAST all-pairs: one warp per (source body, stage slot); lanes stride over the targets of a
+// tile and keep private partial sums, a fixed xor-butterfly of warp shuffles combines them
+// (summation order differs from the reference's sequential fold -> tolerance, not bit
+// parity; EXACT uses graph_dense_kernel).  blockDim = (32, kFastSrc, NS): the 8 sources x 3
+// slots of a CTA share one shared-memory tile of stage positions, and N = 1024, M = 1 still
+// spreads over 128 CTAs x 24 warps.
+static constexpr int kFastSrc = 8;
+
+// SPLIT = true : blockDim (32, kFastSrc, NS), one warp per (source, slot)  — small batches
+// SPLIT = false: blockDim (32, kFastSrc, 1),  one warp per source, NS slots — large batches
+// TJ = targets per shared-memory tile: 256 (3 CTAs/SM) for big grids; 1024 for small grids, where
+// the whole world of an N <= 1024 system is staged in ONE load phase instead of four dependent ones.
+template <bool RK4, bool SPLIT, int TJ>
+__global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) graph_dense_fast_kernel(const __grid_constant__ GraphParams G)
+{
+    constexpr int NS = RK4 ? 3 : 1;       // stage slots of a tick
+    constexpr int NW = SPLIT ? 1 : NS;    // slots folded by one warp
+    constexpr int NT = 32 * kFastSrc * (SPLIT ? NS : 1);
+    constexpr int kFastTJ = TJ;
+    extern __shared__ double dsm[];
+    double(*sx)[3][TJ] = reinterpret_cast<double(*)[3][TJ]>(dsm);
+    double *sm = dsm + NS * 3 * TJ;
+
+    const uint32_t N = G.n_entities;
+    const uint32_t groups = (N + kFastSrc - 1) / kFastSrc;
+    const uint32_t world = blockIdx.x / groups;
+    const uint32_t grp = blockIdx.x % groups;
+    const uint32_t lane = threadIdx.x, src = threadIdx.y, sl0 = SPLIT ? threadIdx.z : 0;
+    const uint32_t flat = (threadIdx.z * kFastSrc + src) * 32 + lane;
+    const uint32_t i = grp * kFastSrc + src;
+    const uint64_t wbase = (uint64_t)world * N;
+    const bool active = i < N;
+    const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
+    const double soft = newton ? 0.0 : G.p1;
+    auto dtf_of = [&](uint32_t sl) { return sl == 0 ? 0.0 : (sl == 1 ? 0.5 * G.dt_stage : G.dt_stage); };
+
+    Vec3 xi[NW], acc[NW];
+    double mi = 0.0;
+#pragma unroll
+    for (int s = 0; s < NW; ++s) { xi[s] = Vec3{0, 0, 0}; acc[s] = Vec3{0, 0, 0}; }
+    if (active) {
+        const uint64_t b = wbase + i;
+        const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+        const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+        mi = ldp(G.ine, G.ld, 6, b);
+#pragma unroll
+        for (int s = 0; s < NW; ++s) xi[s] = RK4 ? stage_pos<false>(x, v, dtf_of(sl0 + s)) : x;
+    }
+    for (uint32_t j0 = 0; j0 < N; j0 += kFastTJ) {
+        __syncthreads();
+        // NT threads fill the (kFastTJ x NS) tile: element t -> target t % TJ, slot t / TJ
+        for (uint32_t t = flat; t < kFastTJ * NS; t += NT) {
+            const uint32_t jt = t % kFastTJ, st = t / kFastTJ;
+            const uint32_t j = j0 + jt;
+            if (j < N) {
+                const uint64_t b = wbase + j;
+                const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+                Vec3 pnt = x;
+                if (RK4) {
+                    const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+                    pnt = stage_pos<false>(x, v, dtf_of(st));
+                }
+                sx[st][0][jt] = pnt.x; sx[st][1][jt] = pnt.y; sx[st][2][jt] = pnt.z;
+                if (st == 0) sm[jt] = ldp(G.ine, G.ld, 6, b);
+            }
+        }
+        __syncthreads();
+        const uint32_t jn = min((uint32_t)kFastTJ, N - j0);
+        if (active) {
+#pragma unroll 4
+            for (uint32_t jj = lane; jj < jn; jj += 32) {
+                // the self pair contributes exactly nothing (and would be 0 * inf for Newton)
+                const double mj = (j0 + jj == i) ? 0.0 : sm[jj];
+                const bool self = j0 + jj == i;
+#pragma unroll
+                for (int s = 0; s < NW; ++s) {
+                    const Vec3 r = {sx[sl0 + s][0][jj] - xi[s].x, sx[sl0 + s][1][jj] - xi[s].y, sx[sl0 + s][2][jj] - xi[s].z};
+                    const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, soft)));
+                    const double inv = fa::rsqrt_nr(d2);
+                    const double w = self ? 0.0 : mj * inv * inv * inv;
+                    acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NW; ++s) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            acc[s].x += __shfl_xor_sync(0xffffffffu, acc[s].x, off);
+            acc[s].y += __shfl_xor_sync(0xffffffffu, acc[s].y, off);
+            acc[s].z += __shfl_xor_sync(0xffffffffu, acc[s].z, off);
+        }
+    }
+    if (active && lane == 0) {
+        const uint64_t b = wbase + i;
+        const double k = G.p0 * mi;
+#pragma unroll
+        for (int s = 0; s < NW; ++s) {
+            stp(G.gforce, G.ld, (sl0 + s) * 3 + 0, b, k * acc[s].x);
+            stp(G.gforce, G.ld, (sl0 + s) * 3 + 1, b, k * acc[s].y);
+            stp(G.gforce, G.ld, (sl0 + s) * 3 + 2, b, k * acc[s].z);
+        }
+    }
+}
+
+// Small grids (one or a few worlds): gravity AND the body tick in ONE launch.  The CTA computes the
+// three stage-slot forces of its 8 sources exactly like graph_dense_fast_kernel<RK4, SPLIT>, then 8 of
+// its threads integrate those sources.  Other CTAs are still reading this tick's positions, so the
+// new pose / velocity go to a second set of planes (ping-pong, swapped by the host after the launch).
+// Saves the dependent second launch (~7 us of pure latency per tick at N = 1024, M = 1).
+template <int TJ>
+__global__ void __launch_bounds__(32 * kFastSrc * 3) nbody_tick_fused_kernel(const __grid_constant__ GraphParams G,
+                                                                              const __grid_constant__ StepParams P,
+                                                                              double *__restrict__ pos_out,
+                                                                              double *__restrict__ vel_out)
+{
+    constexpr int NS = 3;
+    constexpr int NT = 32 * kFastSrc * NS;
+    extern __shared__ double dsm[];
+    double(*sx)[3][TJ] = reinterpret_cast<double(*)[3][TJ]>(dsm);
+    double *sm = dsm + NS * 3 * TJ;
+
+    const uint32_t N = G.n_entities;
+    const uint32_t groups = (N + kFastSrc - 1) / kFastSrc;
+    const uint32_t world = blockIdx.x / groups;
+    const uint32_t grp = blockIdx.x % groups;
+    const uint32_t lane = threadIdx.x, src = threadIdx.y, sl = threadIdx.z;
+    const uint32_t flat = (sl * kFastSrc + src) * 32 + lane;
+    const uint32_t i = grp * kFastSrc + src;
+    const uint64_t wbase = (uint64_t)world * N;
+    const bool active = i < N;
+    const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
+    const double soft = newton ? 0.0 : G.p1;
+    auto dtf_of = [&](uint32_t k) { return k == 0 ? 0.0 : (k == 1 ? 0.5 * G.dt_stage : G.dt_stage); };
+
+    Vec3 xi = {0, 0, 0}, acc = {0, 0, 0};
+    double mi = 0.0;
+    if (active) {
+        const uint64_t b = wbase + i;
+        const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+        const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+        mi = ldp(G.ine, G.ld, 6, b);
+        xi = stage_pos<false>(x, v, dtf_of(sl));
+    }
+    for (uint32_t j0 = 0; j0 < N; j0 += TJ) {
+        __syncthreads();
+        for (uint32_t t = flat; t < TJ * NS; t += NT) {
+            const uint32_t jt = t % TJ, st = t / TJ;
+            const uint32_t j = j0 + jt;
+            if (j < N) {
+                const uint64_t b = wbase + j;
+                const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+                const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+                const Vec3 pnt = stage_pos<false>(x, v, dtf_of(st));
+                sx[st][0][jt] = pnt.x; sx[st][1][jt] = pnt.y; sx[st][2][jt] = pnt.z;
+                if (st == 0) sm[jt] = ldp(G.ine, G.ld, 6, b);
+            }
+        }
+        __syncthreads();
+        const uint32_t jn = min((uint32_t)TJ, N - j0);
+        if (active) {
+#pragma unroll 4
+            for (uint32_t jj = lane; jj < jn; jj += 32) {
+                const bool self = j0 + jj == i;
+                const Vec3 r = {sx[sl][0][jj] - xi.x, sx[sl][1][jj] - xi.y, sx[sl][2][jj] - xi.z};
+                const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, soft)));
+                const double inv = fa::rsqrt_nr(d2);
+                const double w = self ? 0.0 : sm[jj] * inv * inv * inv;
+                acc.x = fma(w, r.x, acc.x); acc.y = fma(w, r.y, acc.y); acc.z = fma(w, r.z, acc.z);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+    }
+    if (active && lane == 0) {
+        const uint64_t b = wbase + i;
+        const double k = G.p0 * mi;
+        stp(G.gforce, G.ld, sl * 3 + 0, b, k * acc.x);
+        stp(G.gforce, G.ld, sl * 3 + 1, b, k * acc.y);
+        stp(G.gforce, G.ld, sl * 3 + 2, b, k * acc.z);
+    }
+    __syncthreads(); // the CTA's gforce entries are visible to its integrating threads
+    if (active && lane == 0 && sl == 0) {
+        const uint64_t b = wbase + i;
+        Pose x0 = load_pose(P.pos, P.ld, b);
+        Motion v0 = load_motion(P.vel, P.ld, b);
+        const Inertia I = load_inertia(P.ine, P.ld, b);
+        Motion a_last, f_last;
+        fast_ticks<B200_INTEGRATOR_RK4, true>(P, b, x0, v0, I, a_last, f_last, P.n_ticks, P.tick0, P.write_fa != 0, GravReg{});
+        store_pose(pos_out, P.ld, b, x0);
+        store_motion(vel_out, P.ld, b, v0);
+        if (P.write_fa) {
+            store_motion(P.acc, P.ld, b, a_last);
+            store_motion(P.frc, P.ld, b, f_last);
+        }
+    }
+}
+
+// General edge list (CSR by source, spawn order inside a row): one thread per
+// (world, source) gathers its targets.  Used for sparse / irregular graphs.
+template <bool EXACT, bool RK4>
+__global__ void __launch_bounds__(kBlockG) graph_csr_kernel(const __grid_constant__ GraphParams G)
+{
+    constexpr int NS = RK4 ? 3 : 1;
+    const uint64_t t = (uint64_t)blockIdx.x * kBlockG + threadIdx.x;
+    const uint64_t total = (uint64_t)G.n_entities * G.n_worlds;
+    if (t >= total) return;
+    const uint32_t i = (uint32_t)(t % G.n_entities);
+    const uint64_t wbase = t - i;
+    const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
+    double dtf[3];
+    dtf[0] = EXACT ? ex::mul(G.dt_stage, 0.0) : 0.0;
+    dtf[1] = EXACT ? ex::mul(G.dt_stage, 0.5) : 0.5 * G.dt_stage;
+    dtf[2] = EXACT ? ex::mul(G.dt_stage, 1.0) : G.dt_stage;
+
+    const Vec3 x = {ldp(G.pos, G.ld, 4, t), ldp(G.pos, G.ld, 5, t), ldp(G.pos, G.ld, 6, t)};
+    const Vec3 v = {ldp(G.vel, G.ld, 3, t), ldp(G.vel, G.ld, 4, t), ldp(G.vel, G.ld, 5, t)};
+    const double mi = ldp(G.ine, G.ld, 6, t);
+    Vec3 xi[NS], acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { xi[s] = RK4 ? stage_pos<EXACT>(x, v, dtf[s]) : x; acc[s] = Vec3{0, 0, 0}; }
+
+    for (uint32_t e = G.row_ptr[i]; e < G.row_ptr[i + 1]; ++e) {
+        const uint64_t bj = wbase + G.col_idx[e];
+        const Vec3 xj0 = {ldp(G.pos, G.ld, 4, bj), ldp(G.pos, G.ld, 5, bj), ldp(G.pos, G.ld, 6, bj)};
+        const Vec3 vj = {ldp(G.vel, G.ld, 3, bj), ldp(G.vel, G.ld, 4, bj), ldp(G.vel, G.ld, 5, bj)};
+        const double mj = ldp(G.ine, G.ld, 6, bj);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const Vec3 xj = RK4 ? stage_pos<EXACT>(xj0, vj, dtf[s]) : xj0;
+            if (EXACT) {
+                if (newton) ex::fold_newton(G.p0, xi[s], mi, xj, mj, acc[s]);
+                else ex::fold_softened(G.p0, G.p1, xi[s], mi, xj, mj, acc[s]);
+            } else {
+                const Vec3 r = {xj.x - xi[s].x, xj.y - xi[s].y, xj.z - xi[s].z};
+                const double d2 = r.x * r.x + r.y * r.y + r.z * r.z + (newton ? 0.0 : G.p1);
+                const double inv = fa::rsqrt_nr(d2);
+                const double w = mj * inv * inv * inv;
+                acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
+            }
+        }
+    }
+    const double k = EXACT ? 1.0 : G.p0 * mi;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        stp(G.gforce, G.ld, s * 3 + 0, t, EXACT ? acc[s].x : k * acc[s].x);
+        stp(G.gforce, G.ld, s * 3 + 1, t, EXACT ? acc[s].y : k * acc[s].y);
+        stp(G.gforce, G.ld, s * 3 + 2, t, EXACT ? acc[s].z : k * acc[s].z);
+    }
+}
+
+// ================================================================== small graph worlds: whole ticks in one warp
+//
+// A world of N <= 32 bodies fits in a warp: lane = body, floor(32/N) whole worlds per warp.  The edge_fold
+// gravity of a tick needs the other bodies' three stage positions — functions of (x0, v0) only — which the
+// lanes exchange with warp shuffles, so the state never leaves registers between ticks: one launch integrates
+// n_ticks ticks (the generic route is two launches and a round trip of the 9 gravity planes through HBM per
+// tick).  Every lane folds its out-edges sequentially in CSR (= spawn) order with the same ex:: functions as
+// graph_dense_kernel / graph_csr_kernel, then runs the same tick function as body_exact_kernel — EXACT stays
+// bit-identical to the oracle.  FAST folds sequentially too (no tree), with the FAST kernels' arithmetic.
+template <bool EXACT, int INTEG, int MINB>
+__global__ void __launch_bounds__(128, MINB) small_world_kernel(const __grid_constant__ GraphParams G,
+                                                          const __grid_constant__ StepParams P)
+{
+    constexpr bool RK4 = INTEG == B200_INTEGRATOR_RK4;
+    constexpr int NS = RK4 ? 3 : 1;
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t N = G.n_entities;
+    const uint32_t wpw = 32u / N; // worlds per warp
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t wl = lane / N, ent = lane - wl * N;
+    const uint64_t world = warp * wpw + wl;
+    const bool live = wl < wpw && world < G.n_worlds;
+    const uint64_t b = live ? world * N + ent : 0;
+    const uint32_t lane0 = lane - ent; // first lane of this lane's world
+    const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
+
+    Pose x0 = {{0.0, 0.0, 0.0, 1.0}, {0.0, 0.0, 0.0}};
+    Motion v0 = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}}, a_out = v0, f_out = v0;
+    Inertia I = {{1.0, 1.0, 1.0}, 1.0};
+    uint32_t e0 = 0, deg = 0;
+    if (live) {
+        x0 = load_pose(P.pos, P.ld, b);
+        v0 = load_motion(P.vel, P.ld, b);
+        if (EXACT) a_out = load_motion(P.acc, P.ld, b);
+        I = load_inertia(P.ine, P.ld, b);
+        e0 = G.row_ptr[ent];
+        deg = G.row_ptr[ent + 1] - e0;
+    }
+    GravReg g;
+    g.g0 = g.g1 = g.g2 = Vec3{0.0, 0.0, 0.0};
+    g.has = deg != 0;
+
+    for (uint32_t t = 0; t < P.n_ticks; ++t) {
+        // stage positions of this body and the running folds, one per distinct stage position
+        Vec3 p[NS], acc[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const double fac = s == 0 ? 0.0 : (s == 1 ? 0.5 : 1.0);
+            const double dtf = EXACT ? ex::mul(G.dt_stage, fac) : fac * G.dt_stage;
+            p[s] = RK4 ? stage_pos<EXACT>(x0.x, v0.lin, dtf) : x0.x;
+            acc[s] = Vec3{0.0, 0.0, 0.0};
+        }
+        for (uint32_t k = 0; k < G.max_deg; ++k) { // warp-uniform trip count: every lane takes part in the shuffles
+            const bool on = k < deg;
+            const uint32_t src = lane0 + (on ? G.col_idx[e0 + k] : ent);
+            const double mj = __shfl_sync(FULL, I.m, src);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const Vec3 xj = {__shfl_sync(FULL, p[s].x, src), __shfl_sync(FULL, p[s].y, src), __shfl_sync(FULL, p[s].z, src)};
+                if (!on) continue;
+                if (EXACT) {
+                    if (newton) ex::fold_newton(G.p0, p[s], I.m, xj, mj, acc[s]);
+                    else ex::fold_softened(G.p0, G.p1, p[s], I.m, xj, mj, acc[s]);
+                } else {
+                    const Vec3 r = {xj.x - p[s].x, xj.y - p[s].y, xj.z - p[s].z};
+                    const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, newton ? 0.0 : G.p1)));
+                    const double inv = fa::rsqrt_nr(d2);
+                    const double w = mj * inv * inv * inv;
+                    acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
+                }
+            }
+        }
+        const double kf = EXACT ? 1.0 : G.p0 * I.m; // FAST: common factor (G | K^2) * m_i applied once
+        g.g0 = EXACT ? acc[0] : Vec3{kf * acc[0].x, kf * acc[0].y, kf * acc[0].z};
+        if (RK4) {
+            g.g1 = EXACT ? acc[NS - 2] : Vec3{kf * acc[NS - 2].x, kf * acc[NS - 2].y, kf * acc[NS - 2].z};
+            g.g2 = EXACT ? acc[NS - 1] : Vec3{kf * acc[NS - 1].x, kf * acc[NS - 1].y, kf * acc[NS - 1].z};
+        }
+        if (!live) continue;
+        if (EXACT) {
+            exact_tick<INTEG, true>(P, b, x0, v0, a_out, f_out, I, g);
+            uint64_t slot;
+            if (traj_due(P, P.tick0 + t + 1, slot)) {
+                traj_store_state(P, b, slot, x0, v0);
+                if (P.traj_planes == 25) traj_store_af(P, b, slot, a_out, f_out);
+            }
+        } else {
+            fast_ticks<INTEG, true, true>(P, b, x0, v0, I, a_out, f_out, 1u, P.tick0 + t, P.write_fa && t + 1 == P.n_ticks, g);
+        }
+    }
+    if (!live) return;
+    store_pose(P.pos, P.ld, b, x0);
+    store_motion(P.vel, P.ld, b, v0);
+    if (P.write_fa) {
+        store_motion(P.acc, P.ld, b, a_out);
+        store_motion(P.frc, P.ld, b, f_out);
+    }
+}
+
+// ================================================================== launchers
+
+cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, cudaStream_t s)
+{
+    const bool exact = math_mode == B200_MATH_EXACT;
+    const bool rk4 = G.integrator == B200_INTEGRATOR_RK4;
+    if (G.n_entities == 0 || G.n_worlds == 0) return cudaSuccess;
+    if (dense) {
+        const unsigned tiles = (G.n_entities + kBlockG - 1) / kBlockG;
+        const unsigned grid = tiles * G.n_worlds;
+        static const int gcfg = [] { const char *e = getenv("B200_GRAPH_CFG"); return e ? atoi(e) : 1; }();
+        const dim3 blk3(kBlockG, 3), blk1(kBlockG, 1);
+        if (exact) { if (rk4) graph_dense_kernel<true, true><<<grid, blk3, 0, s>>>(G); else graph_dense_kernel<true, false><<<grid, blk1, 0, s>>>(G); }
+        else if (gcfg == 0) { if (rk4) graph_dense_kernel<false, true><<<grid, blk3, 0, s>>>(G); else graph_dense_kernel<false, false><<<grid, blk1, 0, s>>>(G); }
+        else {
+            const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
+            // few CTAs: split the stage slots over warps to fill the machine; many CTAs: keep
+            // 3 slots per warp (more ILP per lane, 3 CTAs/SM) — measured on N = 1024, M = 1 / 8
+            const bool split = gcfg == 2 || (gcfg == 1 && gridf < 3u * 148u);
+            constexpr size_t smem256 = (3 * 3 + 1) * 256 * sizeof(double), smem1024 = (3 * 3 + 1) * 1024 * sizeof(double);
+            if (!rk4) graph_dense_fast_kernel<false, false, 256><<<gridf, dim3(32, kFastSrc, 1), smem256, s>>>(G);
+            else if (split) {
+                const cudaError_t e = ensure_dynamic_smem(graph_dense_fast_kernel<true, true, 1024>, smem1024);
+                if (e != cudaSuccess) return e;
+                graph_dense_fast_kernel<true, true, 1024><<<gridf, dim3(32, kFastSrc, 3), smem1024, s>>>(G);
+            } else graph_dense_fast_kernel<true, false, 256><<<gridf, dim3(32, kFastSrc, 1), smem256, s>>>(G);
+        }
+    } else {
+        const uint64_t total = (uint64_t)G.n_entities * G.n_worlds;
+        const unsigned grid = (unsigned)((total + kBlockG - 1) / kBlockG);
+        if (exact) { if (rk4) graph_csr_kernel<true, true><<<grid, kBlockG, 0, s>>>(G); else graph_csr_kernel<true, false><<<grid, kBlockG, 0, s>>>(G); }
+        else { if (rk4) graph_csr_kernel<false, true><<<grid, kBlockG, 0, s>>>(G); else graph_csr_kernel<false, false><<<grid, kBlockG, 0, s>>>(G); }
+    }
+    return cudaGetLastError();
+}
+
+bool nbody_fused_applicable(const GraphParams &G, int math_mode, bool dense)
+{
+    if (math_mode != B200_MATH_FAST || !dense || G.integrator != B200_INTEGRATOR_RK4) return false;
+    static const int fcfg = [] { const char *e = getenv("B200_NBODY_FUSED"); return e ? atoi(e) : 1; }();
+    const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
+    return fcfg != 0 && gridf < 3u * 148u; // the same "small grid" rule as the split gravity kernel
+}
+
+cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, double *pos_out, double *vel_out, cudaStream_t s)
+{
+    constexpr size_t smem = (3 * 3 + 1) * 1024 * sizeof(double);
+    const cudaError_t e = ensure_dynamic_smem(nbody_tick_fused_kernel<1024>, smem);
+    if (e != cudaSuccess) return e;
+    const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
+    nbody_tick_fused_kernel<1024><<<gridf, dim3(32, kFastSrc, 3), smem, s>>>(G, P, pos_out, vel_out);
+    return cudaGetLastError();
+}
+
+bool small_world_applicable(const GraphParams &G, int math_mode)
+{
+    // measured (profiles/r01_small_world.md): faster than the two-launch route over the whole range a warp can
+    // hold, in both arithmetic modes (N = 3: 53x FAST / 4.4x EXACT; N = 32: 3.6x / 1.35x)
+    (void)math_mode;
+    static const int cfg = [] { const char *e = getenv("B200_SMALL_WORLD"); return e ? atoi(e) : 1; }();
+    return cfg != 0 && G.n_entities >= 1 && G.n_entities <= 32;
+}
+
+template <int MINB>
+static void launch_small_world_cfg(const GraphParams &G, const StepParams &P, int math_mode, unsigned grid, cudaStream_t s)
+{
+    const bool rk4 = G.integrator == B200_INTEGRATOR_RK4;
+    if (math_mode == B200_MATH_EXACT) {
+        if (rk4) small_world_kernel<true, B200_INTEGRATOR_RK4, MINB><<<grid, 128, 0, s>>>(G, P);
+        else small_world_kernel<true, B200_INTEGRATOR_SEMI_IMPLICIT, MINB><<<grid, 128, 0, s>>>(G, P);
+    } else {
+        if (rk4) small_world_kernel<false, B200_INTEGRATOR_RK4, MINB><<<grid, 128, 0, s>>>(G, P);
+        else small_world_kernel<false, B200_INTEGRATOR_SEMI_IMPLICIT, MINB><<<grid, 128, 0, s>>>(G, P);
+    }
+}
+
+cudaError_t launch_small_world(const GraphParams &G, const StepParams &P, int math_mode, cudaStream_t s)
+{
+    if (G.n_entities == 0 || G.n_worlds == 0) return cudaSuccess;
+    const uint32_t wpw = 32u / G.n_entities;
+    const uint64_t warps = ((uint64_t)G.n_worlds + wpw - 1) / wpw;
+    const unsigned grid = (unsigned)((warps + 3) / 4); // 4 warps per CTA
+    // resident CTAs per SM the register allocation is bounded for (B200_SMALL_WORLD_CFG = 2 | 3 | 4): the kernel
+    // is latency-bound, 16 warps/SM at 128 registers (a few spilled doubles) beat 8 warps at 196 by 1.3-1.45x
+    static const int cfg = [] { const char *e = getenv("B200_SMALL_WORLD_CFG"); return e ? atoi(e) : 4; }();
+    switch (cfg) {
+    case 2: launch_small_world_cfg<2>(G, P, math_mode, grid, s); break;
+    case 3: launch_small_world_cfg<3>(G, P, math_mode, grid, s); break;
+    default: launch_small_world_cfg<4>(G, P, math_mode, grid, s); break;
+    }
+    return cudaGetLastError();
+}
+
+
+} // namespace b200

@@ -44,6 +44,17 @@ struct StepParams {
     uint32_t traj_every;  // 0 = off
     uint32_t traj_planes; // 13 (pos, vel) or 25 (+ accel, force)
     uint64_t tick0;     // global tick count before this launch
+    // compile-time-specialised FAST kernels (sixdof_tick.cuh SIG_*): what body_kernels.cu:spec_signature
+    // distilled from eff[] — uniform constants and the plane bases of the per-body input columns
+    struct Spec {
+        double g[3];        // sum of the GRAVITY_CONST vectors
+        double axis[3];     // THRUST_BODY body axis
+        double kd;          // 0.5 * Cd*rho * area of a DRAG_QUADRATIC without per-body parameters
+        double mu, om[3];   // GRAVITY_FRAME
+        const double *thrust;        // 1 plane
+        const double *wr_t, *wr_f;   // 3 planes each: body-frame torque / force of the wrench column
+        const double *drag;          // wind(3) [+ Cd*rho, area]
+    } spec;
     EffDev eff[B200_MAX_EFFECTORS];
 };
 

@@ -1,0 +1,479 @@
+// Per-body tick functions of the six_dof() hot path, shared by every kernel that integrates bodies
+// (body_kernels.cu, graph_kernels.cu: nbody_tick_fused_kernel / small_world_kernel).
+//
+//   exact_tick   one tick in EXACT arithmetic (literal operation order, bit-identical to the oracle)
+//   fast_ticks   n ticks in FAST arithmetic, state in registers; templated on an effector
+//                signature SIG: SIG_GENERIC interprets the effector list at run time, any other value
+//                is a compile-time set of built-in effectors whose per-body inputs
+//                arrive in registers (EffIn) — no interpreter loop, no dead members, no parameter reads.
+#pragma once
+#include "sixdof_device.cuh"
+#include "sixdof_internal.h"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ column access
+__device__ __forceinline__ double ldp(const double *base, uint64_t ld, int plane, uint64_t b)
+{
+    return base[(uint64_t)plane * ld + b];
+}
+__device__ __forceinline__ void stp(double *base, uint64_t ld, int plane, uint64_t b, double v)
+{
+    base[(uint64_t)plane * ld + b] = v;
+}
+
+__device__ __forceinline__ Pose load_pose(const double *p, uint64_t ld, uint64_t b)
+{
+    Pose o;
+    o.q = Quat{ldp(p, ld, 0, b), ldp(p, ld, 1, b), ldp(p, ld, 2, b), ldp(p, ld, 3, b)};
+    o.x = Vec3{ldp(p, ld, 4, b), ldp(p, ld, 5, b), ldp(p, ld, 6, b)};
+    return o;
+}
+__device__ __forceinline__ Motion load_motion(const double *p, uint64_t ld, uint64_t b)
+{
+    Motion m;
+    m.ang = Vec3{ldp(p, ld, 0, b), ldp(p, ld, 1, b), ldp(p, ld, 2, b)};
+    m.lin = Vec3{ldp(p, ld, 3, b), ldp(p, ld, 4, b), ldp(p, ld, 5, b)};
+    return m;
+}
+__device__ __forceinline__ Inertia load_inertia(const double *p, uint64_t ld, uint64_t b)
+{
+    Inertia I;
+    I.diag = Vec3{ldp(p, ld, 0, b), ldp(p, ld, 1, b), ldp(p, ld, 2, b)};
+    I.m = ldp(p, ld, 6, b);
+    return I;
+}
+__device__ __forceinline__ void store_pose(double *p, uint64_t ld, uint64_t b, const Pose &o)
+{
+    stp(p, ld, 0, b, o.q.i); stp(p, ld, 1, b, o.q.j); stp(p, ld, 2, b, o.q.k); stp(p, ld, 3, b, o.q.w);
+    stp(p, ld, 4, b, o.x.x); stp(p, ld, 5, b, o.x.y); stp(p, ld, 6, b, o.x.z);
+}
+__device__ __forceinline__ void store_motion(double *p, uint64_t ld, uint64_t b, const Motion &m)
+{
+    stp(p, ld, 0, b, m.ang.x); stp(p, ld, 1, b, m.ang.y); stp(p, ld, 2, b, m.ang.z);
+    stp(p, ld, 3, b, m.lin.x); stp(p, ld, 4, b, m.lin.y); stp(p, ld, 5, b, m.lin.z);
+}
+
+// slot of the telemetry sample due after `tick_after` ticks, if any
+__device__ __forceinline__ bool traj_due(const StepParams &P, uint64_t tick_after, uint64_t &slot)
+{
+    if (P.traj_every == 0 || (tick_after % P.traj_every) != 0) return false;
+    slot = tick_after / P.traj_every - 1;
+    return slot < P.traj_capacity;
+}
+__device__ __forceinline__ void traj_store_state(const StepParams &P, uint64_t b, uint64_t slot, const Pose &x, const Motion &v)
+{
+    double *t = P.traj + slot * (uint64_t)P.traj_planes * P.ld;
+    store_pose(t, P.ld, b, x);
+    store_motion(t + 7ull * P.ld, P.ld, b, v);
+}
+// B200_TRAJ_FULL: WorldAccel and Force as the tick leaves them in the ECS columns
+__device__ __forceinline__ void traj_store_af(const StepParams &P, uint64_t b, uint64_t slot, const Motion &a, const Motion &f)
+{
+    double *t = P.traj + (slot * (uint64_t)P.traj_planes + 13ull) * P.ld;
+    store_motion(t, P.ld, b, a);
+    store_motion(t + 6ull * P.ld, P.ld, b, f);
+}
+
+// ================================================================== EXACT body kernel
+
+// edge_fold gravity of one body at the three stage positions, held in registers by the kernels that
+// compute it themselves (small_world_kernel) instead of reading the gforce planes
+struct GravReg {
+    Vec3 g0, g1, g2;
+    bool has; // the body owns >= 1 out-edge
+};
+__device__ __forceinline__ Vec3 grav_slot(const GravReg &g, int slot) { return slot == 0 ? g.g0 : (slot == 1 ? g.g1 : g.g2); }
+
+// clear_forces | effectors (array order) on the stage state; six_dof.rs:148-150,195
+template <bool GREG>
+__device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t b, int slot, const Pose &sx,
+                                                  const ex::PoseInv &pi, const Motion &sv, const Inertia &I,
+                                                  const GravReg &greg)
+{
+    using namespace ex;
+    Motion F = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+    for (uint32_t e = 0; e < P.n_eff; ++e) {
+        const EffDev &E = P.eff[e];
+        if (E.mask && !E.mask[b % P.n_entities]) continue; // entity does not own the effector's components (query join)
+        switch (E.kind) {
+        case B200_EFF_GRAVITY_CONST: { // ball/sim.py:56-58: f + SpatialForce(linear=g*m)
+            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+            F.lin = Vec3{add(F.lin.x, mul(E.p[0], I.m)), add(F.lin.y, mul(E.p[1], I.m)),
+                         add(F.lin.z, mul(E.p[2], I.m))};
+            break;
+        }
+        case B200_EFF_DRAG_QUADRATIC: { // ball/sim.py:99-116; result torque is zero
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+            if (E.col) { w0 = ldp(E.col, P.ld, 0, b); w1 = ldp(E.col, P.ld, 1, b); w2 = ldp(E.col, P.ld, 2, b); }
+            const Vec3 fl = {sub(w0, sv.lin.x), sub(w1, sv.lin.y), sub(w2, sv.lin.z)};
+            const double speed = sqr(dot3(fl));
+            const double cd_rho = E.col_width == 5 ? ldp(E.col, P.ld, 3, b) : E.p[0];
+            const double area = E.col_width == 5 ? ldp(E.col, P.ld, 4, b) : E.p[1];
+            const double drag = mul(0.5, mul(mul(cd_rho, mul(speed, speed)), area));
+            F.ang = Vec3{0.0, 0.0, 0.0};
+            F.lin = Vec3{add(F.lin.x, mul(drag, div(fl.x, speed))), add(F.lin.y, mul(drag, div(fl.y, speed))),
+                         add(F.lin.z, mul(drag, div(fl.z, speed)))};
+            break;
+        }
+        case B200_EFF_THRUST_BODY: { // rocket/main.py:429-431
+            const double t = E.col ? ldp(E.col, P.ld, 0, b) : 0.0;
+            const Vec3 d = qrot_with(sx.q, pi.qi, Vec3{E.p[0], E.p[1], E.p[2]});
+            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+            F.lin = Vec3{add(F.lin.x, mul(d.x, t)), add(F.lin.y, mul(d.y, t)), add(F.lin.z, mul(d.z, t))};
+            break;
+        }
+        case B200_EFF_WRENCH_BODY: { // rocket/main.py:407-413, falcon9/sim.py:659-672
+            Vec3 a = {0.0, 0.0, 0.0}, c = {0.0, 0.0, 0.0};
+            if (E.col) {
+                a = Vec3{ldp(E.col, P.ld, 0, b), ldp(E.col, P.ld, 1, b), ldp(E.col, P.ld, 2, b)};
+                c = Vec3{ldp(E.col, P.ld, 3, b), ldp(E.col, P.ld, 4, b), ldp(E.col, P.ld, 5, b)};
+            }
+            const bool lin_first = (E.flags & B200_EFF_FLAG_WRENCH_LINEAR_FIRST) != 0;
+            const Vec3 tw = qrot_with(sx.q, pi.qi, lin_first ? c : a);
+            const Vec3 fw = qrot_with(sx.q, pi.qi, lin_first ? a : c);
+            F.ang = Vec3{add(F.ang.x, tw.x), add(F.ang.y, tw.y), add(F.ang.z, tw.z)};
+            F.lin = Vec3{add(F.lin.x, fw.x), add(F.lin.y, fw.y), add(F.lin.z, fw.z)};
+            break;
+        }
+        case B200_EFF_GRAVITY_FRAME: { // falcon9/sim.py:350-361, frames.py:91-109
+            const double mu = E.p[0];
+            const Vec3 om = {E.p[1], E.p[2], E.p[3]};
+            const Vec3 r = sx.x, v = sv.lin;
+            const double rn = sqr(dot3(r));
+            const double rn3 = mul(mul(rn, rn), rn);
+            const Vec3 g = {div(mul(-mu, r.x), rn3), div(mul(-mu, r.y), rn3), div(mul(-mu, r.z), rn3)};
+            const Vec3 c = cross(om, v);
+            const Vec3 c2 = cross(om, cross(om, r));
+            const Vec3 acc = {add(g.x, add(mul(-2.0, c.x), -c2.x)), add(g.y, add(mul(-2.0, c.y), -c2.y)),
+                              add(g.z, add(mul(-2.0, c.z), -c2.z))};
+            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+            F.lin = Vec3{add(F.lin.x, mul(acc.x, I.m)), add(F.lin.y, mul(acc.y, I.m)), add(F.lin.z, mul(acc.z, I.m))};
+            break;
+        }
+        case B200_EFF_GRAVITY_EDGES_NEWTON:
+        case B200_EFF_GRAVITY_EDGES_SOFTENED: { // Force := edge_fold(init 0) for bodies that own an edge
+            if (GREG) {
+                if (greg.has) { F.ang = Vec3{0.0, 0.0, 0.0}; F.lin = grav_slot(greg, slot); }
+            } else if (P.gforce && P.has_edge && P.has_edge[b % P.n_entities]) {
+                F.ang = Vec3{0.0, 0.0, 0.0};
+                F.lin = Vec3{ldp(P.gforce, P.ld, slot * 3 + 0, b), ldp(P.gforce, P.ld, slot * 3 + 1, b),
+                             ldp(P.gforce, P.ld, slot * 3 + 2, b)};
+            }
+            break;
+        }
+        default: break;
+        }
+    }
+    return F;
+}
+
+// one tick of one body in EXACT arithmetic (state in registers)
+template <int INTEG, bool GREG>
+__device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose &x0, Motion &v0, Motion &a_out,
+                                           Motion &f_out, const Inertia &I, const GravReg &greg)
+{
+    using namespace ex;
+    if (INTEG == B200_INTEGRATOR_RK4) {
+        // rk4.rs:85-123 (see the header comment of oracle/sixdof_oracle.c for the derivation)
+        Motion sa = a_out; // du.a before stage 1 is the WorldAccel column
+        Motion kv, ka;
+        // three distinct stage poses (f = 0, .5, 1), functions of (x0, v0) only; stages 2 and 3 share
+        // the f = .5 pose and its inverses — identical inputs, identical bits — so each is built once
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+            const double dtf = mul(P.dt_stage, k == 0 ? 0.0 : (k == 1 ? 0.5 : 1.0));
+            const Pose sx = tadd(x0, scale(dtf, v0));
+            const PoseInv pi = pose_inverses(sx.q);
+            const int n_stages = (k == 1) ? 2 : 1;
+#pragma unroll 1
+            for (int j = 0; j < n_stages; ++j) {
+                const int s = (k == 0) ? 0 : (k == 1 ? 1 + j : 3);
+                const Motion sv = madd(v0, scale(dtf, sa));
+                f_out = effectors_exact<GREG>(P, b, k, sx, pi, sv, I, greg);
+                sa = calc_accel_with(sx, pi, f_out, I);
+                if (s == 0) { kv = sv; ka = sa; }
+                else if (s == 3) { kv = madd(kv, sv); ka = madd(ka, sa); }
+                else { kv = madd(kv, scale(2.0, sv)); ka = madd(ka, scale(2.0, sa)); }
+            }
+        }
+        const double c = mul(P.dt_final, 1.0 / 6.0);
+        x0 = tadd(x0, scale(c, kv));
+        v0 = madd(v0, scale(c, ka));
+        a_out = sa;
+    } else {
+        // semi_implicit.rs:42-62
+        const PoseInv pi = pose_inverses(x0.q);
+        f_out = effectors_exact<GREG>(P, b, 0, x0, pi, v0, I, greg);
+        a_out = calc_accel_with(x0, pi, f_out, I);
+        v0 = madd(v0, scale(P.dt_final, a_out));
+        x0 = tadd(x0, scale(P.dt_final, v0));
+    }
+}
+
+
+// ================================================================== FAST ticks
+
+// Compile-time effector signature of the specialised FAST kernels ("template on an
+// effector bitmask").  The host maps an effector list onto a signature when it can (body_kernels.cu:
+// spec_signature); lists it cannot map (entity masks, repeated kinds, a wrench ahead of a drag) run
+// through SIG_GENERIC, the run-time interpreter.  Constant gravity is part of every signature: its
+// (summed) g sits in the constant bank and costs three multiplies.
+enum : uint32_t {
+    SIG_DRAG = 1u,            // DRAG_QUADRATIC with a wind column (width 3)
+    SIG_DRAG_PB = 2u,         //   ... whose column also carries per-body [Cd*rho, area] (width 5)
+    SIG_THRUST = 4u,          // THRUST_BODY
+    SIG_WRENCH = 8u,          // WRENCH_BODY (either layout: the host hands over torque / force plane bases)
+    SIG_FRAME = 16u,          // GRAVITY_FRAME
+    SIG_GRAPH = 32u,          // GRAVITY_EDGES_*: 9 planes of edge_fold gravity
+    SIG_GENERIC = 0x80000000u // interpret StepParams::eff[] at run time
+};
+
+// per-body effector inputs of a specialised kernel: loaded next to the state, before any arithmetic
+struct EffIn {
+    double thrust;
+    Vec3 wr_t, wr_f; // body-frame torque / force of the wrench column
+    Vec3 wind;
+    double cd_rho, area;
+};
+
+// Everything the effector list contributes, folded once per launch:
+//   F_lin(stage) = fw + R(q) fb + drag(v) + m*frame(x, v) + gforce[slot]
+//   a_ang(stage) = R(q) u,   u = (sum of body-frame torques) / diag(I)   (R^-1 then R cancel)
+struct Folded {
+    Vec3 fw;      // world-frame constant force (GRAVITY_CONST: g*m)
+    Vec3 fb;      // body-frame force (THRUST_BODY axis*thrust, WRENCH_BODY force part)
+    Vec3 u;       // body-frame angular acceleration
+    Vec3 wind;    // DRAG_QUADRATIC
+    double kd;    // 0.5*Cd*rho*A
+    double mu;    // GRAVITY_FRAME
+    Vec3 om;
+    bool drag, frame, graph;
+};
+
+template <bool GREG>
+__device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b, const Inertia &I, const Vec3 &invI,
+                                                 const GravReg &greg)
+{
+    Folded f;
+    f.fw = f.fb = f.u = f.wind = f.om = Vec3{0.0, 0.0, 0.0};
+    f.kd = f.mu = 0.0;
+    f.drag = f.frame = f.graph = false;
+    Vec3 tb = {0.0, 0.0, 0.0};
+    for (uint32_t e = 0; e < P.n_eff; ++e) {
+        const EffDev &E = P.eff[e];
+        if (E.mask && !E.mask[b % P.n_entities]) continue; // query join: not a member
+        switch (E.kind) {
+        case B200_EFF_GRAVITY_CONST:
+            f.fw.x = fma(E.p[0], I.m, f.fw.x); f.fw.y = fma(E.p[1], I.m, f.fw.y); f.fw.z = fma(E.p[2], I.m, f.fw.z);
+            break;
+        case B200_EFF_DRAG_QUADRATIC:
+            f.drag = true;
+            f.kd = E.col_width == 5 ? 0.5 * ldp(E.col, P.ld, 3, b) * ldp(E.col, P.ld, 4, b) : 0.5 * E.p[0] * E.p[1];
+            if (E.col) f.wind = Vec3{ldp(E.col, P.ld, 0, b), ldp(E.col, P.ld, 1, b), ldp(E.col, P.ld, 2, b)};
+            tb = Vec3{0.0, 0.0, 0.0}; // the reference's apply_drag returns SpatialForce(linear=...): torque reset
+            break;
+        case B200_EFF_THRUST_BODY: {
+            const double t = E.col ? ldp(E.col, P.ld, 0, b) : 0.0;
+            f.fb.x = fma(E.p[0], t, f.fb.x); f.fb.y = fma(E.p[1], t, f.fb.y); f.fb.z = fma(E.p[2], t, f.fb.z);
+            break;
+        }
+        case B200_EFF_WRENCH_BODY:
+            if (E.col) {
+                const int to = (E.flags & B200_EFF_FLAG_WRENCH_LINEAR_FIRST) ? 3 : 0;
+                const int fo = 3 - to;
+                tb.x += ldp(E.col, P.ld, to + 0, b); tb.y += ldp(E.col, P.ld, to + 1, b); tb.z += ldp(E.col, P.ld, to + 2, b);
+                f.fb.x += ldp(E.col, P.ld, fo + 0, b); f.fb.y += ldp(E.col, P.ld, fo + 1, b); f.fb.z += ldp(E.col, P.ld, fo + 2, b);
+            }
+            break;
+        case B200_EFF_GRAVITY_FRAME:
+            f.frame = true;
+            f.mu = E.p[0];
+            f.om = Vec3{E.p[1], E.p[2], E.p[3]};
+            break;
+        case B200_EFF_GRAVITY_EDGES_NEWTON:
+        case B200_EFF_GRAVITY_EDGES_SOFTENED: // host guarantees this is effector 0 in FAST mode
+            f.graph = GREG ? greg.has : (P.gforce && P.has_edge && P.has_edge[b % P.n_entities]);
+            break;
+        default: break;
+        }
+    }
+    f.u = Vec3{tb.x * invI.x, tb.y * invI.y, tb.z * invI.z};
+    return f;
+}
+
+// the same fold for a compile-time signature: constants from StepParams::spec (constant bank), per-body inputs
+// from registers; members the signature does not use are literal zeros the optimiser removes
+template <uint32_t SIG>
+__device__ __forceinline__ Folded fold_spec(const StepParams &P, uint64_t b, const EffIn &in, const Inertia &I, const Vec3 &invI)
+{
+    Folded f;
+    f.fw = Vec3{P.spec.g[0] * I.m, P.spec.g[1] * I.m, P.spec.g[2] * I.m};
+    f.fb = f.u = f.wind = f.om = Vec3{0.0, 0.0, 0.0};
+    f.kd = f.mu = 0.0;
+    f.drag = (SIG & SIG_DRAG) != 0;
+    f.frame = (SIG & SIG_FRAME) != 0;
+    f.graph = (SIG & SIG_GRAPH) ? (P.has_edge[b % P.n_entities] != 0) : false;
+    if (SIG & SIG_THRUST) f.fb = Vec3{P.spec.axis[0] * in.thrust, P.spec.axis[1] * in.thrust, P.spec.axis[2] * in.thrust};
+    if (SIG & SIG_WRENCH) {
+        f.fb = Vec3{f.fb.x + in.wr_f.x, f.fb.y + in.wr_f.y, f.fb.z + in.wr_f.z};
+        f.u = Vec3{in.wr_t.x * invI.x, in.wr_t.y * invI.y, in.wr_t.z * invI.z};
+    }
+    if (SIG & SIG_DRAG) {
+        f.wind = in.wind;
+        f.kd = (SIG & SIG_DRAG_PB) ? 0.5 * in.cd_rho * in.area : P.spec.kd;
+    }
+    if (SIG & SIG_FRAME) {
+        f.mu = P.spec.mu;
+        f.om = Vec3{P.spec.om[0], P.spec.om[1], P.spec.om[2]};
+    }
+    return f;
+}
+
+// linear acceleration of one stage: everything that depends on (q, x, v)
+template <bool GREG>
+__device__ __forceinline__ Vec3 lin_accel_fast(const StepParams &P, const Folded &f, uint64_t b, int slot,
+                                               const Vec3 &fbw, const Vec3 &x, const Vec3 &v, double m, double inv_m,
+                                               const GravReg &greg)
+{
+    Vec3 F = {f.fw.x + fbw.x, f.fw.y + fbw.y, f.fw.z + fbw.z};
+    if (f.drag) {
+        const Vec3 fl = {f.wind.x - v.x, f.wind.y - v.y, f.wind.z - v.z};
+        const double s2 = fl.x * fl.x + fl.y * fl.y + fl.z * fl.z;
+        // drag*dir = (kd*speed^2) * fl/speed = kd*speed*fl, speed = s2 * rsqrt(s2); speed == 0 gives 0 * inf = NaN
+        // like the reference's 0/0
+        const double k = f.kd * (s2 * fa::rsqrt_nr(s2));
+        F.x = fma(k, fl.x, F.x); F.y = fma(k, fl.y, F.y); F.z = fma(k, fl.z, F.z);
+    }
+    if (f.frame) {
+        const double r2 = x.x * x.x + x.y * x.y + x.z * x.z;
+        const double ir = fa::rsqrt_nr(r2);
+        const double g = -f.mu * ir * ir * ir;
+        const Vec3 c = fa::cross(f.om, v);
+        const Vec3 c2 = fa::cross(f.om, fa::cross(f.om, x));
+        F.x = fma(fma(g, x.x, -2.0 * c.x - c2.x), m, F.x);
+        F.y = fma(fma(g, x.y, -2.0 * c.y - c2.y), m, F.y);
+        F.z = fma(fma(g, x.z, -2.0 * c.z - c2.z), m, F.z);
+    }
+    if (f.graph) {
+        if (GREG) {
+            const Vec3 g = grav_slot(greg, slot);
+            F.x += g.x; F.y += g.y; F.z += g.z;
+        } else {
+            F.x += ldp(P.gforce, P.ld, slot * 3 + 0, b);
+            F.y += ldp(P.gforce, P.ld, slot * 3 + 1, b);
+            F.z += ldp(P.gforce, P.ld, slot * 3 + 2, b);
+        }
+    }
+    return Vec3{F.x * inv_m, F.y * inv_m, F.z * inv_m};
+}
+
+// world-frame force this stage's state produced (only materialised when Force is written back)
+__device__ __forceinline__ Motion force_out_fast(const Vec3 &a_lin, const Vec3 &a_ang_body_u, const Quat &q,
+                                                 const Inertia &I)
+{
+    // torque_world = R (I .* u)
+    const Vec3 tb = {a_ang_body_u.x * I.diag.x, a_ang_body_u.y * I.diag.y, a_ang_body_u.z * I.diag.z};
+    Motion F;
+    F.ang = fa::rot(q, tb);
+    F.lin = Vec3{a_lin.x * I.m, a_lin.y * I.m, a_lin.z * I.m};
+    return F;
+}
+
+// n_ticks ticks of one body, state in registers (shared by the direct and the TMA-pipelined kernel)
+// (n_ticks, tick0, want_f) are P.n_ticks, P.tick0, P.write_fa for the kernels that integrate a launch's ticks
+// in one call; small_world_kernel calls it once per tick with that tick's gravity in `greg`
+template <int INTEG, bool TRAJ, bool GREG = false, uint32_t SIG = SIG_GENERIC>
+__device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose &x0, Motion &v0, const Inertia &I,
+                                           Motion &a_last, Motion &f_last, uint32_t n_ticks, uint64_t tick0, bool want_f,
+                                           const GravReg &greg, const EffIn &in = EffIn{})
+{
+    constexpr bool GEN = SIG == SIG_GENERIC;
+    constexpr bool NEED_INVI = GEN || (SIG & SIG_WRENCH);
+    const Vec3 invI = NEED_INVI ? Vec3{fa::rcp_nr(I.diag.x), fa::rcp_nr(I.diag.y), fa::rcp_nr(I.diag.z)} : Vec3{0.0, 0.0, 0.0};
+    const double inv_m = fa::rcp_nr(I.m);
+    Folded f;
+    if constexpr (GEN) f = fold_effectors<GREG>(P, b, I, invI, greg);
+    else f = fold_spec<SIG>(P, b, in, I, invI);
+
+    a_last = Motion{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+    Quat q_last = x0.q;
+    const double dt = P.dt_stage;
+    // generic: data-dependent (most bodies of a heterogeneous world carry no body-frame wrench; NaNs compare
+    // unequal to zero and take the full path); specialised: a property of the signature
+    const bool has_u = GEN ? ((f.u.x != 0.0) | (f.u.y != 0.0) | (f.u.z != 0.0)) : (SIG & SIG_WRENCH) != 0;
+    const bool has_fb = GEN ? ((f.fb.x != 0.0) | (f.fb.y != 0.0) | (f.fb.z != 0.0)) : (SIG & (SIG_THRUST | SIG_WRENCH)) != 0;
+
+    for (uint32_t t = 0; t < n_ticks; ++t) {
+        if (INTEG == B200_INTEGRATOR_RK4) {
+            const Vec3 w0 = v0.ang, u0 = v0.lin;
+            // the three distinct stage poses depend on (x0, v0) only (rk4.rs:85-111)
+            // (the stage attitudes only matter to bodies that carry a body-frame force or torque)
+            const double h2 = 0.25 * dt, h4 = 0.5 * dt;
+            Quat q1 = x0.q, q2 = x0.q, q4 = x0.q;
+            if (has_u | has_fb) {
+                q1 = fa::normalize(x0.q); // x0 (+) 0*v0 still renormalises (spatial.rs:540-545)
+                q2 = fa::advance(x0.q, Vec3{h2 * w0.x, h2 * w0.y, h2 * w0.z});
+                q4 = fa::advance(x0.q, Vec3{h4 * w0.x, h4 * w0.y, h4 * w0.z});
+            }
+            const Vec3 x2 = {fma(h4, u0.x, x0.x.x), fma(h4, u0.y, x0.x.y), fma(h4, u0.z, x0.x.z)};
+            const Vec3 x4 = {fma(dt, u0.x, x0.x.x), fma(dt, u0.y, x0.x.y), fma(dt, u0.z, x0.x.z)};
+            // angular acceleration R(q) u and rotated body force, once per distinct attitude
+            const Vec3 zero3 = {0.0, 0.0, 0.0};
+            Vec3 aa1 = zero3, aa2 = zero3, aa4 = zero3, fb1 = zero3, fb2 = zero3, fb4 = zero3;
+            if (has_u) { aa1 = fa::rot(q1, f.u); aa2 = fa::rot(q2, f.u); aa4 = fa::rot(q4, f.u); }
+            if (has_fb) { fb1 = fa::rot(q1, f.fb); fb2 = fa::rot(q2, f.fb); fb4 = fa::rot(q4, f.fb); }
+            // stage 1: v = v0
+            const Vec3 al1 = lin_accel_fast<GREG>(P, f, b, 0, fb1, x0.x, u0, I.m, inv_m, greg);
+            // stage 2: v = v0 + dt/2 a1
+            const Vec3 u2 = {fma(h4, al1.x, u0.x), fma(h4, al1.y, u0.y), fma(h4, al1.z, u0.z)};
+            const Vec3 al2 = lin_accel_fast<GREG>(P, f, b, 1, fb2, x2, u2, I.m, inv_m, greg);
+            // stage 3: same pose as stage 2, v = v0 + dt/2 a2
+            const Vec3 u3 = {fma(h4, al2.x, u0.x), fma(h4, al2.y, u0.y), fma(h4, al2.z, u0.z)};
+            const Vec3 al3 = lin_accel_fast<GREG>(P, f, b, 1, fb2, x2, u3, I.m, inv_m, greg);
+            // stage 4: v = v0 + dt a3
+            const Vec3 u4 = {fma(dt, al3.x, u0.x), fma(dt, al3.y, u0.y), fma(dt, al3.z, u0.z)};
+            const Vec3 al4 = lin_accel_fast<GREG>(P, f, b, 2, fb4, x4, u4, I.m, inv_m, greg);
+            // k.v sum = 6 v0 + dt (a1 + a2 + a3);  k.a sum = a1 + 2 a2 + 2 a3 + a4   (a3.ang == a2.ang)
+            const double c = P.dt_final * (1.0 / 6.0);
+            const Vec3 kw = {fma(dt, aa1.x + 2.0 * aa2.x, 6.0 * w0.x), fma(dt, aa1.y + 2.0 * aa2.y, 6.0 * w0.y),
+                             fma(dt, aa1.z + 2.0 * aa2.z, 6.0 * w0.z)};
+            const Vec3 ku = {fma(dt, al1.x + al2.x + al3.x, 6.0 * u0.x), fma(dt, al1.y + al2.y + al3.y, 6.0 * u0.y),
+                             fma(dt, al1.z + al2.z + al3.z, 6.0 * u0.z)};
+            const double hc = 0.5 * c;
+            x0.q = fa::advance(x0.q, Vec3{hc * kw.x, hc * kw.y, hc * kw.z});
+            x0.x = Vec3{fma(c, ku.x, x0.x.x), fma(c, ku.y, x0.x.y), fma(c, ku.z, x0.x.z)};
+            v0.ang = Vec3{fma(c, aa1.x + 4.0 * aa2.x + aa4.x, w0.x), fma(c, aa1.y + 4.0 * aa2.y + aa4.y, w0.y),
+                          fma(c, aa1.z + 4.0 * aa2.z + aa4.z, w0.z)};
+            v0.lin = Vec3{fma(c, al1.x + 2.0 * (al2.x + al3.x) + al4.x, u0.x),
+                          fma(c, al1.y + 2.0 * (al2.y + al3.y) + al4.y, u0.y),
+                          fma(c, al1.z + 2.0 * (al2.z + al3.z) + al4.z, u0.z)};
+            a_last.ang = aa4; a_last.lin = al4; q_last = q4;
+        } else {
+            // semi_implicit.rs:42-62; calc_accel rotates by q/|q| whatever |q| is
+            const double n2 = x0.q.i * x0.q.i + x0.q.j * x0.q.j + x0.q.k * x0.q.k + x0.q.w * x0.q.w;
+            const double rn = fa::rsqrt_nr(n2);
+            const Quat qn = {x0.q.i * rn, x0.q.j * rn, x0.q.k * rn, x0.q.w * rn};
+            const Vec3 aa = has_u ? fa::rot(qn, f.u) : Vec3{0.0, 0.0, 0.0};
+            const Vec3 fbw = has_fb ? fa::rot(qn, f.fb) : Vec3{0.0, 0.0, 0.0};
+            const Vec3 al = lin_accel_fast<GREG>(P, f, b, 0, fbw, x0.x, v0.lin, I.m, inv_m, greg);
+            const double d = P.dt_final;
+            v0.ang = Vec3{fma(d, aa.x, v0.ang.x), fma(d, aa.y, v0.ang.y), fma(d, aa.z, v0.ang.z)};
+            v0.lin = Vec3{fma(d, al.x, v0.lin.x), fma(d, al.y, v0.lin.y), fma(d, al.z, v0.lin.z)};
+            const double hd = 0.5 * d;
+            x0.q = fa::advance(x0.q, Vec3{hd * v0.ang.x, hd * v0.ang.y, hd * v0.ang.z});
+            x0.x = Vec3{fma(d, v0.lin.x, x0.x.x), fma(d, v0.lin.y, x0.x.y), fma(d, v0.lin.z, x0.x.z)};
+            a_last.ang = aa; a_last.lin = al; q_last = qn;
+        }
+        if (TRAJ) { // compiled out of the launches that record nothing (the roofline case)
+            uint64_t slot;
+            if (traj_due(P, tick0 + t + 1, slot)) {
+                traj_store_state(P, b, slot, x0, v0);
+                if (P.traj_planes == 25) traj_store_af(P, b, slot, a_last, force_out_fast(a_last.lin, f.u, q_last, I));
+            }
+        }
+    }
+    if (want_f) f_last = force_out_fast(a_last.lin, f.u, q_last, I);
+}
+
+} // namespace b200
