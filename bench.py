@@ -15,16 +15,22 @@ configs[1] latency chain (1 body, dependent steps) is reported beside it as
 value     whole-job entity-steps/s, inputs resident in HBM, CUDA-event timed on the
           launching stream, max over ranks.
 e2e       the same metric through the reference-shaped C-ABI call
-          b200_sixdof_invoke_batch with pinned HOST buffers: every call uploads all
-          input columns, integrates `e2e_ticks_per_call` ticks, downloads all outputs.
+          b200_sixdof_invoke_batch with pinned HOST buffers (NUMA-local to the GPU): every call
+          uploads every live input column (pos, vel, inertia), integrates `ticks_per_call` ticks and
+          downloads the state (pos, vel); `e2e.curve` repeats it at 1 / 10 / 100 / 1000 ticks per call,
+          `e2e.all_outputs` with every output column (the round-1 contract), `e2e.pcie` is the
+          concurrent host<->device copy bandwidth of all ranks — the ceiling e2e sits under.
 verified  the timed executor's final state (256 strided worlds) against the CPU oracle advanced the
           same number of ticks: the timed launches did the work.
 roofline  algorithmic 264 B/entity-step / mean kernel time vs the measured
           HBM copy peak (MEASURED_PEAKS.json, else the 6.65 TB/s fallback).
+multi_gpu BASELINE configs[3] (n-body 1024, sharded worlds; one world: replicas vs row shards) and
+          configs[4] (falcon9-style Monte-Carlo, 100 000 rollouts over the N GPUs, wall time including
+          the end-of-run NCCL gather done inside libb200_sixdof.so).
 cpu_baseline / --impl reference
           the CPU oracle port of the reference arithmetic (oracle/, the reference's
-          Rust+JAX+Cranelift stack cannot be built here) on all host threads, on a
-          bounded sample of the same workload.
+          Rust+JAX+Cranelift stack cannot be built here) on every CPU this process may use,
+          one driver call for the whole run (threads created once), >= 1 s timed.
 """
 
 from __future__ import annotations
@@ -136,49 +142,75 @@ class ClockSampler:
         return [r for (_, r) in self.rows]
 
 
-def cpu_oracle_rate(worlds: int, ticks: int, threads: int, seed: int = 1):
-    """entity-steps/s of the CPU oracle port (checker code, timed as the CPU baseline only)."""
+def effective_cores() -> int:
+    """CPUs this process may run on: scheduler affinity clipped by the cgroup quota (not os.cpu_count())."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except Exception:
+        pass
+    return max(n, 1)
+
+
+def cpu_oracle_run(worlds: int, ticks: int, threads: int, warm_ticks: int = 1, seed: int = 1):
+    """One driver call of the CPU oracle port (checker code, timed as the CPU baseline only): every thread is
+    created once and integrates its share of the worlds for all `ticks` (the reference's Monte-Carlo workers run a
+    world to completion each, libs/monte-carlo/src/lib.rs:2530-2538).  Returns (entity-steps/s, seconds)."""
     from oracle import oracle as O
 
     pos, vel, ine = synth_world(worlds, seed)
     w = O.World(pos, vel, ine)
-    w.rk4(DT, 1, threads=threads)  # warm
+    if warm_ticks:
+        w.rk4(DT, warm_ticks, threads=threads)
     t0 = time.perf_counter()
     w.rk4(DT, ticks, threads=threads)
     dt = time.perf_counter() - t0
     return worlds * ticks / dt, dt
 
 
-def run_reference(args):
-    """--impl reference: the reference's CPU path.  Its Rust/JAX/Cranelift stack cannot be
-    built in this image, so this arm times the oracle port (oracle/sixdof_oracle.c, validated
-    bit-for-bit against the reference's golden telemetry) with every host thread."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
+def cpu_arm(steps: int, warmup: int, target_s: float):
+    """The CPU arm both `--impl reference` and the GPU arm's `cpu_baseline` report: the same function, the same
+    sample rule, so the two agree on one box.  A step = one tick over `worlds` worlds; `worlds` is the largest power
+    of two (2^12..2^22 = the GPU arm's batch) that keeps `steps` ticks near `target_s` seconds on this host."""
     from oracle import oracle as O
 
     O.build()
-    threads = O.max_threads()
-    worlds = 1 << 18  # bounded sample of the M-world workload, per step (enough work per thread to amortise the fork/join)
-    # calibrate so the K-step run stays within ~minutes
-    for _ in range(max(args.warmup, 1)):
-        cpu_oracle_rate(worlds, 1, threads)
-    pos, vel, ine = synth_world(worlds, 1)
-    w = O.World(pos, vel, ine)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        w.rk4(DT, 1, threads=threads)
-    el_s = time.perf_counter() - t0
-    value = worlds * args.steps / el_s
+    threads = min(O.max_threads(), effective_cores())
+    r1, _ = cpu_oracle_run(1 << 12, 100, 1)                      # one thread, 0.2 s
+    rN, _ = cpu_oracle_run(1 << 16, 40, threads)                 # calibration, all threads
+    worlds = 1 << 12
+    while worlds < (1 << 22) and 2 * worlds * steps <= rN * target_s:
+        worlds *= 2
+    ticks = steps
+    if worlds * ticks < rN * 1.0:                                # keep the timed region >= ~1 s: more ticks per world
+        ticks = int(rN * 1.2 / worlds) + 1
+    rate, secs = cpu_oracle_run(worlds, ticks, threads, warm_ticks=max(warmup, 1))
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "one_thread_value": r1, "all_threads_over_one": rate / r1,
+            "sample": f"{worlds} worlds x {ticks} ticks in {secs:.2f} s, oracle/sixdof_oracle.c, {threads} threads created once "
+                      f"(one orc_rk4_ticks call); 1 thread: {r1:.3e} entity-steps/s",
+            "worlds": worlds, "ticks": ticks, "seconds": secs}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  Its Rust/JAX/Cranelift stack cannot be
+    built in this image, so this arm times the oracle port (oracle/sixdof_oracle.c, validated
+    bit-for-bit against the reference's golden telemetry) on every CPU the process may use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cpu = cpu_arm(args.steps, args.warmup, target_s=20.0)
+    value = cpu["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": el_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": cpu["seconds"] / cpu["ticks"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cube-sat 6DOF RK4 dt=1e-3, 1 body x M worlds (configs[1] batched); CPU sample of 262144 worlds per step",
-                   "worlds_per_step": worlds, "dt": DT, "integrator": "rk4"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{worlds} worlds x {args.steps} ticks, oracle/sixdof_oracle.c on {threads} threads"},
+        "config": {"workload": "cube-sat 6DOF RK4 dt=1e-3, 1 body x M worlds (BASELINE configs[1] batched over the Monte-Carlo world axis); "
+                               f"CPU sample of {cpu['worlds']} worlds per step",
+                   "worlds_per_step": cpu["worlds"], "ticks_timed": cpu["ticks"], "dt": DT, "integrator": "rk4"},
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "one_thread_value", "all_threads_over_one")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -337,6 +369,10 @@ def run_b200(args):
     K, W = args.steps, max(args.warmup, 3)
     pos, vel, ine = synth_world(M, 1000 + rank)
     stream = torch.cuda.Stream()
+    from elodin_b200 import _lib
+
+    fp64_peak = float(_lib.lib().b200_probe_fp64_gflops(local, 20000))   # DFMA issue rate of this GPU, GFLOP/s
+    copy_probe = float(_lib.lib().b200_probe_copy_gbs(local, 1 << 30, 5))  # D2D copy, read + write GB/s
 
     def barrier():
         if distributed:
@@ -487,66 +523,10 @@ def run_b200(args):
             sb.close()
 
     # ------------------------------------------------------------------ e2e through the C ABI with host buffers
-    T = args.e2e_ticks
-    eM = args.e2e_worlds
-    epos, evel, eine = synth_world(eM, 2000 + rank)
-    ee = el.B200Exec(1, eM, DT, None, [], "rk4", "fast", device=local, max_fused_ticks=args.fuse)
-    host = {WORLD_POS: epos, WORLD_VEL: evel, INERTIA: eine, WORLD_ACCEL: np.zeros((eM, 1, 6)), FORCE: np.zeros((eM, 1, 6)),
-            el.component_id("tick"): np.zeros(1, dtype=np.uint64), el.component_id("simulation_time_step"): np.array([DT])}
-    pin_in, pin_out = [], []
-    for cid in ee.input_ids:
-        a = el.pinned_empty(host[cid].shape, host[cid].dtype)
-        a[...] = host[cid]
-        pin_in.append(a)
-    for cid in ee.output_ids:
-        pin_out.append(el.pinned_empty(host[cid].shape, host[cid].dtype))
-    in_ptrs = [a.ctypes.data for a in pin_in]
-    out_ptrs = [a.ctypes.data for a in pin_out]
-    # bytes that actually cross PCIe per call: the library does not upload dead inputs (Force is cleared
-    # before any effector runs; WorldAccel only enters as 0*a_prev, which FAST math does not evaluate)
-    h2d = sum(a.nbytes for cid, a in zip(ee.input_ids, pin_in) if cid not in (FORCE, WORLD_ACCEL))
-    # pass-through outputs (Inertia) are filled host-to-host by the library, not over PCIe
-    d2h = sum(a.nbytes for cid, a in zip(ee.output_ids, pin_out) if cid != INERTIA)
-    ee.invoke_batch_ptrs(in_ptrs, out_ptrs, T)  # warm
-    barrier()
-    calls = args.e2e_calls
-    t0 = time.perf_counter()
-    for _ in range(calls):
-        ee.invoke_batch_ptrs(in_ptrs, out_ptrs, T)  # synchronous: returns with the outputs on the host
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_ms = max_over_ranks(e2e_s * 1e3)
-    e2e_value = world_size * eM * T * calls / (e2e_ms * 1e-3)
-    tm = ee.timings()
-    checksum = float(np.sum(pin_out[ee.output_ids.index(WORLD_POS)][:1024]))  # the host really has the result
-    ee.close()
+    e2e = run_e2e(args, el, local, rank, world_size, barrier, max_over_ranks, numa_cpus)
 
-    # ------------------------------------------------------------------ end-of-run trajectory gather (NCCL, outside the timed region)
-    gather = None
-    if distributed:
-        from elodin_b200.sharding import gather_worlds
-
-        gM, g_ticks, g_every = 1 << 16, 50, 10
-        gpos, gvel, gine = synth_world(gM, 3000 + rank)
-        gx = el.B200Exec(1, gM, DT, None, [], "rk4", "fast", device=local, max_fused_ticks=10, trajectory_every=g_every,
-                         trajectory_capacity=g_ticks // g_every)
-        gx.set_state(gpos, gvel, gine)
-        gx.step(g_ticks, sync=True)
-        n_s = gx.trajectory_len()
-        traj = torch.empty((n_s, gM, 1, 13), device="cuda", dtype=torch.float64)
-        gx.trajectory_to_ptr(traj.data_ptr(), traj.numel() * 8)  # device -> device, [samples][worlds][entities][13]
-        local_traj = traj.permute(1, 0, 2, 3).contiguous()      # world-major for the world-axis gather
-        gather_worlds(local_traj[:128], 128 * world_size)  # warm the communicator
-        torch.cuda.synchronize()
-        dist.barrier()
-        g0 = time.perf_counter()
-        full = gather_worlds(local_traj, gM * world_size)
-        torch.cuda.synchronize()
-        g_ms = (time.perf_counter() - g0) * 1e3
-        gather = {"collective": "nccl all_gather of the trajectory ring (pos+vel samples), world-sharded",
-                  "samples": int(n_s), "worlds_total": int(full.shape[0]), "bytes_gathered": int(full.numel() * 8),
-                  "ms": g_ms, "gbps": full.numel() * 8 / (g_ms * 1e-3) / 1e9}
-        gx.close()
+    # ------------------------------------------------------------------ BASELINE configs[3] / configs[4] at N GPUs
+    multi = run_multi_gpu(args, torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, fp64_peak)
     ex.close()
 
     if rank == 0:
@@ -556,20 +536,14 @@ def run_b200(args):
         if world_size == 1:
             from oracle import oracle as O
 
-            O.build()
-            threads = O.max_threads()
-            r1, _ = cpu_oracle_rate(1 << 12, 50, 1)
-            n_ticks = max(20, int(args.cpu_seconds * r1 * min(threads, 8) / (1 << 16)))
-            rate, dt_s = cpu_oracle_rate(1 << 16, n_ticks, threads)
-            chk = O.World(pos[vidx], vel[vidx], ine[vidx]).rk4(DT, ticks_total, threads=min(threads, 64))
+            cpu_full = cpu_arm(args.steps, args.warmup, target_s=args.cpu_seconds)
+            cpu = {k: cpu_full[k] for k in ("value", "unit", "cores", "kind", "sample", "one_thread_value", "all_threads_over_one")}
+            chk = O.World(pos[vidx], vel[vidx], ine[vidx]).rk4(DT, ticks_total, threads=min(cpu_full["cores"], 64))
             scale = lambda a: max(float(np.max(np.abs(a))), 1e-300)
             verified = {"worlds_checked": int(len(vidx)), "ticks": int(ticks_total), "against": "CPU oracle (exact arithmetic)",
                         "max_rel_err_q": float(np.max(np.abs(final_pos[..., :4] - chk.pos[..., :4])) / scale(chk.pos[..., :4])),
                         "max_rel_err_x": float(np.max(np.abs(final_pos[..., 4:] - chk.pos[..., 4:])) / scale(chk.pos[..., 4:])),
                         "max_rel_err_vel": float(np.max(np.abs(final_vel - chk.vel)) / scale(chk.vel))}
-            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"65536 worlds x {n_ticks} ticks of the same workload in {dt_s:.1f} s (oracle port, {threads} threads); "
-                             f"1 thread: {r1:.3e} entity-steps/s"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K, "warmup": W,
             "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -578,28 +552,24 @@ def run_b200(args):
                        "worlds_per_gpu": M, "bodies_per_world": 1, "dt": DT, "integrator": "rk4", "math": "fast (<=1e-12/tick vs exact)",
                        "ticks_per_launch": 1, "parallelism": f"worlds sharded x{world_size}, no data-path collective",
                        "l2_policy": "inputs larger than L2 (read set %.0f MB per tick > 126 MB)" % (160 * M / 1e6),
-                       "e2e_ticks_per_call": T, "e2e_worlds_per_gpu": eM},
+                       "e2e_ticks_per_call": e2e["ticks_per_call"], "e2e_worlds_per_gpu": args.e2e_worlds},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_entity_step": B_ALG, "kernel": "body_fast_kernel<RK4,128,4>",
+                         "algorithmic_bytes_per_entity_step": B_ALG, "kernel": "body_fast_spec_kernel<RK4, sig 0, 128 x 3, 2 bodies/thread>",
                          "kernel_ms": kernel_ms,
                          "dram_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None,
-                         "note": "frac counts the algorithmic 264 B/entity-step; the ncu capture shows ~14% fewer DRAM bytes per "
-                                 "launch (part of the previous launch's state is still in the 126 MB L2), so frac can read slightly "
-                                 "above 1.0 while dram_frac (measured DRAM bytes / time / peak) stays below it"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / T, "d2h_bytes_per_step": d2h / T,
-                    "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h, "ticks_per_call": T, "calls": calls,
-                    "ms_per_call": e2e_ms / calls, "engine_busy_ms_last_call": {k: tm[k] for k in ("h2d_upload_ms", "kernel_invoke_ms", "d2h_download_ms", "invoke_wall_ms")},
-                    "api": "b200_sixdof_invoke_batch (pinned host columns in/out)", "checksum": checksum,
-                    "host_cpus_bound": numa_cpus},
+                         "copy_probe_GBps_this_run": copy_probe, "fp64_probe_GFLOPs_this_run": fp64_peak,
+                         "note": "frac counts the algorithmic 264 B/entity-step against the measured copy peak; the ncu capture shows "
+                                 "fewer DRAM bytes per launch than that (part of the previous launch's writes is still in the 126 MB "
+                                 "L2), so frac reads above 1.0 while dram_frac (measured DRAM bytes / time / peak) stays below it"},
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "verified": verified,
             "clocks": clocks,
             "cpu_baseline": cpu,
+            "multi_gpu": multi,
             **extras,
         }
-        if gather:
-            line["gather"] = gather
         if args.configs:
             line["baseline_configs"] = run_baseline_configs(args, torch, el, stream, local, rank, world_size)
         print(json.dumps(line))
@@ -607,6 +577,225 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def run_e2e(args, el, local, rank, world_size, barrier, max_over_ranks, numa_cpus):
+    """entity-steps/s through b200_sixdof_invoke_batch with pinned host columns: every call uploads the live input
+    columns and downloads the outputs the caller reads.  Headline point: `--e2e-ticks` ticks per call, state outputs."""
+    import ctypes as C
+
+    from elodin_b200 import _lib
+    from elodin_b200.executor import FORCE, INERTIA, WORLD_ACCEL, WORLD_POS, WORLD_VEL
+
+    L = _lib.lib()
+    eM = args.e2e_worlds
+    epos, evel, eine = synth_world(eM, 2000 + rank)
+    ee = el.B200Exec(1, eM, DT, None, [], "rk4", "fast", device=local, max_fused_ticks=args.fuse)
+    tick_id, dt_id = el.component_id("tick"), el.component_id("simulation_time_step")
+    host = {WORLD_POS: epos, WORLD_VEL: evel, INERTIA: eine, WORLD_ACCEL: np.zeros((eM, 1, 6)), FORCE: np.zeros((eM, 1, 6)),
+            tick_id: np.zeros(1, dtype=np.uint64), dt_id: np.array([DT])}
+    pin_in, pin_out = {}, {}
+    for cid in ee.input_ids:
+        a = el.pinned_empty(host[cid].shape, host[cid].dtype, device=local)  # on the NUMA node of this GPU's PCIe root
+        a[...] = host[cid]
+        pin_in[cid] = a
+    for cid in ee.output_ids:
+        pin_out[cid] = el.pinned_empty(host[cid].shape, host[cid].dtype, device=local)
+    nodes = {"gpu_numa_node": int(L.b200_device_numa_node(local)), "host_buffer_node": int(L.b200_host_node_of(C.c_void_p(pin_in[WORLD_POS].ctypes.data)))}
+    in_ptrs = [pin_in[c].ctypes.data for c in ee.input_ids]
+    # the library does not upload dead inputs (Force is cleared before any effector runs; WorldAccel only enters as
+    # 0*a_prev, which FAST math does not evaluate): these are the bytes that cross PCIe
+    h2d = sum(pin_in[c].nbytes for c in ee.input_ids if c not in (FORCE, WORLD_ACCEL))
+
+    def measure(T, calls, outputs):
+        want = (WORLD_POS, WORLD_VEL, tick_id) if outputs == "state" else tuple(ee.output_ids)
+        out_ptrs = [pin_out[c].ctypes.data if c in want else None for c in ee.output_ids]
+        d2h = sum(pin_out[c].nbytes for c in ee.output_ids if c in want and c not in (INERTIA,))  # Inertia: host-to-host fill
+        ee.invoke_batch_ptrs(in_ptrs, out_ptrs, T)  # warm
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(calls):
+            ee.invoke_batch_ptrs(in_ptrs, out_ptrs, T)  # synchronous: returns with the outputs on the host
+        el_s = time.perf_counter() - t0
+        ms = max_over_ranks(el_s * 1e3)
+        return {"ticks_per_call": T, "outputs": outputs, "value": world_size * eM * T * calls / (ms * 1e-3), "unit": UNIT,
+                "ms_per_call": ms / calls, "calls": calls, "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h,
+                "h2d_bytes_per_step": h2d / T, "d2h_bytes_per_step": d2h / T}
+
+    head = measure(args.e2e_ticks, args.e2e_calls, "state")
+    tm = ee.timings()
+    checksum = float(np.sum(pin_out[WORLD_POS][:1024]))  # the host really has the result
+    curve = [measure(T, max(3, min(args.e2e_calls, 5)), "state") for T in (1, 10, 100, 1000)]
+    full = measure(args.e2e_ticks, args.e2e_calls, "all")
+    ee.close()
+    # the ceiling: every rank's H2D and D2H engines busy at once with the same byte counts, no kernels
+    probe_h2d, probe_d2h = head["h2d_bytes_per_call"], head["d2h_bytes_per_call"]
+    scratch = el.pinned_empty((probe_h2d + probe_d2h) // 8 + 1, np.float64, device=local)
+    out2 = (C.c_double * 2)()
+    barrier()
+    L.b200_probe_pcie_gbs(local, C.c_void_p(scratch.ctypes.data), probe_h2d, probe_d2h, 5, out2)
+    barrier()
+    t_copy_ms = max(probe_h2d / max(out2[0], 1e-9), probe_d2h / max(out2[1], 1e-9)) / 1e6  # the slower direction bounds a call
+    t_copy_ms = max_over_ranks(t_copy_ms)
+    pcie = {"h2d_GBps_rank0": out2[0], "d2h_GBps_rank0": out2[1], "concurrent_ranks": world_size,
+            "copy_bound_ms_per_call": t_copy_ms,
+            "copy_bound_value": world_size * eM * head["ticks_per_call"] / (t_copy_ms * 1e-3),
+            "e2e_frac_of_copy_bound": head["value"] / (world_size * eM * head["ticks_per_call"] / (t_copy_ms * 1e-3)),
+            "note": "both copy engines of every rank moving one call's bytes at the same time, no kernels: what PCIe Gen5 x16 and "
+                    "the host memory system allow; at 4-8 ranks the sockets' memory bandwidth, not the links, sets it"}
+    el.pinned_free(scratch)
+    for a in list(pin_in.values()) + list(pin_out.values()):
+        el.pinned_free(a)
+    return {**head, "curve": curve, "all_outputs": full,
+            "engine_busy_ms_last_call": {k: tm[k] for k in ("h2d_upload_ms", "kernel_invoke_ms", "d2h_download_ms", "invoke_wall_ms")},
+            "api": "b200_sixdof_invoke_batch (pinned host columns in; WorldPos/WorldVel/tick out, other outputs NULL = not read)",
+            "checksum": checksum, "host_cpus_bound": numa_cpus, "pcie": pcie, **nodes}
+
+
+def run_multi_gpu(args, torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, fp64_peak):
+    """BASELINE configs[3] and configs[4] on the N GPUs of this run (also at N = 1, so the scaling run has a base)."""
+    from elodin_b200.executor import WORLD_POS
+    from elodin_b200.sharding import Comm, shard_sizes, shard_worlds
+
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    distributed = world_size > 1
+
+    def timed(step, ticks, warm):
+        with torch.cuda.stream(stream):
+            step(warm)
+            barrier()
+            a, b = ev(), ev()
+            a.record(stream)
+            step(ticks)
+            b.record(stream)
+            barrier()
+        return max_over_ranks(a.elapsed_time(b))
+
+    # ---- configs[3]: n-body, 1024 bodies, softened all-pairs gravity + 6DOF (SURVEY §8d C4)
+    N = 1024
+    rng = np.random.default_rng(7)  # the same world(s) on every rank where a single world is replicated
+
+    def nbody_world(Mw, gen):
+        p = np.zeros((Mw, N, 7)); p[..., 3] = 1.0; p[..., 4:] = gen.uniform(-30, 30, (Mw, N, 3))
+        v = np.zeros((Mw, N, 6)); v[..., 3:] = gen.normal(0, 1e-7, (Mw, N, 3))
+        m = 10 ** gen.uniform(-10, -3, (Mw, N)); m[:, 0] = 1.0
+        I = np.zeros((Mw, N, 7)); I[..., :3] = m[..., None]; I[..., 6] = m
+        return p, v, I
+
+    grav = lambda: el.GravityEdges("softened", k_squared=2.9591220828e-4 / 86400.0 ** 2, softening=1e-10, edges=el.all_pairs_edges(N))
+    FLOP_PAIR, SLOT_PAIR = 27.0, 18.0  # per pair evaluation: flops (FMA = 2) / FP64-pipe instruction slots (DESIGN.md §5)
+    # (a) worlds sharded: M = 8 worlds per GPU (weak scaling), no collective
+    Mw = 8
+    p, v, I = nbody_world(Mw, np.random.default_rng(100 + rank))
+    ex = el.B200Exec(N, Mw, 3600.0, None, [grav()], "rk4", "fast", device=local)
+    ex.set_stream(stream.cuda_stream)
+    ex.set_state(p, v, I)
+    ticks = 200
+    ms = timed(ex.step, ticks, 10)
+    ex.close()
+    pair_rate = 3.0 * N * (N - 1) * Mw * world_size * ticks / (ms * 1e-3)
+    out["nbody_1024_sharded_worlds"] = {
+        "config": "BASELINE configs[3]: 1024 bodies, softened all-pairs gravity + 6DOF RK4, dt = 3600 s, 8 worlds per GPU", "worlds_per_gpu": Mw,
+        "ticks": ticks, "us_per_tick": ms * 1e3 / ticks, "value": N * Mw * world_size * ticks / (ms * 1e-3), "unit": UNIT,
+        "pair_evals_per_s": pair_rate, "scaling": "weak",
+        "roofline": {"bound": "fp64", "achieved": pair_rate * FLOP_PAIR / 1e9 / world_size, "peak": fp64_peak, "unit": "GFLOP/s",
+                     "frac": pair_rate * FLOP_PAIR / 1e9 / world_size / fp64_peak if fp64_peak else None,
+                     "pipe_frac": pair_rate * SLOT_PAIR / world_size / (fp64_peak * 1e9 / 2.0) if fp64_peak else None,
+                     "peak_source": "b200_probe_fp64_gflops (dependent-free DFMA chains), this run, per GPU",
+                     "flops_per_pair_eval": FLOP_PAIR, "fp64_slots_per_pair_eval": SLOT_PAIR,
+                     "note": "3 N (N-1) pair evaluations per world-tick (three distinct stage positions); pipe_frac = FP64-pipe "
+                             "instruction slots of the pair arithmetic / the DFMA issue rate (a non-fused op takes a whole slot)"}}
+    # (b) ONE world on N GPUs: replicas (every GPU integrates the whole world, zero communication) ...
+    p1, v1, I1 = nbody_world(1, rng)
+    ex = el.B200Exec(N, 1, 3600.0, None, [grav()], "rk4", "fast", device=local)
+    ex.set_stream(stream.cuda_stream)
+    ex.set_state(p1, v1, I1)
+    ms_rep = timed(ex.step, 400, 20)
+    ref_pos = ex.download(WORLD_POS)
+    ex.close()
+    single = {"config": "BASELINE configs[3], M = 1: one 1024-body world on N GPUs",
+              "replicas": {"us_per_tick": ms_rep * 1e3 / 400, "value": N * 400 / (ms_rep * 1e-3), "unit": UNIT,
+                           "note": "every GPU integrates the whole world; no communication; value counts the world once"}}
+    # ... vs row shards (each GPU folds N / n_gpus sources, stage positions exchanged through NVLink peer memory)
+    single["row_shards"] = run_row_shards(args, torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks,
+                                          (p1, v1, I1), grav, ref_pos)
+    out["nbody_1024_single_world"] = single
+
+    # ---- configs[4]: falcon9-style Monte-Carlo, 100 000 rollouts over the N GPUs (strong scaling: total work fixed)
+    TOTAL = args.mc_rollouts
+    w0, w1 = shard_worlds(TOTAL, rank, world_size)
+    Ml = w1 - w0
+    gen = np.random.default_rng(20170814 + rank)
+    pos = np.tile(np.array([0, 0, 0, 1.0, 6.4e6, 0, 0]), (Ml, 1, 1)) + np.concatenate([np.zeros((Ml, 1, 4)), gen.normal(0, 10, (Ml, 1, 3))], -1)
+    vel = np.concatenate([gen.normal(0, 0.01, (Ml, 1, 3)), gen.normal(0, 50, (Ml, 1, 3))], -1)
+    ine = np.tile(np.array([4e6, 4e6, 1e5, 0, 0, 0, 3e4]), (Ml, 1, 1))
+    steps, every = args.mc_steps, max(args.mc_steps // 50, 1)
+    ex = el.B200Exec(1, Ml, 1e-3, None, [el.GravityFrame(), el.WrenchBody("body_wrench", "linear_first")], "rk4", "fast", device=local,
+                     max_fused_ticks=100, trajectory_every=every, trajectory_capacity=steps // every)
+    ex.set_stream(stream.cuda_stream)
+    ex.set_state(pos, vel, ine, body_wrench=gen.normal(0, 1e4, (Ml, 1, 6)))
+    ex.step(100)  # warm (kernel image, clocks); the ring restarts below
+    ex.sync()
+    ex.trajectory_reset()
+    with torch.cuda.stream(stream):
+        barrier()
+        a, b = ev(), ev()
+        a.record(stream)
+        ex.step(steps)
+        b.record(stream)
+        barrier()
+    ms_steps = max_over_ranks(a.elapsed_time(b))
+    # end-of-run gather of the trajectory ring inside the library (NCCL over NVLink), every rank gets every world
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.tensor(list(Comm.unique_id()), dtype=torch.uint8, device="cuda")
+    if distributed:
+        dist.broadcast(uid, 0)
+    comm = Comm(bytes(uid.cpu().tolist()), world_size, rank, local)
+    sizes = shard_sizes(TOTAL, world_size)
+    n_s, Wt = ex.trajectory_len(), ex.trajectory_width()
+    full = torch.empty((TOTAL, n_s, 1, Wt), device="cuda", dtype=torch.float64)
+    gms = []
+    for i in range(7):  # 2 warm-ups at full size (NCCL builds its channels on first use), 5 timed
+        barrier()
+        comm.trajectory_allgather(ex, sizes, out_ptr=full.data_ptr())
+        if i >= 2:
+            gms.append(max_over_ranks(comm.last_ms))
+    g_ms = float(np.median(gms))
+    recv_bytes = full.numel() * 8 * (world_size - 1) / world_size  # what one GPU receives over NVLink
+    # integrity of the gathered array: rank r's first world sits at offset sum(sizes[:r]) with its own sample 0
+    own = ex.trajectory()[:, 0, 0, :]
+    got = full[w0, :, 0, :].cpu().numpy() if Ml else own
+    gather_ok = bool(np.array_equal(own, got))
+    ex.close()
+    comm.close()
+    out["falcon9_mc_rollouts"] = {
+        "config": f"BASELINE configs[4]: falcon9-style worlds (rotating-frame gravity + body wrench), {TOTAL} rollouts sharded over "
+                  f"{world_size} GPU(s), dt = 1e-3, {steps} steps, trajectory sample every {every} ticks",
+        "rollouts_total": TOTAL, "rollouts_per_gpu": sizes, "steps": steps, "scaling": "strong",
+        "seconds_steps": ms_steps * 1e-3, "seconds_gather": g_ms * 1e-3, "seconds_total": (ms_steps + g_ms) * 1e-3,
+        "value": TOTAL * steps / ((ms_steps + g_ms) * 1e-3), "value_steps_only": TOTAL * steps / (ms_steps * 1e-3), "unit": UNIT,
+        "gather": {"collective": "b200_sixdof_trajectory_allgather: layout kernel + ncclAllGather (ragged: grouped ncclBroadcast) "
+                                 "inside libb200_sixdof.so, device-timed on the handle's stream",
+                   "nccl_version": int(__import__("elodin_b200")._lib.lib().b200_comm_version()),
+                   "bytes_result_per_gpu": int(full.numel() * 8), "bytes_received_per_gpu": int(recv_bytes),
+                   "ms_median_of_5": g_ms, "ms_all": gms, "recv_GBps_per_gpu": recv_bytes / (g_ms * 1e-3) / 1e9 if world_size > 1 else None,
+                   "nvlink5_peak_GBps_per_direction": 900.0,
+                   "frac_of_nvlink_peak": recv_bytes / (g_ms * 1e-3) / 1e9 / 900.0 if world_size > 1 else None,
+                   "result_checked": gather_ok}}
+    return out
+
+
+def run_row_shards(args, torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, world, grav, ref_pos):
+    """One 1024-body world split by source rows over the GPUs of the node ("report both")."""
+    if world_size == 1:
+        return {"skipped": "needs more than one GPU"}
+    try:
+        from elodin_b200.sharding import RowShardedWorld
+    except ImportError:
+        return {"skipped": "row sharding is not built in this version"}
+    return RowShardedWorld.bench(args, torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, world, grav, ref_pos)
 
 
 def main():
@@ -621,6 +810,8 @@ def main():
     ap.add_argument("--e2e-worlds", type=int, default=1 << 20)
     ap.add_argument("--e2e-calls", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--mc-rollouts", type=int, default=100000, help="configs[4]: Monte-Carlo rollouts over all GPUs")
+    ap.add_argument("--mc-steps", type=int, default=1000, help="configs[4]: ticks per rollout (dt = 1e-3)")
     ap.add_argument("--configs", action="store_true", help="also time the other BASELINE.json configs (adds ~1 min)")
     ap.add_argument("--kernel-only", action="store_true", help="profiling aid: only the main timed loop (no e2e / cpu / extras)")
     args = ap.parse_args()

@@ -37,12 +37,16 @@ EFF_WRENCH_BODY = 4
 EFF_GRAVITY_FRAME = 5
 EFF_GRAVITY_EDGES_NEWTON = 6
 EFF_GRAVITY_EDGES_SOFTENED = 7
+EFF_WRENCH_WORLD = 8
+EFF_TORQUE_BODY_FOLD = 9
+EFF_GRAVITY_J2 = 10
 EFF_FLAG_WRENCH_LINEAR_FIRST = 1
 TRAJ_FULL = 1
 
 # every symbol include/b200_sixdof.h declares (tests/test_abi.py checks the export table against it)
 SYMBOLS = [
-    "b200_component_id", "b200_last_error", "b200_device_count", "b200_host_alloc", "b200_host_free",
+    "b200_component_id", "b200_last_error", "b200_device_count", "b200_host_alloc", "b200_host_alloc_local", "b200_host_free",
+    "b200_device_numa_node", "b200_host_node_of",
     "b200_sixdof_create", "b200_sixdof_destroy", "b200_sixdof_input_ids", "b200_sixdof_output_ids",
     "b200_sixdof_column_bytes", "b200_sixdof_upload", "b200_sixdof_download", "b200_sixdof_step",
     "b200_sixdof_sync", "b200_sixdof_invoke_batch", "b200_sixdof_bind_tick", "b200_sixdof_tick",
@@ -50,7 +54,11 @@ SYMBOLS = [
     "b200_sixdof_trajectory_reset",
     "b200_sixdof_tick_count", "b200_sixdof_set_stream", "b200_sixdof_timings", "b200_sixdof_status",
     "b200_sixdof_device_plane", "b200_sixdof_plane_stride", "b200_probe_copy_gbs", "b200_probe_fp64_gflops",
+    "b200_comm_available", "b200_comm_version", "b200_comm_unique_id", "b200_comm_create", "b200_comm_destroy",
+    "b200_comm_rank", "b200_comm_size", "b200_comm_last_ms", "b200_sixdof_trajectory_gather_bytes",
+    "b200_sixdof_trajectory_allgather", "b200_probe_pcie_gbs",
 ]
+COMM_ID_BYTES = 128
 
 
 class Effector(C.Structure):
@@ -135,6 +143,12 @@ def lib():
     L.b200_device_count.restype = C.c_int
     L.b200_host_alloc.argtypes = [u64]
     L.b200_host_alloc.restype = vp
+    L.b200_host_alloc_local.argtypes = [u64, C.c_int]
+    L.b200_host_alloc_local.restype = vp
+    L.b200_device_numa_node.argtypes = [C.c_int]
+    L.b200_device_numa_node.restype = C.c_int
+    L.b200_host_node_of.argtypes = [vp]
+    L.b200_host_node_of.restype = C.c_int
     L.b200_host_free.argtypes = [vp]
     L.b200_host_free.restype = None
     L.b200_sixdof_create.argtypes = [C.POINTER(Desc), C.POINTER(vp)]
@@ -169,6 +183,20 @@ def lib():
     L.b200_sixdof_device_plane.restype = vp
     L.b200_sixdof_plane_stride.argtypes = [vp]
     L.b200_sixdof_plane_stride.restype = u64
+    L.b200_comm_available.restype = C.c_int
+    L.b200_comm_version.restype = C.c_int
+    L.b200_comm_unique_id.argtypes = [vp, u32]
+    L.b200_comm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.b200_comm_destroy.argtypes = [vp]
+    L.b200_comm_destroy.restype = None
+    L.b200_comm_rank.argtypes = [vp]
+    L.b200_comm_size.argtypes = [vp]
+    L.b200_comm_last_ms.argtypes = [vp]
+    L.b200_comm_last_ms.restype = C.c_double
+    L.b200_sixdof_trajectory_gather_bytes.argtypes = [vp, C.POINTER(u64), C.c_int]
+    L.b200_sixdof_trajectory_gather_bytes.restype = u64
+    L.b200_sixdof_trajectory_allgather.argtypes = [vp, vp, C.POINTER(u64), vp, u64]
+    L.b200_probe_pcie_gbs.argtypes = [C.c_int, vp, u64, u64, C.c_int, C.POINTER(C.c_double)]
     L.b200_probe_copy_gbs.argtypes = [C.c_int, u64, C.c_int]
     L.b200_probe_copy_gbs.restype = C.c_double
     L.b200_probe_fp64_gflops.argtypes = [C.c_int, C.c_int]

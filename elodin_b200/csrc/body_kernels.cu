@@ -468,12 +468,21 @@ cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode,
     if (P.n_bodies == 0) return cudaSuccess;
     const bool rk4 = integrator == B200_INTEGRATOR_RK4;
     if (math_mode == B200_MATH_EXACT) {
+#ifdef B200_TUNE
+        const int xcfg = env_int("B200_EXACT_CFG", 3);
+#else
         static const int xcfg = env_int("B200_EXACT_CFG", 3);
+#endif
         auto g = [&](int blk) { return (unsigned)((P.n_bodies + blk - 1) / blk); };
         if (!rk4) body_exact_kernel<B200_INTEGRATOR_SEMI_IMPLICIT, 256, 1><<<g(256), 256, 0, s>>>(P);
         else switch (xcfg) {
         case 1: body_exact_kernel<B200_INTEGRATOR_RK4, 256, 2><<<g(256), 256, 0, s>>>(P); break;
         case 0: body_exact_kernel<B200_INTEGRATOR_RK4, 256, 1><<<g(256), 256, 0, s>>>(P); break;
+#ifdef B200_TUNE
+        case 4: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 5><<<g(128), 128, 0, s>>>(P); break;
+        case 5: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 6><<<g(128), 128, 0, s>>>(P); break;
+        case 6: body_exact_kernel<B200_INTEGRATOR_RK4, 64, 12><<<g(64), 64, 0, s>>>(P); break;
+#endif
         default: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 4><<<g(128), 128, 0, s>>>(P); break; // 4.3e9 vs 2.7e9 (256x1)
         }
         return cudaGetLastError();

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) grap
     const uint64_t wbase = (uint64_t)world * N;
     const bool active = i < N;
     const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
-    const double soft = newton ? 0.0 : G.p1;
+    const double soft = (newton || !(G.p1 > 0.0)) ? fa::kNewtonSelfSoft : G.p1;
     auto dtf_of = [&](uint32_t sl) { return sl == 0 ? 0.0 : (sl == 1 ? 0.5 * G.dt_stage : G.dt_stage); };
 
     Vec3 xi[NW], acc[NW];
@@ -172,17 +172,10 @@ __global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) grap
         if (active) {
 #pragma unroll 4
             for (uint32_t jj = lane; jj < jn; jj += 32) {
-                // the self pair contributes exactly nothing (and would be 0 * inf for Newton)
-                const double mj = (j0 + jj == i) ? 0.0 : sm[jj];
-                const bool self = j0 + jj == i;
+                const double mj = sm[jj]; // the self pair contributes exactly 0: r = 0 and soft > 0 (pair_fold)
 #pragma unroll
-                for (int s = 0; s < NW; ++s) {
-                    const Vec3 r = {sx[sl0 + s][0][jj] - xi[s].x, sx[sl0 + s][1][jj] - xi[s].y, sx[sl0 + s][2][jj] - xi[s].z};
-                    const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, soft)));
-                    const double inv = fa::rsqrt_nr(d2);
-                    const double w = self ? 0.0 : mj * inv * inv * inv;
-                    acc[s].x = fma(w, r.x, acc[s].x); acc[s].y = fma(w, r.y, acc[s].y); acc[s].z = fma(w, r.z, acc[s].z);
-                }
+                for (int s = 0; s < NW; ++s)
+                    fa::pair_fold(xi[s], sx[sl0 + s][0][jj], sx[sl0 + s][1][jj], sx[sl0 + s][2][jj], mj, soft, acc[s]);
             }
         }
     }
@@ -203,6 +196,82 @@ __global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) grap
             stp(G.gforce, G.ld, (sl0 + s) * 3 + 0, b, k * acc[s].x);
             stp(G.gforce, G.ld, (sl0 + s) * 3 + 1, b, k * acc[s].y);
             stp(G.gforce, G.ld, (sl0 + s) * 3 + 2, b, k * acc[s].z);
+        }
+    }
+}
+
+// FAST all-pairs for worlds of N <= TJ bodies, persistent: a CTA keeps ONE world's three stage-position tiles and
+// masses in shared memory (80 KB at TJ = 1024) and folds many sources against them — the round-1 kernel re-staged
+// the world for every 8 sources and its grid (one CTA per 8 sources) quantised badly against the 148 SMs (M = 8:
+// 1024 CTAs on 444 slots = 2.3 waves).  Work items are (source, stage slot) pairs, one warp each, lanes striding the
+// targets; with fewer worlds than CTAs a world's sources are split over grid/M CTAs, otherwise a CTA walks whole
+// worlds.  No self test (pair_fold), one third-order rsqrt step: 18 FP64-pipe slots per pair evaluation.
+template <bool RK4, int TJ>
+__global__ void __launch_bounds__(256, 2) graph_dense_world_kernel(const __grid_constant__ GraphParams G)
+{
+    constexpr int NS = RK4 ? 3 : 1;
+    constexpr int NT = 256, NWARP = NT / 32;
+    extern __shared__ double dsm[];
+    double(*sx)[3][TJ] = reinterpret_cast<double(*)[3][TJ]>(dsm);
+    double *sm = dsm + NS * 3 * TJ;
+
+    const uint32_t N = G.n_entities, M = G.n_worlds;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const double soft = (G.kind == B200_EFF_GRAVITY_EDGES_NEWTON || !(G.p1 > 0.0)) ? fa::kNewtonSelfSoft : G.p1;
+    // CTAs per world (cpw >= 1) when the grid outnumbers the worlds; otherwise worlds stride the grid
+    const uint32_t cpw = gridDim.x > M ? gridDim.x / M : 1u;
+    const uint32_t part = cpw > 1 ? blockIdx.x % cpw : 0u;
+    uint32_t world = cpw > 1 ? blockIdx.x / cpw : blockIdx.x;
+    const uint32_t wstep = cpw > 1 ? M : gridDim.x; // cpw > 1: one world per CTA (CTAs beyond M * cpw idle)
+    auto dtf_of = [&](uint32_t sl) { return sl == 0 ? 0.0 : (sl == 1 ? 0.5 * G.dt_stage : G.dt_stage); };
+
+    for (; world < M; world += wstep) {
+        const uint64_t wbase = (uint64_t)world * N;
+        __syncthreads(); // the previous world's folds are done with the tiles
+        for (uint32_t j = threadIdx.x; j < N; j += NT) {
+            const uint64_t b = wbase + j;
+            const Vec3 x = {ldp(G.pos, G.ld, 4, b), ldp(G.pos, G.ld, 5, b), ldp(G.pos, G.ld, 6, b)};
+            if (RK4) {
+                const Vec3 v = {ldp(G.vel, G.ld, 3, b), ldp(G.vel, G.ld, 4, b), ldp(G.vel, G.ld, 5, b)};
+#pragma unroll
+                for (int st = 0; st < NS; ++st) {
+                    const Vec3 pnt = stage_pos<false>(x, v, dtf_of(st));
+                    sx[st][0][j] = pnt.x; sx[st][1][j] = pnt.y; sx[st][2][j] = pnt.z;
+                }
+            } else {
+                sx[0][0][j] = x.x; sx[0][1][j] = x.y; sx[0][2][j] = x.z;
+            }
+            sm[j] = ldp(G.ine, G.ld, 6, b);
+        }
+        __syncthreads();
+        const uint32_t i0 = (uint32_t)((uint64_t)N * part / cpw), i1 = (uint32_t)((uint64_t)N * (part + 1) / cpw);
+        const uint32_t items = (i1 - i0) * NS;
+        for (uint32_t it = warp; it < items; it += NWARP) {
+            const uint32_t i = i0 + it / NS, sl = it - (it / NS) * NS;
+            const Vec3 xi = {sx[sl][0][i], sx[sl][1][i], sx[sl][2][i]};
+            Vec3 a0 = {0, 0, 0}, a1 = {0, 0, 0};
+            uint32_t jj = lane;
+            for (; jj + 96 < N; jj += 128) { // 4 targets per lane and trip: independent chains for the FP64 pipe
+                fa::pair_fold(xi, sx[sl][0][jj], sx[sl][1][jj], sx[sl][2][jj], sm[jj], soft, a0);
+                fa::pair_fold(xi, sx[sl][0][jj + 32], sx[sl][1][jj + 32], sx[sl][2][jj + 32], sm[jj + 32], soft, a1);
+                fa::pair_fold(xi, sx[sl][0][jj + 64], sx[sl][1][jj + 64], sx[sl][2][jj + 64], sm[jj + 64], soft, a0);
+                fa::pair_fold(xi, sx[sl][0][jj + 96], sx[sl][1][jj + 96], sx[sl][2][jj + 96], sm[jj + 96], soft, a1);
+            }
+            for (; jj < N; jj += 32) fa::pair_fold(xi, sx[sl][0][jj], sx[sl][1][jj], sx[sl][2][jj], sm[jj], soft, a0);
+            Vec3 acc = {a0.x + a1.x, a0.y + a1.y, a0.z + a1.z};
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+            }
+            if (lane == 0) {
+                const uint64_t b = wbase + i;
+                const double k = G.p0 * sm[i];
+                stp(G.gforce, G.ld, sl * 3 + 0, b, k * acc.x);
+                stp(G.gforce, G.ld, sl * 3 + 1, b, k * acc.y);
+                stp(G.gforce, G.ld, sl * 3 + 2, b, k * acc.z);
+            }
         }
     }
 }
@@ -234,7 +303,7 @@ __global__ void __launch_bounds__(32 * kFastSrc * 3) nbody_tick_fused_kernel(con
     const uint64_t wbase = (uint64_t)world * N;
     const bool active = i < N;
     const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
-    const double soft = newton ? 0.0 : G.p1;
+    const double soft = (newton || !(G.p1 > 0.0)) ? fa::kNewtonSelfSoft : G.p1;
     auto dtf_of = [&](uint32_t k) { return k == 0 ? 0.0 : (k == 1 ? 0.5 * G.dt_stage : G.dt_stage); };
 
     Vec3 xi = {0, 0, 0}, acc = {0, 0, 0};
@@ -264,14 +333,8 @@ __global__ void __launch_bounds__(32 * kFastSrc * 3) nbody_tick_fused_kernel(con
         const uint32_t jn = min((uint32_t)TJ, N - j0);
         if (active) {
 #pragma unroll 4
-            for (uint32_t jj = lane; jj < jn; jj += 32) {
-                const bool self = j0 + jj == i;
-                const Vec3 r = {sx[sl][0][jj] - xi.x, sx[sl][1][jj] - xi.y, sx[sl][2][jj] - xi.z};
-                const double d2 = fma(r.x, r.x, fma(r.y, r.y, fma(r.z, r.z, soft)));
-                const double inv = fa::rsqrt_nr(d2);
-                const double w = self ? 0.0 : sm[jj] * inv * inv * inv;
-                acc.x = fma(w, r.x, acc.x); acc.y = fma(w, r.y, acc.y); acc.z = fma(w, r.z, acc.z);
-            }
+            for (uint32_t jj = lane; jj < jn; jj += 32)
+                fa::pair_fold(xi, sx[sl][0][jj], sx[sl][1][jj], sx[sl][2][jj], sm[jj], soft, acc);
         }
     }
 #pragma unroll
@@ -472,6 +535,30 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
         if (exact) { if (rk4) graph_dense_kernel<true, true><<<grid, blk3, 0, s>>>(G); else graph_dense_kernel<true, false><<<grid, blk1, 0, s>>>(G); }
         else if (gcfg == 0) { if (rk4) graph_dense_kernel<false, true><<<grid, blk3, 0, s>>>(G); else graph_dense_kernel<false, false><<<grid, blk1, 0, s>>>(G); }
         else {
+            if (gcfg == 1 && G.n_entities <= 1024 && G.n_entities >= 64) {
+                // worlds that fit one shared-memory tile set: persistent world-resident kernel, 2 CTAs per SM
+                int dev = 0, sms = 148;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                const unsigned slots = 2u * (unsigned)sms;
+                unsigned grid_w;
+                if (G.n_worlds >= slots) grid_w = slots;
+                else {
+                    // every CTA of a world takes at least ~2 rounds of (source, slot) items for its 8 warps
+                    const unsigned cpw = std::max(1u, std::min(slots / G.n_worlds, (G.n_entities * 3u + 15u) / 16u));
+                    grid_w = cpw * G.n_worlds;
+                }
+                if (rk4) {
+                    constexpr size_t smem = (3 * 3 + 1) * 1024 * sizeof(double);
+                    const cudaError_t e = ensure_dynamic_smem(graph_dense_world_kernel<true, 1024>, smem);
+                    if (e != cudaSuccess) return e;
+                    graph_dense_world_kernel<true, 1024><<<grid_w, 256, smem, s>>>(G);
+                } else {
+                    constexpr size_t smem = (3 + 1) * 1024 * sizeof(double);
+                    graph_dense_world_kernel<false, 1024><<<grid_w, 256, smem, s>>>(G);
+                }
+                return cudaGetLastError();
+            }
             const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
             // few CTAs: split the stage slots over warps to fill the machine; many CTAs: keep
             // 3 slots per warp (more ILP per lane, 3 CTAs/SM) — measured on N = 1024, M = 1 / 8

@@ -5,8 +5,15 @@
 // column buffers in and out, and drives the sm_100a kernels.  There is no CPU
 // fallback anywhere in this file: without a CUDA device every entry point fails
 // with B200_ERR_NO_DEVICE.
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <cctype>
 #include <chrono>
+#include <map>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -17,14 +24,13 @@
 #include <thread>
 #include <vector>
 
-#include "sixdof_internal.h"
+#include "sixdof_handle.h"
 
 using namespace b200;
 
-namespace {
+namespace b200 {
 
-thread_local std::string g_last_error = "";
-thread_local b200_sixdof *g_tick_handle = nullptr;
+static thread_local std::string g_last_error = "";
 
 int fail(int code, const char *fmt, ...)
 {
@@ -37,73 +43,7 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
-struct Column {
-    uint64_t id;
-    uint32_t width;     // f64 per body (globals: 1)
-    bool global;        // tick / simulation_time_step: one 8-byte scalar, host resident
-    double *dev;        // width planes of ld doubles
-};
-
-uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
-
-} // namespace
-
-struct b200_sixdof {
-    b200_sixdof_desc desc{};
-    std::vector<b200_effector> effectors;
-    std::vector<uint8_t *> eff_masks; // device copies of the per-effector entity masks (nullptr = all)
-    int device = 0;
-    uint64_t n_bodies = 0;
-    uint64_t ld = 0;
-    std::vector<Column> cols;
-    std::vector<uint64_t> input_ids, output_ids;
-    double sim_time_step = 0.0;   // SimulationTimeStep column value
-    uint64_t tick = 0;            // Tick column value
-    uint64_t ticks_done = 0;      // ticks since create / trajectory reset (trajectory slot index base)
-    // graph effector
-    int graph_eff = -1;
-    bool graph_dense = false;
-    uint32_t *row_ptr = nullptr, *col_idx = nullptr;
-    uint8_t *has_edge = nullptr;
-    double *gforce = nullptr;
-    double *pos_alt = nullptr, *vel_alt = nullptr; // ping-pong planes of the one-launch n-body tick
-    bool nbody_fused = false;                       // decided once per handle (whole-batch grid size)
-    bool small_world = false;                       // <= 32 bodies per world: whole ticks in one warp, n ticks per launch
-    uint32_t max_deg = 0;
-    // staging for AoS <-> SoA
-    double *staging = nullptr;
-    uint64_t staging_bytes = 0;
-    // trajectory
-    double *traj = nullptr;
-    uint32_t traj_planes = 13;   // 25 with B200_TRAJ_FULL
-    // plumbing
-    cudaStream_t stream = nullptr;
-    bool own_stream = true;
-    // pipelined invoke_batch: copy engines on their own streams, whole-batch AoS staging
-    cudaStream_t copy_in = nullptr, copy_out = nullptr;
-    double *stage_in = nullptr, *stage_out = nullptr;
-    uint64_t stage_in_bytes = 0, stage_out_bytes = 0;
-    std::vector<cudaEvent_t> chunk_in, chunk_out;
-    // small batches: packed pinned host staging (one PCIe transfer per direction)
-    uint8_t *host_pack = nullptr;
-    uint64_t host_pack_bytes = 0;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // [0,1] H2D span, [2,3] compute span, [4,5] D2H span
-    int status = B200_OK;
-    b200_timings timings{};
-
-    Column *find(uint64_t id)
-    {
-        for (auto &c : cols) if (c.id == id) return &c;
-        return nullptr;
-    }
-    const Column *find(uint64_t id) const
-    {
-        for (auto &c : cols) if (c.id == id) return &c;
-        return nullptr;
-    }
-};
-
-namespace {
+const char *last_error_message() { return g_last_error.c_str(); }
 
 int cuda_fail(b200_sixdof *h, cudaError_t e, const char *what)
 {
@@ -111,12 +51,6 @@ int cuda_fail(b200_sixdof *h, cudaError_t e, const char *what)
     return fail(e == cudaErrorMemoryAllocation ? B200_ERR_OUT_OF_MEMORY : B200_ERR_CUDA, "CUDA error in %s: %s", what,
                 cudaGetErrorString(e));
 }
-
-#define CU(h, call)                                                        \
-    do {                                                                   \
-        cudaError_t e_ = (call);                                           \
-        if (e_ != cudaSuccess) return cuda_fail((h), e_, #call);           \
-    } while (0)
 
 int ensure_staging(b200_sixdof *h, uint64_t bytes)
 {
@@ -126,6 +60,12 @@ int ensure_staging(b200_sixdof *h, uint64_t bytes)
     h->staging_bytes = bytes;
     return B200_OK;
 }
+
+} // namespace b200
+
+namespace {
+
+thread_local b200_sixdof *g_tick_handle = nullptr;
 
 uint64_t column_bytes(const b200_sixdof *h, const Column &c)
 {
@@ -398,7 +338,7 @@ uint64_t b200_component_id(const char *name)
     return h & ~(1ull << 63); // types.rs:43
 }
 
-const char *b200_last_error(void) { return g_last_error.c_str(); }
+const char *b200_last_error(void) { return last_error_message(); }
 
 int b200_device_count(void)
 {
@@ -419,7 +359,84 @@ void *b200_host_alloc(uint64_t bytes)
     return p;
 }
 
-void b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+// NUMA node of a GPU's PCIe root: /sys/bus/pci/devices/<domain:bus:dev.fn>/numa_node
+int b200_device_numa_node(int device)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    for (char *c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+// NUMA node the first page of a host buffer lives on (move_pages query), -1 if unknown
+int b200_host_node_of(const void *p)
+{
+#ifdef SYS_move_pages
+    void *page = (void *)((uintptr_t)p & ~(uintptr_t)4095);
+    int status = -1;
+    if (syscall(SYS_move_pages, 0, 1ul, &page, nullptr, &status, 0) == 0) return status;
+#endif
+    return -1;
+}
+
+namespace {
+std::mutex g_local_mu;
+std::map<void *, size_t> g_local_allocs; // b200_host_alloc_local blocks: base -> mapped length
+}
+
+// Page-locked host memory on the NUMA node of `device`'s PCIe root: anonymous mapping, mbind(MPOL_BIND) to that
+// node, first touch, cudaHostRegister.  With 4 GPUs per socket moving ~100 GB/s each way, buffers that sit on the
+// other socket (or interleaved) make the inter-socket link the bottleneck.  Falls back to b200_host_alloc when the
+// node is unknown or the policy cannot be applied.
+void *b200_host_alloc_local(uint64_t bytes, int device)
+{
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) { (void)cudaGetLastError(); return b200_host_alloc(bytes); }
+    const int node = b200_device_numa_node(device);
+    if (node < 0 || node >= 1024) return b200_host_alloc(bytes);
+    const size_t len = (size_t)round_up(std::max<uint64_t>(bytes, 1), 2ull << 20);
+    void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return b200_host_alloc(bytes);
+#ifdef SYS_mbind
+    unsigned long mask[16] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    if (syscall(SYS_mbind, p, len, 2 /* MPOL_BIND */, mask, sizeof mask * 8, 0u) != 0) {
+        munmap(p, len); // the node is not in this process's allowed set: plain first-touch allocation instead
+        return b200_host_alloc(bytes);
+    }
+#endif
+    std::memset(p, 0, len); // first touch under the policy
+    if (cudaHostRegister(p, len, cudaHostRegisterDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        munmap(p, len);
+        return b200_host_alloc(bytes);
+    }
+    std::lock_guard<std::mutex> lock(g_local_mu);
+    g_local_allocs[p] = len;
+    return p;
+}
+
+void b200_host_free(void *p)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lock(g_local_mu);
+        auto it = g_local_allocs.find(p);
+        if (it != g_local_allocs.end()) {
+            cudaHostUnregister(p);
+            munmap(p, it->second);
+            g_local_allocs.erase(it);
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
 
 int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
 {
@@ -472,7 +489,13 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
         case B200_EFF_GRAVITY_CONST: case B200_EFF_GRAVITY_FRAME: want_w = 0; break;
         case B200_EFF_DRAG_QUADRATIC: want_w = 3; ++n_drag; break;
         case B200_EFF_THRUST_BODY: want_w = 1; break;
-        case B200_EFF_WRENCH_BODY: want_w = 6; break;
+        case B200_EFF_WRENCH_BODY: case B200_EFF_WRENCH_WORLD: want_w = 6; break;
+        case B200_EFF_GRAVITY_J2: want_w = 0; break;
+        case B200_EFF_TORQUE_BODY_FOLD:
+            want_w = e.column_width; // 3 per wheel
+            if (e.column_width == 0 || e.column_width % 3 != 0 || e.column_width > 24)
+                return bail(fail(B200_ERR_VALUE_SIZE_MISMATCH, "effector %zu: a wheel-torque column holds 3 f64 per wheel, 1..8 wheels (got width %u)", i, e.column_width));
+            break;
         case B200_EFF_GRAVITY_EDGES_NEWTON: case B200_EFF_GRAVITY_EDGES_SOFTENED:
             if (h->graph_eff >= 0) return bail(fail(B200_ERR_UNSUPPORTED, "only one edge_fold gravity effector is supported"));
             if (e.n_edges && (!e.edge_from || !e.edge_to)) return bail(fail(B200_ERR_INVALID_ARGUMENT, "edge arrays are null"));
@@ -487,7 +510,8 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
         if (e.column_id) {
             if (e.column_width != want_w && !(e.kind == B200_EFF_DRAG_QUADRATIC && e.column_width == 5))
                 return bail(fail(B200_ERR_VALUE_SIZE_MISMATCH, "effector %zu: column width %u, kind %u needs %u", i, e.column_width, e.kind, want_w));
-        } else if (e.kind == B200_EFF_THRUST_BODY || e.kind == B200_EFF_WRENCH_BODY) {
+        } else if (e.kind == B200_EFF_THRUST_BODY || e.kind == B200_EFF_WRENCH_BODY || e.kind == B200_EFF_WRENCH_WORLD ||
+                   e.kind == B200_EFF_TORQUE_BODY_FOLD) {
             return bail(fail(B200_ERR_INVALID_ARGUMENT, "effector %zu (kind %u) needs an input column", i, e.kind));
         }
     }
@@ -653,6 +677,7 @@ static int invoke_small(b200_sixdof *h, const uint8_t *const *in_cols, uint8_t *
     std::vector<std::pair<size_t, uint64_t>> in_map, out_map; // (column index, byte offset in the packed block)
     for (size_t i = 0; i < h->input_ids.size(); ++i) {
         Column *c = h->find(h->input_ids[i]);
+        if (!in_cols[i]) continue; // not dirty: the device-resident copy stands
         if (c->global) { int rc = do_upload(h, c->id, in_cols[i], 8); if (rc) return rc; continue; }
         if (!input_is_live(h, c->id)) continue;
         mi.col[mi.n++] = {in_total, c->dev, c->width, 0};
@@ -661,7 +686,7 @@ static int invoke_small(b200_sixdof *h, const uint8_t *const *in_cols, uint8_t *
     }
     for (size_t i = 0; i < h->output_ids.size(); ++i) {
         Column *c = h->find(h->output_ids[i]);
-        if (c->global || output_is_pass_through(c->id)) continue;
+        if (!out_cols[i] || c->global || output_is_pass_through(c->id)) continue;
         mo.col[mo.n++] = {out_total, c->dev, c->width, 0};
         out_map.push_back({i, out_total * 8});
         out_total += h->n_bodies * c->width;
@@ -704,10 +729,16 @@ static int invoke_small(b200_sixdof *h, const uint8_t *const *in_cols, uint8_t *
     }
     for (size_t i = 0; i < h->output_ids.size(); ++i) {
         const Column *c = h->find(h->output_ids[i]);
+        if (!out_cols[i]) continue;
         if (c->global) { rc = do_download(h, c->id, out_cols[i], 8); if (rc) return rc; continue; }
         if (!output_is_pass_through(c->id)) continue;
+        bool filled = false;
         for (size_t k = 0; k < h->input_ids.size(); ++k)
-            if (h->input_ids[k] == c->id && in_cols[k] != out_cols[i]) std::memcpy(out_cols[i], in_cols[k], h->n_bodies * c->width * 8);
+            if (h->input_ids[k] == c->id && in_cols[k]) {
+                if (in_cols[k] != out_cols[i]) std::memcpy(out_cols[i], in_cols[k], h->n_bodies * c->width * 8);
+                filled = true;
+            }
+        if (!filled) { rc = do_download(h, c->id, out_cols[i], h->n_bodies * c->width * 8); if (rc) return rc; } // input was not dirty: the device copy is the value
     }
     h->timings.h2d_upload_ms = h->timings.kernel_invoke_ms = h->timings.d2h_download_ms = 0.0; // not separable here
     return B200_OK;
@@ -735,22 +766,24 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
     for (size_t i = 0; i < h->input_ids.size(); ++i) {
         const Column *c = h->find(h->input_ids[i]);
         in_off[i] = in_total;
-        if (!c->global && input_is_live(h, c->id)) in_total += h->n_bodies * c->width;
+        if (in_cols[i] && !c->global && input_is_live(h, c->id)) in_total += h->n_bodies * c->width;
     }
     for (size_t i = 0; i < h->output_ids.size(); ++i) {
         const Column *c = h->find(h->output_ids[i]);
         out_off[i] = out_total;
-        if (!c->global && !output_is_pass_through(c->id)) out_total += h->n_bodies * c->width;
+        if (out_cols[i] && !c->global && !output_is_pass_through(c->id)) out_total += h->n_bodies * c->width;
     }
     // host-to-host fill of the pass-through outputs, split over a few worker threads
+    std::vector<size_t> late_downloads;
     std::vector<std::thread> fillers;
     struct Joiner { std::vector<std::thread> &v; ~Joiner() { for (auto &t : v) if (t.joinable()) t.join(); } } joiner{fillers};
     for (size_t i = 0; i < h->output_ids.size(); ++i) {
         const Column *c = h->find(h->output_ids[i]);
-        if (c->global || !output_is_pass_through(c->id)) continue;
+        if (!out_cols[i] || c->global || !output_is_pass_through(c->id)) continue;
         const uint8_t *src = nullptr;
         for (size_t k = 0; k < h->input_ids.size(); ++k) if (h->input_ids[k] == c->id) src = in_cols[k];
-        if (!src || src == out_cols[i]) continue;
+        if (!src) { late_downloads.push_back(i); continue; } // input not dirty: its value is the device-resident column
+        if (src == out_cols[i]) continue;
         cudaPointerAttributes a_in{}, a_out{};
         const bool dev_in = cudaPointerGetAttributes(&a_in, src) == cudaSuccess && a_in.type == cudaMemoryTypeDevice;
         const bool dev_out = cudaPointerGetAttributes(&a_out, out_cols[i]) == cudaSuccess && a_out.type == cudaMemoryTypeDevice;
@@ -782,7 +815,7 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
     // globals first (host-resident scalars)
     for (size_t i = 0; i < h->input_ids.size(); ++i) {
         const Column *c = h->find(h->input_ids[i]);
-        if (c->global) { int rc = do_upload(h, c->id, in_cols[i], 8); if (rc) return rc; }
+        if (c->global && in_cols[i]) { int rc = do_upload(h, c->id, in_cols[i], 8); if (rc) return rc; }
     }
     // the copy streams must not run ahead of work already queued on the compute stream
     CU(h, cudaEventRecord(h->ev[2], h->stream));
@@ -796,7 +829,7 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
         // H2D of this world range, every live input column (copy engine 1)
         for (size_t i = 0; i < h->input_ids.size(); ++i) {
             const Column *c = h->find(h->input_ids[i]);
-            if (c->global || !input_is_live(h, c->id)) continue;
+            if (!in_cols[i] || c->global || !input_is_live(h, c->id)) continue;
             CU(h, cudaMemcpyAsync(h->stage_in + in_off[i] + b0 * c->width, (const double *)in_cols[i] + b0 * c->width,
                                   nb * c->width * 8, cudaMemcpyDefault, h->copy_in));
         }
@@ -806,7 +839,7 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
         CU(h, cudaStreamWaitEvent(h->stream, h->chunk_in[k], 0));
         for (size_t i = 0; i < h->input_ids.size(); ++i) {
             const Column *c = h->find(h->input_ids[i]);
-            if (c->global || !input_is_live(h, c->id)) continue;
+            if (!in_cols[i] || c->global || !input_is_live(h, c->id)) continue;
             CU(h, launch_aos_to_soa(h->stage_in + in_off[i] + b0 * c->width, c->dev + b0, nb, c->width, h->ld, h->stream));
             h->timings.kernel_launches++;
         }
@@ -815,7 +848,7 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
         const bool flipped = h->nbody_fused && (n_ticks & 1); // live pose / velocity sit in the other plane set
         for (size_t i = 0; i < h->output_ids.size(); ++i) {
             const Column *c = h->find(h->output_ids[i]);
-            if (c->global || output_is_pass_through(c->id)) continue;
+            if (!out_cols[i] || c->global || output_is_pass_through(c->id)) continue;
             const double *live = c->dev;
             if (flipped && c->id == B200_ID_WORLD_POS) live = h->pos_alt;
             if (flipped && c->id == B200_ID_WORLD_VEL) live = h->vel_alt;
@@ -829,7 +862,7 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
         if (k == 0) CU(h, cudaEventRecord(h->ev[4], h->copy_out));
         for (size_t i = 0; i < h->output_ids.size(); ++i) {
             const Column *c = h->find(h->output_ids[i]);
-            if (c->global || output_is_pass_through(c->id)) continue;
+            if (!out_cols[i] || c->global || output_is_pass_through(c->id)) continue;
             CU(h, cudaMemcpyAsync((double *)out_cols[i] + b0 * c->width, h->stage_out + out_off[i] + b0 * c->width,
                                   nb * c->width * 8, cudaMemcpyDefault, h->copy_out));
         }
@@ -840,12 +873,17 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
     h->timings.ticks += n_ticks;
     for (size_t i = 0; i < h->output_ids.size(); ++i) {
         const Column *c = h->find(h->output_ids[i]);
-        if (c->global) { int rc = do_download(h, c->id, out_cols[i], 8); if (rc) return rc; }
+        if (c->global && out_cols[i]) { int rc = do_download(h, c->id, out_cols[i], 8); if (rc) return rc; }
     }
     CU(h, cudaEventRecord(h->ev[5], h->copy_out));
     CU(h, cudaStreamSynchronize(h->copy_out));
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaStreamSynchronize(h->copy_in));
+    for (size_t i : late_downloads) {
+        const Column *c = h->find(h->output_ids[i]);
+        int rc = do_download(h, c->id, out_cols[i], h->n_bodies * c->width * 8ull);
+        if (rc) return rc;
+    }
     // busy spans of the three engines; they overlap, so they do not add up to the call time
     h->timings.h2d_upload_ms = ev_ms(h->ev[0], h->ev[1]);
     h->timings.kernel_invoke_ms = ev_ms(h->ev[2], h->ev[3]);
@@ -859,10 +897,8 @@ int b200_sixdof_invoke_batch(b200_sixdof *h, const uint8_t *const *in_cols, uint
     if (!in_cols || !out_cols) return fail(B200_ERR_INVALID_ARGUMENT, "null column tables");
     if (h->status != B200_OK) return fail(h->status, "handle is in a failed state");
     CU(h, cudaSetDevice(h->device));
-    for (size_t i = 0; i < h->input_ids.size(); ++i)
-        if (!in_cols[i] && column_bytes(h, *h->find(h->input_ids[i]))) return fail(B200_ERR_INVALID_ARGUMENT, "null input column %zu", i);
-    for (size_t i = 0; i < h->output_ids.size(); ++i)
-        if (!out_cols[i] && column_bytes(h, *h->find(h->output_ids[i]))) return fail(B200_ERR_INVALID_ARGUMENT, "null output column %zu", i);
+    // A NULL in_cols[i] means "not dirty" (World::dirty_components, world.rs:43,249-252): the device-resident copy of
+    // that column stands.  A NULL out_cols[j] means the caller does not read that column after this batch.
     n_ticks = std::max<uint64_t>(n_ticks, 1); // `n.max(1)`, cranelift_exec.rs:135
 
     // World ranges of ~kChunkBodies bodies: range k's PCIe download overlaps range k+1's upload
@@ -880,16 +916,14 @@ int b200_sixdof_invoke_batch(b200_sixdof *h, const uint8_t *const *in_cols, uint
                  !h->desc.invoke_chunk_bodies;
     if (small) { // the packed path memcpy()s: only for host-resident caller buffers
         for (size_t i = 0; i < h->input_ids.size() && small; ++i) {
-            if (h->find(h->input_ids[i])->global) continue;
+            if (!in_cols[i] || h->find(h->input_ids[i])->global) continue;
             cudaPointerAttributes at{};
             if (cudaPointerGetAttributes(&at, in_cols[i]) == cudaSuccess && at.type == cudaMemoryTypeDevice) small = false;
-            break;
         }
         for (size_t i = 0; i < h->output_ids.size() && small; ++i) {
-            if (h->find(h->output_ids[i])->global) continue;
+            if (!out_cols[i] || h->find(h->output_ids[i])->global) continue;
             cudaPointerAttributes at{};
             if (cudaPointerGetAttributes(&at, out_cols[i]) == cudaSuccess && at.type == cudaMemoryTypeDevice) small = false;
-            break;
         }
         (void)cudaGetLastError();
     }

@@ -1,0 +1,293 @@
+// Multi-GPU plumbing of libb200_sixdof behind the C ABI (include/b200_sixdof.h, "multi-GPU" section).
+//
+// Worlds shard across GPUs with no data-path collective; the one exchange the path has is the
+// end-of-run gather of the device trajectory ring.  It runs over NCCL (NVLink 5 / NVSwitch), which this library
+// binds at run time: dlopen("libnccl.so.2") — the copy a host process already loaded (e.g. torch's) if there is
+// one, the system one otherwise — so libb200_sixdof.so itself links nothing but the CUDA runtime and a host
+// that never gathers never needs NCCL installed.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include <nccl.h> // types and prototypes only; every call goes through the table below
+
+#include "sixdof_handle.h"
+#include "sixdof_launch.h"
+
+using namespace b200;
+
+namespace {
+
+struct NcclApi {
+    void *lib = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetVersion) GetVersion = nullptr;
+    bool ok = false;
+};
+
+NcclApi &nccl()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); // the host process's copy, if any
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return;
+        api.lib = lib;
+#define SYM(name) api.name = reinterpret_cast<decltype(api.name)>(dlsym(lib, "nccl" #name))
+        SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(GetErrorString); SYM(Broadcast); SYM(AllGather);
+        SYM(GroupStart); SYM(GroupEnd); SYM(GetVersion);
+#undef SYM
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GetErrorString && api.Broadcast &&
+                 api.AllGather && api.GroupStart && api.GroupEnd;
+    });
+    return api;
+}
+
+int nccl_fail(ncclResult_t r, const char *what)
+{
+    return fail(B200_ERR_CUDA, "NCCL error in %s: %s", what, nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+}
+
+#define NC(call)                                             \
+    do {                                                     \
+        ncclResult_t r_ = (call);                            \
+        if (r_ != ncclSuccess) return nccl_fail(r_, #call);  \
+    } while (0)
+
+} // namespace
+
+struct b200_comm {
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0, device = 0;
+    double *send = nullptr, *recv = nullptr; // device staging of the gather
+    uint64_t send_bytes = 0, recv_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+};
+
+namespace b200 {
+
+// trajectory ring (SoA: sample s, plane p at traj + (s*W + p)*ld) -> world-major rows
+//   out[((world*S + s)*N + entity)*W + p]
+// so that a rank's worlds are one contiguous block of the world-sharded result.
+static constexpr int kGTile = 128;
+__global__ void __launch_bounds__(kGTile) traj_world_major_kernel(const double *__restrict__ traj, double *__restrict__ out,
+                                                                  uint64_t n_bodies, uint32_t n_entities, uint32_t W, uint64_t S,
+                                                                  uint64_t ld)
+{
+    extern __shared__ double tile[]; // kGTile * (W | 1)
+    const uint32_t pitch = W | 1u;
+    const uint64_t base = (uint64_t)blockIdx.x * kGTile, s = blockIdx.y;
+    const uint32_t nb = (uint32_t)min((uint64_t)kGTile, n_bodies - base);
+    const double *src = traj + s * (uint64_t)W * ld;
+    if (threadIdx.x < nb)
+        for (uint32_t k = 0; k < W; ++k) tile[threadIdx.x * pitch + k] = src[(uint64_t)k * ld + base + threadIdx.x];
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nb * W; i += kGTile) {
+        const uint32_t r = i / W, k = i - r * W;
+        const uint64_t b = base + r, world = b / n_entities, ent = b - world * n_entities;
+        out[((world * S + s) * n_entities + ent) * W + k] = tile[r * pitch + k];
+    }
+}
+
+} // namespace b200
+
+extern "C" {
+
+int b200_comm_available(void) { return nccl().ok ? 1 : 0; }
+
+int b200_comm_version(void)
+{
+    int v = 0;
+    if (nccl().ok && nccl().GetVersion) nccl().GetVersion(&v);
+    return v;
+}
+
+int b200_comm_unique_id(uint8_t *out, uint32_t bytes)
+{
+    if (!out || bytes < B200_COMM_ID_BYTES) return fail(B200_ERR_INVALID_ARGUMENT, "unique id buffer must hold %u bytes", B200_COMM_ID_BYTES);
+    if (!nccl().ok) return fail(B200_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "not found");
+    static_assert(sizeof(ncclUniqueId) == B200_COMM_ID_BYTES, "NCCL unique id size");
+    ncclUniqueId id;
+    NC(nccl().GetUniqueId(&id));
+    std::memcpy(out, &id, sizeof id);
+    return B200_OK;
+}
+
+int b200_comm_create(const uint8_t *id_bytes, int n_ranks, int rank, int device, b200_comm **out)
+{
+    if (!id_bytes || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(B200_ERR_INVALID_ARGUMENT, "bad communicator arguments");
+    *out = nullptr;
+    if (!nccl().ok) return fail(B200_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return cuda_fail(nullptr, cudaGetLastError(), "cudaGetDevice");
+    if (cudaSetDevice(device) != cudaSuccess) return cuda_fail(nullptr, cudaGetLastError(), "cudaSetDevice");
+    ncclUniqueId id;
+    std::memcpy(&id, id_bytes, sizeof id);
+    b200_comm *c = new (std::nothrow) b200_comm();
+    if (!c) return fail(B200_ERR_OUT_OF_MEMORY, "out of host memory");
+    c->n_ranks = n_ranks; c->rank = rank; c->device = device;
+    ncclResult_t r = nccl().CommInitRank(&c->comm, n_ranks, id, rank);
+    if (r != ncclSuccess) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return B200_OK;
+}
+
+void b200_comm_destroy(b200_comm *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->send) cudaFree(c->send);
+    if (c->recv) cudaFree(c->recv);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    (void)cudaGetLastError();
+    delete c;
+}
+
+int b200_comm_rank(const b200_comm *c) { return c ? c->rank : -1; }
+int b200_comm_size(const b200_comm *c) { return c ? c->n_ranks : 0; }
+double b200_comm_last_ms(const b200_comm *c) { return c ? c->last_ms : 0.0; }
+
+uint64_t b200_sixdof_trajectory_gather_bytes(const b200_sixdof *h, const uint64_t *worlds_per_rank, int n_ranks)
+{
+    if (!h || !worlds_per_rank) return 0;
+    uint64_t worlds = 0;
+    for (int r = 0; r < n_ranks; ++r) worlds += worlds_per_rank[r];
+    return worlds * b200_sixdof_trajectory_len(h) * h->desc.n_entities * (uint64_t)h->traj_planes * 8ull;
+}
+
+// World-sharded all-gather of the trajectory ring: rank r holds worlds_per_rank[r] worlds (every rank the same
+// number of samples, entities and ring width); afterwards `dst` on every rank holds
+// [sum(worlds)][samples][n_entities][width] in rank order.  dst may be a device or a host pointer.
+int b200_sixdof_trajectory_allgather(b200_sixdof *h, b200_comm *c, const uint64_t *worlds_per_rank, void *dst, uint64_t dst_bytes)
+{
+    if (!h || !c || !worlds_per_rank || !dst) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (h->status != B200_OK) return fail(h->status, "handle is in a failed state");
+    if (h->device != c->device) return fail(B200_ERR_INVALID_ARGUMENT, "handle is on device %d, communicator on %d", h->device, c->device);
+    CU(h, cudaSetDevice(h->device));
+    if (worlds_per_rank[c->rank] != h->desc.n_worlds)
+        return fail(B200_ERR_VALUE_SIZE_MISMATCH, "rank %d holds %llu worlds, worlds_per_rank says %llu", c->rank,
+                    (unsigned long long)h->desc.n_worlds, (unsigned long long)worlds_per_rank[c->rank]);
+    const uint64_t S = b200_sixdof_trajectory_len(h), N = h->desc.n_entities, W = h->traj_planes;
+    const uint64_t want = b200_sixdof_trajectory_gather_bytes(h, worlds_per_rank, c->n_ranks);
+    if (dst_bytes != want) return fail(B200_ERR_VALUE_SIZE_MISMATCH, "gathered trajectory is %llu bytes, got %llu", (unsigned long long)want, (unsigned long long)dst_bytes);
+    if (want == 0) return B200_OK;
+    const uint64_t row = S * N * W; // doubles per world
+    const uint64_t mine = h->desc.n_worlds * row;
+    if (c->send_bytes < mine * 8) {
+        if (c->send) CU(h, cudaFree(c->send));
+        c->send = nullptr; c->send_bytes = 0;
+        CU(h, cudaMalloc(&c->send, std::max<uint64_t>(mine * 8, 8)));
+        c->send_bytes = mine * 8;
+    }
+    cudaPointerAttributes at{};
+    const bool dst_dev = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+    (void)cudaGetLastError();
+    double *recv = (double *)dst;
+    if (!dst_dev) {
+        if (c->recv_bytes < want) {
+            if (c->recv) CU(h, cudaFree(c->recv));
+            c->recv = nullptr; c->recv_bytes = 0;
+            CU(h, cudaMalloc(&c->recv, want));
+            c->recv_bytes = want;
+        }
+        recv = c->recv;
+    }
+    CU(h, cudaEventRecord(c->ev0, h->stream));
+    if (mine) {
+        const size_t smem = (size_t)kGTile * (W | 1u) * sizeof(double);
+        for (uint64_t s0 = 0; s0 < S; s0 += 32768) {
+            const dim3 grid((unsigned)((h->n_bodies + kGTile - 1) / kGTile), (unsigned)std::min<uint64_t>(32768, S - s0));
+            // the kernel indexes samples from blockIdx.y: shift the ring, and the output by s0 rows of N*W inside each world
+            traj_world_major_kernel<<<grid, kGTile, smem, h->stream>>>(h->traj + s0 * W * h->ld, c->send + s0 * N * W, h->n_bodies,
+                                                                     (uint32_t)N, (uint32_t)W, S, h->ld);
+        }
+        CU(h, cudaGetLastError());
+        h->timings.kernel_launches++;
+    }
+    bool even = true;
+    for (int r = 0; r < c->n_ranks; ++r) even = even && worlds_per_rank[r] == worlds_per_rank[0];
+    if (even) {
+        NC(nccl().AllGather(c->send, recv, mine, ncclDouble, c->comm, h->stream));
+    } else {
+        // ragged shards: one broadcast per rank, fused into one NCCL group
+        NC(nccl().GroupStart());
+        uint64_t off = 0;
+        for (int r = 0; r < c->n_ranks; ++r) {
+            const uint64_t cnt = worlds_per_rank[r] * row;
+            if (cnt) {
+                ncclResult_t rr = nccl().Broadcast(c->send, recv + off, cnt, ncclDouble, r, c->comm, h->stream);
+                if (rr != ncclSuccess) { nccl().GroupEnd(); return nccl_fail(rr, "ncclBroadcast"); }
+            }
+            off += cnt;
+        }
+        NC(nccl().GroupEnd());
+    }
+    CU(h, cudaEventRecord(c->ev1, h->stream));
+    if (!dst_dev) CU(h, cudaMemcpyAsync(dst, recv, want, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->last_ms = ms; // layout kernel + collective, device-timed on the handle's stream
+    return B200_OK;
+}
+
+// Concurrent host<->device bandwidth of one GPU (pinned `host` of >= max(h2d, d2h) * 2 bytes): an H2D stream and a
+// D2H stream run `iters` copies each at the same time; out[0] = H2D GB/s, out[1] = D2H GB/s.  bench.py runs it on
+// every rank at once to report the PCIe / host-memory ceiling its e2e number sits under.
+int b200_probe_pcie_gbs(int device, void *host, uint64_t h2d_bytes, uint64_t d2h_bytes, int iters, double *out)
+{
+    if (!host || !out || iters < 1) return fail(B200_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (b200_device_count() <= 0) return B200_ERR_NO_DEVICE;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return cuda_fail(nullptr, cudaGetLastError(), "cudaSetDevice");
+    void *din = nullptr, *dout = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    int rc = B200_OK;
+    if (cudaMalloc(&din, std::max<uint64_t>(h2d_bytes, 8)) != cudaSuccess || cudaMalloc(&dout, std::max<uint64_t>(d2h_bytes, 8)) != cudaSuccess)
+        rc = cuda_fail(nullptr, cudaGetLastError(), "cudaMalloc(probe)");
+    if (!rc) {
+        cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking);
+        for (auto &x : e) cudaEventCreate(&x);
+        char *hin = (char *)host, *hout = (char *)host + h2d_bytes;
+        for (int w = 0; w < 2; ++w) { // warm-up pass, then the timed pass
+            cudaEventRecord(e[0], s0); cudaEventRecord(e[2], s1);
+            for (int i = 0; i < (w ? iters : 1); ++i) {
+                if (h2d_bytes) cudaMemcpyAsync(din, hin, h2d_bytes, cudaMemcpyHostToDevice, s0);
+                if (d2h_bytes) cudaMemcpyAsync(hout, dout, d2h_bytes, cudaMemcpyDeviceToHost, s1);
+            }
+            cudaEventRecord(e[1], s0); cudaEventRecord(e[3], s1);
+            cudaStreamSynchronize(s0); cudaStreamSynchronize(s1);
+        }
+        float m0 = 0.f, m1 = 0.f;
+        cudaEventElapsedTime(&m0, e[0], e[1]);
+        cudaEventElapsedTime(&m1, e[2], e[3]);
+        out[0] = m0 > 0 ? (double)h2d_bytes * iters / (m0 * 1e-3) / 1e9 : 0.0;
+        out[1] = m1 > 0 ? (double)d2h_bytes * iters / (m1 * 1e-3) / 1e9 : 0.0;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(B200_ERR_CUDA, "PCIe probe failed");
+    }
+    for (auto &x : e) if (x) cudaEventDestroy(x);
+    if (s0) cudaStreamDestroy(s0);
+    if (s1) cudaStreamDestroy(s1);
+    if (din) cudaFree(din);
+    if (dout) cudaFree(dout);
+    return rc;
+}
+
+} // extern "C"

@@ -151,6 +151,46 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
             F.lin = Vec3{add(F.lin.x, mul(acc.x, I.m)), add(F.lin.y, mul(acc.y, I.m)), add(F.lin.z, mul(acc.z, I.m))};
             break;
         }
+        case B200_EFF_WRENCH_WORLD: { // cube-sat/main.py:516-527, drone/sim.py:99-103: force + SpatialForce(..)
+            if (E.col) {
+                F.ang = Vec3{add(F.ang.x, ldp(E.col, P.ld, 0, b)), add(F.ang.y, ldp(E.col, P.ld, 1, b)), add(F.ang.z, ldp(E.col, P.ld, 2, b))};
+                F.lin = Vec3{add(F.lin.x, ldp(E.col, P.ld, 3, b)), add(F.lin.y, ldp(E.col, P.ld, 4, b)), add(F.lin.z, ldp(E.col, P.ld, 5, b))};
+            }
+            break;
+        }
+        case B200_EFF_TORQUE_BODY_FOLD: { // cube-sat/main.py:492-505: Force := fold_k (f + SpatialForce(torque = q @ tau_k))
+            if (E.col) {
+                Motion acc = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+                const uint32_t K = E.col_width / 3u;
+                for (uint32_t k = 0; k < K; ++k) {
+                    const Vec3 t = qrot_with(sx.q, pi.qi, Vec3{ldp(E.col, P.ld, 3 * k + 0, b), ldp(E.col, P.ld, 3 * k + 1, b),
+                                                               ldp(E.col, P.ld, 3 * k + 2, b)});
+                    acc.ang = Vec3{add(acc.ang.x, t.x), add(acc.ang.y, t.y), add(acc.ang.z, t.z)};
+                    acc.lin = Vec3{add(acc.lin.x, 0.0), add(acc.lin.y, 0.0), add(acc.lin.z, 0.0)};
+                }
+                F = acc;
+            }
+            break;
+        }
+        case B200_EFF_GRAVITY_J2: { // python/elodin/j2.py:5-29, operation order of oracle/sixdof_oracle.c:eff_gravity_j2
+            const double mu = E.p[0], J2 = E.p[1], r_ref = E.p[2];
+            const Vec3 r = sx.x;
+            const double norm = sqr(dot3(r));
+            const Vec3 e_r = {div(r.x, norm), div(r.y, norm), div(r.z, norm)};
+            const double n3 = mul(mul(norm, norm), norm);
+            const double c0 = mul(-mu, I.m);
+            const double n2 = mul(norm, norm), n4 = mul(n2, n2), n5 = mul(norm, n4);
+            const double n6 = pow(norm, 6.0); // float exponent: lax.pow (CUDA's pow is within 1 ulp of libm's)
+            const double kz = div(mul(3.0, r.z), n5);
+            const double kr = sub(div(3.0, mul(2.0, n4)), div(mul(15.0, mul(r.z, r.z)), mul(2.0, n6)));
+            const double c1 = mul(mul(c0, J2), mul(r_ref, r_ref));
+            const Vec3 g = {add(div(mul(c0, r.x), n3), mul(c1, add(mul(kz, 0.0), mul(kr, e_r.x)))),
+                            add(div(mul(c0, r.y), n3), mul(c1, add(mul(kz, 0.0), mul(kr, e_r.y)))),
+                            add(div(mul(c0, r.z), n3), mul(c1, add(mul(kz, 1.0), mul(kr, e_r.z))))};
+            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+            F.lin = Vec3{add(F.lin.x, g.x), add(F.lin.y, g.y), add(F.lin.z, g.z)};
+            break;
+        }
         case B200_EFF_GRAVITY_EDGES_NEWTON:
         case B200_EFF_GRAVITY_EDGES_SOFTENED: { // Force := edge_fold(init 0) for bodies that own an edge
             if (GREG) {
@@ -248,7 +288,9 @@ struct Folded {
     double kd;    // 0.5*Cd*rho*A
     double mu;    // GRAVITY_FRAME
     Vec3 om;
-    bool drag, frame, graph;
+    Vec3 tw;      // world-frame torque (WRENCH_WORLD): needs R^-1 per stage attitude
+    double j2_mu, j2_k; // GRAVITY_J2: mu, J2 * r_ref^2
+    bool drag, frame, graph, wtorque, j2;
 };
 
 template <bool GREG>
@@ -257,8 +299,9 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
 {
     Folded f;
     f.fw = f.fb = f.u = f.wind = f.om = Vec3{0.0, 0.0, 0.0};
-    f.kd = f.mu = 0.0;
-    f.drag = f.frame = f.graph = false;
+    f.kd = f.mu = f.j2_mu = f.j2_k = 0.0;
+    f.tw = Vec3{0.0, 0.0, 0.0};
+    f.drag = f.frame = f.graph = f.wtorque = f.j2 = false;
     Vec3 tb = {0.0, 0.0, 0.0};
     for (uint32_t e = 0; e < P.n_eff; ++e) {
         const EffDev &E = P.eff[e];
@@ -291,6 +334,29 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
             f.mu = E.p[0];
             f.om = Vec3{E.p[1], E.p[2], E.p[3]};
             break;
+        case B200_EFF_WRENCH_WORLD:
+            if (E.col) {
+                f.tw.x += ldp(E.col, P.ld, 0, b); f.tw.y += ldp(E.col, P.ld, 1, b); f.tw.z += ldp(E.col, P.ld, 2, b);
+                f.fw.x += ldp(E.col, P.ld, 3, b); f.fw.y += ldp(E.col, P.ld, 4, b); f.fw.z += ldp(E.col, P.ld, 5, b);
+                f.wtorque = true;
+            }
+            break;
+        case B200_EFF_TORQUE_BODY_FOLD: // Force := fold: everything accumulated before it is overwritten
+            if (E.col) {
+                tb = Vec3{0.0, 0.0, 0.0};
+                f.fw = f.fb = f.tw = Vec3{0.0, 0.0, 0.0};
+                f.drag = f.frame = f.wtorque = f.j2 = false;
+                const uint32_t K = E.col_width / 3u;
+                for (uint32_t k = 0; k < K; ++k) {
+                    tb.x += ldp(E.col, P.ld, 3 * k + 0, b); tb.y += ldp(E.col, P.ld, 3 * k + 1, b); tb.z += ldp(E.col, P.ld, 3 * k + 2, b);
+                }
+            }
+            break;
+        case B200_EFF_GRAVITY_J2:
+            f.j2 = true;
+            f.j2_mu = E.p[0];
+            f.j2_k = E.p[1] * E.p[2] * E.p[2];
+            break;
         case B200_EFF_GRAVITY_EDGES_NEWTON:
         case B200_EFF_GRAVITY_EDGES_SOFTENED: // host guarantees this is effector 0 in FAST mode
             f.graph = GREG ? greg.has : (P.gforce && P.has_edge && P.has_edge[b % P.n_entities]);
@@ -310,7 +376,9 @@ __device__ __forceinline__ Folded fold_spec(const StepParams &P, uint64_t b, con
     Folded f;
     f.fw = Vec3{P.spec.g[0] * I.m, P.spec.g[1] * I.m, P.spec.g[2] * I.m};
     f.fb = f.u = f.wind = f.om = Vec3{0.0, 0.0, 0.0};
-    f.kd = f.mu = 0.0;
+    f.kd = f.mu = f.j2_mu = f.j2_k = 0.0;
+    f.tw = Vec3{0.0, 0.0, 0.0};
+    f.wtorque = f.j2 = false;
     f.drag = (SIG & SIG_DRAG) != 0;
     f.frame = (SIG & SIG_FRAME) != 0;
     f.graph = (SIG & SIG_GRAPH) ? (P.has_edge[b % P.n_entities] != 0) : false;
@@ -355,6 +423,17 @@ __device__ __forceinline__ Vec3 lin_accel_fast(const StepParams &P, const Folded
         F.y = fma(fma(g, x.y, -2.0 * c.y - c2.y), m, F.y);
         F.z = fma(fma(g, x.z, -2.0 * c.z - c2.z), m, F.z);
     }
+    if (f.j2) {
+        // -mu m [ r/n^3 + J2 r_ref^2 ( 3 z/n^5 e_z + (3/(2 n^4) - 15 z^2/(2 n^6)) r/n ) ]   (j2.py:12-27)
+        const double r2 = x.x * x.x + x.y * x.y + x.z * x.z;
+        const double ir = fa::rsqrt_nr(r2), ir2 = ir * ir, ir3 = ir2 * ir, ir5 = ir3 * ir2;
+        const double kr = f.j2_k * ir5 * (1.5 - 7.5 * x.z * x.z * ir2); // coefficient of r (e_r = r/n folded in)
+        const double kz = 3.0 * f.j2_k * x.z * ir5;
+        const double c = -f.j2_mu * m;
+        F.x = fma(c, (ir3 + kr) * x.x, F.x);
+        F.y = fma(c, (ir3 + kr) * x.y, F.y);
+        F.z = fma(c, fma(ir3 + kr, x.z, kz), F.z);
+    }
     if (f.graph) {
         if (GREG) {
             const Vec3 g = grav_slot(greg, slot);
@@ -370,12 +449,13 @@ __device__ __forceinline__ Vec3 lin_accel_fast(const StepParams &P, const Folded
 
 // world-frame force this stage's state produced (only materialised when Force is written back)
 __device__ __forceinline__ Motion force_out_fast(const Vec3 &a_lin, const Vec3 &a_ang_body_u, const Quat &q,
-                                                 const Inertia &I)
+                                                 const Inertia &I, const Vec3 &tw)
 {
-    // torque_world = R (I .* u)
+    // torque_world = R (I .* u) + the world-frame torque column
     const Vec3 tb = {a_ang_body_u.x * I.diag.x, a_ang_body_u.y * I.diag.y, a_ang_body_u.z * I.diag.z};
     Motion F;
     F.ang = fa::rot(q, tb);
+    F.ang = Vec3{F.ang.x + tw.x, F.ang.y + tw.y, F.ang.z + tw.z};
     F.lin = Vec3{a_lin.x * I.m, a_lin.y * I.m, a_lin.z * I.m};
     return F;
 }
@@ -403,6 +483,11 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
     // unequal to zero and take the full path); specialised: a property of the signature
     const bool has_u = GEN ? ((f.u.x != 0.0) | (f.u.y != 0.0) | (f.u.z != 0.0)) : (SIG & SIG_WRENCH) != 0;
     const bool has_fb = GEN ? ((f.fb.x != 0.0) | (f.fb.y != 0.0) | (f.fb.z != 0.0)) : (SIG & (SIG_THRUST | SIG_WRENCH)) != 0;
+    const bool has_tw = GEN ? f.wtorque : false; // world-frame torque: a_ang = R (invI .* (R^-1 tau_w)) per stage attitude
+    auto ang_world = [&](const Quat &q) { // angular acceleration the world-frame torque produces at attitude q
+        const Vec3 tbody = fa::rot(Quat{-q.i, -q.j, -q.k, q.w}, f.tw);
+        return fa::rot(q, Vec3{tbody.x * invI.x, tbody.y * invI.y, tbody.z * invI.z});
+    };
 
     for (uint32_t t = 0; t < n_ticks; ++t) {
         if (INTEG == B200_INTEGRATOR_RK4) {
@@ -411,7 +496,7 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
             // (the stage attitudes only matter to bodies that carry a body-frame force or torque)
             const double h2 = 0.25 * dt, h4 = 0.5 * dt;
             Quat q1 = x0.q, q2 = x0.q, q4 = x0.q;
-            if (has_u | has_fb) {
+            if (has_u | has_fb | has_tw) {
                 q1 = fa::normalize(x0.q); // x0 (+) 0*v0 still renormalises (spatial.rs:540-545)
                 q2 = fa::advance(x0.q, Vec3{h2 * w0.x, h2 * w0.y, h2 * w0.z});
                 q4 = fa::advance(x0.q, Vec3{h4 * w0.x, h4 * w0.y, h4 * w0.z});
@@ -423,6 +508,12 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
             Vec3 aa1 = zero3, aa2 = zero3, aa4 = zero3, fb1 = zero3, fb2 = zero3, fb4 = zero3;
             if (has_u) { aa1 = fa::rot(q1, f.u); aa2 = fa::rot(q2, f.u); aa4 = fa::rot(q4, f.u); }
             if (has_fb) { fb1 = fa::rot(q1, f.fb); fb2 = fa::rot(q2, f.fb); fb4 = fa::rot(q4, f.fb); }
+            if (has_tw) {
+                const Vec3 w1 = ang_world(q1), w2 = ang_world(q2), w4 = ang_world(q4);
+                aa1 = Vec3{aa1.x + w1.x, aa1.y + w1.y, aa1.z + w1.z};
+                aa2 = Vec3{aa2.x + w2.x, aa2.y + w2.y, aa2.z + w2.z};
+                aa4 = Vec3{aa4.x + w4.x, aa4.y + w4.y, aa4.z + w4.z};
+            }
             // stage 1: v = v0
             const Vec3 al1 = lin_accel_fast<GREG>(P, f, b, 0, fb1, x0.x, u0, I.m, inv_m, greg);
             // stage 2: v = v0 + dt/2 a1
@@ -454,7 +545,8 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
             const double n2 = x0.q.i * x0.q.i + x0.q.j * x0.q.j + x0.q.k * x0.q.k + x0.q.w * x0.q.w;
             const double rn = fa::rsqrt_nr(n2);
             const Quat qn = {x0.q.i * rn, x0.q.j * rn, x0.q.k * rn, x0.q.w * rn};
-            const Vec3 aa = has_u ? fa::rot(qn, f.u) : Vec3{0.0, 0.0, 0.0};
+            Vec3 aa = has_u ? fa::rot(qn, f.u) : Vec3{0.0, 0.0, 0.0};
+            if (has_tw) { const Vec3 w = ang_world(qn); aa = Vec3{aa.x + w.x, aa.y + w.y, aa.z + w.z}; }
             const Vec3 fbw = has_fb ? fa::rot(qn, f.fb) : Vec3{0.0, 0.0, 0.0};
             const Vec3 al = lin_accel_fast<GREG>(P, f, b, 0, fbw, x0.x, v0.lin, I.m, inv_m, greg);
             const double d = P.dt_final;
@@ -469,11 +561,11 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
             uint64_t slot;
             if (traj_due(P, tick0 + t + 1, slot)) {
                 traj_store_state(P, b, slot, x0, v0);
-                if (P.traj_planes == 25) traj_store_af(P, b, slot, a_last, force_out_fast(a_last.lin, f.u, q_last, I));
+                if (P.traj_planes == 25) traj_store_af(P, b, slot, a_last, force_out_fast(a_last.lin, f.u, q_last, I, f.tw));
             }
         }
     }
-    if (want_f) f_last = force_out_fast(a_last.lin, f.u, q_last, I);
+    if (want_f) f_last = force_out_fast(a_last.lin, f.u, q_last, I, f.tw);
 }
 
 } // namespace b200

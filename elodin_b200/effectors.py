@@ -149,6 +149,47 @@ class GravityFrame(Effector):
 
 
 @dataclass
+class WrenchWorld(Effector):
+    """`force + SpatialForce(..)` with a world-frame wrench column [tau(3), f(3)] computed outside six_dof (a host
+    system, recorded telemetry) — the shape of examples/cube-sat/main.py:516-527 (gravity_effector adds a
+    precomputed linear force) and examples/drone/sim.py:99-103 (f + SpatialForce(linear=drag))."""
+
+    column: str = "external_force"
+
+    def lower(self, world):
+        return self._attach_mask(_base(_lib.EFF_WRENCH_WORLD, column=self.column, width=6))
+
+
+@dataclass
+class TorqueBodyFold(Effector):
+    """Reaction-wheel edge fold, examples/cube-sat/main.py:492-505 (rw_effector): Force := fold over the body's
+    wheels (out-edges, spawn order) of SpatialForce(torque = q @ tau_k).  The column holds the `n_wheels` body-frame
+    wheel torques of each body, [tau_1 .. tau_K] (the torque halves of the wheels' rw_force rows).  Like every
+    edge_fold it overwrites what earlier effectors put into Force."""
+
+    column: str = "wheel_torques"
+    n_wheels: int = 3
+
+    def lower(self, world):
+        if not 1 <= int(self.n_wheels) <= 8:
+            raise ValueError("TorqueBodyFold supports 1..8 wheels per body")
+        return self._attach_mask(_base(_lib.EFF_TORQUE_BODY_FOLD, column=self.column, width=3 * int(self.n_wheels)))
+
+
+@dataclass
+class GravityJ2(Effector):
+    """Point-mass + J2 zonal gravity: `force + SpatialForce(linear=J2().compute_field(x, y, z, m))` —
+    libs/nox-py/python/elodin/j2.py:5-29 (constants :7-9)."""
+
+    mu: float = 3.986004418e14
+    j2: float = 1.08262668e-3
+    r_ref: float = 6.378e6
+
+    def lower(self, world):
+        return self._attach_mask(_base(_lib.EFF_GRAVITY_J2, (self.mu, self.j2, self.r_ref)))
+
+
+@dataclass
 class GravityEdges(Effector):
     """GraphQuery.edge_fold gravity (python/elodin/__init__.py:454-557).
 

@@ -175,6 +175,9 @@ class B200Exec:
             raise _lib.B200ValueError(_lib.ERR_VALUE_SIZE_MISMATCH, "wrong number of input columns")
         ins = []
         for cid, a in zip(self.input_ids, in_cols):
+            if a is None:  # not dirty: the device-resident copy stands (world.rs:43,249-252)
+                ins.append(None)
+                continue
             a = np.ascontiguousarray(a, dtype=np.uint64 if cid == TICK else np.float64)
             if a.nbytes != self.column_bytes(cid):
                 raise _lib.B200ValueError(_lib.ERR_VALUE_SIZE_MISMATCH, "value size mismatch")
@@ -182,12 +185,16 @@ class B200Exec:
         if out_cols is None:
             out_cols = [np.empty(self.column_shape(cid), dtype=np.uint64 if cid == TICK else np.float64)
                         for cid in self.output_ids]
-        in_ptrs = (C.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
-        out_ptrs = (C.c_void_p * len(out_cols))(*[a.ctypes.data for a in out_cols])
+        elif len(out_cols) != len(self.output_ids):
+            raise _lib.B200ValueError(_lib.ERR_VALUE_SIZE_MISMATCH, "wrong number of output columns")
+        in_ptrs = (C.c_void_p * len(ins))(*[None if a is None else a.ctypes.data for a in ins])
+        out_ptrs = (C.c_void_p * len(out_cols))(*[None if a is None else a.ctypes.data for a in out_cols])
         _lib.check(self._L.b200_sixdof_invoke_batch(self._h, in_ptrs, out_ptrs, int(n_ticks)))
         return list(out_cols)
 
-    def invoke_batch_ptrs(self, in_ptrs: Sequence[int], out_ptrs: Sequence[int], n_ticks: int) -> None:
+    def invoke_batch_ptrs(self, in_ptrs: Sequence[Optional[int]], out_ptrs: Sequence[Optional[int]], n_ticks: int) -> None:
+        """Raw-pointer form.  A None / 0 input = "not dirty" (the device-resident copy stands, world.rs:43,249-252);
+        a None / 0 output = not read back after this batch."""
         ip = (C.c_void_p * len(in_ptrs))(*in_ptrs)
         op = (C.c_void_p * len(out_ptrs))(*out_ptrs)
         _lib.check(self._L.b200_sixdof_invoke_batch(self._h, ip, op, int(n_ticks)))
@@ -256,12 +263,13 @@ def device_count() -> int:
     return max(int(n), 0)
 
 
-def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
-    """numpy array over page-locked host memory (b200_host_alloc)."""
+def pinned_empty(shape, dtype=np.float64, device: Optional[int] = None) -> np.ndarray:
+    """numpy array over page-locked host memory (b200_host_alloc); with `device`, on the NUMA node of that
+    GPU's PCIe root (b200_host_alloc_local)."""
     L = _lib.lib()
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
-    p = L.b200_host_alloc(max(n, 1))
+    p = L.b200_host_alloc(max(n, 1)) if device is None else L.b200_host_alloc_local(max(n, 1), int(device))
     if not p:
         raise _lib.B200Error(_lib.ERR_OUT_OF_MEMORY, L.b200_last_error().decode())
     buf = (C.c_char * max(n, 1)).from_address(p)

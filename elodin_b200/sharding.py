@@ -8,8 +8,10 @@ only; on GPUs that is NCCL over NVLink, in the CPU tests gloo.
 
 from __future__ import annotations
 
-from typing import List, Tuple
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 
 
 def shard_worlds(n_worlds: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -55,3 +57,66 @@ def total_entity_steps(local_entity_steps: int, group=None) -> int:
     t = torch.tensor([int(local_entity_steps)], dtype=torch.int64, device=dev)
     dist.all_reduce(t, group=group)
     return int(t.item())
+
+
+class Comm:
+    """One rank of the library's own NCCL communicator (include/b200_sixdof.h `b200_comm`): the C-ABI route of
+    the end-of-run trajectory gather, usable by a host without torch.  Rank 0 creates the 128-byte id with
+    `Comm.unique_id()` and hands it to every rank over whatever channel the host has (here: a
+    `torch.distributed` broadcast; the reference's Monte-Carlo driver would write it into context.json)."""
+
+    def __init__(self, unique_id: bytes, n_ranks: int, rank: int, device: int = -1):
+        from . import _lib
+
+        self._L = _lib.lib()
+        buf = (C.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        h = C.c_void_p()
+        _lib.check(self._L.b200_comm_create(buf, int(n_ranks), int(rank), int(device), C.byref(h)))
+        self._h = h
+        self.n_ranks, self.rank = int(n_ranks), int(rank)
+
+    @staticmethod
+    def available() -> bool:
+        from . import _lib
+
+        return bool(_lib.lib().b200_comm_available())
+
+    @staticmethod
+    def unique_id() -> bytes:
+        from . import _lib
+
+        buf = (C.c_uint8 * _lib.COMM_ID_BYTES)()
+        _lib.check(_lib.lib().b200_comm_unique_id(buf, _lib.COMM_ID_BYTES))
+        return bytes(buf)
+
+    @property
+    def last_ms(self) -> float:
+        return float(self._L.b200_comm_last_ms(self._h))
+
+    def trajectory_allgather(self, exec_, worlds_per_rank: Sequence[int], out: Optional[np.ndarray] = None,
+                             out_ptr: Optional[int] = None):
+        """World-sharded all-gather of `exec_`'s device trajectory ring: [sum(worlds), samples, n_entities, width]
+        on every rank, in rank order.  `out_ptr` may be a device pointer (e.g. a torch CUDA tensor's data_ptr())."""
+        from . import _lib
+
+        wpr = (C.c_uint64 * self.n_ranks)(*[int(w) for w in worlds_per_rank])
+        nbytes = int(self._L.b200_sixdof_trajectory_gather_bytes(exec_._h, wpr, self.n_ranks))
+        if out_ptr is None:
+            if out is None:
+                out = np.empty((int(sum(worlds_per_rank)), exec_.trajectory_len(), exec_.n_entities, exec_.trajectory_width()))
+            if out.nbytes != nbytes:
+                raise _lib.B200ValueError(_lib.ERR_VALUE_SIZE_MISMATCH, f"gathered trajectory is {nbytes} bytes, buffer has {out.nbytes}")
+            out_ptr = out.ctypes.data
+        _lib.check(self._L.b200_sixdof_trajectory_allgather(exec_._h, self._h, wpr, C.c_void_p(out_ptr), nbytes))
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.b200_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

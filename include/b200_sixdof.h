@@ -118,7 +118,18 @@ enum {
      * NEWTON  : examples/three-body/main.py:63-70    p[0] = G
      * SOFTENED: examples/n-body/sim.py:349-361       p[0] = K^2, p[1] = softening */
     B200_EFF_GRAVITY_EDGES_NEWTON = 6,
-    B200_EFF_GRAVITY_EDGES_SOFTENED = 7
+    B200_EFF_GRAVITY_EDGES_SOFTENED = 7,
+    /* F += column, a world-frame wrench [tau(3), f(3)] whose value is computed outside six_dof (a host system,
+     * recorded telemetry): `force + SpatialForce(..)` of examples/cube-sat/main.py:516-527,
+     * examples/drone/sim.py:99-103.  column (width 6). */
+    B200_EFF_WRENCH_WORLD = 8,
+    /* Reaction-wheel edge fold, examples/cube-sat/main.py:492-505: Force := fold over the body's K wheels (its
+     * out-edges, spawn order) of SpatialForce(torque = q @ tau_k), init SpatialForce().  column (width 3K, K <= 8)
+     * = the K wheel torques [tau_1 .. tau_K] of each body, body frame.  Like every edge_fold it OVERWRITES Force. */
+    B200_EFF_TORQUE_BODY_FOLD = 9,
+    /* point mass + J2 zonal gravity, libs/nox-py/python/elodin/j2.py:5-29 (J2.compute_field), applied as
+     * force + SpatialForce(linear=field).  p[0] = mu, p[1] = J2, p[2] = r_ref */
+    B200_EFF_GRAVITY_J2 = 10
 };
 
 #define B200_EFF_FLAG_WRENCH_LINEAR_FIRST 1u /* wrench column is [f(3), tau(3)] (falcon9) */
@@ -189,7 +200,14 @@ int b200_device_count(void);
 /* Page-locked host memory for column buffers (optional: any host pointer works,
  * pinned ones copy at full PCIe speed and asynchronously). */
 void *b200_host_alloc(uint64_t bytes);
-void b200_host_free(void *p);
+/* ... on the NUMA node of `device`'s PCIe root (-1 = current device): mmap + mbind + cudaHostRegister; falls back to
+ * b200_host_alloc when the node is unknown.  With 4 GPUs per socket the host memory system, not PCIe, bounds the
+ * columns' round trip unless every rank's buffers are node-local. */
+void *b200_host_alloc_local(uint64_t bytes, int device);
+void b200_host_free(void *p); /* either kind */
+/* diagnostics: NUMA node of a GPU's PCIe root / of the first page of a host buffer; -1 = unknown */
+int b200_device_numa_node(int device);
+int b200_host_node_of(const void *p);
 
 /* Build an executor for one world batch.  Replaces CraneliftExec::new
  * (cranelift_exec.rs:54-127): allocates device-resident SoA columns and the
@@ -222,7 +240,12 @@ int b200_sixdof_sync(b200_sixdof *h);
  * in_cols[i]  = host buffer of input_ids[i]  (borrowed for the call only)
  * out_cols[j] = host buffer of output_ids[j] (caller-owned, never aliasing an input)
  * Uploads every input column, integrates max(n_ticks,1) ticks on the device,
- * downloads every output column, synchronises. */
+ * downloads every output column, synchronises.
+ * Because the state is device-resident between calls, two entries may be NULL:
+ *   in_cols[i]  == NULL: the column is not dirty — the host has not modified it since the previous call
+ *                        (World::dirty_components, libs/nox-py/src/world.rs:43,249-252) — the device copy stands;
+ *   out_cols[j] == NULL: the caller does not read that column after this batch (e.g. WorldAccel / Force between
+ *                        telemetry cycles, pass-through Inertia): it is neither downloaded nor filled. */
 int b200_sixdof_invoke_batch(b200_sixdof *h, const uint8_t *const *in_cols,
                              uint8_t *const *out_cols, uint64_t n_ticks);
 
@@ -252,6 +275,35 @@ int b200_sixdof_status(const b200_sixdof *h);                  /* sticky status 
 /* raw device plane pointer (plane p of a column), for zero-copy interop (NCCL gather) */
 void *b200_sixdof_device_plane(b200_sixdof *h, uint64_t component_id, uint32_t plane);
 uint64_t b200_sixdof_plane_stride(const b200_sixdof *h); /* doubles between planes */
+
+/* ---- multi-GPU.  Worlds shard across GPUs — one handle per GPU, one process (or thread) per
+ * handle, no data-path collective — exactly like the reference's one-OS-process-per-world Monte-Carlo driver
+ * (libs/monte-carlo/src/lib.rs:2083).  The one exchange is the end-of-run gather of the trajectory ring, over
+ * NCCL (NVLink 5 / NVSwitch).  NCCL is bound at run time (dlopen of libnccl.so.2: the copy the host process already
+ * loaded, else the system one); b200_comm_available() == 0 means it could not be found. ---- */
+#define B200_COMM_ID_BYTES 128u                      /* sizeof(ncclUniqueId) */
+typedef struct b200_comm b200_comm;                   /* opaque: one NCCL communicator rank */
+int b200_comm_available(void);
+int b200_comm_version(void);                          /* NCCL version code, 0 if unavailable */
+/* rank 0 creates the id and hands its bytes to every rank over any channel the host has (the reference's
+ * Monte-Carlo driver would put it in context.json); then every rank calls b200_comm_create. */
+int b200_comm_unique_id(uint8_t *out, uint32_t bytes);
+int b200_comm_create(const uint8_t *id, int n_ranks, int rank, int device, b200_comm **out);
+void b200_comm_destroy(b200_comm *c);
+int b200_comm_rank(const b200_comm *c);
+int b200_comm_size(const b200_comm *c);
+double b200_comm_last_ms(const b200_comm *c);         /* device time of the last gather (layout kernel + collective) */
+/* World-sharded all-gather of the trajectory ring.  Rank r holds worlds_per_rank[r] worlds (same samples, entities
+ * and ring width everywhere; ragged world counts allowed).  On return `dst` (device or host memory) holds
+ * [sum(worlds)][samples][n_entities][width] f64 in rank order on every rank; dst_bytes must equal
+ * b200_sixdof_trajectory_gather_bytes(). */
+uint64_t b200_sixdof_trajectory_gather_bytes(const b200_sixdof *h, const uint64_t *worlds_per_rank, int n_ranks);
+int b200_sixdof_trajectory_allgather(b200_sixdof *h, b200_comm *c, const uint64_t *worlds_per_rank, void *dst,
+                                     uint64_t dst_bytes);
+
+/* Concurrent host<->device copy bandwidth of one GPU through pinned `host` (>= h2d_bytes + d2h_bytes): out[0] = H2D
+ * GB/s, out[1] = D2H GB/s, both directions running at once — the ceiling an invoke_batch round trip sits under. */
+int b200_probe_pcie_gbs(int device, void *host, uint64_t h2d_bytes, uint64_t d2h_bytes, int iters, double *out);
 
 /* FP64 / HBM probes used by bench.py to report the roofs next to the kernel
  * numbers (device-timed, returns GB/s resp. GFLOP/s, <0 on error) */

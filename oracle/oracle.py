@@ -24,6 +24,9 @@ EFF_WRENCH_BODY = 4
 EFF_GRAVITY_FRAME = 5
 EFF_GRAVITY_EDGES_NEWTON = 6
 EFF_GRAVITY_EDGES_SOFTENED = 7
+EFF_WRENCH_WORLD = 8
+EFF_TORQUE_BODY_FOLD = 9
+EFF_GRAVITY_J2 = 10
 FLAG_WRENCH_LINEAR_FIRST = 1
 
 

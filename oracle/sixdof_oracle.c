@@ -7,13 +7,15 @@
  *   gcc -O2 -ffp-contract=off -fno-fast-math      (oracle/Makefile)
  * so no multiply-add is ever contracted.
  */
-#define _POSIX_C_SOURCE 200809L
+#define _GNU_SOURCE /* sched_getaffinity / CPU_COUNT for orc_max_threads */
 #include "sixdof_oracle.h"
 
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <sched.h>
+#include <stdio.h>
 #include <unistd.h>
 
 /* ---- libs/nox/src/quaternion.rs:268-281 — Mul for &Quaternion; storage [i,j,k,w]
@@ -206,6 +208,59 @@ static void eff_wrench_body(const orc_effector *e, const double *wr, const doubl
     F[3] = F[3] + fw[0]; F[4] = F[4] + fw[1]; F[5] = F[5] + fw[2];
 }
 
+/* World-frame wrench column [tau(3), f(3)] added to Force: `force + SpatialForce(...)` of effectors whose value is
+ * computed outside six_dof — examples/cube-sat/main.py:516-527 (gravity_effector: force + SpatialForce(linear=f)),
+ * examples/drone/sim.py:99-103 (f + SpatialForce(linear=drag)). */
+static void eff_wrench_world(const double *wr, double F[6])
+{
+    if (!wr) return;
+    for (int k = 0; k < 6; ++k) F[k] = F[k] + wr[k];
+}
+
+/* Reaction-wheel edge fold, examples/cube-sat/main.py:492-505:
+ *   rw_force.edge_fold(.., el.SpatialForce(), lambda f, pos, force: f + SpatialForce(torque=pos.angular() @ force.torque()))
+ * per body, over its out-edges in spawn order; the column carries the K wheel torques of the body, [tau_1 .. tau_K]. */
+static void eff_torque_body_fold(const orc_effector *e, const double *col, const double pos[7], double F[6])
+{
+    if (!col) return;
+    double acc[6] = {0, 0, 0, 0, 0, 0}; /* edge_fold init: SpatialForce() */
+    const uint32_t K = e->column_width / 3;
+    for (uint32_t k = 0; k < K; ++k) {
+        double t[3];
+        orc_qrot(pos, col + 3 * k, t);
+        acc[0] = acc[0] + t[0]; acc[1] = acc[1] + t[1]; acc[2] = acc[2] + t[2];
+        acc[3] = acc[3] + 0.0; acc[4] = acc[4] + 0.0; acc[5] = acc[5] + 0.0;
+    }
+    /* the fold's result IS the Force column of the bodies that own an edge (edge_fold writes el.Force) */
+    for (int k = 0; k < 6; ++k) F[k] = acc[k];
+}
+
+/* libs/nox-py/python/elodin/j2.py:5-29 (J2.compute_field), applied as `force + SpatialForce(linear=field)`.
+ * p = [mu, J2, r_ref].  Integer powers follow lax.integer_pow's square-and-multiply (x**5 = x * (x^2)^2,
+ * x**4 = (x^2)^2); `norm**6.0` has a float exponent and lowers to pow().  Parity unpinned: no golden uses J2. */
+static void eff_gravity_j2(const orc_effector *e, const double pos[7], const double inertia[7], double F[6])
+{
+    const double mu = e->p[0], J2 = e->p[1], r_ref = e->p[2];
+    const double *r = pos + 4;
+    const double m = inertia[6], z = r[2];
+    const double norm = sqrt(dot3(r, r));
+    const double e_r[3] = {r[0] / norm, r[1] / norm, r[2] / norm};
+    const double n3 = (norm * norm) * norm;
+    const double c0 = (-mu) * m;
+    const double n2 = norm * norm, n4 = n2 * n2, n5 = norm * n4;
+    const double n6 = pow(norm, 6.0);
+    const double kz = (3.0 * z) / n5;
+    const double kr = 3.0 / (2.0 * n4) - (15.0 * (z * z)) / (2.0 * n6);
+    const double c1 = ((c0 * J2) * (r_ref * r_ref));
+    const double e_z[3] = {0.0, 0.0, 1.0};
+    for (int k = 0; k < 3; ++k) {
+        const double f = (c0 * r[k]) / n3;
+        const double j2 = c1 * (kz * e_z[k] + kr * e_r[k]);
+        F[3 + k] = F[3 + k] + (f + j2);
+    }
+    F[0] = F[0] + 0.0; F[1] = F[1] + 0.0; F[2] = F[2] + 0.0;
+}
+
 /* examples/falcon9/sim.py:350-361 + frames.py:91-109 (parity unpinned: no golden) */
 static void eff_gravity_frame(const orc_effector *e, const double pos[7], const double vel[6],
                               const double inertia[7], double F[6])
@@ -308,6 +363,9 @@ static void eval_pipe(uint64_t n, uint64_t world, const double *inertia, uint32_
             case ORC_EFF_GRAVITY_FRAME:
                 eff_gravity_frame(e, pos + 7 * i, vel + 6 * i, inertia + 7 * i, F + 6 * i);
                 break;
+            case ORC_EFF_WRENCH_WORLD: eff_wrench_world(col, F + 6 * i); break;
+            case ORC_EFF_TORQUE_BODY_FOLD: eff_torque_body_fold(e, col, pos + 7 * i, F + 6 * i); break;
+            case ORC_EFF_GRAVITY_J2: eff_gravity_j2(e, pos + 7 * i, inertia + 7 * i, F + 6 * i); break;
             default: break;
             }
         }
@@ -392,9 +450,25 @@ static void semi_world_tick(uint64_t n, uint64_t world, double *pos, double *vel
 /* ---- world-parallel driver (bench baseline only): static partition of the
  * world axis over pthreads, mirroring `elodin monte-carlo` workers = logical
  * cores (libs/monte-carlo/src/lib.rs:2530-2538). ---- */
+/* CPUs this process may actually run on: the scheduler affinity set, clipped by the cgroup CPU quota
+ * (cpu.max = "<quota> <period>") — not the number of CPUs the machine has online. */
 int orc_max_threads(void)
 {
     long n = sysconf(_SC_NPROCESSORS_ONLN);
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) n = CPU_COUNT(&set);
+    FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r");
+    if (f) {
+        char q[32] = {0};
+        long period = 0;
+        if (fscanf(f, "%31s %ld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) {
+            long quota = atol(q);
+            long cpus = (quota + period - 1) / period;
+            if (cpus > 0 && cpus < n) n = cpus;
+        }
+        fclose(f);
+    }
     return n > 0 ? (int)n : 1;
 }
 

@@ -34,7 +34,10 @@ enum {
     ORC_EFF_WRENCH_BODY = 4,
     ORC_EFF_GRAVITY_FRAME = 5,
     ORC_EFF_GRAVITY_EDGES_NEWTON = 6,
-    ORC_EFF_GRAVITY_EDGES_SOFTENED = 7
+    ORC_EFF_GRAVITY_EDGES_SOFTENED = 7,
+    ORC_EFF_WRENCH_WORLD = 8,
+    ORC_EFF_TORQUE_BODY_FOLD = 9,
+    ORC_EFF_GRAVITY_J2 = 10
 };
 #define ORC_FLAG_WRENCH_LINEAR_FIRST 1u
 

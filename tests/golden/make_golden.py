@@ -54,6 +54,13 @@ def main() -> int:
     for comp in ("world_pos", "world_vel", "world_accel", "force", "inertia"):
         out[f"cube_sat.earth.{comp}"] = read("cube-sat", f"earth.{comp}")
     out["cube_sat.simulation_time_step"] = read("cube-sat", "globals.simulation_time_step")
+    # the satellite itself: Force = reaction-wheel edge fold (main.py:492-505) + EGM08 gravity (main.py:516-527), integrated
+    # by Integrator.SemiImplicit.  The recorded wheel commands pin the fold, the recorded Force pins semi-implicit with a
+    # full wrench (the EGM08 coefficient tables are a download the reference tree does not hold)
+    for comp in ("world_pos", "world_vel", "world_accel", "force", "inertia"):
+        out[f"cube_sat.ore_sat.{comp}"] = read("cube-sat", f"ore_sat.{comp}")
+    for k in (1, 2, 3):  # edge spawn order sat_to_rw_1..3
+        out[f"cube_sat.rw_{k}.rw_force"] = read("cube-sat", f"rw_{k}.rw_force")
     # layout of the exported directory (file stems + header rows), for the CSV-export parity test
     layout = {}
     d = os.path.join(BASE, "three-body-csv")

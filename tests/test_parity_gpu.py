@@ -1160,3 +1160,137 @@ def test_compiled_consumers_of_the_abi_run_on_the_gpu(lang, tmp_path):
                           "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and want in out.stdout, out.stdout + out.stderr
+
+
+# --------------------------------------------------------------------------- round 2: dirty inputs / unread outputs
+@pytest.mark.parametrize("M,N", [(3, 2), (3000, 1)])  # packed small path and pipelined world ranges
+@pytest.mark.parametrize("math", ["exact", "fast"])
+def test_invoke_batch_null_columns_mean_not_dirty_and_not_read(oracle, math, M, N):
+    """in_cols[i] = None: the column is not dirty (World::dirty_components, world.rs:43,249-252), the device copy
+    stands; out_cols[j] = None: not read back.  Two calls that only hand over what changed must equal two full calls."""
+    O = oracle
+    pos, vel, ine = random_world(91, M, N)
+    rng = np.random.default_rng(3)
+    thrust = rng.uniform(0, 10, (M, N, 1))
+    o2, g2, _ = effector_pair(O, "thrust", thrust=thrust)
+    want = _run_oracle(O, pos, vel, ine, [o2], 0.01, 7)
+    tick, dt = el.component_id("tick"), el.component_id("simulation_time_step")
+    with el.B200Exec(N, M, 0.01, None, [g2], "rk4", math, invoke_chunk_bodies=0 if M < 100 else 1024) as ex:
+        table = {tick: np.array([0], dtype=np.uint64), FORCE: np.zeros((M, N, 6)), INERTIA: ine, WORLD_POS: pos,
+                 WORLD_ACCEL: np.zeros((M, N, 6)), dt: np.array([0.01]), WORLD_VEL: vel, el.component_id("thrust"): thrust}
+        # call 1: everything uploaded, nothing read back
+        ex.invoke_batch([table[c] for c in ex.input_ids], 3, out_cols=[None] * len(ex.output_ids))
+        # call 2: nothing is dirty; read back the state, Force and the pass-through Inertia, not WorldAccel / thrust
+        outs = [None if c in (WORLD_ACCEL, el.component_id("thrust")) else np.full(ex.column_shape(c), np.nan, dtype=np.uint64 if c == tick else np.float64)
+                for c in ex.output_ids]
+        ex.invoke_batch([None] * len(ex.input_ids), 4, out_cols=outs)
+        o = dict(zip(ex.output_ids, outs))
+        acc = ex.download(WORLD_ACCEL)
+    got = (o[WORLD_POS], o[WORLD_VEL], acc, o[FORCE])
+    if math == "exact":
+        _assert_exact(got, want)
+    else:
+        _assert_close(got, want, 7 * FAST_TOL_TICK)
+    assert int(o[tick][0]) == 7
+    assert np.array_equal(o[INERTIA], ine)  # pass-through of a non-dirty input = the device-resident column
+
+
+@pytest.mark.parametrize("integrator", ["rk4", "semi_implicit"])
+def test_signature_kernels_match_the_interpreter_kernel(oracle, integrator):
+    """Every effector signature with a compiled FAST kernel (one body and body pairs per thread, odd and even range
+    lengths) against the oracle, and masked / repeated lists that must take the run-time interpreter."""
+    O = oracle
+    rng = np.random.default_rng(17)
+    for M in (1, 2, 257, 120001):  # 120001 >= one wave of body pairs: the double2 kernel with an odd tail
+        pos, vel, ine = random_world(400 + M, M, 1)
+        pos[..., 4:] += np.array([6.4e6, 0.0, 0.0])
+        wind = rng.normal(0, 3, (M, 1, 3))
+        thrust = rng.uniform(0, 10, (M, 1, 1))
+        wrench = rng.normal(0, 5, (M, 1, 6))
+        lists = {
+            "free": [],
+            "g": [("gravity", {})],
+            "drag": [("gravity", {}), ("drag", dict(wind=wind))],
+            "rocket": [("gravity", {}), ("thrust", dict(thrust=thrust)), ("drag", dict(wind=wind))],
+            "rocket_golden": [("gravity", {}), ("thrust", dict(thrust=thrust)), ("wrench", dict(wrench=wrench))],
+            "falcon9": [("frame", {}), ("wrench", dict(wrench=wrench, linear_first=True))],
+            "frame": [("frame", {})],
+            "wrench": [("wrench", dict(wrench=wrench))],
+            "thrust": [("thrust", dict(thrust=thrust))],
+            "two_g (summed)": [("gravity", {}), ("gravity", dict(g=(0.5, 0.0, 1.0)))],
+            "wrench_then_drag (interpreter: torque reset)": [("wrench", dict(wrench=wrench)), ("drag", dict(wind=wind))],
+        }
+        for name, spec in lists.items():
+            oe, ge, cols = [], [], {}
+            for kind, kw in spec:
+                a, b, c = effector_pair(O, kind, **kw)
+                oe.append(a); ge.append(b); cols.update(c)
+            want = _run_oracle(O, pos, vel, ine, oe, 0.01, 3, integrator)
+            got = _run_gpu(pos, vel, ine, ge, cols, 0.01, 3, "fast", integrator)
+            _assert_close(got, want, 3 * FAST_TOL_TICK, f"M={M} {name}")
+
+
+# --------------------------------------------------------------------------- round 2: §8f-4 effectors
+@pytest.mark.parametrize("integrator", ["rk4", "semi_implicit"])
+def test_wrench_world_wheel_fold_and_j2_effectors(oracle, integrator):
+    """WRENCH_WORLD, TORQUE_BODY_FOLD (cube-sat/main.py:492-505) and GRAVITY_J2 (j2.py:5-29): EXACT bit-identical to
+    the oracle for the first two (J2's `norm**6.0` is a pow() call: <= 1e-14), FAST within tolerance; the fold
+    overwrites what earlier effectors accumulated, as every edge_fold does."""
+    O = oracle
+    rng = np.random.default_rng(23)
+    M, N = 5, 3
+    pos, vel, ine = random_world(77, M, N)
+    pos[..., 4:] = rng.normal(size=(M, N, 3))
+    pos[..., 4:] *= 6.9e6 / np.linalg.norm(pos[..., 4:], axis=-1, keepdims=True)
+    wr = rng.normal(0, 3, (M, N, 6))
+    tq = rng.normal(0, 2e-3, (M, N, 9))
+    combos = {
+        "wrench_world": [("wrench_world", dict(wrench=wr))],
+        "wheels": [("wheels", dict(torques=tq))],
+        "gravity then wheels (fold overwrites) then wrench_world": [("gravity", {}), ("wheels", dict(torques=tq)), ("wrench_world", dict(wrench=wr))],
+        "j2": [("j2", {})],
+        "wheels + j2 (cube-sat shape)": [("wheels", dict(torques=tq)), ("j2", {})],
+    }
+    n = 4
+    for name, spec in combos.items():
+        oe, ge, cols = [], [], {}
+        for kind, kw in spec:
+            a, b, c = effector_pair(O, kind, **kw)
+            oe.append(a); ge.append(b); cols.update(c)
+        want = _run_oracle(O, pos, vel, ine, oe, 0.01, n, integrator)
+        got = _run_gpu(pos, vel, ine, ge, cols, 0.01, n, "exact", integrator)
+        if "j2" in name:
+            _assert_close(got, want, 1e-14, f"exact {name}")
+        else:
+            _assert_exact(got, want, f"exact {name}")
+        fast = _run_gpu(pos, vel, ine, ge, cols, 0.01, n, "fast", integrator)
+        _assert_close(fast, want, n * FAST_TOL_TICK, f"fast {name}")
+
+
+def test_cube_sat_ore_sat_golden_on_gpu(golden):
+    """The reference's cube-sat golden, satellite entity: (1) the reaction-wheel fold on the recorded wheel commands,
+    (2) one semi-implicit tick per recorded row with the recorded Force as a world-frame wrench.  Same bars as the
+    oracle-side tests (tests/test_oracle_golden.py): the golden came from XLA-CPU, whose FMA contraction the IEEE-plain
+    EXACT path does not imitate — <= 5e-16 (fold) / 2e-15 (tick) vector-relative, most rows bit-identical."""
+    g = golden
+    pos, vel, acc, frc = (g[f"cube_sat.ore_sat.{c}"] for c in ("world_pos", "world_vel", "world_accel", "force"))
+    ine = g["cube_sat.ore_sat.inertia"]
+    dt = float(g["cube_sat.simulation_time_step"][0, 0])
+    T = len(pos)
+    P, V, I = pos[:-1].reshape(T - 1, 1, 7), vel[:-1].reshape(T - 1, 1, 6), np.tile(ine[0], (T - 1, 1, 1))
+    rw = np.concatenate([g[f"cube_sat.rw_{k}.rw_force"][:, :3] for k in (1, 2, 3)], -1)[1:].reshape(T - 1, 1, 9)
+    rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.max(np.abs(b), axis=-1, keepdims=True), 1e-300)))
+    # (1) every recorded row as one world of a batch: Force after one tick = the fold at the row's start pose
+    got = _run_gpu(P, V, I, [el.TorqueBodyFold("wheel_torques", 3)], {"wheel_torques": rw}, dt, 1, "exact", "semi_implicit")
+    assert np.all(got[3][:, 0, 3:] == 0.0)
+    assert rel(got[3][:, 0, :3], frc[1:, :3]) <= 5e-16
+    assert int(np.sum(np.all(got[3][:, 0, :3] == frc[1:, :3], axis=-1))) >= 50
+    # (2) semi-implicit tick with the recorded wrench
+    for math, tol in (("exact", 2e-15), ("fast", 1e-12)):
+        p, v, a, f = _run_gpu(P, V, I, [el.WrenchWorld("external_force")], {"external_force": frc[1:].reshape(T - 1, 1, 6)}, dt, 1,
+                              math, "semi_implicit")
+        assert rel(a[:, 0], acc[1:]) <= tol and rel(v[:, 0], vel[1:]) <= tol
+        assert rel(p[:, 0, :4], pos[1:, :4]) <= tol and rel(p[:, 0, 4:], pos[1:, 4:]) <= tol
+        if math == "exact":
+            assert np.array_equal(f[:, 0], frc[1:])
+            assert int(np.sum(np.all(p[:, 0] == pos[1:], axis=-1))) >= 90

@@ -42,6 +42,16 @@ def effector_pair(O, kind, **kw):
     if kind == "frame":
         mu, om = kw.get("mu", 3.986004418e14), kw.get("omega", (0.0, 0.0, 7.292115e-5))
         return O.Effector(O.EFF_GRAVITY_FRAME, p=(mu, *om)), el.GravityFrame(mu, om), {}
+    if kind == "wrench_world":
+        wr = kw["wrench"]
+        return O.Effector(O.EFF_WRENCH_WORLD, column=wr), el.WrenchWorld("external_force"), {"external_force": wr}
+    if kind == "wheels":
+        tq = kw["torques"]
+        return (O.Effector(O.EFF_TORQUE_BODY_FOLD, column=tq), el.TorqueBodyFold("wheel_torques", tq.shape[-1] // 3),
+                {"wheel_torques": tq})
+    if kind == "j2":
+        mu, j2, rr = kw.get("mu", 3.986004418e14), kw.get("j2", 1.08262668e-3), kw.get("r_ref", 6.378e6)
+        return O.Effector(O.EFF_GRAVITY_J2, p=(mu, j2, rr)), el.GravityJ2(mu, j2, rr), {}
     if kind == "newton":
         return (O.Effector(O.EFF_GRAVITY_EDGES_NEWTON, p=(kw.get("G", 6.6743e-11),), edges=kw["edges"]),
                 el.GravityEdges("newton", G=kw.get("G", 6.6743e-11), edges=kw["edges"]), {})
