@@ -367,17 +367,17 @@ class DbSink:
         self.close()
 
 
-def sample_timestamps(start_us: int, sim_time_step: float, ticks_per_telemetry: int, n_samples: int) -> np.ndarray:
-    """Timestamps of the recorded samples, as the server stamps them (impeller2_server.rs:560-580, 631-636):
-    sample 0 is the initial state at `start`; the cycle that starts at tick t and runs b ticks is committed at
-    `start + floor(dt_ns * (t + b - 1) / 1000)` µs — so with b = 1 the first tick shares the start timestamp."""
+def sample_timestamps(start_us: int, sim_time_step: float, sample_ticks) -> np.ndarray:
+    """Timestamps of the recorded samples, as the reference stamps them (exec.rs:134-152, impeller2_server.rs:560-580,
+    631-636): sample 0 is the initial state at `start`; a batch that ends after `tick` ticks in total is committed at
+    `start + floor(dt_ns * (tick - 1) / 1000)` µs — whatever its length, so short tail batches (`this_batch` override,
+    exec.rs:131-139) and repeated run() calls are stamped by the ticks they really covered.  `sample_ticks[k]` is the
+    tick counter of recorded row k (Exec._globals_hist)."""
     dt_ns = duration_ns(sim_time_step)
-    out = np.empty(n_samples, dtype=np.int64)
-    if n_samples:
-        out[0] = start_us
-    for k in range(1, n_samples):
-        end_tick = (k - 1) * ticks_per_telemetry + ticks_per_telemetry - 1
-        out[k] = start_us + (dt_ns * end_tick) // 1000
+    ticks = [int(t) for t in sample_ticks]
+    out = np.empty(len(ticks), dtype=np.int64)
+    for k, tick in enumerate(ticks):
+        out[k] = start_us + (dt_ns * max(tick - 1, 0)) // 1000 if k else start_us
     return out
 
 
@@ -388,7 +388,7 @@ def write_db(exec_, path: str, start_timestamp_us: int = 1_767_225_600_000_000, 
 
     w = exec_.world
     n = len(exec_._globals_hist)
-    ts = sample_timestamps(start_timestamp_us, exec_.sim_time_step, exec_.ticks_per_telemetry, n)
+    ts = sample_timestamps(start_timestamp_us, exec_.sim_time_step, [g[0] for g in exec_._globals_hist])
     sink = DbSink(path, start_timestamp_us)
     g = exec_._globals_hist
     for comp, md, vals, prim in (("tick", {"priority": 7}, [x[0] for x in g], "u64"),

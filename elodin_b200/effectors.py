@@ -230,3 +230,55 @@ def all_pairs_edges(n: int) -> np.ndarray:
     i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
     m = i != j
     return np.stack([i[m], j[m]], 1).astype(np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CompiledSystem.system_names -> built-in effectors (the host-side half of a `WorldExec::B200` arm, SURVEY §8f-3;
+# same table and rules as include/b200_world.hpp:match_effectors)
+_STRUCTURAL = {"<system>", "<compiled>", "<empty>", "clear_forces", "calc_accel", "six_dof", "rk4", "semi_implicit_euler",
+               "increment_sim_tick", "advance_time"}
+
+
+def default_effector_registry() -> dict:
+    """Effector systems of the reference's own examples by function name (system.rs:213-222,908 carries the repr
+    of the Python function, "<function NAME at 0x..>")."""
+    return {
+        "gravity": lambda: GravityConst((0.0, 0.0, -9.81)),                      # ball/sim.py:56-58, rocket/main.py:292-294
+        "apply_drag": lambda: DragQuadratic(),                                    # ball/sim.py:99-116
+        "apply_thrust": lambda: ThrustBody((-1.0, 0.0, 0.0), "thrust"),           # rocket/main.py:429-431
+        "apply_aero_forces": lambda: WrenchBody("aero_force", "torque_first"),    # rocket/main.py:407-413
+        "apply_body_wrenches": lambda: WrenchBody("body_wrench", "linear_first"), # falcon9/sim.py:659-672
+        "gravity_and_frame_forces": lambda: GravityFrame(),                       # falcon9/sim.py:350-361
+        "rw_effector": lambda: TorqueBodyFold("wheel_torques", 3),                # cube-sat/main.py:492-505
+        "j2_gravity": lambda: GravityJ2(),                                        # python/elodin/j2.py:5-29
+    }
+
+
+def system_function_name(system_name: str) -> str:
+    if not system_name.startswith("<function "):
+        return system_name
+    at = system_name.rfind(" at 0x")
+    return system_name[len("<function "): at if at >= 0 else len(system_name) - 1]
+
+
+def match_effectors(system_names: Sequence[str], registry: Optional[dict] = None) -> list:
+    """Built-in effectors for a compiled pipeline's `system_names`, in order.  Structural six_dof() entries are
+    skipped; any other system that is not in the registry raises B200Error(ERR_UNSUPPORTED) naming it — the B200
+    backend has no tracing compiler and no CPU fallback."""
+    registry = default_effector_registry() if registry is None else registry
+    out = []
+    for raw in system_names:
+        name = system_function_name(raw)
+        if name in _STRUCTURAL:
+            continue
+        make = registry.get(name)
+        if make is None:
+            why = f"system '{name}' is not a built-in B200 effector"
+            if "<locals>" in name:
+                why += (" (an @el.map wrapper: the wrapped function's name is not visible in system_names; register it under "
+                        "the name you give it, or pass the effector list explicitly)")
+            raise _lib.B200Error(_lib.ERR_UNSUPPORTED, why + "; the B200 backend cannot trace arbitrary systems and has no CPU fallback")
+        out.append(make() if callable(make) else make)
+    if len(out) > _lib.MAX_EFFECTORS:
+        raise _lib.B200Error(_lib.ERR_UNSUPPORTED, f"too many effectors ({len(out)} > {_lib.MAX_EFFECTORS})")
+    return out

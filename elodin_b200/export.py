@@ -55,9 +55,11 @@ def export_csv(exec_, out_dir: str, start_timestamp: Optional[_dt.datetime] = No
     os.makedirs(out_dir, exist_ok=True)
     w = exec_.world
     t0 = start_timestamp or _dt.datetime(2026, 1, 1)
-    n_rows = len(exec_._globals_hist)
-    dt_row = exec_.sim_time_step * exec_.ticks_per_telemetry
-    times = [(t0 + _dt.timedelta(seconds=dt_row * i)).isoformat() for i in range(n_rows)]
+    # the same time base as the elodin-db sink: row k is stamped by the ticks it really covers (exec.rs:134-152)
+    from .db_sink import sample_timestamps
+
+    us = sample_timestamps(0, exec_.sim_time_step, [g[0] for g in exec_._globals_hist])
+    times = [(t0 + _dt.timedelta(microseconds=int(u))).isoformat() for u in us]
     written = []
 
     def write(stem: str, header: List[str], rows) -> None:

@@ -18,6 +18,7 @@ from __future__ import annotations
 import dataclasses
 import enum
 import re
+import copy
 import os
 import sys
 import time
@@ -28,7 +29,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import component_id
-from .effectors import System, _flatten
+from .effectors import Effector, System, _flatten
 from .executor import B200Exec
 
 # --------------------------------------------------------------------------- value types
@@ -410,6 +411,20 @@ class World:
         out = [(rows[a], rows[b]) for (_, a, b) in self.edges if a in rows and b in rows]
         return np.asarray(out, dtype=np.uint32).reshape(-1, 2)
 
+    def _clone_for_exec(self) -> "World":
+        """Private copy for one Exec: same entities / names / edges, its own Column objects and buffers."""
+        w = copy.copy(self)
+        w.columns = {}
+        for cid, col in self.columns.items():
+            c = Column(col.component, col.width, col.dtype)
+            c.entity_ids = list(col.entity_ids)
+            c.rows = [r.copy() for r in col.rows]
+            c.buffer = None if col.buffer is None else col.buffer.copy()
+            w.columns[cid] = c
+        w.entity_names = dict(self.entity_names)
+        w.edges = list(self.edges)
+        return w
+
     def finalize(self, n_worlds: int = 1) -> None:
         for col in self.columns.values():
             base = np.stack(col.rows).astype(col.dtype) if col.rows else np.zeros((0, col.width), col.dtype)
@@ -507,7 +522,15 @@ class Exec:
                 raise _lib.B200Error(_lib.ERR_UNSUPPORTED,
                                      f"{s!r}: only host_system() callbacks may surround six_dof() (no tracing compiler)")
         self.pre_systems, self.post_systems = pre, post
+        # The reference's build yields an independent exec: this one owns private copies of the world's columns
+        # (a later World.build() re-finalises the World's own buffers) and of the effector objects (the query-join
+        # masks below are per build — the caller's effectors are never mutated).
+        world = world._clone_for_exec()
         self.world = world
+        self._effectors = [copy.copy(e) for e in self.six.effectors]
+        for e in self._effectors:
+            if isinstance(e, Effector):
+                e.with_mask(None)
         self.n_worlds = int(n_worlds)
         self.sim_time_step = quantised_time_step(simulation_rate)
         self.ticks_per_telemetry = ticks_per_telemetry(simulation_rate, telemetry_rate)
@@ -526,7 +549,7 @@ class Exec:
         # component.  Full membership -> no mask; partial (order-preserving) membership -> entity mask +
         # a body-row-expanded copy of the column for the device; no members / foreign order -> error.
         self._partial: Dict[int, tuple] = {}
-        for e in self.six.effectors:
+        for e in self._effectors:
             cname = e.column_name()
             if not cname:
                 continue
@@ -554,7 +577,7 @@ class Exec:
             ld = (n_bodies + 127) // 128 * 128
             self._ring_cap = int(max(1, min(4096, (64 << 20) // (25 * ld * 8))))
         # ticks of one invoke_batch stay in registers up to 32 at a time (no effect on results)
-        self.backend = B200Exec(len(bodies), self.n_worlds, self.sim_time_step, self.six.time_step, self.six.effectors,
+        self.backend = B200Exec(len(bodies), self.n_worlds, self.sim_time_step, self.six.time_step, self._effectors,
                                 self.six.integrator.value, math, device, max_fused_ticks=32, world=world,
                                 trajectory_every=self.ticks_per_telemetry if self._ring_cap else 0,
                                 trajectory_capacity=self._ring_cap, trajectory_full=bool(self._ring_cap))
@@ -679,8 +702,6 @@ class Exec:
             self._run_resident(whole)
             remaining -= whole * self.ticks_per_telemetry
         while remaining > 0:
-            if is_canceled is not None and is_canceled():
-                break
             n = min(self.ticks_per_telemetry, remaining)
             per_call = 1 if host_cb else n
             done = 0
@@ -705,6 +726,9 @@ class Exec:
             self._record()
             self._prof["add_to_history"].append((time.perf_counter() - t_hist) * 1e3)
             remaining -= n
+            # like the reference (exec.rs:130-165): run the batch, commit it, then ask
+            if is_canceled is not None and is_canceled():
+                break
         return self
 
     def history(self, names: Union[str, Sequence[str]]):

@@ -14,8 +14,11 @@
 // Nothing here computes: every tick runs in libb200_sixdof.so (include/b200_sixdof.h).
 #pragma once
 
+#include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -132,6 +135,108 @@ class World {
         c.entity_ids.push_back(entity);
     }
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backend selection and effector matching: what the third `WorldExec` arm needs on the host side.
+//
+// parse_backend_config mirrors libs/nox-py/src/world_builder.rs:245-260: ELODIN_BACKEND overrides the requested
+// string, the match is case-insensitive and trimmed; the B200 arm adds "b200" (= FAST math), "b200-fast" and
+// "b200-exact" (bit-identical to the CPU arithmetic).  Every other name — including the reference's own
+// "cranelift" / "jax-cpu" / "jax-gpu", which this library does not provide — is the reference's UnknownCommand error.
+struct BackendConfig {
+    uint32_t math_mode; // B200_MATH_*
+    const char *device; // "gpu": there is no CPU arm behind this library
+};
+
+inline BackendConfig parse_backend_config(const std::string &requested_backend)
+{
+    const char *env = std::getenv("ELODIN_BACKEND");
+    std::string s = env ? env : requested_backend;
+    auto not_space = [](unsigned char c) { return !std::isspace(c); };
+    s.erase(s.begin(), std::find_if(s.begin(), s.end(), not_space));
+    s.erase(std::find_if(s.rbegin(), s.rend(), not_space).base(), s.end());
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    if (s == "b200" || s == "b200-fast") return BackendConfig{B200_MATH_FAST, "gpu"};
+    if (s == "b200-exact") return BackendConfig{B200_MATH_EXACT, "gpu"};
+    throw Error(B200_ERR_INVALID_ARGUMENT, "unknown backend '" + s + "': expected one of 'b200', 'b200-fast', 'b200-exact'");
+}
+
+// One entry of the effector registry: the Python-level system name -> the built-in effector it lowers to.
+struct EffectorSpec {
+    b200_effector effector; // kind / flags / constants / column width (column_id filled from `column`)
+    std::string column;     // component name of the per-body input column, "" = none
+};
+
+inline EffectorSpec make_spec(uint32_t kind, std::initializer_list<double> p, const char *column, uint32_t width, uint32_t flags = 0)
+{
+    EffectorSpec s;
+    std::memset(&s.effector, 0, sizeof s.effector);
+    s.effector.kind = kind;
+    s.effector.flags = flags;
+    size_t i = 0;
+    for (double v : p) if (i < 8) s.effector.p[i++] = v;
+    s.column = column ? column : "";
+    s.effector.column_width = width;
+    return s;
+}
+
+// The effector systems of the reference's own examples, by function name (what `CompiledSystem.system_names`
+// carries, libs/nox-py/src/system.rs:213-222,908: the repr of the Python function, "<function NAME at 0x..>").
+// A host extends / overrides the table for its own simulation; names are matched exactly.
+inline std::map<std::string, EffectorSpec> default_effector_registry()
+{
+    std::map<std::string, EffectorSpec> r;
+    r["gravity"] = make_spec(B200_EFF_GRAVITY_CONST, {0.0, 0.0, -9.81}, nullptr, 0);               // ball/sim.py:56-58, rocket/main.py:292-294, drone/sim.py:106-108
+    r["apply_drag"] = make_spec(B200_EFF_DRAG_QUADRATIC, {0.5 * 1.225, 2 * 3.1415 * 0.2 * 0.2}, "wind", 3); // ball/sim.py:99-116
+    r["apply_thrust"] = make_spec(B200_EFF_THRUST_BODY, {-1.0, 0.0, 0.0}, "thrust", 1);             // rocket/main.py:429-431
+    r["apply_aero_forces"] = make_spec(B200_EFF_WRENCH_BODY, {}, "aero_force", 6);                   // rocket/main.py:407-413
+    r["apply_body_wrenches"] = make_spec(B200_EFF_WRENCH_BODY, {}, "body_wrench", 6, B200_EFF_FLAG_WRENCH_LINEAR_FIRST); // falcon9/sim.py:659-672
+    r["gravity_and_frame_forces"] = make_spec(B200_EFF_GRAVITY_FRAME, {3.986004418e14, 0.0, 0.0, 7.292115e-5}, nullptr, 0); // falcon9/sim.py:350-361
+    r["rw_effector"] = make_spec(B200_EFF_TORQUE_BODY_FOLD, {}, "wheel_torques", 9);                 // cube-sat/main.py:492-505 (3 wheels)
+    r["j2_gravity"] = make_spec(B200_EFF_GRAVITY_J2, {3.986004418e14, 1.08262668e-3, 6.378e6}, nullptr, 0); // python/elodin/j2.py:5-29
+    return r;
+}
+
+// "<function apply_drag at 0x7f..>" -> "apply_drag"; "<function map.<locals>.inner at 0x..>" -> "map.<locals>.inner";
+// anything else is returned unchanged
+inline std::string system_function_name(const std::string &system_name)
+{
+    const std::string pre = "<function ";
+    if (system_name.compare(0, pre.size(), pre) != 0) return system_name;
+    const size_t at = system_name.rfind(" at 0x");
+    return system_name.substr(pre.size(), (at == std::string::npos ? system_name.size() - 1 : at) - pre.size());
+}
+
+// CompiledSystem.system_names -> built-in effectors, in pipeline order.  Structural entries of the six_dof()
+// pipeline ("<system>", "<compiled>", "<empty>", clear_forces, calc_accel, the integrator wrappers) are skipped; every
+// other system must be in the registry — the B200 arm has no tracing compiler and no CPU fallback, so an unknown
+// system is a hard B200_ERR_UNSUPPORTED error that names it.  Edge-fold gravity is declared through
+// `graph_effector` (its edge list comes from the world, not from a name).
+inline std::vector<b200_effector> match_effectors(const std::vector<std::string> &system_names,
+                                                  const std::map<std::string, EffectorSpec> &registry = default_effector_registry())
+{
+    static const char *structural[] = {"<system>", "<compiled>", "<empty>", "clear_forces", "calc_accel", "six_dof", "rk4",
+                                        "semi_implicit_euler", "increment_sim_tick", "advance_time"};
+    std::vector<b200_effector> out;
+    for (const std::string &raw : system_names) {
+        const std::string name = system_function_name(raw);
+        if (std::any_of(std::begin(structural), std::end(structural), [&](const char *s) { return name == s; })) continue;
+        auto it = registry.find(name);
+        if (it == registry.end()) {
+            std::string why = "system '" + name + "' is not a built-in B200 effector";
+            if (name.find("<locals>") != std::string::npos)
+                why += " (an @el.map wrapper: the wrapped function's name is not visible in system_names; register it under the name "
+                       "you give it, or declare the effector list explicitly)";
+            throw Error(B200_ERR_UNSUPPORTED, why + "; the B200 backend cannot trace arbitrary systems and has no CPU fallback");
+        }
+        b200_effector e = it->second.effector;
+        e.column_id = it->second.column.empty() ? 0 : component_id(it->second.column.c_str());
+        out.push_back(e);
+        if (out.size() > B200_MAX_EFFECTORS)
+            throw Error(B200_ERR_UNSUPPORTED, "too many effectors (" + std::to_string(out.size()) + " > " + std::to_string(B200_MAX_EFFECTORS) + ")");
+    }
+    return out;
+}
 
 // cranelift_exec.rs:13-195
 class Exec {

@@ -2,10 +2,12 @@
 //   * test_six_dof            libs/nox-py/python/tests/test_all.py:67-83   x = dt after one tick of six_dof(1/60)
 //   * three-body tick 1       scripts/ci/baseline/three-body-csv/a.world_pos.csv row 2, bit for bit
 //   * ValueSizeMismatch / ComponentNotFound error mapping (error.rs:7-58)
+//   * parse_backend_config (world_builder.rs:245-260) and the system_names -> built-in effector matcher (system.rs:213-222)
 // Without a GPU the only legal outcome is a loud B200_ERR_NO_DEVICE.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "b200_world.hpp"
 
@@ -18,6 +20,42 @@ int main()
 {
     using namespace b200;
     REQUIRE(component_id("world_pos") == B200_ID_WORLD_POS);
+    { // host-side logic that needs no device: backend strings and the effector matcher
+        unsetenv("ELODIN_BACKEND");
+        REQUIRE(parse_backend_config("b200").math_mode == B200_MATH_FAST);
+        REQUIRE(parse_backend_config("  B200-Exact ").math_mode == B200_MATH_EXACT);
+        REQUIRE(parse_backend_config("b200-fast").math_mode == B200_MATH_FAST);
+        for (const char *other : {"cranelift", "jax-cpu", "jax-gpu", "cpu", ""}) {
+            bool threw = false;
+            try { parse_backend_config(other); } catch (const Error &e) { threw = std::string(e.what()).find("unknown backend") != std::string::npos; }
+            REQUIRE(threw);
+        }
+        setenv("ELODIN_BACKEND", "b200-exact", 1); // the environment wins, as in the reference
+        REQUIRE(parse_backend_config("b200").math_mode == B200_MATH_EXACT);
+        unsetenv("ELODIN_BACKEND");
+        // the rocket example's pipeline as CompiledSystem.system_names would list it
+        const std::vector<std::string> rocket = {"<system>", "<function clear_forces at 0x7f00aa>", "<function gravity at 0x7f00bb>",
+                                                 "<function apply_thrust at 0x7f00cc>", "<function apply_aero_forces at 0x7f00dd>",
+                                                 "<function calc_accel at 0x7f00ee>"};
+        const std::vector<b200_effector> effs = match_effectors(rocket);
+        REQUIRE(effs.size() == 3);
+        REQUIRE(effs[0].kind == B200_EFF_GRAVITY_CONST && effs[0].p[2] == -9.81 && effs[0].column_id == 0);
+        REQUIRE(effs[1].kind == B200_EFF_THRUST_BODY && effs[1].column_id == component_id("thrust") && effs[1].column_width == 1);
+        REQUIRE(effs[2].kind == B200_EFF_WRENCH_BODY && effs[2].column_id == component_id("aero_force") && effs[2].flags == 0);
+        const std::vector<b200_effector> f9 = match_effectors({"<function gravity_and_frame_forces at 0x1>", "<function apply_body_wrenches at 0x2>"});
+        REQUIRE(f9.size() == 2 && f9[0].kind == B200_EFF_GRAVITY_FRAME && f9[1].flags == B200_EFF_FLAG_WRENCH_LINEAR_FIRST);
+        // an arbitrary user system is a hard error that names it; an @el.map wrapper says why it cannot be matched
+        for (const char *bad : {"<function kalman_filter at 0x3>", "<function map.<locals>.inner at 0x4>"}) {
+            bool ok = false;
+            try { match_effectors({"<function gravity at 0x1>", bad}); }
+            catch (const Error &e) { ok = e.code == B200_ERR_UNSUPPORTED && std::string(e.what()).find(system_function_name(bad)) != std::string::npos; }
+            REQUIRE(ok);
+        }
+        // a host registers its own names
+        auto reg = default_effector_registry();
+        reg["wind_drag"] = make_spec(B200_EFF_DRAG_QUADRATIC, {0.6, 0.01}, "wind", 3);
+        REQUIRE(match_effectors({"<function wind_drag at 0x5>"}, reg)[0].kind == B200_EFF_DRAG_QUADRATIC);
+    }
     if (b200_device_count() <= 0) {
         World w;
         w.spawn(Body{});
