@@ -676,14 +676,14 @@ def run_multi_gpu(args, torch, dist, el, stream, local, rank, world_size, barrie
     N = 1024
     rng = np.random.default_rng(7)  # the same world(s) on every rank where a single world is replicated
 
-    def nbody_world(Mw, gen):
-        p = np.zeros((Mw, N, 7)); p[..., 3] = 1.0; p[..., 4:] = gen.uniform(-30, 30, (Mw, N, 3))
-        v = np.zeros((Mw, N, 6)); v[..., 3:] = gen.normal(0, 1e-7, (Mw, N, 3))
-        m = 10 ** gen.uniform(-10, -3, (Mw, N)); m[:, 0] = 1.0
-        I = np.zeros((Mw, N, 7)); I[..., :3] = m[..., None]; I[..., 6] = m
+    def nbody_world(Mw, gen, n=N):
+        p = np.zeros((Mw, n, 7)); p[..., 3] = 1.0; p[..., 4:] = gen.uniform(-30, 30, (Mw, n, 3))
+        v = np.zeros((Mw, n, 6)); v[..., 3:] = gen.normal(0, 1e-7, (Mw, n, 3))
+        m = 10 ** gen.uniform(-10, -3, (Mw, n)); m[:, 0] = 1.0
+        I = np.zeros((Mw, n, 7)); I[..., :3] = m[..., None]; I[..., 6] = m
         return p, v, I
 
-    grav = lambda: el.GravityEdges("softened", k_squared=2.9591220828e-4 / 86400.0 ** 2, softening=1e-10, edges=el.all_pairs_edges(N))
+    grav = lambda n=N: el.GravityEdges("softened", k_squared=2.9591220828e-4 / 86400.0 ** 2, softening=1e-10, edges=el.all_pairs_edges(n))
     FLOP_PAIR, SLOT_PAIR = 27.0, 18.0  # per pair evaluation: flops (FMA = 2) / FP64-pipe instruction slots
     # (a) worlds sharded: M = 8 worlds per GPU (weak scaling), no collective
     Mw = 8
@@ -721,6 +721,28 @@ def run_multi_gpu(args, torch, dist, el, stream, local, rank, world_size, barrie
     single["row_shards"] = run_row_shards(args, torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks,
                                           (p1, v1, I1), grav, ref_pos)
     out["nbody_1024_single_world"] = single
+    # the same comparison for a world large enough that the pair folds, not the per-tick latency, dominate
+    NL = 8192
+    pl, vl, Il = nbody_world(1, np.random.default_rng(11), NL)
+    ex = el.B200Exec(NL, 1, 3600.0, None, [grav(NL)], "rk4", "fast", device=local)
+    ex.set_stream(stream.cuda_stream)
+    ex.set_state(pl, vl, Il)
+    ms_big = timed(ex.step, 40, 5)
+    ref_big = ex.download(WORLD_POS)
+    ex.close()
+    big = {"config": "one 8192-body world on N GPUs (beyond BASELINE: where row shards start to pay)",
+           "replicas": {"us_per_tick": ms_big * 1e3 / 40, "value": NL * 40 / (ms_big * 1e-3), "unit": UNIT}}
+    if world_size > 1:
+        try:
+            from elodin_b200.sharding import RowShardedWorld
+
+            big["row_shards"] = RowShardedWorld.bench_large(torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks,
+                                                            (pl, vl, Il), grav, ref_big, 5, 40)
+        except Exception as e:  # the comparison is secondary: never lose the line over it
+            big["row_shards"] = {"error": repr(e)[:200]}
+    else:
+        big["row_shards"] = {"skipped": "needs more than one GPU"}
+    out["nbody_8192_single_world"] = big
 
     # ---- configs[4]: falcon9-style Monte-Carlo, 100 000 rollouts over the N GPUs (strong scaling: total work fixed)
     TOTAL = args.mc_rollouts

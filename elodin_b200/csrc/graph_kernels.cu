@@ -38,13 +38,14 @@ __global__ void __launch_bounds__(kBlockG * 3) graph_dense_kernel(const __grid_c
     __shared__ double sm[kBlockG];
 
     const uint32_t N = G.n_entities;
-    const uint32_t tiles = (N + kBlockG - 1) / kBlockG;
+    const uint32_t s0 = G.src_n ? G.src0 : 0u, sn = G.src_n ? G.src_n : N; // source rows this launch folds
+    const uint32_t tiles = (sn + kBlockG - 1) / kBlockG;
     const uint32_t world = blockIdx.x / tiles;
     const uint32_t tile = blockIdx.x % tiles;
     const uint32_t tx = threadIdx.x, sl = threadIdx.y; // sl = stage slot
-    const uint32_t i = tile * kBlockG + tx;
+    const uint32_t i = s0 + tile * kBlockG + tx;
     const uint64_t wbase = (uint64_t)world * N;
-    const bool active = i < N;
+    const bool active = i < s0 + sn;
     const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
 
     const double fac = sl == 0 ? 0.0 : (sl == 1 ? 0.5 : 1.0);
@@ -125,14 +126,15 @@ __global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) grap
     double *sm = dsm + NS * 3 * TJ;
 
     const uint32_t N = G.n_entities;
-    const uint32_t groups = (N + kFastSrc - 1) / kFastSrc;
+    const uint32_t s0 = G.src_n ? G.src0 : 0u, sn = G.src_n ? G.src_n : N; // source rows this launch folds
+    const uint32_t groups = (sn + kFastSrc - 1) / kFastSrc;
     const uint32_t world = blockIdx.x / groups;
     const uint32_t grp = blockIdx.x % groups;
     const uint32_t lane = threadIdx.x, src = threadIdx.y, sl0 = SPLIT ? threadIdx.z : 0;
     const uint32_t flat = (threadIdx.z * kFastSrc + src) * 32 + lane;
-    const uint32_t i = grp * kFastSrc + src;
+    const uint32_t i = s0 + grp * kFastSrc + src;
     const uint64_t wbase = (uint64_t)world * N;
-    const bool active = i < N;
+    const bool active = i < s0 + sn;
     const bool newton = G.kind == B200_EFF_GRAVITY_EDGES_NEWTON;
     const double soft = (newton || !(G.p1 > 0.0)) ? fa::kNewtonSelfSoft : G.p1;
     auto dtf_of = [&](uint32_t sl) { return sl == 0 ? 0.0 : (sl == 1 ? 0.5 * G.dt_stage : G.dt_stage); };
@@ -244,7 +246,8 @@ __global__ void __launch_bounds__(256, 2) graph_dense_world_kernel(const __grid_
             sm[j] = ldp(G.ine, G.ld, 6, b);
         }
         __syncthreads();
-        const uint32_t i0 = (uint32_t)((uint64_t)N * part / cpw), i1 = (uint32_t)((uint64_t)N * (part + 1) / cpw);
+        const uint32_t s0 = G.src_n ? G.src0 : 0u, sn = G.src_n ? G.src_n : N; // source rows this launch folds
+        const uint32_t i0 = s0 + (uint32_t)((uint64_t)sn * part / cpw), i1 = s0 + (uint32_t)((uint64_t)sn * (part + 1) / cpw);
         const uint32_t items = (i1 - i0) * NS;
         for (uint32_t it = warp; it < items; it += NWARP) {
             const uint32_t i = i0 + it / NS, sl = it - (it / NS) * NS;
@@ -528,7 +531,8 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
     const bool rk4 = G.integrator == B200_INTEGRATOR_RK4;
     if (G.n_entities == 0 || G.n_worlds == 0) return cudaSuccess;
     if (dense) {
-        const unsigned tiles = (G.n_entities + kBlockG - 1) / kBlockG;
+        const unsigned n_src = G.src_n ? G.src_n : G.n_entities; // sources folded by this launch
+        const unsigned tiles = (n_src + kBlockG - 1) / kBlockG;
         const unsigned grid = tiles * G.n_worlds;
         static const int gcfg = [] { const char *e = getenv("B200_GRAPH_CFG"); return e ? atoi(e) : 1; }();
         const dim3 blk3(kBlockG, 3), blk1(kBlockG, 1);
@@ -545,7 +549,7 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
                 if (G.n_worlds >= slots) grid_w = slots;
                 else {
                     // every CTA of a world takes at least ~2 rounds of (source, slot) items for its 8 warps
-                    const unsigned cpw = std::max(1u, std::min(slots / G.n_worlds, (G.n_entities * 3u + 15u) / 16u));
+                    const unsigned cpw = std::max(1u, std::min(slots / G.n_worlds, (n_src * 3u + 15u) / 16u));
                     grid_w = cpw * G.n_worlds;
                 }
                 if (rk4) {
@@ -559,7 +563,7 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
                 }
                 return cudaGetLastError();
             }
-            const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
+            const unsigned gridf = ((n_src + kFastSrc - 1) / kFastSrc) * G.n_worlds;
             // few CTAs: split the stage slots over warps to fill the machine; many CTAs: keep
             // 3 slots per warp (more ILP per lane, 3 CTAs/SM) — measured on N = 1024, M = 1 / 8
             const bool split = gcfg == 2 || (gcfg == 1 && gridf < 3u * 148u);

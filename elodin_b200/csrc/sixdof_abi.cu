@@ -145,6 +145,10 @@ int build_graph(b200_sixdof *h, const b200_effector &e)
     return B200_OK;
 }
 
+} // namespace
+
+namespace b200 {
+
 void fill_step_params(b200_sixdof *h, StepParams &P)
 {
     std::memset(&P, 0, sizeof P);
@@ -176,6 +180,10 @@ void fill_step_params(b200_sixdof *h, StepParams &P)
         P.eff[i].mask = i < h->eff_masks.size() ? h->eff_masks[i] : nullptr;
     }
 }
+
+} // namespace b200
+
+namespace {
 
 // Integrate n_ticks ticks of the worlds [w0, w0+nw) on `stream`.  Worlds are independent, so a
 // world range can run to completion before the next one starts (used by the pipelined

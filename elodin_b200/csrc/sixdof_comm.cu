@@ -247,6 +247,70 @@ int b200_sixdof_trajectory_allgather(b200_sixdof *h, b200_comm *c, const uint64_
     return B200_OK;
 }
 
+// One world, rows split over the ranks of `c` (second case).  Every rank holds the whole world (same
+// handle description, same initial state) but folds and integrates only its own source rows
+// [rank * N / R, (rank + 1) * N / R); after each tick the rows' new linear position and velocity planes — all the
+// other ranks' gravity needs — are exchanged with an in-place ncclAllGather per plane (one NCCL group per tick,
+// 6 planes x N/R doubles per rank over NVLink); the last tick of the call gathers every plane of WorldPos, WorldVel,
+// WorldAccel and Force so that each rank ends with the complete world.  Stage positions depend on the tick's input
+// state only (rk4.rs:85-111), so one exchange per tick suffices.
+int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks)
+{
+    if (!h || !c) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (h->status != B200_OK) return fail(h->status, "handle is in a failed state");
+    if (h->device != c->device) return fail(B200_ERR_INVALID_ARGUMENT, "handle is on device %d, communicator on %d", h->device, c->device);
+    if (h->graph_eff < 0 || !h->graph_dense || h->desc.n_worlds != 1)
+        return fail(B200_ERR_UNSUPPORTED, "row sharding applies to one world with dense (all-pairs) edge_fold gravity");
+    const uint64_t N = h->desc.n_entities, R = (uint64_t)c->n_ranks;
+    if (N % R != 0) return fail(B200_ERR_UNSUPPORTED, "row sharding needs n_entities (%llu) divisible by the rank count (%llu)", (unsigned long long)N, (unsigned long long)R);
+    CU(h, cudaSetDevice(h->device));
+    const uint64_t rows = N / R, i0 = rows * (uint64_t)c->rank;
+    const bool exact = h->desc.math_mode == B200_MATH_EXACT;
+    const b200_effector &e = h->effectors[h->graph_eff];
+    for (uint64_t t = 0; t < n_ticks; ++t) {
+        const bool last = t + 1 == n_ticks;
+        StepParams P;
+        fill_step_params(h, P);
+        GraphParams G{};
+        G.pos = P.pos; G.vel = P.vel; G.ine = P.ine; G.gforce = h->gforce;
+        G.ld = h->ld; G.n_entities = (uint32_t)N; G.n_worlds = 1;
+        G.dt_stage = P.dt_stage; G.kind = e.kind; G.integrator = h->desc.integrator;
+        G.p0 = e.p[0]; G.p1 = e.p[1]; G.row_ptr = h->row_ptr; G.col_idx = h->col_idx; G.max_deg = h->max_deg;
+        G.src0 = (uint32_t)i0; G.src_n = (uint32_t)rows;
+        CU(h, launch_graph_force(G, (int)h->desc.math_mode, true, h->stream));
+        // the body kernel on this rank's rows only: shift every per-body plane, keep the entity numbering
+        P.pos += i0; P.vel += i0; P.acc += i0; P.frc += i0; P.ine += i0;
+        if (P.gforce) P.gforce += i0;
+        if (P.traj) P.traj += i0;
+        for (uint32_t k = 0; k < P.n_eff; ++k) if (P.eff[k].col) P.eff[k].col += i0;
+        P.n_bodies = rows;
+        P.ent0 = (uint32_t)i0;
+        P.n_ticks = 1;
+        P.tick0 = h->ticks_done + t;
+        P.write_fa = (exact || last) ? 1u : 0u;
+        CU(h, launch_body_step(P, (int)h->desc.integrator, (int)h->desc.math_mode, h->stream));
+        h->timings.kernel_launches += 2;
+        // exchange: in-place all-gather of the row slices, plane by plane
+        double *pos = h->find(B200_ID_WORLD_POS)->dev, *vel = h->find(B200_ID_WORLD_VEL)->dev;
+        double *acc = h->find(B200_ID_WORLD_ACCEL)->dev, *frc = h->find(B200_ID_FORCE)->dev;
+        NC(nccl().GroupStart());
+        auto gather_plane = [&](double *plane) { return nccl().AllGather(plane + i0, plane, rows, ncclDouble, c->comm, h->stream); };
+        ncclResult_t r = ncclSuccess;
+        for (int k = 0; k < 7 && r == ncclSuccess; ++k) if (last || k >= 4) r = gather_plane(pos + (uint64_t)k * h->ld);
+        for (int k = 0; k < 6 && r == ncclSuccess; ++k) if (last || k >= 3) r = gather_plane(vel + (uint64_t)k * h->ld);
+        if (last) {
+            for (int k = 0; k < 6 && r == ncclSuccess; ++k) r = gather_plane(acc + (uint64_t)k * h->ld);
+            for (int k = 0; k < 6 && r == ncclSuccess; ++k) r = gather_plane(frc + (uint64_t)k * h->ld);
+        }
+        if (r != ncclSuccess) { nccl().GroupEnd(); return nccl_fail(r, "ncclAllGather(row slice)"); }
+        NC(nccl().GroupEnd());
+    }
+    h->ticks_done += n_ticks;
+    h->tick += n_ticks;
+    h->timings.ticks += n_ticks;
+    return B200_OK;
+}
+
 // Concurrent host<->device bandwidth of one GPU (pinned `host` of >= max(h2d, d2h) * 2 bytes): an H2D stream and a
 // D2H stream run `iters` copies each at the same time; out[0] = H2D GB/s, out[1] = D2H GB/s.  bench.py runs it on
 // every rank at once to report the PCIe / host-memory ceiling its e2e number sits under.

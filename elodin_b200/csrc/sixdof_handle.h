@@ -84,6 +84,7 @@ namespace b200 {
 
 int cuda_fail(b200_sixdof *h, cudaError_t e, const char *what);
 int ensure_staging(b200_sixdof *h, uint64_t bytes);
+void fill_step_params(b200_sixdof *h, StepParams &P); // every plane base, constant and effector of the handle
 
 #define CU(h, call)                                                        \
     do {                                                                   \

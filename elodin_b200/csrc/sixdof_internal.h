@@ -44,6 +44,8 @@ struct StepParams {
     uint32_t traj_every;  // 0 = off
     uint32_t traj_planes; // 13 (pos, vel) or 25 (+ accel, force)
     uint64_t tick0;     // global tick count before this launch
+    uint32_t ent0;      // entity row of body 0 of this launch (row-sharded single worlds start inside a world)
+    uint32_t pad0;
     // compile-time-specialised FAST kernels (sixdof_tick.cuh SIG_*): what body_kernels.cu:spec_signature
     // distilled from eff[] — uniform constants and the plane bases of the per-body input columns
     struct Spec {
@@ -72,6 +74,8 @@ struct GraphParams {
     const uint32_t *row_ptr; // CSR over sources (n_entities+1), spawn order kept inside a row
     const uint32_t *col_idx;
     uint32_t max_deg;        // largest out-degree (uniform trip count of small_world_kernel's shuffle loop)
+    uint32_t src0;           // dense kernels: fold only the source rows [src0, src0 + src_n) of every world (row-sharded
+    uint32_t src_n;          // single worlds); src_n = 0 means every source
     uint32_t pad;
 };
 

@@ -95,7 +95,7 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
     Motion F = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
     for (uint32_t e = 0; e < P.n_eff; ++e) {
         const EffDev &E = P.eff[e];
-        if (E.mask && !E.mask[b % P.n_entities]) continue; // entity does not own the effector's components (query join)
+        if (E.mask && !E.mask[(b + P.ent0) % P.n_entities]) continue; // entity does not own the effector's components (query join)
         switch (E.kind) {
         case B200_EFF_GRAVITY_CONST: { // ball/sim.py:56-58: f + SpatialForce(linear=g*m)
             F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
@@ -195,7 +195,7 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
         case B200_EFF_GRAVITY_EDGES_SOFTENED: { // Force := edge_fold(init 0) for bodies that own an edge
             if (GREG) {
                 if (greg.has) { F.ang = Vec3{0.0, 0.0, 0.0}; F.lin = grav_slot(greg, slot); }
-            } else if (P.gforce && P.has_edge && P.has_edge[b % P.n_entities]) {
+            } else if (P.gforce && P.has_edge && P.has_edge[(b + P.ent0) % P.n_entities]) {
                 F.ang = Vec3{0.0, 0.0, 0.0};
                 F.lin = Vec3{ldp(P.gforce, P.ld, slot * 3 + 0, b), ldp(P.gforce, P.ld, slot * 3 + 1, b),
                              ldp(P.gforce, P.ld, slot * 3 + 2, b)};
@@ -305,7 +305,7 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
     Vec3 tb = {0.0, 0.0, 0.0};
     for (uint32_t e = 0; e < P.n_eff; ++e) {
         const EffDev &E = P.eff[e];
-        if (E.mask && !E.mask[b % P.n_entities]) continue; // query join: not a member
+        if (E.mask && !E.mask[(b + P.ent0) % P.n_entities]) continue; // query join: not a member
         switch (E.kind) {
         case B200_EFF_GRAVITY_CONST:
             f.fw.x = fma(E.p[0], I.m, f.fw.x); f.fw.y = fma(E.p[1], I.m, f.fw.y); f.fw.z = fma(E.p[2], I.m, f.fw.z);
@@ -359,7 +359,7 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
             break;
         case B200_EFF_GRAVITY_EDGES_NEWTON:
         case B200_EFF_GRAVITY_EDGES_SOFTENED: // host guarantees this is effector 0 in FAST mode
-            f.graph = GREG ? greg.has : (P.gforce && P.has_edge && P.has_edge[b % P.n_entities]);
+            f.graph = GREG ? greg.has : (P.gforce && P.has_edge && P.has_edge[(b + P.ent0) % P.n_entities]);
             break;
         default: break;
         }
@@ -381,7 +381,7 @@ __device__ __forceinline__ Folded fold_spec(const StepParams &P, uint64_t b, con
     f.wtorque = f.j2 = false;
     f.drag = (SIG & SIG_DRAG) != 0;
     f.frame = (SIG & SIG_FRAME) != 0;
-    f.graph = (SIG & SIG_GRAPH) ? (P.has_edge[b % P.n_entities] != 0) : false;
+    f.graph = (SIG & SIG_GRAPH) ? (P.has_edge[(b + P.ent0) % P.n_entities] != 0) : false;
     if (SIG & SIG_THRUST) f.fb = Vec3{P.spec.axis[0] * in.thrust, P.spec.axis[1] * in.thrust, P.spec.axis[2] * in.thrust};
     if (SIG & SIG_WRENCH) {
         f.fb = Vec3{f.fb.x + in.wr_f.x, f.fb.y + in.wr_f.y, f.fb.z + in.wr_f.z};

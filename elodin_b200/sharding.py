@@ -110,6 +110,14 @@ class Comm:
         _lib.check(self._L.b200_sixdof_trajectory_allgather(exec_._h, self._h, wpr, C.c_void_p(out_ptr), nbytes))
         return out
 
+    def step_row_sharded(self, exec_, n_ticks: int) -> None:
+        """ONE world, source rows split over the ranks (b200_sixdof_step_row_sharded): every rank holds the whole
+        world and integrates rows [rank * N / R, (rank + 1) * N / R); the rows' new position / velocity planes are
+        all-gathered over NCCL after every tick."""
+        from . import _lib
+
+        _lib.check(self._L.b200_sixdof_step_row_sharded(exec_._h, self._h, int(n_ticks)))
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._L.b200_comm_destroy(self._h)
@@ -120,3 +128,80 @@ class Comm:
             self.close()
         except Exception:
             pass
+
+
+class RowShardedWorld:
+    """bench.py helper for SURVEY §8e's second case ("report both"): one n-body world on N GPUs as replicas vs row
+    shards.  Not a product class: the product entry is Comm.step_row_sharded / b200_sixdof_step_row_sharded."""
+
+    @staticmethod
+    def bench(args, torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, world, grav, ref_pos):
+        from .executor import WORLD_POS
+
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(Comm.unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        comm = Comm(bytes(uid.cpu().tolist()), world_size, rank, local)
+        out = {}
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+
+        def run(p, v, I, N, warm, ticks, math="fast"):
+            ex = el.B200Exec(N, 1, 3600.0, None, [grav(N)], "rk4", math, device=local)
+            ex.set_stream(stream.cuda_stream)
+            ex.set_state(p, v, I)
+            with torch.cuda.stream(stream):
+                comm.step_row_sharded(ex, warm)
+                barrier()
+                a, b = ev(), ev()
+                a.record(stream)
+                comm.step_row_sharded(ex, ticks)
+                b.record(stream)
+                barrier()
+            ms = max_over_ranks(a.elapsed_time(b))
+            pos = ex.download(WORLD_POS)
+            ex.close()
+            return ms, pos
+
+        p1, v1, I1 = world
+        N = p1.shape[1]
+        ms, pos = run(p1, v1, I1, N, 20, 400)
+        scale = float(np.max(np.abs(ref_pos[..., 4:])))
+        out = {"us_per_tick": ms * 1e3 / 400, "value": N * 400 / (ms * 1e-3), "unit": "entity-steps/s", "ranks": world_size,
+               "rows_per_gpu": N // world_size,
+               "exchange": "6 planes x N/R f64 per rank, in-place ncclAllGather per plane, one NCCL group per tick (inside libb200_sixdof.so)",
+               "max_rel_diff_vs_replica_after_420_ticks": float(np.max(np.abs(pos[..., 4:] - ref_pos[..., 4:])) / scale)}
+        comm.close()
+        return out
+
+    @staticmethod
+    def bench_large(torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, world, grav, ref_pos, warm, ticks):
+        from .executor import WORLD_POS
+
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(Comm.unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        comm = Comm(bytes(uid.cpu().tolist()), world_size, rank, local)
+        p, v, I = world
+        N = p.shape[1]
+        ex = el.B200Exec(N, 1, 3600.0, None, [grav(N)], "rk4", "fast", device=local)
+        ex.set_stream(stream.cuda_stream)
+        ex.set_state(p, v, I)
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            comm.step_row_sharded(ex, warm)
+            barrier()
+            a, b = ev(), ev()
+            a.record(stream)
+            comm.step_row_sharded(ex, ticks)
+            b.record(stream)
+            barrier()
+        ms = max_over_ranks(a.elapsed_time(b))
+        pos = ex.download(WORLD_POS)
+        ex.close()
+        comm.close()
+        scale = float(np.max(np.abs(ref_pos[..., 4:])))
+        return {"us_per_tick": ms * 1e3 / ticks, "value": N * ticks / (ms * 1e-3), "unit": "entity-steps/s", "ranks": world_size,
+                "rows_per_gpu": N // world_size,
+                "max_rel_diff_vs_replica": float(np.max(np.abs(pos[..., 4:] - ref_pos[..., 4:])) / scale)}

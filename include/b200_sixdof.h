@@ -301,6 +301,15 @@ uint64_t b200_sixdof_trajectory_gather_bytes(const b200_sixdof *h, const uint64_
 int b200_sixdof_trajectory_allgather(b200_sixdof *h, b200_comm *c, const uint64_t *worlds_per_rank, void *dst,
                                      uint64_t dst_bytes);
 
+/* ONE world, source rows split over the ranks (SURVEY §8e second case; needs dense edge_fold gravity, n_worlds = 1,
+ * n_entities divisible by the rank count).  Every rank creates the same handle and uploads the same initial state,
+ * then calls this instead of b200_sixdof_step: per tick it folds and integrates its own rows and all-gathers the
+ * rows' new position / velocity planes over NCCL; after the call every rank holds the complete world.
+ * At N = 1024 replicas (every GPU integrates the whole world, no exchange) are faster — the tick is a ~15 us
+ * latency chain and the exchange adds to it; row shards pay off for worlds of several thousand bodies
+ * (measured by bench.py `multi_gpu.nbody_1024_single_world`). */
+int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks);
+
 /* Concurrent host<->device copy bandwidth of one GPU through pinned `host` (>= h2d_bytes + d2h_bytes): out[0] = H2D
  * GB/s, out[1] = D2H GB/s, both directions running at once — the ceiling an invoke_batch round trip sits under. */
 int b200_probe_pcie_gbs(int device, void *host, uint64_t h2d_bytes, uint64_t d2h_bytes, int iters, double *out);

@@ -1294,3 +1294,83 @@ def test_cube_sat_ore_sat_golden_on_gpu(golden):
         if math == "exact":
             assert np.array_equal(f[:, 0], frc[1:])
             assert int(np.sum(np.all(p[:, 0] == pos[1:], axis=-1))) >= 90
+
+
+# --------------------------------------------------------------------------- round 2: the library's own NCCL paths (needs 2 GPUs)
+def _two_rank_worker(rank, uid, q):
+    import numpy as np
+
+    import elodin_b200 as el
+    from elodin_b200.executor import FORCE, WORLD_ACCEL, WORLD_POS, WORLD_VEL
+    from elodin_b200.sharding import Comm, shard_sizes, shard_worlds
+    from oracle import oracle as O
+    from tests.util import random_world
+
+    try:
+        comm = Comm(uid, 2, rank, rank)
+        # (1) world-sharded trajectory all-gather, ragged shards (3 + 2 worlds), host destination
+        total = 5
+        pos, vel, ine = random_world(5, total, 2)
+        w0, w1 = shard_worlds(total, rank, 2)
+        with el.B200Exec(2, w1 - w0, 0.01, None, [], "rk4", "exact", device=rank, trajectory_every=2, trajectory_capacity=3) as ex:
+            ex.set_state(pos[w0:w1], vel[w0:w1], ine[w0:w1])
+            ex.step(6, sync=True)
+            full = comm.trajectory_allgather(ex, shard_sizes(total, 2))
+        want = O.World(pos.copy(), vel.copy(), ine)
+        rows = []
+        for _ in range(3):
+            want.rk4(0.01, 2)
+            rows.append(np.concatenate([want.pos, want.vel], -1))
+        ok_gather = bool(np.array_equal(full, np.stack(rows, 1)))  # [world][sample][entity][13], global world order
+        # (2) one world, rows split over the two GPUs: EXACT folds are sequential per source, so the result is
+        # bit-identical to the oracle's whole-world run
+        N = 96
+        p, v, I = random_world(9, 1, N)
+        p[..., 4:] *= 1e-2
+        edges = el.all_pairs_edges(N)
+        o = O.World(p.copy(), v.copy(), I).rk4(0.01, 5, [O.Effector(O.EFF_GRAVITY_EDGES_SOFTENED, p=(0.3, 1e-4), edges=edges)])
+        res = {}
+        for math in ("exact", "fast"):
+            with el.B200Exec(N, 1, 0.01, None, [el.GravityEdges("softened", k_squared=0.3, softening=1e-4, edges=edges)], "rk4", math,
+                             device=rank) as ex:
+                ex.set_state(p, v, I)
+                comm.step_row_sharded(ex, 5)
+                ex.sync()
+                got = [ex.download(c) for c in (WORLD_POS, WORLD_VEL, WORLD_ACCEL, FORCE)]
+                tick = ex.tick
+            wants = (o.pos, o.vel, o.accel, o.force)
+            if math == "exact":
+                res[math] = all(np.array_equal(a, b) for a, b in zip(got, wants)) and tick == 5
+            else:
+                res[math] = max(float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)) for a, b in zip(got, wants))
+        comm.close()
+        q.put((rank, ok_gather, res["exact"], res["fast"], None))
+    except Exception as e:  # surface the failure in the parent
+        import traceback
+
+        q.put((rank, False, False, 1.0, traceback.format_exc()))
+
+
+def test_library_nccl_gather_and_row_sharded_world_on_two_gpus():
+    """b200_sixdof_trajectory_allgather (ragged world shards, global order) and b200_sixdof_step_row_sharded
+    (one world, source rows over two GPUs: EXACT bit-identical to the oracle) — two processes, one GPU each."""
+    if el.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from elodin_b200.sharding import Comm
+
+    uid = Comm.unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, uid, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok_gather, ok_exact, fast_err, err in got:
+        assert err is None, err
+        assert ok_gather, f"rank {rank}: gathered trajectory differs from the oracle"
+        assert ok_exact, f"rank {rank}: row-sharded EXACT differs from the oracle"
+        assert fast_err <= 5 * FAST_TOL_TICK * 10, fast_err
