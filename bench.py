@@ -499,8 +499,11 @@ def run_b200(args):
                 q1.record(stream)
                 torch.cuda.synchronize()
                 t_ms = q0.elapsed_time(q1) / 100
-                eff_out[name] = {"value": M / (t_ms * 1e-3), "unit": UNIT, "bytes_per_entity_step": bytes_per,
-                                 "achieved_GBps": bytes_per * M / (t_ms * 1e-3) / 1e9, "frac": bytes_per * M / (t_ms * 1e-3) / 1e9 / peak}
+                tr = ncu_traffic("body_fast_rk4_%s_bytes_per_launch_M%d" % (name, M))
+                eff_out[name] = {"value": M / (t_ms * 1e-3), "unit": UNIT, "bytes_per_entity_step": bytes_per, "us_per_tick": t_ms * 1e3,
+                                 "achieved_GBps": bytes_per * M / (t_ms * 1e-3) / 1e9, "frac": bytes_per * M / (t_ms * 1e-3) / 1e9 / peak,
+                                 "traffic": tr, "dram_frac": (tr / (t_ms * 1e-3) / 1e9 / peak) if tr else None,
+                                 "kernel": "body_fast_spec_kernel<RK4, sig %s, 128 x 3, 2 bodies/thread>" % ("THRUST|DRAG" if name == "rocket" else "FRAME|WRENCH")}
                 sx.close()
                 del p2, cols
             extras["effector_sets"] = eff_out

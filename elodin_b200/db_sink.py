@@ -381,42 +381,73 @@ def sample_timestamps(start_us: int, sim_time_step: float, sample_ticks) -> np.n
     return out
 
 
+class LiveDbWriter:
+    """The telemetry sink while a run is in flight: `init_db` once (every (entity, component) pair registered, row 0 =
+    the initial state), then `flush()` appends the history rows recorded since the last flush — one
+    `commit_world_head_unified` (impeller2_server.rs:390-438) per telemetry cycle.  `Exec.attach_db` calls flush after
+    every recorded cycle on the invoke_batch route and after every ring read-back (<= ring capacity cycles, still one
+    AppendLog row per cycle with that cycle's timestamp) on the device-resident route."""
+
+    def __init__(self, exec_, path: str, start_timestamp_us: int = 1_767_225_600_000_000, world: int = 0):
+        from .export import _entity_key
+
+        self.exec_, self.world, self.start = exec_, int(world), int(start_timestamp_us)
+        self.sink = DbSink(path, start_timestamp_us)
+        self.rows_written = 0
+        w = exec_.world
+        self._globals = []
+        for comp, md, prim in (("tick", {"priority": 7}, "u64"), ("simulation_time_step", {"priority": 8}, "f64")):
+            self._globals.append((self.sink.insert_component("globals", comp, Schema(prim, ()), md), prim))
+        self._pairs = []  # (pair id, column id, row, dtype)
+        names = set()
+        for cid, col in w.columns.items():
+            comp = col.component
+            prim = "u64" if np.dtype(col.dtype) == np.uint64 else "f64"
+            if comp.ty is not None and comp.ty.width == col.width:
+                shape = tuple(comp.ty.shape)                           # the declared ComponentType
+            else:
+                shape = () if col.width == 1 else (col.width,)
+            for row, ent in enumerate(col.entity_ids):
+                ename = w.entity_names.get(ent)
+                if ename is None:
+                    continue
+                key = _entity_key(ename)
+                names.add(key)
+                pid = self.sink.insert_component(key, comp.name, Schema(prim, shape), comp.metadata)
+                self._pairs.append((pid, cid, row, Schema(prim).dtype))
+        self.sink.set_entity_metadata("globals")
+        for key in sorted(names):
+            self.sink.set_entity_metadata(key)
+        self.flush()
+
+    def flush(self) -> int:
+        """Append every history row recorded since the last flush; returns how many."""
+        ex = self.exec_
+        g = ex._globals_hist
+        i0, i1 = self.rows_written, len(g)
+        if i1 <= i0:
+            return 0
+        # a row's timestamp depends on its own tick only (exec.rs:134-152), so a later flush stamps exactly what a
+        # whole-run write would have
+        ts = sample_timestamps(self.start, ex.sim_time_step, [x[0] for x in g[:i1]])[i0:]
+        for (pid, prim), k in zip(self._globals, (0, 1)):
+            self.sink.commit_many(pid, ts, np.asarray([x[k] for x in g[i0:i1]], dtype=Schema(prim).dtype))
+        for pid, cid, row, dtype in self._pairs:
+            rows = np.stack([h[self.world, row] for h in ex._history[cid][i0:i1]]).astype(dtype, copy=False)
+            self.sink.commit_many(pid, ts, rows)
+        self.rows_written = i1
+        return i1 - i0
+
+    def close(self) -> DbSink:
+        self.flush()
+        self.sink.close()
+        return self.sink
+
+
 def write_db(exec_, path: str, start_timestamp_us: int = 1_767_225_600_000_000, world: int = 0) -> DbSink:
     """Write the recorded history of `exec_` (elodin_b200.world.Exec) for world `world` as an elodin-db
     directory: what `init_db` + one `commit_world_head_unified` per telemetry cycle leave on disk."""
-    from .export import _entity_key
-
-    w = exec_.world
-    n = len(exec_._globals_hist)
-    ts = sample_timestamps(start_timestamp_us, exec_.sim_time_step, [g[0] for g in exec_._globals_hist])
-    sink = DbSink(path, start_timestamp_us)
-    g = exec_._globals_hist
-    for comp, md, vals, prim in (("tick", {"priority": 7}, [x[0] for x in g], "u64"),
-                                 ("simulation_time_step", {"priority": 8}, [x[1] for x in g], "f64")):
-        pid = sink.insert_component("globals", comp, Schema(prim, ()), md)
-        sink.commit_many(pid, ts, np.asarray(vals, dtype=Schema(prim).dtype))
-    names = set()
-    for cid, col in w.columns.items():
-        comp = col.component
-        prim = "u64" if np.dtype(col.dtype) == np.uint64 else "f64"
-        if comp.ty is not None and comp.ty.width == col.width:
-            shape = tuple(comp.ty.shape)                           # the declared ComponentType
-        else:
-            shape = () if col.width == 1 else (col.width,)
-        for row, ent in enumerate(col.entity_ids):
-            ename = w.entity_names.get(ent)
-            if ename is None:
-                continue
-            key = _entity_key(ename)
-            names.add(key)
-            pid = sink.insert_component(key, comp.name, Schema(prim, shape), comp.metadata)
-            rows = np.stack([h[world, row] for h in exec_._history[cid]]).astype(Schema(prim).dtype, copy=False)
-            sink.commit_many(pid, ts, rows)
-    sink.set_entity_metadata("globals")
-    for key in sorted(names):
-        sink.set_entity_metadata(key)
-    sink.close()
-    return sink
+    return LiveDbWriter(exec_, path, start_timestamp_us, world).close()
 
 
 # ---------------------------------------------------------------------------------------------------

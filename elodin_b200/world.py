@@ -480,14 +480,16 @@ class World:
             raise ValueError("elodin_b200.World.run is headless: pass max_ticks")
         ex = self.build(system, simulation_rate, generate_real_time, telemetry_rate, default_playback_speed,
                         max_ticks, optimize, db_path, backend, math, n_worlds)
-        ex.run(max_ticks, show_progress=False, is_canceled=is_canceled, pre_step=pre_step, post_step=post_step)
         if db_path:
             # the reference's `World.run(db_path=...)` leaves an elodin-db directory behind (impeller2_server.rs:
-            # 229-309, 390-438); here it is written from the recorded telemetry once the run is over
+            # 229-309, 390-438): init_db now, one commit per telemetry cycle while the run is in flight
             ts = None
             if start_timestamp is not None:
                 ts = int(start_timestamp.timestamp() * 1e6) if hasattr(start_timestamp, "timestamp") else int(start_timestamp)
-            ex.write_db(db_path, ts)
+            ex.attach_db(db_path, ts)
+        ex.run(max_ticks, show_progress=False, is_canceled=is_canceled, pre_step=pre_step, post_step=post_step)
+        if db_path:
+            ex.close_db()
         return ex
 
 
@@ -585,6 +587,7 @@ class Exec:
         self.build_ms = 0.0
         self._prof = {"execute_buffers": [], "add_to_history": [], "h2d_upload": [], "kernel_invoke": [], "d2h_download": []}
         self.dirty: set = set()
+        self._db = None
         self._history: Dict[int, List[np.ndarray]] = {cid: [] for cid in self.world.columns}
         self._globals_hist: List[tuple] = []
         self._record()
@@ -594,6 +597,8 @@ class Exec:
         for cid, col in self.world.columns.items():
             self._history[cid].append(col.buffer.copy())
         self._globals_hist.append((self.tick, self.sim_time_step))
+        if getattr(self, "_db", None) is not None:
+            self._db.flush()  # commit_world_head_unified: one row per (entity, component) per telemetry cycle
 
     def _bind_buffers(self) -> None:
         """Pointer tables for invoke_batch, built once: inputs are the world's own column buffers
@@ -683,6 +688,8 @@ class Exec:
             self.tick += c * tpt
             for cid, lo, hi in body_cols:
                 np.copyto(self.world.columns[cid].buffer, traj[-1, :, :, lo:hi])
+            if getattr(self, "_db", None) is not None:
+                self._db.flush()  # the c cycles of this ring read-back, each with its own timestamp
             hist_ms = (time.perf_counter() - t_hist) * 1e3
             self._prof["execute_buffers"] += [run_ms / c] * c
             self._prof["add_to_history"] += [hist_ms / c] * c
@@ -750,6 +757,23 @@ class Exec:
             row = col.row_of(self.world.entity_by_name(ent))
             out[pair] = np.stack([h[0, row] for h in self._history[cid]]).view(_Series)
         return out
+
+    def attach_db(self, path: str, start_timestamp_us: Optional[int] = None, world: int = 0):
+        """Stream the telemetry of world `world` into an elodin-db directory while the run is in flight: `init_db` now
+        (every pair registered, the rows recorded so far committed), then one commit per telemetry cycle
+        (`commit_world_head_unified`, impeller2_server.rs:390-438) — per ring read-back on the device-resident route.
+        `close_db()` finishes the directory."""
+        from . import db_sink
+
+        if getattr(self, "_db", None) is not None:
+            raise _lib.B200Error(_lib.ERR_INVALID_ARGUMENT, "a database is already attached")
+        self._db = (db_sink.LiveDbWriter(self, path, world=world) if start_timestamp_us is None
+                    else db_sink.LiveDbWriter(self, path, start_timestamp_us, world))
+        return self._db
+
+    def close_db(self):
+        db, self._db = getattr(self, "_db", None), None
+        return db.close() if db is not None else None
 
     def write_db(self, path: str, start_timestamp_us: Optional[int] = None, world: int = 0):
         """Write the recorded telemetry as an elodin-db directory (`elodin_b200.db_sink`): what the
