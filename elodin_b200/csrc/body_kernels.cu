@@ -17,7 +17,7 @@ namespace b200 {
 
 // ================================================================== EXACT body kernel
 
-template <int INTEG, int BLOCK, int MINB>
+template <int INTEG, int BLOCK, int MINB, bool UNR = false, bool NOEFF = false>
 __global__ void __launch_bounds__(BLOCK, MINB) body_exact_kernel(const __grid_constant__ StepParams P)
 {
     const uint64_t b = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_exact_kernel(const __grid_co
     const GravReg no_greg{};
 
     for (uint32_t t = 0; t < P.n_ticks; ++t) {
-        exact_tick<INTEG, false>(P, b, x0, v0, a_out, f_out, I, no_greg);
+        exact_tick<INTEG, false, UNR, NOEFF>(P, b, x0, v0, a_out, f_out, I, no_greg);
         uint64_t slot;
         if (traj_due(P, P.tick0 + t + 1, slot)) {
             traj_store_state(P, b, slot, x0, v0);
@@ -474,14 +474,24 @@ cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode,
         static const int xcfg = env_int("B200_EXACT_CFG", 3);
 #endif
         auto g = [&](int blk) { return (unsigned)((P.n_bodies + blk - 1) / blk); };
-        if (!rk4) body_exact_kernel<B200_INTEGRATOR_SEMI_IMPLICIT, 256, 1><<<g(256), 256, 0, s>>>(P);
-        else switch (xcfg) {
+        if (!rk4) {
+            if (P.n_eff == 0) body_exact_kernel<B200_INTEGRATOR_SEMI_IMPLICIT, 256, 1, false, true><<<g(256), 256, 0, s>>>(P);
+            else body_exact_kernel<B200_INTEGRATOR_SEMI_IMPLICIT, 256, 1><<<g(256), 256, 0, s>>>(P);
+        } else if (P.n_eff == 0 && xcfg == 3) {
+            body_exact_kernel<B200_INTEGRATOR_RK4, 128, 4, false, true><<<g(128), 128, 0, s>>>(P); // free bodies: no interpreter
+        } else switch (xcfg) {
         case 1: body_exact_kernel<B200_INTEGRATOR_RK4, 256, 2><<<g(256), 256, 0, s>>>(P); break;
         case 0: body_exact_kernel<B200_INTEGRATOR_RK4, 256, 1><<<g(256), 256, 0, s>>>(P); break;
 #ifdef B200_TUNE
         case 4: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 5><<<g(128), 128, 0, s>>>(P); break;
         case 5: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 6><<<g(128), 128, 0, s>>>(P); break;
         case 6: body_exact_kernel<B200_INTEGRATOR_RK4, 64, 12><<<g(64), 64, 0, s>>>(P); break;
+        case 7: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 3, true><<<g(128), 128, 0, s>>>(P); break;
+        case 8: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 2, true><<<g(128), 128, 0, s>>>(P); break;
+        case 9: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 4, true><<<g(128), 128, 0, s>>>(P); break;
+        case 10: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 3, true, true><<<g(128), 128, 0, s>>>(P); break;
+        case 11: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 5, false, true><<<g(128), 128, 0, s>>>(P); break;
+        case 12: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 4, false, false><<<g(128), 128, 0, s>>>(P); break; // interpreter kept
 #endif
         default: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 4><<<g(128), 128, 0, s>>>(P); break; // 4.3e9 vs 2.7e9 (256x1)
         }

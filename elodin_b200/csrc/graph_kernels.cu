@@ -248,32 +248,52 @@ __global__ void __launch_bounds__(256, 2) graph_dense_world_kernel(const __grid_
         __syncthreads();
         const uint32_t s0 = G.src_n ? G.src0 : 0u, sn = G.src_n ? G.src_n : N; // source rows this launch folds
         const uint32_t i0 = s0 + (uint32_t)((uint64_t)sn * part / cpw), i1 = s0 + (uint32_t)((uint64_t)sn * (part + 1) / cpw);
-        const uint32_t items = (i1 - i0) * NS;
+        // work item = (pair of sources, stage slot): the two sources share every target they load from shared memory,
+        // which halves the LDS traffic per pair evaluation — at one source per item the 128 B/clk shared-memory pipe
+        // (4 LDS.64 per 18 FP64 slots, four schedulers) ran at ~90 % and co-limited the fold
+        const uint32_t n_pair = (i1 - i0 + 1u) / 2u;
+        const uint32_t items = n_pair * NS;
         for (uint32_t it = warp; it < items; it += NWARP) {
-            const uint32_t i = i0 + it / NS, sl = it - (it / NS) * NS;
-            const Vec3 xi = {sx[sl][0][i], sx[sl][1][i], sx[sl][2][i]};
-            Vec3 a0 = {0, 0, 0}, a1 = {0, 0, 0};
+            const uint32_t pr = it / NS, sl = it - pr * NS;
+            const uint32_t ia = i0 + 2u * pr, ib = min(ia + 1u, i1 - 1u); // odd tail: the last source twice, written once
+            const Vec3 xa = {sx[sl][0][ia], sx[sl][1][ia], sx[sl][2][ia]};
+            const Vec3 xb = {sx[sl][0][ib], sx[sl][1][ib], sx[sl][2][ib]};
+            Vec3 a0 = {0, 0, 0}, a1 = {0, 0, 0}, b0 = {0, 0, 0}, b1 = {0, 0, 0};
             uint32_t jj = lane;
-            for (; jj + 96 < N; jj += 128) { // 4 targets per lane and trip: independent chains for the FP64 pipe
-                fa::pair_fold(xi, sx[sl][0][jj], sx[sl][1][jj], sx[sl][2][jj], sm[jj], soft, a0);
-                fa::pair_fold(xi, sx[sl][0][jj + 32], sx[sl][1][jj + 32], sx[sl][2][jj + 32], sm[jj + 32], soft, a1);
-                fa::pair_fold(xi, sx[sl][0][jj + 64], sx[sl][1][jj + 64], sx[sl][2][jj + 64], sm[jj + 64], soft, a0);
-                fa::pair_fold(xi, sx[sl][0][jj + 96], sx[sl][1][jj + 96], sx[sl][2][jj + 96], sm[jj + 96], soft, a1);
+            for (; jj + 32 < N; jj += 64) { // 2 targets x 2 sources per lane and trip: four independent chains
+                const double x0 = sx[sl][0][jj], y0 = sx[sl][1][jj], z0 = sx[sl][2][jj], m0 = sm[jj];
+                const double x1 = sx[sl][0][jj + 32], y1 = sx[sl][1][jj + 32], z1 = sx[sl][2][jj + 32], m1 = sm[jj + 32];
+                fa::pair_fold(xa, x0, y0, z0, m0, soft, a0);
+                fa::pair_fold(xb, x0, y0, z0, m0, soft, b0);
+                fa::pair_fold(xa, x1, y1, z1, m1, soft, a1);
+                fa::pair_fold(xb, x1, y1, z1, m1, soft, b1);
             }
-            for (; jj < N; jj += 32) fa::pair_fold(xi, sx[sl][0][jj], sx[sl][1][jj], sx[sl][2][jj], sm[jj], soft, a0);
-            Vec3 acc = {a0.x + a1.x, a0.y + a1.y, a0.z + a1.z};
+            for (; jj < N; jj += 32) {
+                const double x0 = sx[sl][0][jj], y0 = sx[sl][1][jj], z0 = sx[sl][2][jj], m0 = sm[jj];
+                fa::pair_fold(xa, x0, y0, z0, m0, soft, a0);
+                fa::pair_fold(xb, x0, y0, z0, m0, soft, b0);
+            }
+            Vec3 accA = {a0.x + a1.x, a0.y + a1.y, a0.z + a1.z}, accB = {b0.x + b1.x, b0.y + b1.y, b0.z + b1.z};
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+                accA.x += __shfl_xor_sync(0xffffffffu, accA.x, off);
+                accA.y += __shfl_xor_sync(0xffffffffu, accA.y, off);
+                accA.z += __shfl_xor_sync(0xffffffffu, accA.z, off);
+                accB.x += __shfl_xor_sync(0xffffffffu, accB.x, off);
+                accB.y += __shfl_xor_sync(0xffffffffu, accB.y, off);
+                accB.z += __shfl_xor_sync(0xffffffffu, accB.z, off);
             }
             if (lane == 0) {
-                const uint64_t b = wbase + i;
-                const double k = G.p0 * sm[i];
-                stp(G.gforce, G.ld, sl * 3 + 0, b, k * acc.x);
-                stp(G.gforce, G.ld, sl * 3 + 1, b, k * acc.y);
-                stp(G.gforce, G.ld, sl * 3 + 2, b, k * acc.z);
+                const double ka = G.p0 * sm[ia];
+                stp(G.gforce, G.ld, sl * 3 + 0, wbase + ia, ka * accA.x);
+                stp(G.gforce, G.ld, sl * 3 + 1, wbase + ia, ka * accA.y);
+                stp(G.gforce, G.ld, sl * 3 + 2, wbase + ia, ka * accA.z);
+                if (ib != ia) {
+                    const double kb = G.p0 * sm[ib];
+                    stp(G.gforce, G.ld, sl * 3 + 0, wbase + ib, kb * accB.x);
+                    stp(G.gforce, G.ld, sl * 3 + 1, wbase + ib, kb * accB.y);
+                    stp(G.gforce, G.ld, sl * 3 + 2, wbase + ib, kb * accB.z);
+                }
             }
         }
     }
@@ -549,7 +569,8 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
                 if (G.n_worlds >= slots) grid_w = slots;
                 else {
                     // every CTA of a world takes at least ~2 rounds of (source, slot) items for its 8 warps
-                    const unsigned cpw = std::max(1u, std::min(slots / G.n_worlds, (n_src * 3u + 15u) / 16u));
+                    // (source pair, slot) items: at least ~2 rounds for a CTA's 8 warps
+                    const unsigned cpw = std::max(1u, std::min(slots / G.n_worlds, ((n_src + 1u) / 2u * 3u + 15u) / 16u));
                     grid_w = cpw * G.n_worlds;
                 }
                 if (rk4) {

@@ -209,7 +209,10 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
 }
 
 // one tick of one body in EXACT arithmetic (state in registers)
-template <int INTEG, bool GREG>
+// UNR: unroll the three independent stage poses (more instruction-level parallelism across the dependent IEEE
+// divisions, more registers) or keep them a loop
+// NOEFF: the effector list is empty (clear_forces only): the interpreter and its registers are compiled out
+template <int INTEG, bool GREG, bool UNR = false, bool NOEFF = false>
 __device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose &x0, Motion &v0, Motion &a_out,
                                            Motion &f_out, const Inertia &I, const GravReg &greg)
 {
@@ -220,7 +223,7 @@ __device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose
         Motion kv, ka;
         // three distinct stage poses (f = 0, .5, 1), functions of (x0, v0) only; stages 2 and 3 share
         // the f = .5 pose and its inverses — identical inputs, identical bits — so each is built once
-#pragma unroll 1
+#pragma unroll(UNR ? 3 : 1)
         for (int k = 0; k < 3; ++k) {
             const double dtf = mul(P.dt_stage, k == 0 ? 0.0 : (k == 1 ? 0.5 : 1.0));
             const Pose sx = tadd(x0, scale(dtf, v0));
@@ -230,7 +233,8 @@ __device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose
             for (int j = 0; j < n_stages; ++j) {
                 const int s = (k == 0) ? 0 : (k == 1 ? 1 + j : 3);
                 const Motion sv = madd(v0, scale(dtf, sa));
-                f_out = effectors_exact<GREG>(P, b, k, sx, pi, sv, I, greg);
+                if (NOEFF) f_out = Motion{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+                else f_out = effectors_exact<GREG>(P, b, k, sx, pi, sv, I, greg);
                 sa = calc_accel_with(sx, pi, f_out, I);
                 if (s == 0) { kv = sv; ka = sa; }
                 else if (s == 3) { kv = madd(kv, sv); ka = madd(ka, sa); }
@@ -244,7 +248,8 @@ __device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose
     } else {
         // semi_implicit.rs:42-62
         const PoseInv pi = pose_inverses(x0.q);
-        f_out = effectors_exact<GREG>(P, b, 0, x0, pi, v0, I, greg);
+        if (NOEFF) f_out = Motion{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+        else f_out = effectors_exact<GREG>(P, b, 0, x0, pi, v0, I, greg);
         a_out = calc_accel_with(x0, pi, f_out, I);
         v0 = madd(v0, scale(P.dt_final, a_out));
         x0 = tadd(x0, scale(P.dt_final, v0));
