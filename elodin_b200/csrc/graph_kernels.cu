@@ -205,14 +205,15 @@ __global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) grap
 // FAST all-pairs for worlds of N <= TJ bodies, persistent: a CTA keeps ONE world's three stage-position tiles and
 // masses in shared memory (80 KB at TJ = 1024) and folds many sources against them — the round-1 kernel re-staged
 // the world for every 8 sources and its grid (one CTA per 8 sources) quantised badly against the 148 SMs (M = 8:
-// 1024 CTAs on 444 slots = 2.3 waves).  Work items are (source, stage slot) pairs, one warp each, lanes striding the
-// targets; with fewer worlds than CTAs a world's sources are split over grid/M CTAs, otherwise a CTA walks whole
-// worlds.  No self test (pair_fold), one third-order rsqrt step: 18 FP64-pipe slots per pair evaluation.
-template <bool RK4, int TJ>
-__global__ void __launch_bounds__(256, 2) graph_dense_world_kernel(const __grid_constant__ GraphParams G)
+// 1024 CTAs on 444 slots = 2.3 waves).  A work item is (SRC sources, one stage slot), one warp each, lanes striding
+// the targets TGT at a time (SRC x TGT independent chains for the FP64 pipe); with fewer worlds than CTAs a world's
+// sources are split over grid/M CTAs, otherwise a CTA walks whole worlds.  No self test (pair_fold), one third-order
+// rsqrt step: 18 FP64-pipe slots per pair evaluation.
+template <bool RK4, int TJ, int NT, int MINB, int SRC, int TGT>
+__global__ void __launch_bounds__(NT, MINB) graph_dense_world_kernel(const __grid_constant__ GraphParams G)
 {
     constexpr int NS = RK4 ? 3 : 1;
-    constexpr int NT = 256, NWARP = NT / 32;
+    constexpr int NWARP = NT / 32;
     extern __shared__ double dsm[];
     double(*sx)[3][TJ] = reinterpret_cast<double(*)[3][TJ]>(dsm);
     double *sm = dsm + NS * 3 * TJ;
@@ -248,51 +249,50 @@ __global__ void __launch_bounds__(256, 2) graph_dense_world_kernel(const __grid_
         __syncthreads();
         const uint32_t s0 = G.src_n ? G.src0 : 0u, sn = G.src_n ? G.src_n : N; // source rows this launch folds
         const uint32_t i0 = s0 + (uint32_t)((uint64_t)sn * part / cpw), i1 = s0 + (uint32_t)((uint64_t)sn * (part + 1) / cpw);
-        // work item = (pair of sources, stage slot): the two sources share every target they load from shared memory,
-        // which halves the LDS traffic per pair evaluation — at one source per item the 128 B/clk shared-memory pipe
-        // (4 LDS.64 per 18 FP64 slots, four schedulers) ran at ~90 % and co-limited the fold
-        const uint32_t n_pair = (i1 - i0 + 1u) / 2u;
-        const uint32_t items = n_pair * NS;
+        const uint32_t n_grp = (i1 - i0 + SRC - 1) / SRC;
+        const uint32_t items = n_grp * NS;
         for (uint32_t it = warp; it < items; it += NWARP) {
-            const uint32_t pr = it / NS, sl = it - pr * NS;
-            const uint32_t ia = i0 + 2u * pr, ib = min(ia + 1u, i1 - 1u); // odd tail: the last source twice, written once
-            const Vec3 xa = {sx[sl][0][ia], sx[sl][1][ia], sx[sl][2][ia]};
-            const Vec3 xb = {sx[sl][0][ib], sx[sl][1][ib], sx[sl][2][ib]};
-            Vec3 a0 = {0, 0, 0}, a1 = {0, 0, 0}, b0 = {0, 0, 0}, b1 = {0, 0, 0};
+            const uint32_t gr = it / NS, sl = it - gr * NS;
+            uint32_t is[SRC];
+            Vec3 xi[SRC], acc[SRC][TGT];
+#pragma unroll
+            for (int a = 0; a < SRC; ++a) {
+                is[a] = min(i0 + SRC * gr + a, i1 - 1u); // ragged tail: the last source again, written once
+                xi[a] = Vec3{sx[sl][0][is[a]], sx[sl][1][is[a]], sx[sl][2][is[a]]};
+#pragma unroll
+                for (int t = 0; t < TGT; ++t) acc[a][t] = Vec3{0.0, 0.0, 0.0};
+            }
             uint32_t jj = lane;
-            for (; jj + 32 < N; jj += 64) { // 2 targets x 2 sources per lane and trip: four independent chains
-                const double x0 = sx[sl][0][jj], y0 = sx[sl][1][jj], z0 = sx[sl][2][jj], m0 = sm[jj];
-                const double x1 = sx[sl][0][jj + 32], y1 = sx[sl][1][jj + 32], z1 = sx[sl][2][jj + 32], m1 = sm[jj + 32];
-                fa::pair_fold(xa, x0, y0, z0, m0, soft, a0);
-                fa::pair_fold(xb, x0, y0, z0, m0, soft, b0);
-                fa::pair_fold(xa, x1, y1, z1, m1, soft, a1);
-                fa::pair_fold(xb, x1, y1, z1, m1, soft, b1);
+            for (; jj + 32u * (TGT - 1) < N; jj += 32u * TGT) {
+#pragma unroll
+                for (int t = 0; t < TGT; ++t) {
+                    const uint32_t j = jj + 32u * t;
+                    const double xj = sx[sl][0][j], yj = sx[sl][1][j], zj = sx[sl][2][j], mj = sm[j];
+#pragma unroll
+                    for (int a = 0; a < SRC; ++a) fa::pair_fold(xi[a], xj, yj, zj, mj, soft, acc[a][t]);
+                }
             }
             for (; jj < N; jj += 32) {
-                const double x0 = sx[sl][0][jj], y0 = sx[sl][1][jj], z0 = sx[sl][2][jj], m0 = sm[jj];
-                fa::pair_fold(xa, x0, y0, z0, m0, soft, a0);
-                fa::pair_fold(xb, x0, y0, z0, m0, soft, b0);
-            }
-            Vec3 accA = {a0.x + a1.x, a0.y + a1.y, a0.z + a1.z}, accB = {b0.x + b1.x, b0.y + b1.y, b0.z + b1.z};
+                const double xj = sx[sl][0][jj], yj = sx[sl][1][jj], zj = sx[sl][2][jj], mj = sm[jj];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                accA.x += __shfl_xor_sync(0xffffffffu, accA.x, off);
-                accA.y += __shfl_xor_sync(0xffffffffu, accA.y, off);
-                accA.z += __shfl_xor_sync(0xffffffffu, accA.z, off);
-                accB.x += __shfl_xor_sync(0xffffffffu, accB.x, off);
-                accB.y += __shfl_xor_sync(0xffffffffu, accB.y, off);
-                accB.z += __shfl_xor_sync(0xffffffffu, accB.z, off);
+                for (int a = 0; a < SRC; ++a) fa::pair_fold(xi[a], xj, yj, zj, mj, soft, acc[a][0]);
             }
-            if (lane == 0) {
-                const double ka = G.p0 * sm[ia];
-                stp(G.gforce, G.ld, sl * 3 + 0, wbase + ia, ka * accA.x);
-                stp(G.gforce, G.ld, sl * 3 + 1, wbase + ia, ka * accA.y);
-                stp(G.gforce, G.ld, sl * 3 + 2, wbase + ia, ka * accA.z);
-                if (ib != ia) {
-                    const double kb = G.p0 * sm[ib];
-                    stp(G.gforce, G.ld, sl * 3 + 0, wbase + ib, kb * accB.x);
-                    stp(G.gforce, G.ld, sl * 3 + 1, wbase + ib, kb * accB.y);
-                    stp(G.gforce, G.ld, sl * 3 + 2, wbase + ib, kb * accB.z);
+#pragma unroll
+            for (int a = 0; a < SRC; ++a) {
+                Vec3 r = acc[a][0];
+#pragma unroll
+                for (int t = 1; t < TGT; ++t) r = Vec3{r.x + acc[a][t].x, r.y + acc[a][t].y, r.z + acc[a][t].z};
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    r.x += __shfl_xor_sync(0xffffffffu, r.x, off);
+                    r.y += __shfl_xor_sync(0xffffffffu, r.y, off);
+                    r.z += __shfl_xor_sync(0xffffffffu, r.z, off);
+                }
+                if (lane == 0 && (a == 0 || is[a] != is[a - 1 < 0 ? 0 : a - 1])) {
+                    const double k = G.p0 * sm[is[a]];
+                    stp(G.gforce, G.ld, sl * 3 + 0, wbase + is[a], k * r.x);
+                    stp(G.gforce, G.ld, sl * 3 + 1, wbase + is[a], k * r.y);
+                    stp(G.gforce, G.ld, sl * 3 + 2, wbase + is[a], k * r.z);
                 }
             }
         }
@@ -452,7 +452,9 @@ __global__ void __launch_bounds__(kBlockG) graph_csr_kernel(const __grid_constan
 // tick).  Every lane folds its out-edges sequentially in CSR (= spawn) order with the same ex:: functions as
 // graph_dense_kernel / graph_csr_kernel, then runs the same tick function as body_exact_kernel — EXACT stays
 // bit-identical to the oracle.  FAST folds sequentially too (no tree), with the FAST kernels' arithmetic.
-template <bool EXACT, int INTEG, int MINB>
+// SIG: SIG_GRAPH when the edge_fold gravity is the only effector (the FAST tick is then compiled for exactly that),
+// SIG_GENERIC otherwise (the run-time interpreter)
+template <bool EXACT, int INTEG, int MINB, uint32_t SIG = SIG_GENERIC>
 __global__ void __launch_bounds__(128, MINB) small_world_kernel(const __grid_constant__ GraphParams G,
                                                           const __grid_constant__ StepParams P)
 {
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(128, MINB) small_world_kernel(const __grid_con
                 if (P.traj_planes == 25) traj_store_af(P, b, slot, a_out, f_out);
             }
         } else {
-            fast_ticks<INTEG, true, true>(P, b, x0, v0, I, a_out, f_out, 1u, P.tick0 + t, P.write_fa && t + 1 == P.n_ticks, g);
+            fast_ticks<INTEG, true, true, SIG>(P, b, x0, v0, I, a_out, f_out, 1u, P.tick0 + t, P.write_fa && t + 1 == P.n_ticks, g);
         }
     }
     if (!live) return;
@@ -560,29 +562,41 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
         else if (gcfg == 0) { if (rk4) graph_dense_kernel<false, true><<<grid, blk3, 0, s>>>(G); else graph_dense_kernel<false, false><<<grid, blk1, 0, s>>>(G); }
         else {
             if (gcfg == 1 && G.n_entities <= 1024 && G.n_entities >= 64) {
-                // worlds that fit one shared-memory tile set: persistent world-resident kernel, 2 CTAs per SM
+                // worlds that fit one shared-memory tile set: persistent world-resident kernel
                 int dev = 0, sms = 148;
                 cudaGetDevice(&dev);
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-                const unsigned slots = 2u * (unsigned)sms;
-                unsigned grid_w;
-                if (G.n_worlds >= slots) grid_w = slots;
-                else {
-                    // every CTA of a world takes at least ~2 rounds of (source, slot) items for its 8 warps
-                    // (source pair, slot) items: at least ~2 rounds for a CTA's 8 warps
-                    const unsigned cpw = std::max(1u, std::min(slots / G.n_worlds, ((n_src + 1u) / 2u * 3u + 15u) / 16u));
-                    grid_w = cpw * G.n_worlds;
-                }
-                if (rk4) {
-                    constexpr size_t smem = (3 * 3 + 1) * 1024 * sizeof(double);
-                    const cudaError_t e = ensure_dynamic_smem(graph_dense_world_kernel<true, 1024>, smem);
+                auto launch_world = [&](auto kern, int nt, int minb, int src) -> cudaError_t {
+                    const unsigned slots = (unsigned)minb * (unsigned)sms;
+                    unsigned grid_w;
+                    if (G.n_worlds >= slots) grid_w = slots;
+                    else {
+                        // every CTA of a world takes at least ~2 rounds of items for its warps
+                        const unsigned items = (n_src + src - 1) / src * (rk4 ? 3u : 1u), warps = (unsigned)nt / 32u;
+                        const unsigned cpw = std::max(1u, std::min(slots / G.n_worlds, (items + 2 * warps - 1) / (2 * warps)));
+                        grid_w = cpw * G.n_worlds;
+                    }
+                    const size_t smem = ((rk4 ? 3 : 1) * 3 + 1) * 1024 * sizeof(double);
+                    const cudaError_t e = ensure_dynamic_smem(kern, smem);
                     if (e != cudaSuccess) return e;
-                    graph_dense_world_kernel<true, 1024><<<grid_w, 256, smem, s>>>(G);
-                } else {
-                    constexpr size_t smem = (3 + 1) * 1024 * sizeof(double);
-                    graph_dense_world_kernel<false, 1024><<<grid_w, 256, smem, s>>>(G);
+                    kern<<<grid_w, nt, smem, s>>>(G);
+                    return cudaGetLastError();
+                };
+#ifdef B200_TUNE
+                if (rk4) switch (env_int("B200_WORLD_CFG", 0)) {
+                case 1: return launch_world(graph_dense_world_kernel<true, 1024, 256, 2, 2, 2>, 256, 2, 2);
+                case 2: return launch_world(graph_dense_world_kernel<true, 1024, 256, 2, 1, 2>, 256, 2, 1);
+                case 3: return launch_world(graph_dense_world_kernel<true, 1024, 256, 2, 1, 8>, 256, 2, 1);
+                case 4: return launch_world(graph_dense_world_kernel<true, 1024, 512, 1, 1, 4>, 512, 1, 1);
+                case 5: return launch_world(graph_dense_world_kernel<true, 1024, 384, 2, 1, 4>, 384, 2, 1);
+                case 6: return launch_world(graph_dense_world_kernel<true, 1024, 256, 2, 3, 2>, 256, 2, 3);
+                case 7: return launch_world(graph_dense_world_kernel<true, 1024, 128, 2, 1, 4>, 128, 2, 1);
+                case 8: return launch_world(graph_dense_world_kernel<true, 1024, 512, 1, 2, 2>, 512, 1, 2);
+                default: break;
                 }
-                return cudaGetLastError();
+#endif
+                if (rk4) return launch_world(graph_dense_world_kernel<true, 1024, 256, 2, 1, 4>, 256, 2, 1);
+                return launch_world(graph_dense_world_kernel<false, 1024, 256, 2, 1, 4>, 256, 2, 1);
             }
             const unsigned gridf = ((n_src + kFastSrc - 1) / kFastSrc) * G.n_worlds;
             // few CTAs: split the stage slots over warps to fill the machine; many CTAs: keep
@@ -640,7 +654,11 @@ static void launch_small_world_cfg(const GraphParams &G, const StepParams &P, in
         if (rk4) small_world_kernel<true, B200_INTEGRATOR_RK4, MINB><<<grid, 128, 0, s>>>(G, P);
         else small_world_kernel<true, B200_INTEGRATOR_SEMI_IMPLICIT, MINB><<<grid, 128, 0, s>>>(G, P);
     } else {
-        if (rk4) small_world_kernel<false, B200_INTEGRATOR_RK4, MINB><<<grid, 128, 0, s>>>(G, P);
+        const bool only_graph = P.n_eff == 1 && !P.eff[0].mask; // three-body / n-body: gravity is the whole effector list
+        if (only_graph) {
+            if (rk4) small_world_kernel<false, B200_INTEGRATOR_RK4, MINB, SIG_GRAPH><<<grid, 128, 0, s>>>(G, P);
+            else small_world_kernel<false, B200_INTEGRATOR_SEMI_IMPLICIT, MINB, SIG_GRAPH><<<grid, 128, 0, s>>>(G, P);
+        } else if (rk4) small_world_kernel<false, B200_INTEGRATOR_RK4, MINB><<<grid, 128, 0, s>>>(G, P);
         else small_world_kernel<false, B200_INTEGRATOR_SEMI_IMPLICIT, MINB><<<grid, 128, 0, s>>>(G, P);
     }
 }

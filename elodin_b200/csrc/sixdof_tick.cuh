@@ -85,6 +85,25 @@ struct GravReg {
 };
 __device__ __forceinline__ Vec3 grav_slot(const GravReg &g, int slot) { return slot == 0 ? g.g0 : (slot == 1 ? g.g1 : g.g2); }
 
+// python/elodin/j2.py:5-29 in the operation order of oracle/sixdof_oracle.c:eff_gravity_j2.  Out of line: its pow()
+// (the reference's `norm**6.0` is a float-exponent lax.pow) would otherwise cost every EXACT kernel registers.
+static __device__ __noinline__ Vec3 j2_field_exact(double mu, double J2, double r_ref, Vec3 r, double m)
+{
+    using namespace ex;
+    const double norm = sqr(dot3(r));
+    const Vec3 e_r = {div(r.x, norm), div(r.y, norm), div(r.z, norm)};
+    const double n3 = mul(mul(norm, norm), norm);
+    const double c0 = mul(-mu, m);
+    const double n2 = mul(norm, norm), n4 = mul(n2, n2), n5 = mul(norm, n4);
+    const double n6 = pow(norm, 6.0);
+    const double kz = div(mul(3.0, r.z), n5);
+    const double kr = sub(div(3.0, mul(2.0, n4)), div(mul(15.0, mul(r.z, r.z)), mul(2.0, n6)));
+    const double c1 = mul(mul(c0, J2), mul(r_ref, r_ref));
+    return Vec3{add(div(mul(c0, r.x), n3), mul(c1, add(mul(kz, 0.0), mul(kr, e_r.x)))),
+                add(div(mul(c0, r.y), n3), mul(c1, add(mul(kz, 0.0), mul(kr, e_r.y)))),
+                add(div(mul(c0, r.z), n3), mul(c1, add(mul(kz, 1.0), mul(kr, e_r.z))))};
+}
+
 // clear_forces | effectors (array order) on the stage state; six_dof.rs:148-150,195
 template <bool GREG>
 __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t b, int slot, const Pose &sx,
@@ -172,21 +191,8 @@ __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t 
             }
             break;
         }
-        case B200_EFF_GRAVITY_J2: { // python/elodin/j2.py:5-29, operation order of oracle/sixdof_oracle.c:eff_gravity_j2
-            const double mu = E.p[0], J2 = E.p[1], r_ref = E.p[2];
-            const Vec3 r = sx.x;
-            const double norm = sqr(dot3(r));
-            const Vec3 e_r = {div(r.x, norm), div(r.y, norm), div(r.z, norm)};
-            const double n3 = mul(mul(norm, norm), norm);
-            const double c0 = mul(-mu, I.m);
-            const double n2 = mul(norm, norm), n4 = mul(n2, n2), n5 = mul(norm, n4);
-            const double n6 = pow(norm, 6.0); // float exponent: lax.pow (CUDA's pow is within 1 ulp of libm's)
-            const double kz = div(mul(3.0, r.z), n5);
-            const double kr = sub(div(3.0, mul(2.0, n4)), div(mul(15.0, mul(r.z, r.z)), mul(2.0, n6)));
-            const double c1 = mul(mul(c0, J2), mul(r_ref, r_ref));
-            const Vec3 g = {add(div(mul(c0, r.x), n3), mul(c1, add(mul(kz, 0.0), mul(kr, e_r.x)))),
-                            add(div(mul(c0, r.y), n3), mul(c1, add(mul(kz, 0.0), mul(kr, e_r.y)))),
-                            add(div(mul(c0, r.z), n3), mul(c1, add(mul(kz, 1.0), mul(kr, e_r.z))))};
+        case B200_EFF_GRAVITY_J2: { // python/elodin/j2.py:5-29
+            const Vec3 g = j2_field_exact(E.p[0], E.p[1], E.p[2], sx.x, I.m);
             F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
             F.lin = Vec3{add(F.lin.x, g.x), add(F.lin.y, g.y), add(F.lin.z, g.z)};
             break;
@@ -375,8 +381,9 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
 
 // the same fold for a compile-time signature: constants from StepParams::spec (constant bank), per-body inputs
 // from registers; members the signature does not use are literal zeros the optimiser removes
-template <uint32_t SIG>
-__device__ __forceinline__ Folded fold_spec(const StepParams &P, uint64_t b, const EffIn &in, const Inertia &I, const Vec3 &invI)
+template <uint32_t SIG, bool GREG>
+__device__ __forceinline__ Folded fold_spec(const StepParams &P, uint64_t b, const EffIn &in, const Inertia &I, const Vec3 &invI,
+                                            const GravReg &greg)
 {
     Folded f;
     f.fw = Vec3{P.spec.g[0] * I.m, P.spec.g[1] * I.m, P.spec.g[2] * I.m};
@@ -386,7 +393,7 @@ __device__ __forceinline__ Folded fold_spec(const StepParams &P, uint64_t b, con
     f.wtorque = f.j2 = false;
     f.drag = (SIG & SIG_DRAG) != 0;
     f.frame = (SIG & SIG_FRAME) != 0;
-    f.graph = (SIG & SIG_GRAPH) ? (P.has_edge[(b + P.ent0) % P.n_entities] != 0) : false;
+    f.graph = (SIG & SIG_GRAPH) ? (GREG ? greg.has : P.has_edge[(b + P.ent0) % P.n_entities] != 0) : false;
     if (SIG & SIG_THRUST) f.fb = Vec3{P.spec.axis[0] * in.thrust, P.spec.axis[1] * in.thrust, P.spec.axis[2] * in.thrust};
     if (SIG & SIG_WRENCH) {
         f.fb = Vec3{f.fb.x + in.wr_f.x, f.fb.y + in.wr_f.y, f.fb.z + in.wr_f.z};
@@ -479,7 +486,7 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
     const double inv_m = fa::rcp_nr(I.m);
     Folded f;
     if constexpr (GEN) f = fold_effectors<GREG>(P, b, I, invI, greg);
-    else f = fold_spec<SIG>(P, b, in, I, invI);
+    else f = fold_spec<SIG, GREG>(P, b, in, I, invI, greg);
 
     a_last = Motion{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
     Quat q_last = x0.q;
