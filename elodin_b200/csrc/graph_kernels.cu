@@ -591,12 +591,20 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
                 case 5: return launch_world(graph_dense_world_kernel<true, 1024, 384, 2, 1, 4>, 384, 2, 1);
                 case 6: return launch_world(graph_dense_world_kernel<true, 1024, 256, 2, 3, 2>, 256, 2, 3);
                 case 7: return launch_world(graph_dense_world_kernel<true, 1024, 128, 2, 1, 4>, 128, 2, 1);
-                case 8: return launch_world(graph_dense_world_kernel<true, 1024, 512, 1, 2, 2>, 512, 1, 2);
+                case 8: return launch_world(graph_dense_world_kernel<true, 1024, 256, 2, 1, 4>, 256, 2, 1);
+                case 9: return launch_world(graph_dense_world_kernel<true, 1024, 512, 1, 3, 2>, 512, 1, 3);
+                case 10: return launch_world(graph_dense_world_kernel<true, 1024, 512, 1, 4, 1>, 512, 1, 4);
+                case 11: return launch_world(graph_dense_world_kernel<true, 1024, 1024, 1, 2, 1>, 1024, 1, 2);
+                case 12: return launch_world(graph_dense_world_kernel<true, 1024, 768, 1, 2, 2>, 768, 1, 2);
+                case 13: return launch_world(graph_dense_world_kernel<true, 1024, 512, 1, 2, 4>, 512, 1, 2);
+                case 14: return launch_world(graph_dense_world_kernel<true, 1024, 1024, 1, 1, 2>, 1024, 1, 1);
                 default: break;
                 }
 #endif
-                if (rk4) return launch_world(graph_dense_world_kernel<true, 1024, 256, 2, 1, 4>, 256, 2, 1);
-                return launch_world(graph_dense_world_kernel<false, 1024, 256, 2, 1, 4>, 256, 2, 1);
+                // default shape by measurement (profiles/r02_tune_world.md): one 512-thread CTA per SM stages each world once
+                // per SM, two sources x two targets per lane and trip = four independent chains for the FP64 pipe
+                if (rk4) return launch_world(graph_dense_world_kernel<true, 1024, 512, 1, 2, 2>, 512, 1, 2);
+                return launch_world(graph_dense_world_kernel<false, 1024, 512, 1, 2, 2>, 512, 1, 2);
             }
             const unsigned gridf = ((n_src + kFastSrc - 1) / kFastSrc) * G.n_worlds;
             // few CTAs: split the stage slots over warps to fill the machine; many CTAs: keep

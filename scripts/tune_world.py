@@ -34,7 +34,7 @@ rows = []
 for Mw in (8, 64, 296):
     p, v, I = world(Mw)
     ref = None
-    for cfg in range(9):
+    for cfg in [int(c) for c in os.environ.get("WORLD_CFGS", "0,1,2,3,4,5,6,7,8").split(",")]:
         os.environ["B200_WORLD_CFG"] = str(cfg)
         ex = el.B200Exec(N, Mw, 3600.0, None, [g], "rk4", "fast")
         ex.set_stream(st.cuda_stream)
