@@ -482,12 +482,16 @@ def run_b200(args):
                            {"thrust": rng.uniform(50, 100, (M, 1, 1)), "wind": rng.normal(0, 1, (M, 1, 3))}, 264 + 8 * 4),
                 "falcon9": ([el.GravityFrame(), el.WrenchBody("body_wrench", "linear_first")],
                             {"body_wrench": rng.normal(0, 1e3, (M, 1, 6))}, 264 + 8 * 6),
+                # the cube-sat example's own effector shape (examples/cube-sat/main.py:492-527): reaction-wheel fold +
+                # orbital gravity (J2 here: the example's EGM08 tables are a download), satellites on a 400 km orbit
+                "cube_sat": ([el.TorqueBodyFold("wheel_torques", 3), el.GravityJ2()],
+                             {"wheel_torques": rng.normal(0, 2e-3, (M, 1, 9))}, 264 + 8 * 9),
             }
             eff_out = {}
             for name, (effs, cols, bytes_per) in sets.items():
                 p2 = pos.copy()
-                if name == "falcon9":
-                    p2[..., 4:] += np.array([6.4e6, 0.0, 0.0])
+                if name in ("falcon9", "cube_sat"):
+                    p2[..., 4:] += np.array([6.778e6 if name == "cube_sat" else 6.4e6, 0.0, 0.0])
                 sx = el.B200Exec(1, M, DT, None, effs, "rk4", "fast", device=local)
                 sx.set_stream(stream.cuda_stream)
                 sx.set_state(p2, vel, ine, **cols)
@@ -503,7 +507,7 @@ def run_b200(args):
                 eff_out[name] = {"value": M / (t_ms * 1e-3), "unit": UNIT, "bytes_per_entity_step": bytes_per, "us_per_tick": t_ms * 1e3,
                                  "achieved_GBps": bytes_per * M / (t_ms * 1e-3) / 1e9, "frac": bytes_per * M / (t_ms * 1e-3) / 1e9 / peak,
                                  "traffic": tr, "dram_frac": (tr / (t_ms * 1e-3) / 1e9 / peak) if tr else None,
-                                 "kernel": "body_fast_spec_kernel<RK4, sig %s, 128 x 3, 2 bodies/thread>" % ("THRUST|DRAG" if name == "rocket" else "FRAME|WRENCH")}
+                                 "kernel": "body_fast_spec_kernel<RK4, sig %s, 128 x 3, 2 bodies/thread>" % {"rocket": "THRUST|DRAG", "falcon9": "FRAME|WRENCH", "cube_sat": "WHEELS|J2"}[name]}
                 sx.close()
                 del p2, cols
             extras["effector_sets"] = eff_out

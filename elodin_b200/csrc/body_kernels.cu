@@ -135,17 +135,27 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_fast_spec_kernel(const __gri
     B200_LDV(P.vel, 0, v[k].ang.x); B200_LDV(P.vel, 1, v[k].ang.y); B200_LDV(P.vel, 2, v[k].ang.z);
     B200_LDV(P.vel, 3, v[k].lin.x); B200_LDV(P.vel, 4, v[k].lin.y); B200_LDV(P.vel, 5, v[k].lin.z);
     // the inertia diagonal only matters to a body-frame torque (or to the Force column written back)
-    if ((SIG & SIG_WRENCH) || true) { B200_LDV(P.ine, 0, I[k].diag.x); B200_LDV(P.ine, 1, I[k].diag.y); B200_LDV(P.ine, 2, I[k].diag.z); }
+    { B200_LDV(P.ine, 0, I[k].diag.x); B200_LDV(P.ine, 1, I[k].diag.y); B200_LDV(P.ine, 2, I[k].diag.z); }
     B200_LDV(P.ine, 6, I[k].m);
 #pragma unroll
     for (int k = 0; k < BPT; ++k) {
         in[k].thrust = 0.0; in[k].cd_rho = in[k].area = 0.0;
-        in[k].wr_t = in[k].wr_f = in[k].wind = Vec3{0.0, 0.0, 0.0};
+        in[k].wr_t = in[k].wr_f = in[k].wind = in[k].wheels = Vec3{0.0, 0.0, 0.0};
     }
     if (SIG & SIG_THRUST) B200_LDV(P.spec.thrust, 0, in[k].thrust);
     if (SIG & SIG_WRENCH) {
         B200_LDV(P.spec.wr_t, 0, in[k].wr_t.x); B200_LDV(P.spec.wr_t, 1, in[k].wr_t.y); B200_LDV(P.spec.wr_t, 2, in[k].wr_t.z);
         B200_LDV(P.spec.wr_f, 0, in[k].wr_f.x); B200_LDV(P.spec.wr_f, 1, in[k].wr_f.y); B200_LDV(P.spec.wr_f, 2, in[k].wr_f.z);
+    }
+    if (SIG & SIG_WHEELS) { // the three wheel torques only ever enter as their sum (the rotation is linear)
+        Vec3 w[BPT][3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            B200_LDV(P.spec.wheels, 3 * q + 0, w[k][q].x); B200_LDV(P.spec.wheels, 3 * q + 1, w[k][q].y); B200_LDV(P.spec.wheels, 3 * q + 2, w[k][q].z);
+        }
+#pragma unroll
+        for (int k = 0; k < BPT; ++k)
+            in[k].wheels = Vec3{w[k][0].x + w[k][1].x + w[k][2].x, w[k][0].y + w[k][1].y + w[k][2].y, w[k][0].z + w[k][1].z + w[k][2].z};
     }
     if (SIG & SIG_DRAG) {
         B200_LDV(P.spec.drag, 0, in[k].wind.x); B200_LDV(P.spec.drag, 1, in[k].wind.y); B200_LDV(P.spec.drag, 2, in[k].wind.z);
@@ -383,6 +393,16 @@ static uint32_t spec_signature(StepParams &Q)
             if (i != 0 || !Q.gforce || !Q.has_edge) return SIG_GENERIC;
             sig |= SIG_GRAPH;
             break;
+        case B200_EFF_GRAVITY_J2:
+            if (sig & SIG_J2) return SIG_GENERIC;
+            sig |= SIG_J2;
+            sp.j2_mu = E.p[0]; sp.j2_k = E.p[1] * E.p[2] * E.p[2];
+            break;
+        case B200_EFF_TORQUE_BODY_FOLD: // the fold overwrites Force: only as the first effector is it a plain torque term
+            if (i != 0 || !E.col || E.col_width != 9) return SIG_GENERIC;
+            sig |= SIG_WHEELS;
+            sp.wheels = E.col;
+            break;
         default: return SIG_GENERIC;
         }
     }
@@ -406,6 +426,7 @@ static bool planes_16B_aligned(const StepParams &Q, uint32_t sig)
     if (sig & SIG_THRUST) a |= (uintptr_t)Q.spec.thrust;
     if (sig & SIG_WRENCH) a |= (uintptr_t)Q.spec.wr_t | (uintptr_t)Q.spec.wr_f;
     if (sig & SIG_DRAG) a |= (uintptr_t)Q.spec.drag;
+    if (sig & SIG_WHEELS) a |= (uintptr_t)Q.spec.wheels;
     return (a & 15u) == 0 && (Q.ld & 1u) == 0;
 }
 
@@ -444,7 +465,8 @@ static void launch_spec(const StepParams &Q, cudaStream_t s)
 #else
 #define B200_SPEC_SIGS(X)                                                                                        \
     X(0u) X(SIG_DRAG) X(SIG_THRUST) X(SIG_WRENCH) X(SIG_FRAME) X(SIG_GRAPH)                                       \
-    X(SIG_THRUST | SIG_DRAG) X(SIG_THRUST | SIG_DRAG | SIG_DRAG_PB) X(SIG_THRUST | SIG_WRENCH) X(SIG_FRAME | SIG_WRENCH)
+    X(SIG_THRUST | SIG_DRAG) X(SIG_THRUST | SIG_DRAG | SIG_DRAG_PB) X(SIG_THRUST | SIG_WRENCH) X(SIG_FRAME | SIG_WRENCH)     \
+    X(SIG_J2) X(SIG_WHEELS | SIG_J2)
 #endif
 
 template <int INTEG>

@@ -277,6 +277,8 @@ enum : uint32_t {
     SIG_WRENCH = 8u,          // WRENCH_BODY (either layout: the host hands over torque / force plane bases)
     SIG_FRAME = 16u,          // GRAVITY_FRAME
     SIG_GRAPH = 32u,          // GRAVITY_EDGES_*: 9 planes of edge_fold gravity
+    SIG_J2 = 64u,             // GRAVITY_J2
+    SIG_WHEELS = 128u,        // TORQUE_BODY_FOLD with three wheels (the cube-sat shape), first in the list
     SIG_GENERIC = 0x80000000u // interpret StepParams::eff[] at run time
 };
 
@@ -286,6 +288,7 @@ struct EffIn {
     Vec3 wr_t, wr_f; // body-frame torque / force of the wrench column
     Vec3 wind;
     double cd_rho, area;
+    Vec3 wheels;     // sum of the body's wheel torques (body frame)
 };
 
 // Everything the effector list contributes, folded once per launch:
@@ -395,9 +398,17 @@ __device__ __forceinline__ Folded fold_spec(const StepParams &P, uint64_t b, con
     f.frame = (SIG & SIG_FRAME) != 0;
     f.graph = (SIG & SIG_GRAPH) ? (GREG ? greg.has : P.has_edge[(b + P.ent0) % P.n_entities] != 0) : false;
     if (SIG & SIG_THRUST) f.fb = Vec3{P.spec.axis[0] * in.thrust, P.spec.axis[1] * in.thrust, P.spec.axis[2] * in.thrust};
+    Vec3 tb = {0.0, 0.0, 0.0};
+    if (SIG & SIG_WHEELS) tb = in.wheels;
     if (SIG & SIG_WRENCH) {
         f.fb = Vec3{f.fb.x + in.wr_f.x, f.fb.y + in.wr_f.y, f.fb.z + in.wr_f.z};
-        f.u = Vec3{in.wr_t.x * invI.x, in.wr_t.y * invI.y, in.wr_t.z * invI.z};
+        tb = Vec3{tb.x + in.wr_t.x, tb.y + in.wr_t.y, tb.z + in.wr_t.z};
+    }
+    if (SIG & (SIG_WRENCH | SIG_WHEELS)) f.u = Vec3{tb.x * invI.x, tb.y * invI.y, tb.z * invI.z};
+    if (SIG & SIG_J2) {
+        f.j2 = true;
+        f.j2_mu = P.spec.j2_mu;
+        f.j2_k = P.spec.j2_k;
     }
     if (SIG & SIG_DRAG) {
         f.wind = in.wind;
@@ -481,7 +492,7 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
                                            const GravReg &greg, const EffIn &in = EffIn{})
 {
     constexpr bool GEN = SIG == SIG_GENERIC;
-    constexpr bool NEED_INVI = GEN || (SIG & SIG_WRENCH);
+    constexpr bool NEED_INVI = GEN || (SIG & (SIG_WRENCH | SIG_WHEELS));
     const Vec3 invI = NEED_INVI ? Vec3{fa::rcp_nr(I.diag.x), fa::rcp_nr(I.diag.y), fa::rcp_nr(I.diag.z)} : Vec3{0.0, 0.0, 0.0};
     const double inv_m = fa::rcp_nr(I.m);
     Folded f;
@@ -493,7 +504,7 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
     const double dt = P.dt_stage;
     // generic: data-dependent (most bodies of a heterogeneous world carry no body-frame wrench; NaNs compare
     // unequal to zero and take the full path); specialised: a property of the signature
-    const bool has_u = GEN ? ((f.u.x != 0.0) | (f.u.y != 0.0) | (f.u.z != 0.0)) : (SIG & SIG_WRENCH) != 0;
+    const bool has_u = GEN ? ((f.u.x != 0.0) | (f.u.y != 0.0) | (f.u.z != 0.0)) : (SIG & (SIG_WRENCH | SIG_WHEELS)) != 0;
     const bool has_fb = GEN ? ((f.fb.x != 0.0) | (f.fb.y != 0.0) | (f.fb.z != 0.0)) : (SIG & (SIG_THRUST | SIG_WRENCH)) != 0;
     const bool has_tw = GEN ? f.wtorque : false; // world-frame torque: a_ang = R (invI .* (R^-1 tau_w)) per stage attitude
     auto ang_world = [&](const Quat &q) { // angular acceleration the world-frame torque produces at attitude q

@@ -14,6 +14,10 @@ if which == "free":
 elif which == "rocket":
     effs = [el.GravityConst(), el.ThrustBody((-1.0, 0, 0), "thrust"), el.DragQuadratic(0.6, 0.01, "wind")]
     cols = {"thrust": rng.uniform(50, 100, (M, 1, 1)), "wind": rng.normal(0, 1, (M, 1, 3))}
+elif which == "cube_sat":
+    pos[..., 4:] += np.array([6.778e6, 0, 0])
+    effs = [el.TorqueBodyFold("wheel_torques", 3), el.GravityJ2()]
+    cols = {"wheel_torques": rng.normal(0, 2e-3, (M, 1, 9))}
 else:
     pos[..., 4:] += np.array([6.4e6, 0, 0])
     effs = [el.GravityFrame(), el.WrenchBody("body_wrench", "linear_first")]

@@ -1207,6 +1207,7 @@ def test_signature_kernels_match_the_interpreter_kernel(oracle, integrator):
         wind = rng.normal(0, 3, (M, 1, 3))
         thrust = rng.uniform(0, 10, (M, 1, 1))
         wrench = rng.normal(0, 5, (M, 1, 6))
+        wheels = rng.normal(0, 2e-2, (M, 1, 9))
         lists = {
             "free": [],
             "g": [("gravity", {})],
@@ -1218,6 +1219,9 @@ def test_signature_kernels_match_the_interpreter_kernel(oracle, integrator):
             "wrench": [("wrench", dict(wrench=wrench))],
             "thrust": [("thrust", dict(thrust=thrust))],
             "two_g (summed)": [("gravity", {}), ("gravity", dict(g=(0.5, 0.0, 1.0)))],
+            "j2": [("j2", {})],
+            "cube_sat (wheel fold first, then J2)": [("wheels", dict(torques=wheels)), ("j2", {})],
+            "g then wheels (interpreter: the fold overwrites)": [("gravity", {}), ("wheels", dict(torques=wheels))],
             "wrench_then_drag (interpreter: torque reset)": [("wrench", dict(wrench=wrench)), ("drag", dict(wind=wind))],
         }
         for name, spec in lists.items():
