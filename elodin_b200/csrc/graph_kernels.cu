@@ -601,10 +601,16 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
                 default: break;
                 }
 #endif
-                // default shape by measurement (profiles/r02_tune_world.md): one 512-thread CTA per SM stages each world once
-                // per SM, two sources x two targets per lane and trip = four independent chains for the FP64 pipe
-                if (rk4) return launch_world(graph_dense_world_kernel<true, 1024, 512, 1, 2, 2>, 512, 1, 2);
-                return launch_world(graph_dense_world_kernel<false, 1024, 512, 1, 2, 2>, 512, 1, 2);
+                // default shapes by measurement (profiles/r02_tune_world.md): one 512-thread CTA per SM stages each world
+                // once per SM.  Big batches (>= 8 rounds of four-source items per resident warp) fold four sources per
+                // item — four chains that share every target load: 0.81 of the DFMA issue rate; small batches keep
+                // two sources x two targets so that the item count still divides over the warps (M = 8: 0.55)
+                const unsigned long long items4 = (unsigned long long)((n_src + 3) / 4) * (rk4 ? 3u : 1u) * G.n_worlds;
+                const bool big = items4 >= 8ull * 16ull * (unsigned)sms;
+                if (rk4) return big ? launch_world(graph_dense_world_kernel<true, 1024, 512, 1, 4, 1>, 512, 1, 4)
+                                    : launch_world(graph_dense_world_kernel<true, 1024, 512, 1, 2, 2>, 512, 1, 2);
+                return big ? launch_world(graph_dense_world_kernel<false, 1024, 512, 1, 4, 1>, 512, 1, 4)
+                           : launch_world(graph_dense_world_kernel<false, 1024, 512, 1, 2, 2>, 512, 1, 2);
             }
             const unsigned gridf = ((n_src + kFastSrc - 1) / kFastSrc) * G.n_worlds;
             // few CTAs: split the stage slots over warps to fill the machine; many CTAs: keep
