@@ -209,8 +209,14 @@ __global__ void __launch_bounds__(32 * kFastSrc * ((RK4 && SPLIT) ? 3 : 1)) grap
 // the targets TGT at a time (SRC x TGT independent chains for the FP64 pipe); with fewer worlds than CTAs a world's
 // sources are split over grid/M CTAs, otherwise a CTA walks whole worlds.  No self test (pair_fold), one third-order
 // rsqrt step: 18 FP64-pipe slots per pair evaluation.
-template <bool RK4, int TJ, int NT, int MINB, int SRC, int TGT>
-__global__ void __launch_bounds__(NT, MINB) graph_dense_world_kernel(const __grid_constant__ GraphParams G)
+//
+// FUSE: the CTA also integrates the sources it folded (all three stage slots of a source belong to one CTA), reading
+// their gravity straight back after a block barrier: one launch per tick for any batch size.  Other CTAs may still be
+// staging this tick's positions, so the new pose / velocity go to the second plane set (ping-pong, swapped by the host).
+template <bool RK4, int TJ, int NT, int MINB, int SRC, int TGT, bool FUSE = false, uint32_t FSIG = SIG_GENERIC>
+__global__ void __launch_bounds__(NT, MINB) graph_dense_world_kernel(const __grid_constant__ GraphParams G,
+                                                                     const __grid_constant__ StepParams P,
+                                                                     double *__restrict__ pos_out, double *__restrict__ vel_out)
 {
     constexpr int NS = RK4 ? 3 : 1;
     constexpr int NWARP = NT / 32;
@@ -293,6 +299,23 @@ __global__ void __launch_bounds__(NT, MINB) graph_dense_world_kernel(const __gri
                     stp(G.gforce, G.ld, sl * 3 + 0, wbase + is[a], k * r.x);
                     stp(G.gforce, G.ld, sl * 3 + 1, wbase + is[a], k * r.y);
                     stp(G.gforce, G.ld, sl * 3 + 2, wbase + is[a], k * r.z);
+                }
+            }
+        }
+        if (FUSE) {
+            __syncthreads(); // this CTA's gravity planes are complete and visible to its integrating threads
+            for (uint32_t t = threadIdx.x; t < i1 - i0; t += NT) {
+                const uint64_t b = wbase + i0 + t;
+                Pose x0 = load_pose(P.pos, P.ld, b);
+                Motion v0 = load_motion(P.vel, P.ld, b);
+                const Inertia I = load_inertia(P.ine, P.ld, b);
+                Motion a_last, f_last;
+                fast_ticks<B200_INTEGRATOR_RK4, true, false, FSIG>(P, b, x0, v0, I, a_last, f_last, P.n_ticks, P.tick0, P.write_fa != 0, GravReg{});
+                store_pose(pos_out, P.ld, b, x0);
+                store_motion(vel_out, P.ld, b, v0);
+                if (P.write_fa) {
+                    store_motion(P.acc, P.ld, b, a_last);
+                    store_motion(P.frc, P.ld, b, f_last);
                 }
             }
         }
@@ -579,7 +602,7 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
                     const size_t smem = ((rk4 ? 3 : 1) * 3 + 1) * 1024 * sizeof(double);
                     const cudaError_t e = ensure_dynamic_smem(kern, smem);
                     if (e != cudaSuccess) return e;
-                    kern<<<grid_w, nt, smem, s>>>(G);
+                    kern<<<grid_w, nt, smem, s>>>(G, StepParams{}, nullptr, nullptr);
                     return cudaGetLastError();
                 };
 #ifdef B200_TUNE
@@ -637,16 +660,43 @@ bool nbody_fused_applicable(const GraphParams &G, int math_mode, bool dense)
 {
     if (math_mode != B200_MATH_FAST || !dense || G.integrator != B200_INTEGRATOR_RK4) return false;
     static const int fcfg = [] { const char *e = getenv("B200_NBODY_FUSED"); return e ? atoi(e) : 1; }();
+    if (fcfg == 0) return false;
     const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
-    return fcfg != 0 && gridf < 3u * 148u; // the same "small grid" rule as the split gravity kernel
+    if (gridf < 3u * 148u) return true; // small grids: nbody_tick_fused_kernel (the "small grid" rule of the split gravity kernel)
+    return fcfg == 3 && G.n_entities >= 64 && G.n_entities <= 1024; // opt-in until measured: worlds that fit the persistent kernel's tile set, any batch size
 }
 
 cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, double *pos_out, double *vel_out, cudaStream_t s)
 {
     constexpr size_t smem = (3 * 3 + 1) * 1024 * sizeof(double);
+    const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
+    if (gridf >= 3u * 148u && G.n_entities >= 64 && G.n_entities <= 1024) {
+        // the persistent world-resident kernel with the integration fused in (same shapes as launch_graph_force picks)
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned long long items4 = (unsigned long long)((G.n_entities + 3) / 4) * 3u * G.n_worlds;
+        const bool big = items4 >= 8ull * 16ull * (unsigned)sms;
+        const unsigned src = big ? 4u : 2u, slots = (unsigned)sms, warps = 16u;
+        unsigned grid_w;
+        if (G.n_worlds >= slots) grid_w = slots;
+        else {
+            const unsigned items = (G.n_entities + src - 1) / src * 3u;
+            grid_w = std::max(1u, std::min(slots / G.n_worlds, (items + 2 * warps - 1) / (2 * warps))) * G.n_worlds;
+        }
+        // gravity is usually the whole effector list (n-body): the integration is then compiled for that signature
+        const bool only_graph = P.n_eff == 1 && !P.eff[0].mask;
+        auto kern = big ? (only_graph ? graph_dense_world_kernel<true, 1024, 512, 1, 4, 1, true, SIG_GRAPH>
+                                      : graph_dense_world_kernel<true, 1024, 512, 1, 4, 1, true, SIG_GENERIC>)
+                        : (only_graph ? graph_dense_world_kernel<true, 1024, 512, 1, 2, 2, true, SIG_GRAPH>
+                                      : graph_dense_world_kernel<true, 1024, 512, 1, 2, 2, true, SIG_GENERIC>);
+        const cudaError_t e = ensure_dynamic_smem(kern, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid_w, 512, smem, s>>>(G, P, pos_out, vel_out);
+        return cudaGetLastError();
+    }
     const cudaError_t e = ensure_dynamic_smem(nbody_tick_fused_kernel<1024>, smem);
     if (e != cudaSuccess) return e;
-    const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
     nbody_tick_fused_kernel<1024><<<gridf, dim3(32, kFastSrc, 3), smem, s>>>(G, P, pos_out, vel_out);
     return cudaGetLastError();
 }

@@ -1378,3 +1378,65 @@ def test_library_nccl_gather_and_row_sharded_world_on_two_gpus():
         assert ok_gather, f"rank {rank}: gathered trajectory differs from the oracle"
         assert ok_exact, f"rank {rank}: row-sharded EXACT differs from the oracle"
         assert fast_err <= 5 * FAST_TOL_TICK * 10, fast_err
+
+
+def test_numa_local_pinned_buffers_and_pcie_probe():
+    """b200_host_alloc_local: page-locked memory bound to the NUMA node of the GPU's PCIe root (falls back to plain
+    pinned memory when the node is unknown), usable as invoke_batch column buffers; b200_probe_pcie_gbs reports both
+    directions."""
+    import ctypes as C
+
+    from elodin_b200 import _lib
+
+    L = _lib.lib()
+    a = el.pinned_empty((1 << 16, 1, 7), np.float64, device=0)
+    a[...] = 1.5
+    node_gpu, node_buf = int(L.b200_device_numa_node(0)), int(L.b200_host_node_of(C.c_void_p(a.ctypes.data)))
+    if node_gpu >= 0 and node_buf >= 0:
+        assert node_buf == node_gpu
+    pos, vel, ine = random_world(3, 1 << 16, 1)
+    a[...] = pos
+    with el.B200Exec(1, 1 << 16, 0.01, None, [], "rk4", "fast") as ex:
+        ex.upload(WORLD_POS, a)
+        ex.upload(WORLD_VEL, vel)
+        ex.upload(INERTIA, ine)
+        ex.step(2, sync=True)
+        got = ex.download(WORLD_POS, out=a)
+    assert np.isfinite(got).all() and not np.array_equal(got, pos)
+    out = (C.c_double * 2)()
+    scratch = el.pinned_empty(1 << 21, np.float64, device=0)  # 16 MB
+    _lib.check(L.b200_probe_pcie_gbs(0, C.c_void_p(scratch.ctypes.data), 8 << 20, 8 << 20, 3, out))
+    assert out[0] > 1.0 and out[1] > 1.0  # GB/s, both directions at once
+    el.pinned_free(scratch)
+    el.pinned_free(a)
+
+
+@pytest.mark.parametrize("n_ticks", [1, 4])
+@pytest.mark.parametrize("extra", [False, True])
+def test_world_resident_pair_kernel_with_fused_integration(oracle, n_ticks, extra):
+    """Batches of 64..1024-body worlds big enough for the persistent pair kernel (graph_dense_world_kernel): gravity
+    and integration in one launch per tick, ping-pong planes; odd / even tick counts, step() then chunked invoke_batch,
+    gravity alone (compiled signature) and with another effector (interpreter), ragged N."""
+    O = oracle
+    M, N = 41, 97
+    pos, vel, ine = random_world(67, M, N)
+    pos[..., 4:] *= 1e-2
+    o, g, _ = effector_pair(O, "softened", edges=el.all_pairs_edges(N), k2=0.3, soft=1e-5)
+    oe, ge, cols = [o], [g], {}
+    if extra:
+        thrust = np.random.default_rng(4).uniform(0, 3, (M, N, 1))
+        o2, g2, c2 = effector_pair(O, "thrust", thrust=thrust)
+        oe.append(o2); ge.append(g2); cols.update(c2)
+    want = _run_oracle(O, pos, vel, ine, oe, 0.01, 2 * n_ticks)
+    with el.B200Exec(N, M, 0.01, None, ge, "rk4", "fast", invoke_chunk_bodies=30 * N) as ex:
+        ex.set_state(pos, vel, ine, **cols)
+        ex.step(n_ticks, sync=True)
+        mid = (ex.download(WORLD_POS), ex.download(WORLD_VEL))
+        table = {el.component_id("tick"): np.array([n_ticks], dtype=np.uint64), FORCE: np.zeros((M, N, 6)), INERTIA: ine,
+                 WORLD_POS: mid[0], WORLD_ACCEL: np.zeros((M, N, 6)), el.component_id("simulation_time_step"): np.array([0.01]),
+                 WORLD_VEL: mid[1]}
+        table.update({el.component_id(k): v for k, v in cols.items()})
+        out = dict(zip(ex.output_ids, ex.invoke_batch([table[c] for c in ex.input_ids], n_ticks)))
+        got = (out[WORLD_POS], out[WORLD_VEL], out[WORLD_ACCEL], out[FORCE])
+        _assert_close(got, want, 1e-11, f"world kernel fused {n_ticks} extra={extra}")
+        assert np.array_equal(ex.download(WORLD_POS), out[WORLD_POS]) and np.array_equal(ex.download(WORLD_VEL), out[WORLD_VEL])
