@@ -533,7 +533,12 @@ def run_b200(args):
     e2e = run_e2e(args, el, local, rank, world_size, barrier, max_over_ranks, numa_cpus)
 
     # ------------------------------------------------------------------ BASELINE configs[3] / configs[4] at N GPUs
-    multi = run_multi_gpu(args, torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, fp64_peak)
+    try:
+        multi = run_multi_gpu(args, torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, fp64_peak)
+    except Exception as e:  # secondary section: never lose the headline line over it (a failure here is the same on every rank)
+        import traceback
+
+        multi = {"error": repr(e)[:300], "traceback_tail": traceback.format_exc()[-600:]}
     ex.close()
 
     if rank == 0:
