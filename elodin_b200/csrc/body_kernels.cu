@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_fast_spec_kernel(const __gri
 #pragma unroll
     for (int k = 0; k < BPT; ++k) {
         in[k].thrust = 0.0; in[k].cd_rho = in[k].area = 0.0;
-        in[k].wr_t = in[k].wr_f = in[k].wind = in[k].wheels = Vec3{0.0, 0.0, 0.0};
+        in[k].wr_t = in[k].wr_f = in[k].wind = in[k].wheels = in[k].ww_t = in[k].ww_f = Vec3{0.0, 0.0, 0.0};
     }
     if (SIG & SIG_THRUST) B200_LDV(P.spec.thrust, 0, in[k].thrust);
     if (SIG & SIG_WRENCH) {
@@ -156,6 +156,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_fast_spec_kernel(const __gri
 #pragma unroll
         for (int k = 0; k < BPT; ++k)
             in[k].wheels = Vec3{w[k][0].x + w[k][1].x + w[k][2].x, w[k][0].y + w[k][1].y + w[k][2].y, w[k][0].z + w[k][1].z + w[k][2].z};
+    }
+    if (SIG & SIG_WWORLD) {
+        B200_LDV(P.spec.wworld, 0, in[k].ww_t.x); B200_LDV(P.spec.wworld, 1, in[k].ww_t.y); B200_LDV(P.spec.wworld, 2, in[k].ww_t.z);
+        B200_LDV(P.spec.wworld, 3, in[k].ww_f.x); B200_LDV(P.spec.wworld, 4, in[k].ww_f.y); B200_LDV(P.spec.wworld, 5, in[k].ww_f.z);
     }
     if (SIG & SIG_DRAG) {
         B200_LDV(P.spec.drag, 0, in[k].wind.x); B200_LDV(P.spec.drag, 1, in[k].wind.y); B200_LDV(P.spec.drag, 2, in[k].wind.z);
@@ -398,6 +402,11 @@ static uint32_t spec_signature(StepParams &Q)
             sig |= SIG_J2;
             sp.j2_mu = E.p[0]; sp.j2_k = E.p[1] * E.p[2] * E.p[2];
             break;
+        case B200_EFF_WRENCH_WORLD:
+            if (!E.col || (sig & SIG_WWORLD)) return SIG_GENERIC;
+            sig |= SIG_WWORLD;
+            sp.wworld = E.col;
+            break;
         case B200_EFF_TORQUE_BODY_FOLD: // the fold overwrites Force: only as the first effector is it a plain torque term
             if (i != 0 || !E.col || E.col_width != 9) return SIG_GENERIC;
             sig |= SIG_WHEELS;
@@ -427,6 +436,7 @@ static bool planes_16B_aligned(const StepParams &Q, uint32_t sig)
     if (sig & SIG_WRENCH) a |= (uintptr_t)Q.spec.wr_t | (uintptr_t)Q.spec.wr_f;
     if (sig & SIG_DRAG) a |= (uintptr_t)Q.spec.drag;
     if (sig & SIG_WHEELS) a |= (uintptr_t)Q.spec.wheels;
+    if (sig & SIG_WWORLD) a |= (uintptr_t)Q.spec.wworld;
     return (a & 15u) == 0 && (Q.ld & 1u) == 0;
 }
 
@@ -466,7 +476,7 @@ static void launch_spec(const StepParams &Q, cudaStream_t s)
 #define B200_SPEC_SIGS(X)                                                                                        \
     X(0u) X(SIG_DRAG) X(SIG_THRUST) X(SIG_WRENCH) X(SIG_FRAME) X(SIG_GRAPH)                                       \
     X(SIG_THRUST | SIG_DRAG) X(SIG_THRUST | SIG_DRAG | SIG_DRAG_PB) X(SIG_THRUST | SIG_WRENCH) X(SIG_FRAME | SIG_WRENCH)     \
-    X(SIG_J2) X(SIG_WHEELS | SIG_J2)
+    X(SIG_J2) X(SIG_WHEELS | SIG_J2) X(SIG_WWORLD) X(SIG_WHEELS | SIG_WWORLD)
 #endif
 
 template <int INTEG>

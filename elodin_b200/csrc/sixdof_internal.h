@@ -55,6 +55,7 @@ struct StepParams {
         double mu, om[3];   // GRAVITY_FRAME
         double j2_mu, j2_k; // GRAVITY_J2: mu, J2 * r_ref^2
         const double *wheels;        // 9 planes: three body-frame wheel torques
+        const double *wworld;        // 6 planes: world-frame wrench [tau, f]
         const double *thrust;        // 1 plane
         const double *wr_t, *wr_f;   // 3 planes each: body-frame torque / force of the wrench column
         const double *drag;          // wind(3) [+ Cd*rho, area]

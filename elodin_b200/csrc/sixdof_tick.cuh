@@ -279,6 +279,7 @@ enum : uint32_t {
     SIG_GRAPH = 32u,          // GRAVITY_EDGES_*: 9 planes of edge_fold gravity
     SIG_J2 = 64u,             // GRAVITY_J2
     SIG_WHEELS = 128u,        // TORQUE_BODY_FOLD with three wheels (the cube-sat shape), first in the list
+    SIG_WWORLD = 256u,        // WRENCH_WORLD: externally computed world-frame wrench column
     SIG_GENERIC = 0x80000000u // interpret StepParams::eff[] at run time
 };
 
@@ -289,6 +290,7 @@ struct EffIn {
     Vec3 wind;
     double cd_rho, area;
     Vec3 wheels;     // sum of the body's wheel torques (body frame)
+    Vec3 ww_t, ww_f; // world-frame torque / force of the WRENCH_WORLD column
 };
 
 // Everything the effector list contributes, folded once per launch:
@@ -410,6 +412,11 @@ __device__ __forceinline__ Folded fold_spec(const StepParams &P, uint64_t b, con
         f.j2_mu = P.spec.j2_mu;
         f.j2_k = P.spec.j2_k;
     }
+    if (SIG & SIG_WWORLD) {
+        f.fw = Vec3{f.fw.x + in.ww_f.x, f.fw.y + in.ww_f.y, f.fw.z + in.ww_f.z};
+        f.tw = in.ww_t;
+        f.wtorque = true;
+    }
     if (SIG & SIG_DRAG) {
         f.wind = in.wind;
         f.kd = (SIG & SIG_DRAG_PB) ? 0.5 * in.cd_rho * in.area : P.spec.kd;
@@ -492,7 +499,7 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
                                            const GravReg &greg, const EffIn &in = EffIn{})
 {
     constexpr bool GEN = SIG == SIG_GENERIC;
-    constexpr bool NEED_INVI = GEN || (SIG & (SIG_WRENCH | SIG_WHEELS));
+    constexpr bool NEED_INVI = GEN || (SIG & (SIG_WRENCH | SIG_WHEELS | SIG_WWORLD));
     const Vec3 invI = NEED_INVI ? Vec3{fa::rcp_nr(I.diag.x), fa::rcp_nr(I.diag.y), fa::rcp_nr(I.diag.z)} : Vec3{0.0, 0.0, 0.0};
     const double inv_m = fa::rcp_nr(I.m);
     Folded f;
@@ -506,7 +513,7 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
     // unequal to zero and take the full path); specialised: a property of the signature
     const bool has_u = GEN ? ((f.u.x != 0.0) | (f.u.y != 0.0) | (f.u.z != 0.0)) : (SIG & (SIG_WRENCH | SIG_WHEELS)) != 0;
     const bool has_fb = GEN ? ((f.fb.x != 0.0) | (f.fb.y != 0.0) | (f.fb.z != 0.0)) : (SIG & (SIG_THRUST | SIG_WRENCH)) != 0;
-    const bool has_tw = GEN ? f.wtorque : false; // world-frame torque: a_ang = R (invI .* (R^-1 tau_w)) per stage attitude
+    const bool has_tw = GEN ? f.wtorque : (SIG & SIG_WWORLD) != 0; // world-frame torque: a_ang = R (invI .* (R^-1 tau_w)) per stage attitude
     auto ang_world = [&](const Quat &q) { // angular acceleration the world-frame torque produces at attitude q
         const Vec3 tbody = fa::rot(Quat{-q.i, -q.j, -q.k, q.w}, f.tw);
         return fa::rot(q, Vec3{tbody.x * invI.x, tbody.y * invI.y, tbody.z * invI.z});

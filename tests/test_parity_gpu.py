@@ -1222,6 +1222,8 @@ def test_signature_kernels_match_the_interpreter_kernel(oracle, integrator):
             "j2": [("j2", {})],
             "cube_sat (wheel fold first, then J2)": [("wheels", dict(torques=wheels)), ("j2", {})],
             "g then wheels (interpreter: the fold overwrites)": [("gravity", {}), ("wheels", dict(torques=wheels))],
+            "external world wrench": [("wrench_world", dict(wrench=wrench))],
+            "wheels + external gravity (the cube-sat golden's replay shape)": [("wheels", dict(torques=wheels)), ("wrench_world", dict(wrench=wrench))],
             "wrench_then_drag (interpreter: torque reset)": [("wrench", dict(wrench=wrench)), ("drag", dict(wind=wind))],
         }
         for name, spec in lists.items():
