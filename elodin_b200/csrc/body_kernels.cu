@@ -17,7 +17,7 @@ namespace b200 {
 
 // ================================================================== EXACT body kernel
 
-template <int INTEG, int BLOCK, int MINB, bool UNR = false, bool NOEFF = false>
+template <int INTEG, int BLOCK, int MINB, bool UNR = false, uint32_t SEQ = SEQ_INTERPRET>
 __global__ void __launch_bounds__(BLOCK, MINB) body_exact_kernel(const __grid_constant__ StepParams P)
 {
     const uint64_t b = (uint64_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_exact_kernel(const __grid_co
     const GravReg no_greg{};
 
     for (uint32_t t = 0; t < P.n_ticks; ++t) {
-        exact_tick<INTEG, false, UNR, NOEFF>(P, b, x0, v0, a_out, f_out, I, no_greg);
+        exact_tick<INTEG, false, UNR, SEQ>(P, b, x0, v0, a_out, f_out, I, no_greg);
         uint64_t slot;
         if (traj_due(P, P.tick0 + t + 1, slot)) {
             traj_store_state(P, b, slot, x0, v0);
@@ -495,6 +495,47 @@ static bool launch_spec_sig(const StepParams &Q, uint32_t sig, cudaStream_t s)
     }
 }
 
+// EXACT effector sequences with a compiled kernel (four bits per effector kind, list order); every other list —
+// and any list with an entity mask — runs the interpreter kernel
+#define B200_SEQ1(a) ((uint32_t)(a))
+#define B200_SEQ2(a, b) ((uint32_t)(a) | ((uint32_t)(b) << 4))
+#define B200_SEQ3(a, b, c) ((uint32_t)(a) | ((uint32_t)(b) << 4) | ((uint32_t)(c) << 8))
+#define B200_EXACT_SEQS(X)                                                                                              \
+    X(0u)                                                                                                               \
+    X(B200_SEQ1(B200_EFF_GRAVITY_CONST))                                                                                \
+    X(B200_SEQ2(B200_EFF_GRAVITY_CONST, B200_EFF_DRAG_QUADRATIC))                            /* ball/sim.py */          \
+    X(B200_SEQ3(B200_EFF_GRAVITY_CONST, B200_EFF_THRUST_BODY, B200_EFF_DRAG_QUADRATIC))      /* rocket Monte-Carlo */   \
+    X(B200_SEQ3(B200_EFF_GRAVITY_CONST, B200_EFF_THRUST_BODY, B200_EFF_WRENCH_BODY))         /* rocket/main.py */       \
+    X(B200_SEQ2(B200_EFF_GRAVITY_FRAME, B200_EFF_WRENCH_BODY))                               /* falcon9/sim.py */       \
+    X(B200_SEQ1(B200_EFF_GRAVITY_EDGES_NEWTON)) X(B200_SEQ1(B200_EFF_GRAVITY_EDGES_SOFTENED))                         \
+    X(B200_SEQ2(B200_EFF_TORQUE_BODY_FOLD, B200_EFF_WRENCH_WORLD))                           /* cube-sat replay */
+
+static uint32_t exact_sequence(const StepParams &P)
+{
+    if (P.n_eff > 5) return SEQ_INTERPRET;
+    uint32_t seq = 0;
+    for (uint32_t i = 0; i < P.n_eff; ++i) {
+        if (P.eff[i].mask || P.eff[i].kind == 0 || P.eff[i].kind > 15) return SEQ_INTERPRET;
+        seq |= P.eff[i].kind << (4 * i);
+    }
+    return seq;
+}
+
+template <int INTEG, int BLOCK, int MINB>
+static bool launch_exact_seq(const StepParams &P, uint32_t seq, cudaStream_t s)
+{
+    const unsigned grid = (unsigned)((P.n_bodies + BLOCK - 1) / BLOCK);
+    switch (seq) {
+#define X(SEQV)                                                                            \
+    case (SEQV):                                                                           \
+        body_exact_kernel<INTEG, BLOCK, MINB, false, (SEQV)><<<grid, BLOCK, 0, s>>>(P);    \
+        return true;
+        B200_EXACT_SEQS(X)
+#undef X
+    default: return false;
+    }
+}
+
 cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode, cudaStream_t s)
 {
     if (P.n_bodies == 0) return cudaSuccess;
@@ -506,12 +547,16 @@ cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode,
         static const int xcfg = env_int("B200_EXACT_CFG", 3);
 #endif
         auto g = [&](int blk) { return (unsigned)((P.n_bodies + blk - 1) / blk); };
-        if (!rk4) {
-            if (P.n_eff == 0) body_exact_kernel<B200_INTEGRATOR_SEMI_IMPLICIT, 256, 1, false, true><<<g(256), 256, 0, s>>>(P);
-            else body_exact_kernel<B200_INTEGRATOR_SEMI_IMPLICIT, 256, 1><<<g(256), 256, 0, s>>>(P);
-        } else if (P.n_eff == 0 && xcfg == 3) {
-            body_exact_kernel<B200_INTEGRATOR_RK4, 128, 4, false, true><<<g(128), 128, 0, s>>>(P); // free bodies: no interpreter
-        } else switch (xcfg) {
+        // default: the kernel compiled for this effector sequence (no interpreter: 5.4e9 vs 4.1e9 entity-steps/s on free
+        // bodies, profiles/r02_tune_misc.md); the interpreter kernel for every other list
+        if (xcfg == 3) {
+            const uint32_t seq = exact_sequence(P);
+            if (seq != SEQ_INTERPRET &&
+                (rk4 ? launch_exact_seq<B200_INTEGRATOR_RK4, 128, 4>(P, seq, s) : launch_exact_seq<B200_INTEGRATOR_SEMI_IMPLICIT, 256, 1>(P, seq, s)))
+                return cudaGetLastError();
+        }
+        if (!rk4) body_exact_kernel<B200_INTEGRATOR_SEMI_IMPLICIT, 256, 1><<<g(256), 256, 0, s>>>(P);
+        else switch (xcfg) {
         case 1: body_exact_kernel<B200_INTEGRATOR_RK4, 256, 2><<<g(256), 256, 0, s>>>(P); break;
         case 0: body_exact_kernel<B200_INTEGRATOR_RK4, 256, 1><<<g(256), 256, 0, s>>>(P); break;
 #ifdef B200_TUNE
@@ -521,11 +566,10 @@ cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode,
         case 7: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 3, true><<<g(128), 128, 0, s>>>(P); break;
         case 8: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 2, true><<<g(128), 128, 0, s>>>(P); break;
         case 9: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 4, true><<<g(128), 128, 0, s>>>(P); break;
-        case 10: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 3, true, true><<<g(128), 128, 0, s>>>(P); break;
-        case 11: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 5, false, true><<<g(128), 128, 0, s>>>(P); break;
-        case 12: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 4, false, false><<<g(128), 128, 0, s>>>(P); break; // interpreter kept
+        case 10: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 3, true, 0u><<<g(128), 128, 0, s>>>(P); break;
+        case 11: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 5, false, 0u><<<g(128), 128, 0, s>>>(P); break;
 #endif
-        default: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 4><<<g(128), 128, 0, s>>>(P); break; // 4.3e9 vs 2.7e9 (256x1)
+        default: body_exact_kernel<B200_INTEGRATOR_RK4, 128, 4><<<g(128), 128, 0, s>>>(P); break; // 12: interpreter kept
         }
         return cudaGetLastError();
     }

@@ -105,120 +105,150 @@ static __device__ __noinline__ Vec3 j2_field_exact(double mu, double J2, double 
 }
 
 // clear_forces | effectors (array order) on the stage state; six_dof.rs:148-150,195
+// One effector applied to the accumulating Force of a stage, in EXACT arithmetic.  `kind` is E.kind for the run-time
+// interpreter and a compile-time constant for effector sequences (the switch then folds away).
+template <bool GREG>
+__device__ __forceinline__ void apply_effector_exact(uint32_t kind, const EffDev &E, const StepParams &P, uint64_t b, int slot,
+                                                     const Pose &sx, const ex::PoseInv &pi, const Motion &sv, const Inertia &I,
+                                                     const GravReg &greg, Motion &F)
+{
+    using namespace ex;
+    switch (kind) {
+    case B200_EFF_GRAVITY_CONST: { // ball/sim.py:56-58: f + SpatialForce(linear=g*m)
+        F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+        F.lin = Vec3{add(F.lin.x, mul(E.p[0], I.m)), add(F.lin.y, mul(E.p[1], I.m)),
+                     add(F.lin.z, mul(E.p[2], I.m))};
+        break;
+    }
+    case B200_EFF_DRAG_QUADRATIC: { // ball/sim.py:99-116; result torque is zero
+        double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+        if (E.col) { w0 = ldp(E.col, P.ld, 0, b); w1 = ldp(E.col, P.ld, 1, b); w2 = ldp(E.col, P.ld, 2, b); }
+        const Vec3 fl = {sub(w0, sv.lin.x), sub(w1, sv.lin.y), sub(w2, sv.lin.z)};
+        const double speed = sqr(dot3(fl));
+        const double cd_rho = E.col_width == 5 ? ldp(E.col, P.ld, 3, b) : E.p[0];
+        const double area = E.col_width == 5 ? ldp(E.col, P.ld, 4, b) : E.p[1];
+        const double drag = mul(0.5, mul(mul(cd_rho, mul(speed, speed)), area));
+        F.ang = Vec3{0.0, 0.0, 0.0};
+        F.lin = Vec3{add(F.lin.x, mul(drag, div(fl.x, speed))), add(F.lin.y, mul(drag, div(fl.y, speed))),
+                     add(F.lin.z, mul(drag, div(fl.z, speed)))};
+        break;
+    }
+    case B200_EFF_THRUST_BODY: { // rocket/main.py:429-431
+        const double t = E.col ? ldp(E.col, P.ld, 0, b) : 0.0;
+        const Vec3 d = qrot_with(sx.q, pi.qi, Vec3{E.p[0], E.p[1], E.p[2]});
+        F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+        F.lin = Vec3{add(F.lin.x, mul(d.x, t)), add(F.lin.y, mul(d.y, t)), add(F.lin.z, mul(d.z, t))};
+        break;
+    }
+    case B200_EFF_WRENCH_BODY: { // rocket/main.py:407-413, falcon9/sim.py:659-672
+        Vec3 a = {0.0, 0.0, 0.0}, c = {0.0, 0.0, 0.0};
+        if (E.col) {
+            a = Vec3{ldp(E.col, P.ld, 0, b), ldp(E.col, P.ld, 1, b), ldp(E.col, P.ld, 2, b)};
+            c = Vec3{ldp(E.col, P.ld, 3, b), ldp(E.col, P.ld, 4, b), ldp(E.col, P.ld, 5, b)};
+        }
+        const bool lin_first = (E.flags & B200_EFF_FLAG_WRENCH_LINEAR_FIRST) != 0;
+        const Vec3 tw = qrot_with(sx.q, pi.qi, lin_first ? c : a);
+        const Vec3 fw = qrot_with(sx.q, pi.qi, lin_first ? a : c);
+        F.ang = Vec3{add(F.ang.x, tw.x), add(F.ang.y, tw.y), add(F.ang.z, tw.z)};
+        F.lin = Vec3{add(F.lin.x, fw.x), add(F.lin.y, fw.y), add(F.lin.z, fw.z)};
+        break;
+    }
+    case B200_EFF_GRAVITY_FRAME: { // falcon9/sim.py:350-361, frames.py:91-109
+        const double mu = E.p[0];
+        const Vec3 om = {E.p[1], E.p[2], E.p[3]};
+        const Vec3 r = sx.x, v = sv.lin;
+        const double rn = sqr(dot3(r));
+        const double rn3 = mul(mul(rn, rn), rn);
+        const Vec3 g = {div(mul(-mu, r.x), rn3), div(mul(-mu, r.y), rn3), div(mul(-mu, r.z), rn3)};
+        const Vec3 c = cross(om, v);
+        const Vec3 c2 = cross(om, cross(om, r));
+        const Vec3 acc = {add(g.x, add(mul(-2.0, c.x), -c2.x)), add(g.y, add(mul(-2.0, c.y), -c2.y)),
+                          add(g.z, add(mul(-2.0, c.z), -c2.z))};
+        F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+        F.lin = Vec3{add(F.lin.x, mul(acc.x, I.m)), add(F.lin.y, mul(acc.y, I.m)), add(F.lin.z, mul(acc.z, I.m))};
+        break;
+    }
+    case B200_EFF_WRENCH_WORLD: { // cube-sat/main.py:516-527, drone/sim.py:99-103: force + SpatialForce(..)
+        if (E.col) {
+            F.ang = Vec3{add(F.ang.x, ldp(E.col, P.ld, 0, b)), add(F.ang.y, ldp(E.col, P.ld, 1, b)), add(F.ang.z, ldp(E.col, P.ld, 2, b))};
+            F.lin = Vec3{add(F.lin.x, ldp(E.col, P.ld, 3, b)), add(F.lin.y, ldp(E.col, P.ld, 4, b)), add(F.lin.z, ldp(E.col, P.ld, 5, b))};
+        }
+        break;
+    }
+    case B200_EFF_TORQUE_BODY_FOLD: { // cube-sat/main.py:492-505: Force := fold_k (f + SpatialForce(torque = q @ tau_k))
+        if (E.col) {
+            Motion acc = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+            const uint32_t K = E.col_width / 3u;
+            for (uint32_t k = 0; k < K; ++k) {
+                const Vec3 t = qrot_with(sx.q, pi.qi, Vec3{ldp(E.col, P.ld, 3 * k + 0, b), ldp(E.col, P.ld, 3 * k + 1, b),
+                                                           ldp(E.col, P.ld, 3 * k + 2, b)});
+                acc.ang = Vec3{add(acc.ang.x, t.x), add(acc.ang.y, t.y), add(acc.ang.z, t.z)};
+                acc.lin = Vec3{add(acc.lin.x, 0.0), add(acc.lin.y, 0.0), add(acc.lin.z, 0.0)};
+            }
+            F = acc;
+        }
+        break;
+    }
+    case B200_EFF_GRAVITY_J2: { // python/elodin/j2.py:5-29
+        const Vec3 g = j2_field_exact(E.p[0], E.p[1], E.p[2], sx.x, I.m);
+        F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+        F.lin = Vec3{add(F.lin.x, g.x), add(F.lin.y, g.y), add(F.lin.z, g.z)};
+        break;
+    }
+    case B200_EFF_GRAVITY_EDGES_NEWTON:
+    case B200_EFF_GRAVITY_EDGES_SOFTENED: { // Force := edge_fold(init 0) for bodies that own an edge
+        if (GREG) {
+            if (greg.has) { F.ang = Vec3{0.0, 0.0, 0.0}; F.lin = grav_slot(greg, slot); }
+        } else if (P.gforce && P.has_edge && P.has_edge[(b + P.ent0) % P.n_entities]) {
+            F.ang = Vec3{0.0, 0.0, 0.0};
+            F.lin = Vec3{ldp(P.gforce, P.ld, slot * 3 + 0, b), ldp(P.gforce, P.ld, slot * 3 + 1, b),
+                         ldp(P.gforce, P.ld, slot * 3 + 2, b)};
+        }
+        break;
+    }
+    default: break;
+    }
+}
+
+// clear_forces | effectors (array order) on the stage state; six_dof.rs:148-150,195
 template <bool GREG>
 __device__ __forceinline__ Motion effectors_exact(const StepParams &P, uint64_t b, int slot, const Pose &sx,
                                                   const ex::PoseInv &pi, const Motion &sv, const Inertia &I,
                                                   const GravReg &greg)
 {
-    using namespace ex;
     Motion F = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
     for (uint32_t e = 0; e < P.n_eff; ++e) {
         const EffDev &E = P.eff[e];
         if (E.mask && !E.mask[(b + P.ent0) % P.n_entities]) continue; // entity does not own the effector's components (query join)
-        switch (E.kind) {
-        case B200_EFF_GRAVITY_CONST: { // ball/sim.py:56-58: f + SpatialForce(linear=g*m)
-            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
-            F.lin = Vec3{add(F.lin.x, mul(E.p[0], I.m)), add(F.lin.y, mul(E.p[1], I.m)),
-                         add(F.lin.z, mul(E.p[2], I.m))};
-            break;
-        }
-        case B200_EFF_DRAG_QUADRATIC: { // ball/sim.py:99-116; result torque is zero
-            double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-            if (E.col) { w0 = ldp(E.col, P.ld, 0, b); w1 = ldp(E.col, P.ld, 1, b); w2 = ldp(E.col, P.ld, 2, b); }
-            const Vec3 fl = {sub(w0, sv.lin.x), sub(w1, sv.lin.y), sub(w2, sv.lin.z)};
-            const double speed = sqr(dot3(fl));
-            const double cd_rho = E.col_width == 5 ? ldp(E.col, P.ld, 3, b) : E.p[0];
-            const double area = E.col_width == 5 ? ldp(E.col, P.ld, 4, b) : E.p[1];
-            const double drag = mul(0.5, mul(mul(cd_rho, mul(speed, speed)), area));
-            F.ang = Vec3{0.0, 0.0, 0.0};
-            F.lin = Vec3{add(F.lin.x, mul(drag, div(fl.x, speed))), add(F.lin.y, mul(drag, div(fl.y, speed))),
-                         add(F.lin.z, mul(drag, div(fl.z, speed)))};
-            break;
-        }
-        case B200_EFF_THRUST_BODY: { // rocket/main.py:429-431
-            const double t = E.col ? ldp(E.col, P.ld, 0, b) : 0.0;
-            const Vec3 d = qrot_with(sx.q, pi.qi, Vec3{E.p[0], E.p[1], E.p[2]});
-            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
-            F.lin = Vec3{add(F.lin.x, mul(d.x, t)), add(F.lin.y, mul(d.y, t)), add(F.lin.z, mul(d.z, t))};
-            break;
-        }
-        case B200_EFF_WRENCH_BODY: { // rocket/main.py:407-413, falcon9/sim.py:659-672
-            Vec3 a = {0.0, 0.0, 0.0}, c = {0.0, 0.0, 0.0};
-            if (E.col) {
-                a = Vec3{ldp(E.col, P.ld, 0, b), ldp(E.col, P.ld, 1, b), ldp(E.col, P.ld, 2, b)};
-                c = Vec3{ldp(E.col, P.ld, 3, b), ldp(E.col, P.ld, 4, b), ldp(E.col, P.ld, 5, b)};
-            }
-            const bool lin_first = (E.flags & B200_EFF_FLAG_WRENCH_LINEAR_FIRST) != 0;
-            const Vec3 tw = qrot_with(sx.q, pi.qi, lin_first ? c : a);
-            const Vec3 fw = qrot_with(sx.q, pi.qi, lin_first ? a : c);
-            F.ang = Vec3{add(F.ang.x, tw.x), add(F.ang.y, tw.y), add(F.ang.z, tw.z)};
-            F.lin = Vec3{add(F.lin.x, fw.x), add(F.lin.y, fw.y), add(F.lin.z, fw.z)};
-            break;
-        }
-        case B200_EFF_GRAVITY_FRAME: { // falcon9/sim.py:350-361, frames.py:91-109
-            const double mu = E.p[0];
-            const Vec3 om = {E.p[1], E.p[2], E.p[3]};
-            const Vec3 r = sx.x, v = sv.lin;
-            const double rn = sqr(dot3(r));
-            const double rn3 = mul(mul(rn, rn), rn);
-            const Vec3 g = {div(mul(-mu, r.x), rn3), div(mul(-mu, r.y), rn3), div(mul(-mu, r.z), rn3)};
-            const Vec3 c = cross(om, v);
-            const Vec3 c2 = cross(om, cross(om, r));
-            const Vec3 acc = {add(g.x, add(mul(-2.0, c.x), -c2.x)), add(g.y, add(mul(-2.0, c.y), -c2.y)),
-                              add(g.z, add(mul(-2.0, c.z), -c2.z))};
-            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
-            F.lin = Vec3{add(F.lin.x, mul(acc.x, I.m)), add(F.lin.y, mul(acc.y, I.m)), add(F.lin.z, mul(acc.z, I.m))};
-            break;
-        }
-        case B200_EFF_WRENCH_WORLD: { // cube-sat/main.py:516-527, drone/sim.py:99-103: force + SpatialForce(..)
-            if (E.col) {
-                F.ang = Vec3{add(F.ang.x, ldp(E.col, P.ld, 0, b)), add(F.ang.y, ldp(E.col, P.ld, 1, b)), add(F.ang.z, ldp(E.col, P.ld, 2, b))};
-                F.lin = Vec3{add(F.lin.x, ldp(E.col, P.ld, 3, b)), add(F.lin.y, ldp(E.col, P.ld, 4, b)), add(F.lin.z, ldp(E.col, P.ld, 5, b))};
-            }
-            break;
-        }
-        case B200_EFF_TORQUE_BODY_FOLD: { // cube-sat/main.py:492-505: Force := fold_k (f + SpatialForce(torque = q @ tau_k))
-            if (E.col) {
-                Motion acc = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
-                const uint32_t K = E.col_width / 3u;
-                for (uint32_t k = 0; k < K; ++k) {
-                    const Vec3 t = qrot_with(sx.q, pi.qi, Vec3{ldp(E.col, P.ld, 3 * k + 0, b), ldp(E.col, P.ld, 3 * k + 1, b),
-                                                               ldp(E.col, P.ld, 3 * k + 2, b)});
-                    acc.ang = Vec3{add(acc.ang.x, t.x), add(acc.ang.y, t.y), add(acc.ang.z, t.z)};
-                    acc.lin = Vec3{add(acc.lin.x, 0.0), add(acc.lin.y, 0.0), add(acc.lin.z, 0.0)};
-                }
-                F = acc;
-            }
-            break;
-        }
-        case B200_EFF_GRAVITY_J2: { // python/elodin/j2.py:5-29
-            const Vec3 g = j2_field_exact(E.p[0], E.p[1], E.p[2], sx.x, I.m);
-            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
-            F.lin = Vec3{add(F.lin.x, g.x), add(F.lin.y, g.y), add(F.lin.z, g.z)};
-            break;
-        }
-        case B200_EFF_GRAVITY_EDGES_NEWTON:
-        case B200_EFF_GRAVITY_EDGES_SOFTENED: { // Force := edge_fold(init 0) for bodies that own an edge
-            if (GREG) {
-                if (greg.has) { F.ang = Vec3{0.0, 0.0, 0.0}; F.lin = grav_slot(greg, slot); }
-            } else if (P.gforce && P.has_edge && P.has_edge[(b + P.ent0) % P.n_entities]) {
-                F.ang = Vec3{0.0, 0.0, 0.0};
-                F.lin = Vec3{ldp(P.gforce, P.ld, slot * 3 + 0, b), ldp(P.gforce, P.ld, slot * 3 + 1, b),
-                             ldp(P.gforce, P.ld, slot * 3 + 2, b)};
-            }
-            break;
-        }
-        default: break;
-        }
+        apply_effector_exact<GREG>(E.kind, E, P, b, slot, sx, pi, sv, I, greg, F);
     }
+    return F;
+}
+
+// The same pipe for an effector list known at compile time: SEQ packs the kinds of effectors 0..4 in list order, four
+// bits each (0 ends the list; SEQ = 0 is the empty list).  Same operations in the same order as the interpreter — the
+// order of accumulation is part of the arithmetic — without its loop, its switch, and the registers they pin.
+static constexpr uint32_t SEQ_INTERPRET = 0xffffffffu;
+template <uint32_t SEQ, bool GREG>
+__device__ __forceinline__ Motion effectors_exact_seq(const StepParams &P, uint64_t b, int slot, const Pose &sx,
+                                                      const ex::PoseInv &pi, const Motion &sv, const Inertia &I,
+                                                      const GravReg &greg)
+{
+    Motion F = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+    if constexpr (((SEQ >> 0) & 15u) != 0) apply_effector_exact<GREG>((SEQ >> 0) & 15u, P.eff[0], P, b, slot, sx, pi, sv, I, greg, F);
+    if constexpr (((SEQ >> 4) & 15u) != 0) apply_effector_exact<GREG>((SEQ >> 4) & 15u, P.eff[1], P, b, slot, sx, pi, sv, I, greg, F);
+    if constexpr (((SEQ >> 8) & 15u) != 0) apply_effector_exact<GREG>((SEQ >> 8) & 15u, P.eff[2], P, b, slot, sx, pi, sv, I, greg, F);
+    if constexpr (((SEQ >> 12) & 15u) != 0) apply_effector_exact<GREG>((SEQ >> 12) & 15u, P.eff[3], P, b, slot, sx, pi, sv, I, greg, F);
+    if constexpr (((SEQ >> 16) & 15u) != 0) apply_effector_exact<GREG>((SEQ >> 16) & 15u, P.eff[4], P, b, slot, sx, pi, sv, I, greg, F);
     return F;
 }
 
 // one tick of one body in EXACT arithmetic (state in registers)
 // UNR: unroll the three independent stage poses (more instruction-level parallelism across the dependent IEEE
 // divisions, more registers) or keep them a loop
-// NOEFF: the effector list is empty (clear_forces only): the interpreter and its registers are compiled out
-template <int INTEG, bool GREG, bool UNR = false, bool NOEFF = false>
+// SEQ: SEQ_INTERPRET = interpret P.eff[] at run time; anything else = the effector list as a compile-time sequence
+// (0 = no effectors: clear_forces only)
+template <int INTEG, bool GREG, bool UNR = false, uint32_t SEQ = SEQ_INTERPRET>
 __device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose &x0, Motion &v0, Motion &a_out,
                                            Motion &f_out, const Inertia &I, const GravReg &greg)
 {
@@ -239,8 +269,8 @@ __device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose
             for (int j = 0; j < n_stages; ++j) {
                 const int s = (k == 0) ? 0 : (k == 1 ? 1 + j : 3);
                 const Motion sv = madd(v0, scale(dtf, sa));
-                if (NOEFF) f_out = Motion{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
-                else f_out = effectors_exact<GREG>(P, b, k, sx, pi, sv, I, greg);
+                if constexpr (SEQ == SEQ_INTERPRET) f_out = effectors_exact<GREG>(P, b, k, sx, pi, sv, I, greg);
+                else f_out = effectors_exact_seq<SEQ, GREG>(P, b, k, sx, pi, sv, I, greg);
                 sa = calc_accel_with(sx, pi, f_out, I);
                 if (s == 0) { kv = sv; ka = sa; }
                 else if (s == 3) { kv = madd(kv, sv); ka = madd(ka, sa); }
@@ -254,8 +284,8 @@ __device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose
     } else {
         // semi_implicit.rs:42-62
         const PoseInv pi = pose_inverses(x0.q);
-        if (NOEFF) f_out = Motion{{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
-        else f_out = effectors_exact<GREG>(P, b, 0, x0, pi, v0, I, greg);
+        if constexpr (SEQ == SEQ_INTERPRET) f_out = effectors_exact<GREG>(P, b, 0, x0, pi, v0, I, greg);
+        else f_out = effectors_exact_seq<SEQ, GREG>(P, b, 0, x0, pi, v0, I, greg);
         a_out = calc_accel_with(x0, pi, f_out, I);
         v0 = madd(v0, scale(P.dt_final, a_out));
         x0 = tadd(x0, scale(P.dt_final, v0));
