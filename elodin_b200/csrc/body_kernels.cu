@@ -30,12 +30,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_exact_kernel(const __grid_co
     const Inertia I = load_inertia(P.ine, P.ld, b);
     const GravReg no_greg{};
 
+    uint32_t traj_phase = 0; // one 64-bit division per launch, not per tick (see fast_ticks)
+    uint64_t traj_slot = 0;
+    if (P.traj_every) { traj_phase = (uint32_t)(P.tick0 % P.traj_every); traj_slot = P.tick0 / P.traj_every; }
     for (uint32_t t = 0; t < P.n_ticks; ++t) {
         exact_tick<INTEG, false, UNR, SEQ>(P, b, x0, v0, a_out, f_out, I, no_greg);
-        uint64_t slot;
-        if (traj_due(P, P.tick0 + t + 1, slot)) {
-            traj_store_state(P, b, slot, x0, v0);
-            if (P.traj_planes == 25) traj_store_af(P, b, slot, a_out, f_out);
+        if (P.traj_every && ++traj_phase == P.traj_every) {
+            traj_phase = 0;
+            if (traj_slot < P.traj_capacity) {
+                traj_store_state(P, b, traj_slot, x0, v0);
+                if (P.traj_planes == 25) traj_store_af(P, b, traj_slot, a_out, f_out);
+            }
+            ++traj_slot;
         }
     }
     store_pose(P.pos, P.ld, b, x0);

@@ -549,6 +549,12 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
         return fa::rot(q, Vec3{tbody.x * invI.x, tbody.y * invI.y, tbody.z * invI.z});
     };
 
+    // telemetry samples: one 64-bit division per call instead of one per tick (a sample is due when the tick count
+    // reaches a multiple of traj_every; its slot is that multiple's index - 1)
+    uint32_t traj_phase = 0;
+    uint64_t traj_slot = 0;
+    if (TRAJ && P.traj_every) { traj_phase = (uint32_t)(tick0 % P.traj_every); traj_slot = tick0 / P.traj_every; }
+
     for (uint32_t t = 0; t < n_ticks; ++t) {
         if (INTEG == B200_INTEGRATOR_RK4) {
             const Vec3 w0 = v0.ang, u0 = v0.lin;
@@ -617,11 +623,14 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
             x0.x = Vec3{fma(d, v0.lin.x, x0.x.x), fma(d, v0.lin.y, x0.x.y), fma(d, v0.lin.z, x0.x.z)};
             a_last.ang = aa; a_last.lin = al; q_last = qn;
         }
-        if (TRAJ) { // compiled out of the launches that record nothing (the roofline case)
-            uint64_t slot;
-            if (traj_due(P, tick0 + t + 1, slot)) {
-                traj_store_state(P, b, slot, x0, v0);
-                if (P.traj_planes == 25) traj_store_af(P, b, slot, a_last, force_out_fast(a_last.lin, f.u, q_last, I, f.tw));
+        if (TRAJ && P.traj_every) { // compiled out of the launches that record nothing (the roofline case)
+            if (++traj_phase == P.traj_every) {
+                traj_phase = 0;
+                if (traj_slot < P.traj_capacity) {
+                    traj_store_state(P, b, traj_slot, x0, v0);
+                    if (P.traj_planes == 25) traj_store_af(P, b, traj_slot, a_last, force_out_fast(a_last.lin, f.u, q_last, I, f.tw));
+                }
+                ++traj_slot;
             }
         }
     }
