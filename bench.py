@@ -511,6 +511,39 @@ def run_b200(args):
                 sx.close()
                 del p2, cols
             extras["effector_sets"] = eff_out
+            # the cube-sat example's integrator (Integrator.SemiImplicit, examples/cube-sat/main.py:710) on the same set
+            sx = el.B200Exec(1, M, DT, None, [el.TorqueBodyFold("wheel_torques", 3), el.GravityJ2()], "semi_implicit", "fast", device=local)
+            sx.set_stream(stream.cuda_stream)
+            p2 = pos.copy(); p2[..., 4:] += np.array([6.778e6, 0.0, 0.0])
+            sx.set_state(p2, vel, ine, wheel_torques=rng.normal(0, 2e-3, (M, 1, 9)))
+            sx.step(5)
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(stream); sx.step(100); q1.record(stream)
+            torch.cuda.synchronize()
+            t_ms = q0.elapsed_time(q1) / 100
+            eff_out["cube_sat_semi_implicit"] = {"value": M / (t_ms * 1e-3), "unit": UNIT, "bytes_per_entity_step": 336, "us_per_tick": t_ms * 1e3,
+                                                 "achieved_GBps": 336 * M / (t_ms * 1e-3) / 1e9, "frac": 336 * M / (t_ms * 1e-3) / 1e9 / peak,
+                                                 "note": "entity-steps of the semi-implicit integrator (one stage per tick), not RK4 ticks"}
+            sx.close()
+            del p2
+            # telemetry on every tick: the trajectory ring adds 104 B per body and tick (13 more planes written)
+            tcap = 16
+            tx = el.B200Exec(1, M, DT, None, [], "rk4", "fast", device=local, trajectory_every=1, trajectory_capacity=tcap)
+            tx.set_stream(stream.cuda_stream)
+            tx.set_state(pos, vel, ine)
+            tx.step(4)
+            tx.sync()
+            tx.trajectory_reset()
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(stream); tx.step(tcap); q1.record(stream)
+            torch.cuda.synchronize()
+            t_ms = q0.elapsed_time(q1) / tcap
+            extras["telemetry_every_tick"] = {"value": M / (t_ms * 1e-3), "unit": UNIT, "bytes_per_entity_step": 264 + 104, "us_per_tick": t_ms * 1e3,
+                                              "achieved_GBps": 368 * M / (t_ms * 1e-3) / 1e9, "frac": 368 * M / (t_ms * 1e-3) / 1e9 / peak,
+                                              "note": "free body, one (WorldPos, WorldVel) sample per tick into the device trajectory ring"}
+            tx.close()
             # BASELINE configs[1] literally: ONE body, dependent steps (latency chain, one persistent launch per 10^4 ticks)
             sb = el.B200Exec(1, 1, DT, None, [], "rk4", "fast", device=local, max_fused_ticks=10000)
             sb.set_stream(stream.cuda_stream)
