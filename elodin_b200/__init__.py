@@ -17,7 +17,7 @@ the CUDA library or without a GPU raises.
 
 from . import _lib, effectors
 from ._lib import B200Error, B200ValueError, component_id
-from .effectors import (DragQuadratic, GravityConst, GravityEdges, GravityFrame, GravityJ2, Pipe, System, ThrustBody,
+from .effectors import (DragQuadratic, GravityConst, GravityEGM08, GravityEdges, GravityFrame, GravityJ2, Pipe, System, ThrustBody,
                         TorqueBodyFold, WrenchBody, WrenchWorld, all_pairs_edges)
 from .executor import B200Exec, device_count, pinned_empty, pinned_free
 from .world import (Annotated, Archetype, Body, Component, ComponentType, Edge, EntityId, Exec, Force, HostSystem,

@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200_sixdof.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_EFFECTORS = 8
 
 OK = 0
@@ -40,6 +40,7 @@ EFF_GRAVITY_EDGES_SOFTENED = 7
 EFF_WRENCH_WORLD = 8
 EFF_TORQUE_BODY_FOLD = 9
 EFF_GRAVITY_J2 = 10
+EFF_GRAVITY_EGM08 = 11
 EFF_FLAG_WRENCH_LINEAR_FIRST = 1
 TRAJ_FULL = 1
 
@@ -73,6 +74,9 @@ class Effector(C.Structure):
         ("edge_from", C.c_void_p),
         ("edge_to", C.c_void_p),
         ("entity_mask", C.c_void_p),
+        ("table0", C.c_void_p),
+        ("table1", C.c_void_p),
+        ("table_len", C.c_uint64),
     ]
 
 

@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "sixdof_tick.cuh"
+#include "egm08_field.cuh"
 #include "sixdof_launch.h"
 
 namespace b200 {
@@ -466,6 +467,36 @@ __global__ void __launch_bounds__(kBlockG) graph_csr_kernel(const __grid_constan
     }
 }
 
+// ================================================================== EGM08 stage forces
+//
+// GRAVITY_EGM08 (python/elodin/egm08.py) is a ~30 k-instruction series per evaluation at degree 64.  Like the edge_fold
+// gravity it depends on the stage POSITION only, and the stage positions of a tick depend on (x0, v0) only, so it runs
+// in its own launch before the body kernel: thread = (body, stage slot), result = 9 planes of additive stage forces the
+// body kernels add where the effector sits in the list.  One arithmetic (the oracle's, IEEE operation by operation) in
+// both math modes: EXACT stays bit-identical, FAST inherits it.
+template <bool EXACT, bool RK4>
+__global__ void __launch_bounds__(128) egm08_force_kernel(const __grid_constant__ EgmParams E)
+{
+    constexpr int NS = RK4 ? 3 : 1;
+    const uint64_t t = (uint64_t)blockIdx.x * 128 + threadIdx.x;
+    if (t >= E.n_bodies * NS) return;
+    const uint64_t b = t % E.n_bodies; // slot-major: the threads of a warp share a stage slot
+    const int sl = (int)(t / E.n_bodies);
+    if (E.mask && !E.mask[(b + E.ent0) % E.n_entities]) return; // not a member: the body kernel skips the effector too
+    const Vec3 x = {ldp(E.pos, E.ld, 4, b), ldp(E.pos, E.ld, 5, b), ldp(E.pos, E.ld, 6, b)};
+    Vec3 p = x;
+    if (RK4) {
+        const Vec3 v = {ldp(E.vel, E.ld, 3, b), ldp(E.vel, E.ld, 4, b), ldp(E.vel, E.ld, 5, b)};
+        const double fac = sl == 0 ? 0.0 : (sl == 1 ? 0.5 : 1.0);
+        // the stage position exactly as the body kernel of the same math mode forms it
+        p = stage_pos<EXACT>(x, v, EXACT ? ex::mul(E.dt_stage, fac) : fac * E.dt_stage);
+    }
+    const Vec3 g = egm08_field(E.table, (int)E.L, E.mu, E.r_ref, p, ldp(E.ine, E.ld, 6, b));
+    stp(E.aforce, E.ld, sl * 3 + 0, b, g.x);
+    stp(E.aforce, E.ld, sl * 3 + 1, b, g.y);
+    stp(E.aforce, E.ld, sl * 3 + 2, b, g.z);
+}
+
 // ================================================================== small graph worlds: whole ticks in one warp
 //
 // A world of N <= 32 bodies fits in a warp: lane = body, floor(32/N) whole worlds per warp.  The edge_fold
@@ -652,6 +683,22 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
         const unsigned grid = (unsigned)((total + kBlockG - 1) / kBlockG);
         if (exact) { if (rk4) graph_csr_kernel<true, true><<<grid, kBlockG, 0, s>>>(G); else graph_csr_kernel<true, false><<<grid, kBlockG, 0, s>>>(G); }
         else { if (rk4) graph_csr_kernel<false, true><<<grid, kBlockG, 0, s>>>(G); else graph_csr_kernel<false, false><<<grid, kBlockG, 0, s>>>(G); }
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_egm08_force(const EgmParams &E, int math_mode, cudaStream_t s)
+{
+    if (E.n_bodies == 0) return cudaSuccess;
+    const bool rk4 = E.integrator == B200_INTEGRATOR_RK4;
+    const uint64_t threads = E.n_bodies * (rk4 ? 3u : 1u);
+    const unsigned grid = (unsigned)((threads + 127) / 128);
+    if (math_mode == B200_MATH_EXACT) {
+        if (rk4) egm08_force_kernel<true, true><<<grid, 128, 0, s>>>(E);
+        else egm08_force_kernel<true, false><<<grid, 128, 0, s>>>(E);
+    } else {
+        if (rk4) egm08_force_kernel<false, true><<<grid, 128, 0, s>>>(E);
+        else egm08_force_kernel<false, false><<<grid, 128, 0, s>>>(E);
     }
     return cudaGetLastError();
 }

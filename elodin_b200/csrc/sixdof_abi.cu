@@ -103,6 +103,42 @@ int add_column(b200_sixdof *h, uint64_t id, uint32_t width, bool global)
     return B200_OK;
 }
 
+// Derived tables of the EGM08 recursion (python/elodin/egm08.py:84-144), laid out behind the caller's C / S tables:
+// [C | S | n1 | n2 | nq1 | nq2] each (L+1)^2 row-major [l][m], then diag[L+1], offc[L+1].  The same formulas, operation
+// for operation, as the test oracle's orc_egm08_tables, so both sides evaluate the series on bit-identical constants.
+double kdelta(int d) { return d == 0 ? 1.0 : 2.0; }
+
+std::vector<double> egm08_tables(int L, const double *c_bar, const double *s_bar)
+{
+    const int n = L + 1;
+    std::vector<double> t((size_t)6 * n * n + 2 * n, 0.0);
+    double *C = t.data(), *S = C + n * n, *n1 = S + n * n, *n2 = n1 + n * n, *nq1 = n2 + n * n, *nq2 = nq1 + n * n;
+    double *diag = nq2 + n * n, *offc = diag + n;
+    std::memcpy(C, c_bar, sizeof(double) * n * n);
+    std::memcpy(S, s_bar, sizeof(double) * n * n);
+    for (int l = 0; l <= L; ++l)
+        for (int m = 0; m <= L; ++m) {
+            double v1 = 0.0, v2 = 0.0;
+            if (l >= m + 2) {
+                v1 = std::sqrt((double)((2 * l + 1) * (2 * l - 1)) / (double)((l + m) * (l - m)));
+                v2 = std::sqrt((double)((l + m - 1) * (l - m - 1) * (2 * l + 1)) / (double)((2 * l - 3) * (l + m) * (l - m)));
+            }
+            n1[l * n + m] = v1;
+            n2[l * n + m] = v2;
+            const double num1 = (double)(l - m) * kdelta(m) * (double)(l + m + 1);
+            nq1[l * n + m] = num1 < 0.0 ? 0.0 : std::sqrt(num1 / kdelta(m + 1));
+            const double num2 = (double)(l + m + 2) * (double)(l + m + 1) * (double)(2 * l + 1) * kdelta(m);
+            nq2[l * n + m] = num2 < 0.0 ? 0.0 : std::sqrt(num2 / ((double)(2 * l + 3) * kdelta(m + 1)));
+        }
+    double cur = 1.0;
+    for (int l = 0; l <= L; ++l) {
+        if (l > 0) cur = cur * std::sqrt(((double)(2 * l + 1) * kdelta(l)) / ((double)(2 * l) * kdelta(l - 1)));
+        diag[l] = cur;
+        offc[l] = l == 0 ? 0.0 : diag[l] * std::sqrt(((double)(2 * l) * kdelta(l - 1)) / kdelta(l));
+    }
+    return t;
+}
+
 int build_graph(b200_sixdof *h, const b200_effector &e)
 {
     const uint32_t N = (uint32_t)h->desc.n_entities;
@@ -159,6 +195,7 @@ void fill_step_params(b200_sixdof *h, StepParams &P)
     P.ine = h->find(B200_ID_INERTIA)->dev;
     P.gforce = h->gforce;
     P.has_edge = h->has_edge;
+    P.aforce = h->aforce;
     P.ld = h->ld;
     P.n_bodies = h->n_bodies;
     P.n_entities = (uint32_t)h->desc.n_entities;
@@ -178,6 +215,7 @@ void fill_step_params(b200_sixdof *h, StepParams &P)
         P.eff[i].col = c ? c->dev : nullptr;
         P.eff[i].col_width = c ? c->width : 0;
         P.eff[i].mask = i < h->eff_masks.size() ? h->eff_masks[i] : nullptr;
+        P.eff[i].table = i < h->eff_tables.size() ? h->eff_tables[i] : nullptr;
     }
 }
 
@@ -198,16 +236,28 @@ int launch_ticks(b200_sixdof *h, uint64_t w0, uint64_t nw, uint64_t n_ticks, cud
     // shift every per-body plane base to the range start; rows inside a world keep their index
     P.pos += b0; P.vel += b0; P.acc += b0; P.frc += b0; P.ine += b0;
     if (P.gforce) P.gforce += b0;
+    if (P.aforce) P.aforce += b0;
     if (P.traj) P.traj += b0;
     for (uint32_t i = 0; i < P.n_eff; ++i) if (P.eff[i].col) P.eff[i].col += b0;
     P.n_bodies = nb;
     const bool exact = h->desc.math_mode == B200_MATH_EXACT;
     const bool graph = h->graph_eff >= 0;
-    const uint64_t fuse = (graph && !h->small_world) ? 1 : std::max<uint32_t>(1u, h->desc.max_fused_ticks);
+    const bool egm = h->egm_eff >= 0; // its stage forces are a function of the tick's input state: one launch per tick
+    const uint64_t fuse = ((graph && !h->small_world) || egm) ? 1 : std::max<uint32_t>(1u, h->desc.max_fused_ticks);
     uint64_t left = n_ticks, done = 0;
     double *pos_next = h->pos_alt ? h->pos_alt + b0 : nullptr, *vel_next = h->vel_alt ? h->vel_alt + b0 : nullptr;
     while (left) {
         const uint64_t n = std::min(left, fuse);
+        if (egm) {
+            const b200_effector &ge = h->effectors[h->egm_eff];
+            EgmParams E{};
+            E.pos = P.pos; E.vel = P.vel; E.ine = P.ine; E.aforce = h->aforce + b0;
+            E.table = h->eff_tables[h->egm_eff]; E.mask = h->eff_masks[h->egm_eff];
+            E.ld = h->ld; E.n_bodies = nb; E.n_entities = P.n_entities; E.ent0 = 0;
+            E.L = (uint32_t)ge.p[2]; E.integrator = h->desc.integrator; E.mu = ge.p[0]; E.r_ref = ge.p[1]; E.dt_stage = P.dt_stage;
+            CU(h, launch_egm08_force(E, (int)h->desc.math_mode, stream));
+            h->timings.kernel_launches++;
+        }
         if (graph) {
             const b200_effector &e = h->effectors[h->graph_eff];
             GraphParams G{};
@@ -499,6 +549,19 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
         case B200_EFF_THRUST_BODY: want_w = 1; break;
         case B200_EFF_WRENCH_BODY: case B200_EFF_WRENCH_WORLD: want_w = 6; break;
         case B200_EFF_GRAVITY_J2: want_w = 0; break;
+        case B200_EFF_GRAVITY_EGM08: {
+            want_w = 0;
+            const double Ld = e.p[2];
+            if (!(Ld >= 0.0) || Ld > 128.0 || Ld != std::floor(Ld))
+                return bail(fail(B200_ERR_INVALID_ARGUMENT, "effector %zu: EGM08 max_degree must be an integer in 0..128 (got %g)", i, Ld));
+            const uint64_t n = (uint64_t)Ld + 1;
+            if (!e.table0 || !e.table1 || e.table_len != n * n)
+                return bail(fail(B200_ERR_VALUE_SIZE_MISMATCH, "effector %zu: EGM08 needs C and S tables of (L+1)^2 = %llu f64 (got %llu)", i,
+                                 (unsigned long long)(n * n), (unsigned long long)e.table_len));
+            if (h->egm_eff >= 0) return bail(fail(B200_ERR_UNSUPPORTED, "only one EGM08 gravity effector is supported"));
+            h->egm_eff = (int)i;
+            break;
+        }
         case B200_EFF_TORQUE_BODY_FOLD:
             want_w = e.column_width; // 3 per wheel
             if (e.column_width == 0 || e.column_width % 3 != 0 || e.column_width > 24)
@@ -555,16 +618,34 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
         e.entity_mask = nullptr;
     }
 
+    // EGM08 coefficient tables: copied (with the derived recursion tables) now, the caller's arrays are only valid for this call
+    h->eff_tables.assign(h->effectors.size(), nullptr);
+    for (size_t i = 0; i < h->effectors.size(); ++i) {
+        b200_effector &e = h->effectors[i];
+        if (e.kind == B200_EFF_GRAVITY_EGM08) {
+            const std::vector<double> t = egm08_tables((int)e.p[2], e.table0, e.table1);
+            if (cudaMalloc(&h->eff_tables[i], t.size() * sizeof(double)) != cudaSuccess)
+                return bail(cuda_fail(nullptr, cudaGetLastError(), "cudaMalloc(EGM08 tables)"));
+            if (cudaMemcpy(h->eff_tables[i], t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess)
+                return bail(cuda_fail(nullptr, cudaGetLastError(), "cudaMemcpy(EGM08 tables)"));
+        }
+        e.table0 = e.table1 = nullptr;
+    }
     if (h->graph_eff >= 0) {
         // copy the edge arrays' content now: the caller's pointers are only valid for this call
         if ((rc = build_graph(h, h->effectors[h->graph_eff]))) return bail(rc);
         {
             GraphParams G{};
             G.n_entities = (uint32_t)d->n_entities; G.n_worlds = (uint32_t)d->n_worlds; G.integrator = d->integrator;
-            h->small_world = small_world_applicable(G, (int)d->math_mode);
-            h->nbody_fused = !h->small_world && h->pos_alt && nbody_fused_applicable(G, (int)d->math_mode, h->graph_dense);
+            // (an EGM08 effector needs its stage-force launch before every body launch: the generic two-launch route)
+            h->small_world = h->egm_eff < 0 && small_world_applicable(G, (int)d->math_mode);
+            h->nbody_fused = h->egm_eff < 0 && !h->small_world && h->pos_alt && nbody_fused_applicable(G, (int)d->math_mode, h->graph_dense);
         }
         h->effectors[h->graph_eff].edge_from = h->effectors[h->graph_eff].edge_to = nullptr;
+    }
+    if (h->egm_eff >= 0) {
+        if (cudaMalloc(&h->aforce, 9ull * h->ld * 8ull) != cudaSuccess) return bail(cuda_fail(nullptr, cudaGetLastError(), "cudaMalloc(EGM08 stage forces)"));
+        if (cudaMemset(h->aforce, 0, 9ull * h->ld * 8ull) != cudaSuccess) return bail(cuda_fail(nullptr, cudaGetLastError(), "cudaMemset(EGM08 stage forces)"));
     }
     if (d->trajectory_every && d->trajectory_capacity) {
         h->traj_planes = (d->trajectory_flags & B200_TRAJ_FULL) ? 25u : 13u;
@@ -584,10 +665,12 @@ void b200_sixdof_destroy(b200_sixdof *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto &c : h->cols) if (c.dev) cudaFree(c.dev);
     for (auto m : h->eff_masks) if (m) cudaFree(m);
+    for (auto t : h->eff_tables) if (t) cudaFree(t);
     if (h->row_ptr) cudaFree(h->row_ptr);
     if (h->col_idx) cudaFree(h->col_idx);
     if (h->has_edge) cudaFree(h->has_edge);
     if (h->gforce) cudaFree(h->gforce);
+    if (h->aforce) cudaFree(h->aforce);
     if (h->pos_alt) cudaFree(h->pos_alt);
     if (h->vel_alt) cudaFree(h->vel_alt);
     if (h->staging) cudaFree(h->staging);

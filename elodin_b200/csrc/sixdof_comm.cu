@@ -259,8 +259,8 @@ int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks)
     if (!h || !c) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
     if (h->status != B200_OK) return fail(h->status, "handle is in a failed state");
     if (h->device != c->device) return fail(B200_ERR_INVALID_ARGUMENT, "handle is on device %d, communicator on %d", h->device, c->device);
-    if (h->graph_eff < 0 || !h->graph_dense || h->desc.n_worlds != 1)
-        return fail(B200_ERR_UNSUPPORTED, "row sharding applies to one world with dense (all-pairs) edge_fold gravity");
+    if (h->graph_eff < 0 || !h->graph_dense || h->desc.n_worlds != 1 || h->egm_eff >= 0)
+        return fail(B200_ERR_UNSUPPORTED, "row sharding applies to one world with dense (all-pairs) edge_fold gravity (and no EGM08 effector)");
     const uint64_t N = h->desc.n_entities, R = (uint64_t)c->n_ranks;
     if (N % R != 0) return fail(B200_ERR_UNSUPPORTED, "row sharding needs n_entities (%llu) divisible by the rank count (%llu)", (unsigned long long)N, (unsigned long long)R);
     CU(h, cudaSetDevice(h->device));

@@ -28,6 +28,9 @@ struct b200_sixdof {
     b200_sixdof_desc desc{};
     std::vector<b200_effector> effectors;
     std::vector<uint8_t *> eff_masks; // device copies of the per-effector entity masks (nullptr = all)
+    std::vector<double *> eff_tables; // device tables of GRAVITY_EGM08 effectors (nullptr = none)
+    int egm_eff = -1;                  // index of the GRAVITY_EGM08 effector (at most one), -1 = none
+    double *aforce = nullptr;          // 9 planes of additive stage forces it fills every tick
     int device = 0;
     uint64_t n_bodies = 0;
     uint64_t ld = 0;

@@ -18,6 +18,7 @@ struct EffDev {
     uint32_t col_width;
     uint32_t pad;
     const uint8_t *mask; // [n_entities] or nullptr (query-join membership)
+    const double *table; // GRAVITY_EGM08: [C | S | n1 | n2 | nq1 | nq2] each (L+1)^2, then diag[L+1], offc[L+1] (device)
 };
 
 // Launch parameters of the per-body integrator kernels.  All columns are SoA:
@@ -30,6 +31,7 @@ struct StepParams {
     const double *ine;  // 7 planes: diag(3) momentum(3) mass
     const double *gforce; // 9 planes: edge_fold gravity at the 3 distinct stage positions (or nullptr)
     const uint8_t *has_edge; // [n_entities]: body owns >= 1 out-edge (or nullptr)
+    const double *aforce;    // 9 planes: additive stage forces (GRAVITY_EGM08) at the 3 distinct stage positions (or nullptr)
     uint64_t ld;        // plane stride in doubles
     uint64_t n_bodies;  // n_worlds * n_entities
     uint32_t n_entities;
@@ -105,6 +107,18 @@ cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, d
 // worlds of <= 32 bodies: gravity + integration of n_ticks ticks in one launch, one warp per floor(32/N) worlds
 bool small_world_applicable(const GraphParams &G, int math_mode);
 cudaError_t launch_small_world(const GraphParams &G, const StepParams &P, int math_mode, cudaStream_t s);
+// GRAVITY_EGM08: the field at the three stage positions of every body -> 9 planes (one launch per tick)
+struct EgmParams {
+    const double *pos, *vel, *ine;
+    double *aforce;
+    const double *table;     // [C | S | n1 | n2 | nq1 | nq2 | diag | offc] (device)
+    const uint8_t *mask;     // entity mask of the effector or nullptr
+    uint64_t ld, n_bodies;
+    uint32_t n_entities, ent0;
+    uint32_t L, integrator;
+    double mu, r_ref, dt_stage;
+};
+cudaError_t launch_egm08_force(const EgmParams &E, int math_mode, cudaStream_t s);
 cudaError_t launch_aos_to_soa(const double *aos, double *soa, uint64_t n_bodies, uint32_t width, uint64_t ld,
                               cudaStream_t s);
 cudaError_t launch_soa_to_aos(const double *soa, double *aos, uint64_t n_bodies, uint32_t width, uint64_t ld,

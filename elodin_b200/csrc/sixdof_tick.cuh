@@ -195,6 +195,14 @@ __device__ __forceinline__ void apply_effector_exact(uint32_t kind, const EffDev
         F.lin = Vec3{add(F.lin.x, g.x), add(F.lin.y, g.y), add(F.lin.z, g.z)};
         break;
     }
+    case B200_EFF_GRAVITY_EGM08: { // python/elodin/egm08.py; force + SpatialForce(linear=field): the field at this stage's
+        if (P.aforce) {                // position was evaluated by egm08_force_kernel before this launch
+            F.ang = Vec3{add(F.ang.x, 0.0), add(F.ang.y, 0.0), add(F.ang.z, 0.0)};
+            F.lin = Vec3{add(F.lin.x, ldp(P.aforce, P.ld, slot * 3 + 0, b)), add(F.lin.y, ldp(P.aforce, P.ld, slot * 3 + 1, b)),
+                         add(F.lin.z, ldp(P.aforce, P.ld, slot * 3 + 2, b))};
+        }
+        break;
+    }
     case B200_EFF_GRAVITY_EDGES_NEWTON:
     case B200_EFF_GRAVITY_EDGES_SOFTENED: { // Force := edge_fold(init 0) for bodies that own an edge
         if (GREG) {
@@ -337,6 +345,7 @@ struct Folded {
     Vec3 tw;      // world-frame torque (WRENCH_WORLD): needs R^-1 per stage attitude
     double j2_mu, j2_k; // GRAVITY_J2: mu, J2 * r_ref^2
     bool drag, frame, graph, wtorque, j2;
+    bool aforce;        // GRAVITY_EGM08: add the stage-force planes egm08_force_kernel filled
 };
 
 template <bool GREG>
@@ -347,7 +356,7 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
     f.fw = f.fb = f.u = f.wind = f.om = Vec3{0.0, 0.0, 0.0};
     f.kd = f.mu = f.j2_mu = f.j2_k = 0.0;
     f.tw = Vec3{0.0, 0.0, 0.0};
-    f.drag = f.frame = f.graph = f.wtorque = f.j2 = false;
+    f.drag = f.frame = f.graph = f.wtorque = f.j2 = f.aforce = false;
     Vec3 tb = {0.0, 0.0, 0.0};
     for (uint32_t e = 0; e < P.n_eff; ++e) {
         const EffDev &E = P.eff[e];
@@ -391,7 +400,7 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
             if (E.col) {
                 tb = Vec3{0.0, 0.0, 0.0};
                 f.fw = f.fb = f.tw = Vec3{0.0, 0.0, 0.0};
-                f.drag = f.frame = f.wtorque = f.j2 = false;
+                f.drag = f.frame = f.wtorque = f.j2 = f.aforce = false;
                 const uint32_t K = E.col_width / 3u;
                 for (uint32_t k = 0; k < K; ++k) {
                     tb.x += ldp(E.col, P.ld, 3 * k + 0, b); tb.y += ldp(E.col, P.ld, 3 * k + 1, b); tb.z += ldp(E.col, P.ld, 3 * k + 2, b);
@@ -402,6 +411,9 @@ __device__ __forceinline__ Folded fold_effectors(const StepParams &P, uint64_t b
             f.j2 = true;
             f.j2_mu = E.p[0];
             f.j2_k = E.p[1] * E.p[2] * E.p[2];
+            break;
+        case B200_EFF_GRAVITY_EGM08:
+            f.aforce = P.aforce != nullptr;
             break;
         case B200_EFF_GRAVITY_EDGES_NEWTON:
         case B200_EFF_GRAVITY_EDGES_SOFTENED: // host guarantees this is effector 0 in FAST mode
@@ -425,7 +437,7 @@ __device__ __forceinline__ Folded fold_spec(const StepParams &P, uint64_t b, con
     f.fb = f.u = f.wind = f.om = Vec3{0.0, 0.0, 0.0};
     f.kd = f.mu = f.j2_mu = f.j2_k = 0.0;
     f.tw = Vec3{0.0, 0.0, 0.0};
-    f.wtorque = f.j2 = false;
+    f.wtorque = f.j2 = f.aforce = false;
     f.drag = (SIG & SIG_DRAG) != 0;
     f.frame = (SIG & SIG_FRAME) != 0;
     f.graph = (SIG & SIG_GRAPH) ? (GREG ? greg.has : P.has_edge[(b + P.ent0) % P.n_entities] != 0) : false;
@@ -493,6 +505,11 @@ __device__ __forceinline__ Vec3 lin_accel_fast(const StepParams &P, const Folded
         F.x = fma(c, (ir3 + kr) * x.x, F.x);
         F.y = fma(c, (ir3 + kr) * x.y, F.y);
         F.z = fma(c, fma(ir3 + kr, x.z, kz), F.z);
+    }
+    if (f.aforce) { // the harmonic series at this stage's position, evaluated by egm08_force_kernel with the oracle's arithmetic
+        F.x += ldp(P.aforce, P.ld, slot * 3 + 0, b);
+        F.y += ldp(P.aforce, P.ld, slot * 3 + 1, b);
+        F.z += ldp(P.aforce, P.ld, slot * 3 + 2, b);
     }
     if (f.graph) {
         if (GREG) {

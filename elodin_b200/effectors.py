@@ -190,6 +190,37 @@ class GravityJ2(Effector):
 
 
 @dataclass
+class GravityEGM08(Effector):
+    """Spherical-harmonic gravity: `force + SpatialForce(linear=EGM08(max_degree).compute_field(x, y, z, m))` —
+    libs/nox-py/python/elodin/egm08.py, examples/cube-sat/main.py:47,516-527.  `c_bar` / `s_bar` are the fully normalised
+    coefficient tables the reference loads from C_normal.npy / S_normal.npy (its constructor downloads them; pass the
+    arrays you have), cut to `[: max_degree + 1, : max_degree + 1]` like egm08.py:51-56.  Evaluated by its own kernel once
+    per tick at the three stage positions; parity: bit-identical to the oracle, equal to `GravityJ2` when only C20 is set."""
+
+    c_bar: Optional[np.ndarray] = None
+    s_bar: Optional[np.ndarray] = None
+    max_degree: Optional[int] = None
+    mu: float = 3.986004418e14
+    r_ref: float = 6.378e6
+    _keep: list = field(default_factory=list, repr=False, compare=False)
+
+    def lower(self, world):
+        if self.c_bar is None or self.s_bar is None:
+            raise ValueError("GravityEGM08 needs the normalised C and S coefficient tables")
+        L = int(self.max_degree) if self.max_degree is not None else int(np.asarray(self.c_bar).shape[0]) - 1
+        if not 0 <= L <= 128:
+            raise ValueError("GravityEGM08 supports max_degree 0..128")
+        c = np.ascontiguousarray(np.asarray(self.c_bar, dtype=np.float64)[: L + 1, : L + 1])
+        s = np.ascontiguousarray(np.asarray(self.s_bar, dtype=np.float64)[: L + 1, : L + 1])
+        if c.shape != (L + 1, L + 1) or s.shape != (L + 1, L + 1):
+            raise ValueError(f"coefficient tables must be at least {(L + 1, L + 1)}")
+        self._keep[:] = [c, s]
+        e = _base(_lib.EFF_GRAVITY_EGM08, (self.mu, self.r_ref, float(L)))
+        e.table0, e.table1, e.table_len = c.ctypes.data, s.ctypes.data, c.size
+        return self._attach_mask(e)
+
+
+@dataclass
 class GravityEdges(Effector):
     """GraphQuery.edge_fold gravity (python/elodin/__init__.py:454-557).
 

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define B200_SIXDOF_ABI_VERSION 2u
+#define B200_SIXDOF_ABI_VERSION 3u
 
 /* ---- status codes (0 = ok).  Names follow libs/nox-py/src/error.rs:7-44 ---- */
 enum {
@@ -129,7 +129,13 @@ enum {
     B200_EFF_TORQUE_BODY_FOLD = 9,
     /* point mass + J2 zonal gravity, libs/nox-py/python/elodin/j2.py:5-29 (J2.compute_field), applied as
      * force + SpatialForce(linear=field).  p[0] = mu, p[1] = J2, p[2] = r_ref */
-    B200_EFF_GRAVITY_J2 = 10
+    B200_EFF_GRAVITY_J2 = 10,
+    /* spherical-harmonic gravity, libs/nox-py/python/elodin/egm08.py (EGM08.compute_field), applied as
+     * force + SpatialForce(linear=field) (examples/cube-sat/main.py:516-527).  p[0] = mu, p[1] = r_ref, p[2] = max_degree L
+     * (<= 128); table0 / table1 = the fully normalised C / S coefficients, [(L+1)][(L+1)] f64 row-major (row = degree) —
+     * what the reference loads from C_normal.npy / S_normal.npy (a run-time download, so no golden pins it: with C20
+     * alone the field equals GRAVITY_J2's to rounding).  Both math modes evaluate it with the oracle's operation order. */
+    B200_EFF_GRAVITY_EGM08 = 11
 };
 
 #define B200_EFF_FLAG_WRENCH_LINEAR_FIRST 1u /* wrench column is [f(3), tau(3)] (falcon9) */
@@ -150,6 +156,9 @@ typedef struct b200_effector {
                                    Mirrors the reference's query join (query.rs:672-710): an @el.map
                                    effector only runs on entities that own every component it reads
                                    (e.g. drag only on bodies with a `wind` component).  Copied at create. */
+    const double *table0;       /* ABI v3.  GRAVITY_EGM08: C coefficients; copied at create; NULL otherwise  */
+    const double *table1;       /*          GRAVITY_EGM08: S coefficients                                     */
+    uint64_t table_len;         /*          (L+1)^2                                                            */
 } b200_effector;
 
 typedef struct b200_sixdof_desc {

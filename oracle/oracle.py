@@ -27,6 +27,7 @@ EFF_GRAVITY_EDGES_SOFTENED = 7
 EFF_WRENCH_WORLD = 8
 EFF_TORQUE_BODY_FOLD = 9
 EFF_GRAVITY_J2 = 10
+EFF_GRAVITY_EGM08 = 11
 FLAG_WRENCH_LINEAR_FIRST = 1
 
 
@@ -42,6 +43,9 @@ class _Effector(C.Structure):
         ("edge_from", C.c_void_p),
         ("edge_to", C.c_void_p),
         ("entity_mask", C.c_void_p),
+        ("table0", C.c_void_p),
+        ("table1", C.c_void_p),
+        ("table_len", C.c_uint64),
     ]
 
 
@@ -133,6 +137,7 @@ class Effector:
     column: np.ndarray | None = None  # [M, N, width]
     edges: np.ndarray | None = None  # [E, 2] (from, to) entity rows
     mask: np.ndarray | None = None  # [N] bool: entity rows the effector applies to (query join)
+    tables: tuple | None = None  # GRAVITY_EGM08: (c_bar, s_bar), each [(L+1), (L+1)]
 
     _keep: list = field(default_factory=list, repr=False)
 
@@ -159,6 +164,10 @@ class Effector:
             m = np.ascontiguousarray(np.asarray(self.mask, dtype=np.uint8))
             self._keep.append(m)
             e.entity_mask = m.ctypes.data
+        if self.tables is not None:
+            c, sbar = (np.ascontiguousarray(t, dtype=np.float64) for t in self.tables)
+            self._keep += [c, sbar]
+            e.table0, e.table1, e.table_len = c.ctypes.data, sbar.ctypes.data, c.size
         return e
 
 

@@ -261,6 +261,112 @@ static void eff_gravity_j2(const orc_effector *e, const double pos[7], const dou
     F[0] = F[0] + 0.0; F[1] = F[1] + 0.0; F[2] = F[2] + 0.0;
 }
 
+/* ------------------------------------------------------------------ EGM08 spherical-harmonic gravity
+ * libs/nox-py/python/elodin/egm08.py (EGM08.compute_field), applied as force + SpatialForce(linear=field)
+ * (examples/cube-sat/main.py:516-527).  p = [mu, r_ref, L]; table0 / table1 = the normalised C / S coefficients
+ * the reference loads from C_normal.npy / S_normal.npy (a download: not in its tree, so no golden can be recomputed;
+ * with C20 alone the field equals j2.py's to rounding, which is what pins the zonal path — tests/test_oracle_golden.py).
+ *
+ * The restatement keeps the reference's formulas, including `m = roll(self.m, -1)` (every term carries m+1, :153),
+ * and fixes two things the source leaves to XLA: the double sum runs column by column (m outer, l = m..L inner; terms
+ * with l < m vanish because a_bar is lower triangular) with one running accumulator per component, and
+ * rho_l = (mu/r) (r_ref/r)^l is built by repeated multiplication instead of pow(). */
+static double kdelta(int d) { return d == 0 ? 1.0 : 2.0; }
+
+void orc_egm08_tables(int L, double *out)
+{
+    const int n = L + 1;
+    double *n1 = out, *n2 = n1 + n * n, *nq1 = n2 + n * n, *nq2 = nq1 + n * n, *diag = nq2 + n * n, *offc = diag + n;
+    for (int l = 0; l <= L; ++l)
+        for (int m = 0; m <= L; ++m) {
+            double v1 = 0.0, v2 = 0.0;
+            if (l >= m + 2) { /* compute_n1 / compute_n2, :98-108 */
+                v1 = sqrt((double)((2 * l + 1) * (2 * l - 1)) / (double)((l + m) * (l - m)));
+                v2 = sqrt((double)((l + m - 1) * (l - m - 1) * (2 * l + 1)) / (double)((2 * l - 3) * (l + m) * (l - m)));
+            }
+            n1[l * n + m] = v1;
+            n2[l * n + m] = v2;
+            const double num1 = (double)(l - m) * kdelta(m) * (double)(l + m + 1);          /* compute_nq1, :126-134 */
+            nq1[l * n + m] = num1 < 0.0 ? 0.0 : sqrt(num1 / kdelta(m + 1));
+            const double num2 = (double)(l + m + 2) * (double)(l + m + 1) * (double)(2 * l + 1) * kdelta(m); /* :136-144 */
+            nq2[l * n + m] = num2 < 0.0 ? 0.0 : sqrt(num2 / ((double)(2 * l + 3) * kdelta(m + 1)));
+        }
+    double cur = 1.0; /* a_0_0 */
+    for (int l = 0; l <= L; ++l) { /* compute_a_bar_diagonal, :84-89 */
+        if (l > 0) cur = cur * sqrt(((double)(2 * l + 1) * kdelta(l)) / ((double)(2 * l) * kdelta(l - 1)));
+        diag[l] = cur;
+        offc[l] = l == 0 ? 0.0 : diag[l] * sqrt(((double)(2 * l) * kdelta(l - 1)) / kdelta(l)); /* :91-96, times u at run time */
+    }
+}
+
+static void eff_gravity_egm08(const orc_effector *e, const double pos[7], const double inertia[7], double F[6])
+{
+    const double mu = e->p[0], r_ref = e->p[1];
+    const int L = (int)e->p[2], n = L + 1;
+    if (!e->table0 || !e->table1 || L < 0 || L > 128 || e->table_len != (uint64_t)n * (uint64_t)n) return;
+    double *tab = (double *)malloc((size_t)(4 * n * n + 2 * n + n + 2) * sizeof(double));
+    orc_egm08_tables(L, tab);
+    const double *n1 = tab, *n2 = n1 + n * n, *nq1 = n2 + n * n, *nq2 = nq1 + n * n, *diag = nq2 + n * n, *offc = diag + n;
+    double *rho = tab + 4 * n * n + 2 * n; /* rho[0 .. L+1], rho[L+1] = 0 (rho_l_1's last entry, :150) */
+    const double *C = e->table0, *S = e->table1;
+    const double x = pos[4], y = pos[5], z = pos[6], mass = inertia[6];
+    const double r = sqrt((x * x + y * y) + z * z);
+    const double s = x / r, t = y / r, u = z / r;
+    rho[0] = mu / r;
+    const double q = r_ref / r;
+    for (int l = 1; l <= L; ++l) rho[l] = rho[l - 1] * q;
+    rho[L + 1] = 0.0;
+    double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
+    double im_prev = 0.0, rm_prev = 0.0, im = 0.0, rm = 1.0; /* (i_0, r_0) = (0, 1), :110-114 */
+    for (int m = 0; m <= L; ++m) {
+        if (m > 0) {
+            const double i_new = s * im + t * rm, r_new = s * rm - t * im;
+            im_prev = im; rm_prev = rm; im = i_new; rm = r_new;
+        }
+        const double rm1 = m == 0 ? 0.0 : rm_prev, im1 = m == 0 ? 0.0 : im_prev; /* roll(.., 1).at[0].set(0), :151-152 */
+        const double mp = m == L ? 0.0 : (double)(m + 1);                          /* roll(self.m, -1).at[-1].set(0), :154 */
+        /* column m (A) and column m+1 (B) of a_bar by the same three-term recursion (:116-124) */
+        double A0 = 0.0, A1 = 0.0; /* a[l-1][m], a[l-2][m] */
+        double B0 = 0.0, B1 = 0.0; /* a[l][m+1] (one step ahead), a[l-1][m+1]  */
+        /* B runs one degree ahead of A: prime it with a[m][m+1] = 0 */
+        for (int l = m; l <= L; ++l) {
+            double Al;
+            if (l == m) Al = diag[m];
+            else if (l == m + 1) Al = offc[l] * u;
+            else Al = (u * n1[l * n + m]) * A0 - n2[l * n + m] * A1;
+            A1 = A0; A0 = Al;
+            /* a[l][m+1] */
+            double Bl = 0.0;
+            if (m + 1 <= L) {
+                if (l == m + 1) Bl = diag[m + 1];
+                else if (l == m + 2) Bl = offc[l] * u;
+                else if (l > m + 2) Bl = (u * n1[l * n + m + 1]) * B0 - n2[l * n + m + 1] * B1;
+            }
+            /* a[l+1][m+1] */
+            double Bn = 0.0;
+            if (m + 1 <= L && l + 1 <= L) {
+                const int l1 = l + 1;
+                if (l1 == m + 1) Bn = diag[m + 1];
+                else if (l1 == m + 2) Bn = offc[l1] * u;
+                else Bn = (u * n1[l1 * n + m + 1]) * Bl - n2[l1 * n + m + 1] * B0;
+            }
+            B1 = B0; B0 = Bl;
+            const double w = rho[l + 1] / r_ref;
+            const double c = C[l * n + m], sv = S[l * n + m];
+            const double ee = c * rm1 + sv * im1, ff = sv * rm1 - c * im1, dd = c * rm + sv * im;
+            a1 = a1 + ((w * Al) * mp) * ee;
+            a2 = a2 + ((w * Al) * mp) * ff;
+            a3 = a3 + (((w * Bl) * mp) * nq1[l * n + m]) * dd;
+            a4 = a4 + ((((w * Bn) * mp) * nq2[l * n + m]) * dd) * (-1.0);
+        }
+    }
+    free(tab);
+    F[3] = F[3] + mass * (a1 + s * a4);
+    F[4] = F[4] + mass * (a2 + t * a4);
+    F[5] = F[5] + mass * (a3 + u * a4);
+    F[0] = F[0] + 0.0; F[1] = F[1] + 0.0; F[2] = F[2] + 0.0;
+}
+
 /* examples/falcon9/sim.py:350-361 + frames.py:91-109 (parity unpinned: no golden) */
 static void eff_gravity_frame(const orc_effector *e, const double pos[7], const double vel[6],
                               const double inertia[7], double F[6])
@@ -366,6 +472,7 @@ static void eval_pipe(uint64_t n, uint64_t world, const double *inertia, uint32_
             case ORC_EFF_WRENCH_WORLD: eff_wrench_world(col, F + 6 * i); break;
             case ORC_EFF_TORQUE_BODY_FOLD: eff_torque_body_fold(e, col, pos + 7 * i, F + 6 * i); break;
             case ORC_EFF_GRAVITY_J2: eff_gravity_j2(e, pos + 7 * i, inertia + 7 * i, F + 6 * i); break;
+            case ORC_EFF_GRAVITY_EGM08: eff_gravity_egm08(e, pos + 7 * i, inertia + 7 * i, F + 6 * i); break;
             default: break;
             }
         }

@@ -37,7 +37,8 @@ enum {
     ORC_EFF_GRAVITY_EDGES_SOFTENED = 7,
     ORC_EFF_WRENCH_WORLD = 8,
     ORC_EFF_TORQUE_BODY_FOLD = 9,
-    ORC_EFF_GRAVITY_J2 = 10
+    ORC_EFF_GRAVITY_J2 = 10,
+    ORC_EFF_GRAVITY_EGM08 = 11
 };
 #define ORC_FLAG_WRENCH_LINEAR_FIRST 1u
 
@@ -52,7 +53,15 @@ typedef struct orc_effector {
     const uint32_t *edge_from;
     const uint32_t *edge_to;
     const uint8_t *entity_mask; /* [n] or NULL: query-join membership (query.rs:672-710) */
+    const double *table0;   /* GRAVITY_EGM08: normalised C coefficients, [(L+1)][(L+1)] row-major (row = degree l) */
+    const double *table1;   /* GRAVITY_EGM08: normalised S coefficients, same shape */
+    uint64_t table_len;     /* (L+1)^2 */
 } orc_effector;
+
+/* Derived tables of the EGM08 recursion (python/elodin/egm08.py:84-141): the same arithmetic in the oracle and in
+ * libb200_sixdof's host code, so both sides hold bit-identical tables.  out = [n1 | n2 | nq1 | nq2] each (L+1)^2 row-major
+ * [l][m], then diag[L+1], then offc[L+1] (sub-diagonal factor without u); out must hold 4 (L+1)^2 + 2 (L+1) doubles. */
+void orc_egm08_tables(int L, double *out);
 
 /* AoS columns [n_worlds][n][width], exactly the host layout of the C ABI */
 typedef struct orc_world {

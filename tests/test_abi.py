@@ -54,7 +54,7 @@ def test_component_id_matches_reference_table(built_lib):
 
 
 def test_struct_layouts_match_header(tmp_path):
-    assert ctypes.sizeof(_lib.Effector) == 4 + 4 + 64 + 8 + 4 + 4 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.Effector) == 4 + 4 + 64 + 8 + 4 + 4 + 8 + 8 + 8 + 8 + 8 + 8 + 8  # ABI v3: + table0, table1, table_len
     assert ctypes.sizeof(_lib.Desc) == 16 + 16 + 16 + 8 + 4 + 4 + 4 + 4 + 8 + 4 + 4
     assert ctypes.sizeof(_lib.Timings) == 48
     # and against the C compiler's view of include/b200_sixdof.h: sizes, every field offset, the ABI version

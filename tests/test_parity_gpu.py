@@ -1442,3 +1442,53 @@ def test_world_resident_pair_kernel_with_fused_integration(oracle, n_ticks, extr
         got = (out[WORLD_POS], out[WORLD_VEL], out[WORLD_ACCEL], out[FORCE])
         _assert_close(got, want, 1e-11, f"world kernel fused {n_ticks} extra={extra}")
         assert np.array_equal(ex.download(WORLD_POS), out[WORLD_POS]) and np.array_equal(ex.download(WORLD_VEL), out[WORLD_VEL])
+
+
+@pytest.mark.parametrize("integrator", ["rk4", "semi_implicit"])
+def test_egm08_gravity_effector(oracle, integrator):
+    """GRAVITY_EGM08 (python/elodin/egm08.py): evaluated by egm08_force_kernel at the tick's three stage positions with
+    the oracle's arithmetic — EXACT bit-identical to the oracle, FAST within tolerance; alone, with the wheel fold ahead
+    of it (the cube-sat pipeline), masked to some entities, and through chunked invoke_batch."""
+    from tests.test_oracle_golden import _egm08_random_tables
+
+    O = oracle
+    rng = np.random.default_rng(31)
+    M, N, L = 4, 3, 12
+    c, s = _egm08_random_tables(L, rng)
+    pos, vel, ine = random_world(88, M, N)
+    pos[..., 4:] = rng.normal(size=(M, N, 3))
+    pos[..., 4:] *= 6.9e6 / np.linalg.norm(pos[..., 4:], axis=-1, keepdims=True)
+    vel[..., 3:] = rng.normal(0, 7.6e3 / np.sqrt(3), (M, N, 3))
+    tq = rng.normal(0, 2e-3, (M, N, 9))
+    combos = {"egm08": [("egm08", dict(c_bar=c, s_bar=s, L=L))],
+              "wheels + egm08 (cube-sat)": [("wheels", dict(torques=tq)), ("egm08", dict(c_bar=c, s_bar=s, L=L))]}
+    n = 3
+    for name, spec in combos.items():
+        oe, ge, cols = [], [], {}
+        for kind, kw in spec:
+            a, b, cc = effector_pair(O, kind, **kw)
+            oe.append(a); ge.append(b); cols.update(cc)
+        want = _run_oracle(O, pos, vel, ine, oe, 0.05, n, integrator)
+        got = _run_gpu(pos, vel, ine, ge, cols, 0.05, n, "exact", integrator)
+        _assert_exact(got, want, f"exact {name}")
+        fast = _run_gpu(pos, vel, ine, ge, cols, 0.05, n, "fast", integrator)
+        _assert_close(fast, want, n * FAST_TOL_TICK, f"fast {name}")
+    # C20 alone == GRAVITY_J2 (the reference's own closed form)
+    c2, s2 = np.zeros((3, 3)), np.zeros((3, 3))
+    c2[0, 0], c2[2, 0] = 1.0, -1.08262668e-3 / np.sqrt(5.0)
+    a = _run_gpu(pos, vel, ine, [el.GravityEGM08(c2, s2, 2)], {}, 0.05, 1, "exact", integrator)
+    b = _run_gpu(pos, vel, ine, [el.GravityJ2()], {}, 0.05, 1, "exact", integrator)
+    assert max_rel(a[3][..., 3:], b[3][..., 3:]) <= 1e-14
+    # entity mask (only entity 1 feels the field) and chunked invoke_batch
+    mask = np.array([0, 1, 0], dtype=np.uint8)
+    oe = [O.Effector(O.EFF_GRAVITY_EGM08, p=(3.986004418e14, 6.378e6, L), tables=(c, s), mask=mask)]
+    ge = [el.GravityEGM08(c, s, L).with_mask(mask)]
+    want = _run_oracle(O, pos, vel, ine, oe, 0.05, 2, integrator)
+    with el.B200Exec(N, M, 0.05, None, ge, integrator, "exact", invoke_chunk_bodies=2 * N) as ex:
+        tick, dt = el.component_id("tick"), el.component_id("simulation_time_step")
+        table = {tick: np.array([0], dtype=np.uint64), FORCE: np.zeros((M, N, 6)), INERTIA: ine, WORLD_POS: pos,
+                 WORLD_ACCEL: np.zeros((M, N, 6)), dt: np.array([0.05]), WORLD_VEL: vel}
+        o = dict(zip(ex.output_ids, ex.invoke_batch([table[k] for k in ex.input_ids], 2)))
+    _assert_exact((o[WORLD_POS], o[WORLD_VEL], o[WORLD_ACCEL], o[FORCE]), want, "masked, chunked")
+    with pytest.raises(el.B200Error):
+        el.B200Exec(N, M, 0.05, None, [el.GravityEGM08(c, s, L), el.GravityEGM08(c, s, L)], integrator, "exact")

@@ -52,6 +52,10 @@ def effector_pair(O, kind, **kw):
     if kind == "j2":
         mu, j2, rr = kw.get("mu", 3.986004418e14), kw.get("j2", 1.08262668e-3), kw.get("r_ref", 6.378e6)
         return O.Effector(O.EFF_GRAVITY_J2, p=(mu, j2, rr)), el.GravityJ2(mu, j2, rr), {}
+    if kind == "egm08":
+        c, s, L = kw["c_bar"], kw["s_bar"], kw["L"]
+        mu, rr = kw.get("mu", 3.986004418e14), kw.get("r_ref", 6.378e6)
+        return O.Effector(O.EFF_GRAVITY_EGM08, p=(mu, rr, L), tables=(c, s)), el.GravityEGM08(c, s, L, mu, rr), {}
     if kind == "newton":
         return (O.Effector(O.EFF_GRAVITY_EDGES_NEWTON, p=(kw.get("G", 6.6743e-11),), edges=kw["edges"]),
                 el.GravityEdges("newton", G=kw.get("G", 6.6743e-11), edges=kw["edges"]), {})
