@@ -51,3 +51,13 @@ with el.B200Exec(2, 5, 0.01, None, [el.TorqueBodyFold("wheel_torques", 3), el.Gr
     ex.set_state(p + np.array([0, 0, 0, 0, 6.9e6, 0, 0]), v, I, wheel_torques=rng.normal(0, 1e-3, (5, 2, 9)))
     ex.step(3, sync=True)
 print("done")
+# EGM08 stage-force kernel (degree 12, masked, RK4 and semi-implicit)
+from tests.test_oracle_golden import _egm08_random_tables
+c, s = _egm08_random_tables(12, rng)
+for integ in ("rk4", "semi_implicit"):
+    with el.B200Exec(3, 37, 0.05, None, [el.GravityEGM08(c, s, 12).with_mask(np.array([1, 0, 1], dtype=np.uint8))], integ, "exact") as ex:
+        p, v, I = random_world(2, 37, 3)
+        p[..., 4:] += 6.9e6
+        ex.set_state(p, v, I)
+        ex.step(2, sync=True)
+print("egm done")

@@ -427,6 +427,11 @@ def test_egm08_oracle_against_the_array_form_and_j2(oracle):
     f_egm = w.eval_stage(0, [O.Effector(O.EFF_GRAVITY_EGM08, p=(3.986004418e14, 6.378e6, 4), tables=(c, s))])[0][0]
     f_j2 = w.eval_stage(0, [O.Effector(O.EFF_GRAVITY_J2, p=(3.986004418e14, 1.08262668e-3, 6.378e6))])[0][0]
     assert np.all(f_egm[:3] == 0.0) and np.max(np.abs(f_egm - f_j2)) <= 1e-15 * np.max(np.abs(f_j2))
+    # the source zeroes rho_{L+1} (`rho_l_1 = roll(rho_l, -1).at[-1].set(0)`, egm08.py:150): the terms of the top degree L
+    # drop out, so max_degree = 2 leaves the point mass alone
+    f_l2 = w.eval_stage(0, [O.Effector(O.EFF_GRAVITY_EGM08, p=(3.986004418e14, 6.378e6, 2), tables=(c[:3, :3], s[:3, :3]))])[0][0]
+    pm0 = -3.986004418e14 * mass * r / np.linalg.norm(r) ** 3
+    assert np.max(np.abs(f_l2[3:] - pm0)) <= 1e-15 * np.max(np.abs(pm0))
     for L in (8, 64):
         c, s = _egm08_random_tables(L, rng)
         got = w.eval_stage(0, [O.Effector(O.EFF_GRAVITY_EGM08, p=(3.986004418e14, 6.378e6, L), tables=(c, s))])[0][0][3:]

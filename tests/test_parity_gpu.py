@@ -1473,10 +1473,11 @@ def test_egm08_gravity_effector(oracle, integrator):
         _assert_exact(got, want, f"exact {name}")
         fast = _run_gpu(pos, vel, ine, ge, cols, 0.05, n, "fast", integrator)
         _assert_close(fast, want, n * FAST_TOL_TICK, f"fast {name}")
-    # C20 alone == GRAVITY_J2 (the reference's own closed form)
-    c2, s2 = np.zeros((3, 3)), np.zeros((3, 3))
+    # C20 alone == GRAVITY_J2 (the reference's own closed form).  max_degree 3: the source zeroes rho_{L+1}
+    # (egm08.py:150), so the terms of the top degree L drop out — degree 2 needs L >= 3
+    c2, s2 = np.zeros((4, 4)), np.zeros((4, 4))
     c2[0, 0], c2[2, 0] = 1.0, -1.08262668e-3 / np.sqrt(5.0)
-    a = _run_gpu(pos, vel, ine, [el.GravityEGM08(c2, s2, 2)], {}, 0.05, 1, "exact", integrator)
+    a = _run_gpu(pos, vel, ine, [el.GravityEGM08(c2, s2, 3)], {}, 0.05, 1, "exact", integrator)
     b = _run_gpu(pos, vel, ine, [el.GravityJ2()], {}, 0.05, 1, "exact", integrator)
     assert max_rel(a[3][..., 3:], b[3][..., 3:]) <= 1e-14
     # entity mask (only entity 1 feels the field) and chunked invoke_batch
