@@ -1,4 +1,5 @@
-"""Sweep B200_BODY_CFG launch variants of the FAST RK4 body kernel (one process per variant)."""
+"""Round-1 sweep (profiles/r01_tuning.md).  Since round 2 the default FAST route is the signature-specialised kernel, swept by scripts/tune_spec.py in a tuning build; B200_BODY_CFG now only selects the opt-in TMA-ring variants 10..14 (any other value = default).
+Sweep B200_BODY_CFG launch variants of the FAST RK4 body kernel (one process per variant)."""
 import os, subprocess, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for cfg in sys.argv[1:] or ["0", "1", "2", "3", "4", "5", "10", "11", "12"]:

@@ -1,6 +1,7 @@
 import os, subprocess, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-code = """
+code = """Round-1 sweep (profiles/r01_tuning.md).  Since round 2: scripts/tune_misc.py (shapes, tuning build) and scripts/tune_exact_seq.py (compiled effector sequences vs the interpreter).
+
 import sys; sys.path.insert(0, %r)
 import numpy as np, torch, elodin_b200 as el, bench
 M = 1 << 20
