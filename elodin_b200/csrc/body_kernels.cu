@@ -128,7 +128,12 @@ template <> struct VecIO<2> {
 template <int INTEG, uint32_t SIG, bool TRAJ, int BLOCK, int MINB, int BPT>
 __global__ void __launch_bounds__(BLOCK, MINB) body_fast_spec_kernel(const __grid_constant__ StepParams P)
 {
-    const uint64_t b0 = ((uint64_t)blockIdx.x * BLOCK + threadIdx.x) * BPT;
+    // Odd launches walk the planes from the far end: the tail of the state the previous launch read and wrote last is
+    // still in the 126 MB L2 when this launch starts — read it first, before this launch's own traffic evicts it, and the
+    // rewrite lands on lines that are still dirty instead of costing a second DRAM write (scripts/tune_snake.py: 152.4 ->
+    // 142.1 us per tick at 2^22 bodies; L2 eviction-class hints on top of it measured nothing and cost registers).
+    const unsigned blk = P.reverse ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+    const uint64_t b0 = ((uint64_t)blk * BLOCK + threadIdx.x) * BPT;
     if (b0 >= P.n_bodies) return;
     const bool both = b0 + (BPT - 1) < P.n_bodies;
 
@@ -615,6 +620,8 @@ cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode,
     static const int no_spec = env_int("B200_NO_SPEC", 0);
 #endif
     StepParams Q = P;
+    static const int snake = env_int("B200_SNAKE", 1);
+    if (!snake) Q.reverse = 0; // A/B switch: always walk forward
     const uint32_t sig = no_spec ? (uint32_t)SIG_GENERIC : spec_signature(Q);
     bool done = false;
     if (sig != SIG_GENERIC) done = rk4 ? launch_spec_sig<B200_INTEGRATOR_RK4>(Q, sig, s)

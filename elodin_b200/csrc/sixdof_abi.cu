@@ -295,6 +295,7 @@ int launch_ticks(b200_sixdof *h, uint64_t w0, uint64_t nw, uint64_t n_ticks, cud
         P.n_ticks = (uint32_t)n;
         P.tick0 = h->ticks_done + done;
         P.write_fa = (exact || left == n) ? 1u : 0u; // Force/WorldAccel are only host-visible after the batch
+        P.reverse = (uint32_t)(h->timings.kernel_launches & 1u); // alternate the traversal direction launch to launch
         CU(h, launch_body_step(P, (int)h->desc.integrator, (int)h->desc.math_mode, stream));
         h->timings.kernel_launches++;
         done += n;

@@ -47,7 +47,7 @@ struct StepParams {
     uint32_t traj_planes; // 13 (pos, vel) or 25 (+ accel, force)
     uint64_t tick0;     // global tick count before this launch
     uint32_t ent0;      // entity row of body 0 of this launch (row-sharded single worlds start inside a world)
-    uint32_t pad0;
+    uint32_t reverse;   // walk the tiles from the last one down (alternating launches: L2 reuse of the previous launch's tail)
     // compile-time-specialised FAST kernels (sixdof_tick.cuh SIG_*): what body_kernels.cu:spec_signature
     // distilled from eff[] — uniform constants and the plane bases of the per-body input columns
     struct Spec {
