@@ -638,10 +638,12 @@ def run_b200(args):
                          "note": "frac counts the algorithmic 264 B/entity-step against the measured copy peak and reads above 1.0 for "
                                  "two reasons: the kernel touches 240 B of them (the free tick never needs the three Inertia momentum "
                                  "planes), and consecutive launches walk the planes in opposite directions, so the tail of the "
-                                 "previous launch's state is served from the 126 MB L2.  traffic = DRAM bytes of one cold-cache "
-                                 "launch (ncu --set full flushes L2 first), traffic_steady = DRAM bytes per launch inside a "
-                                 "back-to-back sequence (ncu --cache-control none); steady_dram_frac is what DRAM actually moves "
-                                 "per second in the timed loop, against the copy peak"},
+                                 "previous launch's state is served from the 126 MB L2 (event-timed 152 -> 142 us per tick, "
+                                 "profiles/r02_tune_snake.txt).  traffic = DRAM bytes of one cold-cache launch (ncu --set full); "
+                                 "traffic_steady = DRAM bytes per launch with ncu --cache-control none (profiles/r02_steady_traffic.txt): "
+                                 "the touched 240 B/body and nothing twice — ncu serialises launches, so the L2 saving of the "
+                                 "alternating traversal is not visible to it and steady_dram_frac (traffic_steady / kernel time / "
+                                 "peak) is an upper bound on what DRAM moves in the timed loop"},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "verified": verified,

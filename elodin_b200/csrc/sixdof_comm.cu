@@ -75,7 +75,20 @@ struct b200_comm {
     uint64_t send_bytes = 0, recv_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
+    // peer window of the row-sharded world (b200_comm_peer_attach): one allocation per rank, mapped into every
+    // other rank's address space through CUDA IPC, written over NVLink by the producing GPU
+    struct Window {
+        const b200_sixdof *owner = nullptr;
+        uint64_t ld = 0;
+        double *base[B200_MAX_PEERS] = {};  // rank r's window as mapped here ([rank] = the local allocation)
+        unsigned *ctr = nullptr;            // block counter of the push kernel (local)
+    } win;
 };
+
+// Layout of a peer window: X[2][6][ld] doubles (parity of the tick count; planes x y z vx vy vz of every row of
+// the world), then B200_MAX_PEERS uint64 delivery counters: flags[r] = ticks whose rows rank r has delivered here.
+static inline uint64_t win_doubles(uint64_t ld) { return 2ull * 6ull * ld; }
+static inline size_t win_bytes(uint64_t ld) { return (size_t)(win_doubles(ld) * 8ull + B200_MAX_PEERS * 8ull + 64); }
 
 namespace b200 {
 
@@ -99,6 +112,71 @@ __global__ void __launch_bounds__(kGTile) traj_world_major_kernel(const double *
         const uint32_t r = i / W, k = i - r * W;
         const uint64_t b = base + r, world = b / n_entities, ent = b - world * n_entities;
         out[((world * S + s) * n_entities + ent) * W + k] = tile[r * pitch + k];
+    }
+}
+
+// ------------------------------------------------------------------ peer-window kernels (row-sharded world)
+
+// X[par] <- the linear position / velocity planes of the whole local world; flags[r] = max(flags[r], T)
+__global__ void __launch_bounds__(256) peer_fill_kernel(const double *__restrict__ pos, const double *__restrict__ vel,
+                                                        double *__restrict__ X, unsigned long long *flags, uint64_t ld,
+                                                        uint32_t n, int n_ranks, unsigned long long T)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            X[(uint64_t)k * ld + i] = pos[(uint64_t)(4 + k) * ld + i];
+            X[(uint64_t)(3 + k) * ld + i] = vel[(uint64_t)(3 + k) * ld + i];
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (unsigned)n_ranks) atomicMax(flags + threadIdx.x, T); // a faster peer may already be one ahead
+}
+
+// Holds the stream until every rank has delivered the rows of tick count `need` into this GPU's window.
+__global__ void peer_wait_kernel(const unsigned long long *flags, int n_ranks, unsigned long long need)
+{
+    if (threadIdx.x >= (unsigned)n_ranks) return;
+    unsigned long long t0, now, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+        if (v >= need) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 20000000000ull) __trap(); // 20 s without the peer's rows: fail the handle instead of hanging the GPU
+        __nanosleep(100);
+    }
+}
+
+struct PeerPush {
+    const double *pos, *vel;      // local planes, already shifted to this rank's first row
+    double *dst[B200_MAX_PEERS];  // X[next parity] of every rank, shifted to this rank's first row
+    unsigned long long *flag[B200_MAX_PEERS]; // &flags_r[me]
+    unsigned *ctr;
+    uint64_t ld_src, ld_dst;
+    uint32_t rows;
+    int n_ranks;
+    unsigned long long value;     // tick count the rows belong to
+};
+
+// This rank's new rows -> every rank's window (NVLink stores), then one release per peer once every block is through.
+__global__ void __launch_bounds__(128) peer_push_kernel(const __grid_constant__ PeerPush a)
+{
+    const uint32_t i = blockIdx.x * 128u + threadIdx.x, k = blockIdx.y; // plane k of x y z vx vy vz
+    if (i < a.rows) {
+        const double v = k < 3 ? a.pos[(uint64_t)(4 + k) * a.ld_src + i] : a.vel[(uint64_t)k * a.ld_src + i];
+        for (int r = 0; r < a.n_ranks; ++r) a.dst[r][(uint64_t)k * a.ld_dst + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        if (atomicAdd(a.ctr, 1u) == total - 1u) {
+            *a.ctr = 0u;
+            __threadfence_system();
+            for (int r = 0; r < a.n_ranks; ++r)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[r]), "l"(a.value) : "memory");
+        }
     }
 }
 
@@ -150,6 +228,7 @@ void b200_comm_destroy(b200_comm *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    b200_comm_peer_detach(c);
     if (c->send) cudaFree(c->send);
     if (c->recv) cudaFree(c->recv);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -247,6 +326,106 @@ int b200_sixdof_trajectory_allgather(b200_sixdof *h, b200_comm *c, const uint64_
     return B200_OK;
 }
 
+// Peer window for the row-sharded world: every rank allocates X[2][6][ld] + delivery counters, the ranks swap the CUDA
+// IPC handles of those allocations through the communicator, and each maps all the others.  From then on
+// b200_sixdof_step_row_sharded exchanges the rows with direct NVLink stores and counter releases — no collective in
+// the tick loop.  Collective call: every rank of the communicator must make it, with handles of the same shape.
+int b200_comm_peer_attach(b200_comm *c, b200_sixdof *h)
+{
+    if (!h || !c) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (h->device != c->device) return fail(B200_ERR_INVALID_ARGUMENT, "handle is on device %d, communicator on %d", h->device, c->device);
+    if (c->n_ranks > B200_MAX_PEERS) return fail(B200_ERR_UNSUPPORTED, "peer windows support up to %d ranks", B200_MAX_PEERS);
+    CU(h, cudaSetDevice(h->device));
+    b200_comm_peer_detach(c);
+    auto &w = c->win;
+    w.ld = h->ld;
+    char *mem = nullptr;
+    CU(h, cudaMalloc(&mem, win_bytes(w.ld) + 64));
+    CU(h, cudaMemsetAsync(mem, 0, win_bytes(w.ld) + 64, h->stream));
+    w.base[c->rank] = (double *)mem;
+    w.ctr = (unsigned *)(mem + win_bytes(w.ld));
+    // swap the IPC handles (64 bytes each) over the communicator
+    cudaIpcMemHandle_t mine{}, all[B200_MAX_PEERS];
+    cudaError_t e = cudaIpcGetMemHandle(&mine, mem);
+    char *xs = nullptr;
+    int rc = B200_OK;
+    if (e != cudaSuccess) { (void)cudaGetLastError(); rc = fail(B200_ERR_UNSUPPORTED, "CUDA IPC export failed: %s", cudaGetErrorString(e)); }
+    if (cudaMalloc(&xs, sizeof(mine) * (size_t)(c->n_ranks + 1)) != cudaSuccess) { // nothing collective has started yet
+        (void)cudaGetLastError();
+        cudaFree(mem);
+        w.base[c->rank] = nullptr;
+        return fail(B200_ERR_OUT_OF_MEMORY, "out of device memory");
+    }
+    if (!rc && cudaMemcpyAsync(xs, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = cuda_fail(h, cudaGetLastError(), "cudaMemcpyAsync(ipc handle)");
+    {   // every rank takes part in the exchange even after a local failure (its handle is then all zeros)
+        ncclResult_t r = nccl().AllGather(xs, xs + sizeof mine, sizeof mine, ncclChar, c->comm, h->stream);
+        if (r != ncclSuccess && !rc) rc = nccl_fail(r, "ncclAllGather(ipc handles)");
+    }
+    if (!rc && (cudaMemcpyAsync(all, xs + sizeof mine, sizeof(mine) * (size_t)c->n_ranks, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+                cudaStreamSynchronize(h->stream) != cudaSuccess))
+        rc = cuda_fail(h, cudaGetLastError(), "ipc handle exchange");
+    cudaFree(xs);
+    for (int r = 0; r < c->n_ranks && !rc; ++r) {
+        if (r == c->rank) continue;
+        void *p = nullptr;
+        e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); rc = fail(B200_ERR_UNSUPPORTED, "CUDA IPC import of rank %d's window failed: %s", r, cudaGetErrorString(e)); }
+        else w.base[r] = (double *)p;
+    }
+    // every rank learns whether every rank mapped every window: all attach or none does
+    int ok_all = 0;
+    {
+        int *flags = nullptr;
+        if (cudaMalloc(&flags, sizeof(int) * (size_t)(c->n_ranks + 1)) == cudaSuccess) {
+            int mine_ok = rc == B200_OK ? 1 : 0, got[B200_MAX_PEERS] = {};
+            cudaMemcpyAsync(flags, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+            if (nccl().AllGather(flags, flags + 1, 1, ncclInt32, c->comm, h->stream) == ncclSuccess &&
+                cudaMemcpyAsync(got, flags + 1, sizeof(int) * (size_t)c->n_ranks, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess &&
+                cudaStreamSynchronize(h->stream) == cudaSuccess) {
+                ok_all = 1;
+                for (int r = 0; r < c->n_ranks; ++r) ok_all &= got[r];
+            }
+            cudaFree(flags);
+        }
+        (void)cudaGetLastError();
+    }
+    if (!ok_all) {
+        b200_comm_peer_detach(c);
+        return rc ? rc : fail(B200_ERR_UNSUPPORTED, "another rank could not map the peer windows");
+    }
+    w.owner = h;
+    return B200_OK;
+}
+
+int b200_comm_peer_attached(const b200_comm *c) { return c && c->win.owner ? 1 : 0; }
+
+// Collective when a window exists: every rank unmaps its imports, then (after a tiny all-gather as the barrier) frees
+// its own allocation — freeing memory a peer still maps is undefined.
+void b200_comm_peer_detach(b200_comm *c)
+{
+    if (!c || !c->win.base[c->rank]) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < B200_MAX_PEERS; ++r) {
+        if (!c->win.base[r] || r == c->rank) continue;
+        cudaIpcCloseMemHandle(c->win.base[r]);
+        c->win.base[r] = nullptr;
+    }
+    if (c->comm && nccl().ok && c->n_ranks > 1) {
+        int *b = nullptr;
+        if (cudaMalloc(&b, sizeof(int) * (size_t)(c->n_ranks + 1)) == cudaSuccess) {
+            cudaMemset(b, 0, sizeof(int) * (size_t)(c->n_ranks + 1));
+            if (nccl().AllGather(b, b + 1, 1, ncclInt32, c->comm, nullptr) == ncclSuccess) cudaDeviceSynchronize();
+            cudaFree(b);
+        }
+    }
+    cudaFree(c->win.base[c->rank]);
+    c->win.base[c->rank] = nullptr;
+    c->win.ctr = nullptr;
+    c->win.owner = nullptr;
+    (void)cudaGetLastError();
+}
+
 // One world, rows split over the ranks of `c` (second case).  Every rank holds the whole world (same
 // handle description, same initial state) but folds and integrates only its own source rows
 // [rank * N / R, (rank + 1) * N / R); after each tick the rows' new linear position and velocity planes — all the
@@ -267,8 +446,23 @@ int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks)
     const uint64_t rows = N / R, i0 = rows * (uint64_t)c->rank;
     const bool exact = h->desc.math_mode == B200_MATH_EXACT;
     const b200_effector &e = h->effectors[h->graph_eff];
+    static const int peer_env = env_int("B200_ROW_PEER", 1);
+    const bool peer = peer_env && c->win.owner == h && c->win.ld == h->ld;
+    double *const pos = h->find(B200_ID_WORLD_POS)->dev, *const vel = h->find(B200_ID_WORLD_VEL)->dev;
+    double *const acc = h->find(B200_ID_WORLD_ACCEL)->dev, *const frc = h->find(B200_ID_FORCE)->dev;
+    auto gather_plane = [&](double *plane) { return nccl().AllGather(plane + i0, plane, rows, ncclDouble, c->comm, h->stream); };
+    unsigned long long *const flags = peer ? (unsigned long long *)(c->win.base[c->rank] + win_doubles(h->ld)) : nullptr;
+    if (peer) {
+        // the window's current-parity half <- the local world (covers uploads and non-sharded steps since the last call)
+        const unsigned long long T = h->ticks_done;
+        peer_fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(pos, vel, c->win.base[c->rank] + (T & 1ull) * 6ull * h->ld, flags,
+                                                                             h->ld, (uint32_t)N, (int)R, T);
+        CU(h, cudaGetLastError());
+        h->timings.kernel_launches++;
+    }
     for (uint64_t t = 0; t < n_ticks; ++t) {
         const bool last = t + 1 == n_ticks;
+        const unsigned long long T = h->ticks_done + t;
         StepParams P;
         fill_step_params(h, P);
         GraphParams G{};
@@ -277,6 +471,15 @@ int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks)
         G.dt_stage = P.dt_stage; G.kind = e.kind; G.integrator = h->desc.integrator;
         G.p0 = e.p[0]; G.p1 = e.p[1]; G.row_ptr = h->row_ptr; G.col_idx = h->col_idx; G.max_deg = h->max_deg;
         G.src0 = (uint32_t)i0; G.src_n = (uint32_t)rows;
+        if (peer) {
+            // gravity reads every row's x, v from the window half of this tick count (the fold kernels touch planes
+            // 4..6 of pos and 3..5 of vel only), once every rank's rows of that count have landed
+            const double *X = c->win.base[c->rank] + (T & 1ull) * 6ull * h->ld;
+            G.pos = X - 4 * h->ld;
+            G.vel = X;
+            peer_wait_kernel<<<1, 32, 0, h->stream>>>(flags, (int)R, T);
+            h->timings.kernel_launches++;
+        }
         CU(h, launch_graph_force(G, (int)h->desc.math_mode, true, h->stream));
         // the body kernel on this rank's rows only: shift every per-body plane, keep the entity numbering
         P.pos += i0; P.vel += i0; P.acc += i0; P.frc += i0; P.ine += i0;
@@ -286,15 +489,27 @@ int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks)
         P.n_bodies = rows;
         P.ent0 = (uint32_t)i0;
         P.n_ticks = 1;
-        P.tick0 = h->ticks_done + t;
+        P.tick0 = T;
         P.write_fa = (exact || last) ? 1u : 0u;
         CU(h, launch_body_step(P, (int)h->desc.integrator, (int)h->desc.math_mode, h->stream));
         h->timings.kernel_launches += 2;
-        // exchange: in-place all-gather of the row slices, plane by plane
-        double *pos = h->find(B200_ID_WORLD_POS)->dev, *vel = h->find(B200_ID_WORLD_VEL)->dev;
-        double *acc = h->find(B200_ID_WORLD_ACCEL)->dev, *frc = h->find(B200_ID_FORCE)->dev;
+        if (peer) {
+            // exchange: this rank's new x, v rows straight into every rank's next-parity half, then one counter release each
+            PeerPush a{};
+            a.pos = pos + i0; a.vel = vel + i0; a.ctr = c->win.ctr;
+            a.ld_src = a.ld_dst = h->ld; a.rows = (uint32_t)rows; a.n_ranks = (int)R; a.value = T + 1;
+            for (uint64_t r = 0; r < R; ++r) {
+                a.dst[r] = c->win.base[r] + ((T + 1) & 1ull) * 6ull * h->ld + i0;
+                a.flag[r] = (unsigned long long *)(c->win.base[r] + win_doubles(h->ld)) + c->rank;
+            }
+            peer_push_kernel<<<dim3((unsigned)((rows + 127) / 128), 6), 128, 0, h->stream>>>(a);
+            CU(h, cudaGetLastError());
+            h->timings.kernel_launches++;
+            if (!last) continue;
+        }
+        // exchange over NCCL: in-place all-gather of the row slices, plane by plane (every tick without a peer window;
+        // with one, only the call's last tick, which completes the attitude / accel / force planes of the other ranks' rows)
         NC(nccl().GroupStart());
-        auto gather_plane = [&](double *plane) { return nccl().AllGather(plane + i0, plane, rows, ncclDouble, c->comm, h->stream); };
         ncclResult_t r = ncclSuccess;
         for (int k = 0; k < 7 && r == ncclSuccess; ++k) if (last || k >= 4) r = gather_plane(pos + (uint64_t)k * h->ld);
         for (int k = 0; k < 6 && r == ncclSuccess; ++k) if (last || k >= 3) r = gather_plane(vel + (uint64_t)k * h->ld);
