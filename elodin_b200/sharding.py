@@ -118,6 +118,22 @@ class Comm:
 
         _lib.check(self._L.b200_sixdof_step_row_sharded(exec_._h, self._h, int(n_ticks)))
 
+    def peer_attach(self, exec_) -> None:
+        """Map every rank's peer window (b200_comm_peer_attach; collective): step_row_sharded then exchanges the rows
+        with direct NVLink stores and counter releases instead of a collective per tick.  Raises B200Error
+        (ERR_UNSUPPORTED) on every rank when the processes cannot share memory over CUDA IPC."""
+        from . import _lib
+
+        _lib.check(self._L.b200_comm_peer_attach(self._h, exec_._h))
+
+    @property
+    def peer_attached(self) -> bool:
+        return bool(self._L.b200_comm_peer_attached(self._h))
+
+    def peer_detach(self) -> None:
+        """Collective: unmap the peers' windows, then free the own one.  Call before closing the attached executor."""
+        self._L.b200_comm_peer_detach(self._h)
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             self._L.b200_comm_destroy(self._h)
@@ -135,59 +151,33 @@ class RowShardedWorld:
     shards.  Not a product class: the product entry is Comm.step_row_sharded / b200_sixdof_step_row_sharded."""
 
     @staticmethod
-    def bench(args, torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, world, grav, ref_pos):
-        from .executor import WORLD_POS
-
+    def _comm(torch, dist, world_size, rank, local):
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid = torch.tensor(list(Comm.unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(uid, 0)
-        comm = Comm(bytes(uid.cpu().tolist()), world_size, rank, local)
-        out = {}
-        ev = lambda: torch.cuda.Event(enable_timing=True)
-
-        def run(p, v, I, N, warm, ticks, math="fast"):
-            ex = el.B200Exec(N, 1, 3600.0, None, [grav(N)], "rk4", math, device=local)
-            ex.set_stream(stream.cuda_stream)
-            ex.set_state(p, v, I)
-            with torch.cuda.stream(stream):
-                comm.step_row_sharded(ex, warm)
-                barrier()
-                a, b = ev(), ev()
-                a.record(stream)
-                comm.step_row_sharded(ex, ticks)
-                b.record(stream)
-                barrier()
-            ms = max_over_ranks(a.elapsed_time(b))
-            pos = ex.download(WORLD_POS)
-            ex.close()
-            return ms, pos
-
-        p1, v1, I1 = world
-        N = p1.shape[1]
-        ms, pos = run(p1, v1, I1, N, 20, 400)
-        scale = float(np.max(np.abs(ref_pos[..., 4:])))
-        out = {"us_per_tick": ms * 1e3 / 400, "value": N * 400 / (ms * 1e-3), "unit": "entity-steps/s", "ranks": world_size,
-               "rows_per_gpu": N // world_size,
-               "exchange": "6 planes x N/R f64 per rank, in-place ncclAllGather per plane, one NCCL group per tick (inside libb200_sixdof.so)",
-               "max_rel_diff_vs_replica_after_420_ticks": float(np.max(np.abs(pos[..., 4:] - ref_pos[..., 4:])) / scale)}
-        comm.close()
-        return out
+        return Comm(bytes(uid.cpu().tolist()), world_size, rank, local)
 
     @staticmethod
-    def bench_large(torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, world, grav, ref_pos, warm, ticks):
+    def _timed(torch, el, stream, local, comm, barrier, max_over_ranks, world, grav, warm, ticks, peer, math="fast"):
+        """One route of the row-sharded world: `peer` = NVLink stores into the peers' windows, else ncclAllGather per tick."""
+        from . import _lib
         from .executor import WORLD_POS
 
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.tensor(list(Comm.unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(uid, 0)
-        comm = Comm(bytes(uid.cpu().tolist()), world_size, rank, local)
         p, v, I = world
         N = p.shape[1]
-        ex = el.B200Exec(N, 1, 3600.0, None, [grav(N)], "rk4", "fast", device=local)
+        ex = el.B200Exec(N, 1, 3600.0, None, [grav(N)], "rk4", math, device=local)
         ex.set_stream(stream.cuda_stream)
         ex.set_state(p, v, I)
+        why = None
+        if peer:
+            try:
+                comm.peer_attach(ex)
+            except _lib.B200Error as e:  # every rank gets the same answer (the attach is agreed across ranks)
+                why = str(e)[:200]
+        if peer and why:
+            ex.close()
+            return None, None, why
         ev = lambda: torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             comm.step_row_sharded(ex, warm)
@@ -199,9 +189,38 @@ class RowShardedWorld:
             barrier()
         ms = max_over_ranks(a.elapsed_time(b))
         pos = ex.download(WORLD_POS)
+        if peer:
+            comm.peer_detach()
         ex.close()
-        comm.close()
+        return ms, pos, None
+
+    @staticmethod
+    def _both(torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, world, grav, ref_pos, warm, ticks):
+        comm = RowShardedWorld._comm(torch, dist, world_size, rank, local)
+        N = world[0].shape[1]
         scale = float(np.max(np.abs(ref_pos[..., 4:])))
-        return {"us_per_tick": ms * 1e3 / ticks, "value": N * ticks / (ms * 1e-3), "unit": "entity-steps/s", "ranks": world_size,
-                "rows_per_gpu": N // world_size,
-                "max_rel_diff_vs_replica": float(np.max(np.abs(pos[..., 4:] - ref_pos[..., 4:])) / scale)}
+        out = {"ranks": world_size, "rows_per_gpu": N // world_size, "unit": "entity-steps/s"}
+        for name, peer in (("nccl", False), ("peer", True)):
+            ms, pos, why = RowShardedWorld._timed(torch, el, stream, local, comm, barrier, max_over_ranks, world, grav, warm, ticks, peer)
+            if why:
+                out[name] = {"unavailable": why}
+                continue
+            out[name] = {"us_per_tick": ms * 1e3 / ticks, "value": N * ticks / (ms * 1e-3),
+                         "max_rel_diff_vs_replica": float(np.max(np.abs(pos[..., 4:] - ref_pos[..., 4:])) / scale)}
+        out["nccl"]["exchange"] = "6 planes x N/R f64 per rank, in-place ncclAllGather per plane, one NCCL group per tick (inside libb200_sixdof.so)"
+        out["peer"]["exchange"] = ("rows stored straight into every rank's CUDA-IPC window over NVLink + one counter release per peer; "
+                                   "the next tick's gravity waits on the counters (no collective in the tick loop)")
+        best = min((o for o in (out["nccl"], out["peer"]) if "us_per_tick" in o), key=lambda o: o["us_per_tick"])
+        out["us_per_tick"], out["value"] = best["us_per_tick"], best["value"]
+        out["max_rel_diff_vs_replica"] = best["max_rel_diff_vs_replica"]
+        comm.close()
+        return out
+
+    @staticmethod
+    def bench(args, torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, world, grav, ref_pos):
+        """ref_pos: the replica's positions after 420 ticks."""
+        return RowShardedWorld._both(torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, world, grav, ref_pos, 20, 400)
+
+    @staticmethod
+    def bench_large(torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, world, grav, ref_pos, warm, ticks):
+        return RowShardedWorld._both(torch, dist, el, stream, local, rank, world_size, barrier, max_over_ranks, world, grav, ref_pos, warm, ticks)

@@ -319,6 +319,21 @@ int b200_sixdof_trajectory_allgather(b200_sixdof *h, b200_comm *c, const uint64_
  * (measured by bench.py `multi_gpu.nbody_1024_single_world`). */
 int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks);
 
+/* Peer window for the row-sharded world: compute and exchange without a collective in the tick loop.  Every rank
+ * allocates a window (the x, v planes of the whole world, twice — tick-count parity — plus one delivery counter per
+ * rank), the ranks swap the windows' CUDA IPC handles through the communicator and map each other's.  With a window
+ * attached, b200_sixdof_step_row_sharded runs per tick: wait until every rank's rows of this tick count have landed
+ * here -> gravity from the window -> integrate own rows -> store the rows' new x, v straight into every rank's window
+ * over NVLink and release each counter.  Only the call's last tick still all-gathers (attitude, WorldAccel, Force of
+ * the other ranks' rows).  Results are bit-identical to the NCCL route and to replicas.
+ * Collective: every rank of `c` calls attach (and detach / b200_comm_destroy) with handles of the same shape; one
+ * window per communicator.  Returns B200_ERR_UNSUPPORTED on every rank if any rank cannot map the windows (no IPC
+ * between the processes) — the NCCL route keeps working.  B200_ROW_PEER=0 ignores an attached window. */
+#define B200_MAX_PEERS 16
+int b200_comm_peer_attach(b200_comm *c, b200_sixdof *h);
+int b200_comm_peer_attached(const b200_comm *c);
+void b200_comm_peer_detach(b200_comm *c);
+
 /* Concurrent host<->device copy bandwidth of one GPU through pinned `host` (>= h2d_bytes + d2h_bytes): out[0] = H2D
  * GB/s, out[1] = D2H GB/s, both directions running at once — the ceiling an invoke_batch round trip sits under. */
 int b200_probe_pcie_gbs(int device, void *host, uint64_t h2d_bytes, uint64_t d2h_bytes, int iters, double *out);

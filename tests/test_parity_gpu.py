@@ -1382,6 +1382,92 @@ def test_library_nccl_gather_and_row_sharded_world_on_two_gpus():
         assert fast_err <= 5 * FAST_TOL_TICK * 10, fast_err
 
 
+def _peer_window_worker(rank, uid, q):
+    import numpy as np
+
+    import elodin_b200 as el
+    from elodin_b200 import _lib
+    from elodin_b200.executor import FORCE, WORLD_ACCEL, WORLD_POS, WORLD_VEL
+    from elodin_b200.sharding import Comm
+    from oracle import oracle as O
+    from tests.util import random_world
+
+    try:
+        comm = Comm(uid, 2, rank, rank)
+        cols = (WORLD_POS, WORLD_VEL, WORLD_ACCEL, FORCE)
+        res = {"unsupported": None}
+        # N = 96: one shared-memory tile set (world kernel in FAST); N = 1280: the tiled fold kernels
+        for N, ticks in ((96, (3, 2)), (1280, (1, 2))):
+            p, v, I = random_world(9 + N, 1, N)
+            p[..., 4:] *= 1e-2
+            edges = el.all_pairs_edges(N)
+            o = O.World(p.copy(), v.copy(), I).rk4(0.01, sum(ticks), [O.Effector(O.EFF_GRAVITY_EDGES_SOFTENED, p=(0.3, 1e-4), edges=edges)])
+            for math in ("exact", "fast"):
+                got = {}
+                for route in ("nccl", "peer"):
+                    with el.B200Exec(N, 1, 0.01, None, [el.GravityEdges("softened", k_squared=0.3, softening=1e-4, edges=edges)], "rk4",
+                                     math, device=rank) as ex:
+                        ex.set_state(p, v, I)
+                        if route == "peer":
+                            try:
+                                comm.peer_attach(ex)
+                            except _lib.B200Error as e:
+                                if e.code != _lib.ERR_UNSUPPORTED:
+                                    raise
+                                res["unsupported"] = str(e)
+                                break
+                            assert comm.peer_attached
+                        for n in ticks:  # two calls: the second one starts from the window state the first one left
+                            comm.step_row_sharded(ex, n)
+                        ex.sync()
+                        got[route] = [ex.download(c) for c in cols]
+                        assert ex.tick == sum(ticks)
+                        if route == "peer":
+                            comm.peer_detach()
+                            assert not comm.peer_attached
+                if res["unsupported"]:
+                    break
+                res[(N, math, "same")] = all(np.array_equal(a, b) for a, b in zip(got["nccl"], got["peer"]))
+                if math == "exact":
+                    res[(N, math, "oracle")] = all(np.array_equal(a, b) for a, b in zip(got["peer"], (o.pos, o.vel, o.accel, o.force)))
+            if res["unsupported"]:
+                break
+        comm.close()
+        q.put((rank, res, None))
+    except Exception:
+        import traceback
+
+        q.put((rank, {}, traceback.format_exc()))
+
+
+def test_row_sharded_world_through_peer_windows_on_two_gpus():
+    """b200_comm_peer_attach: the row-sharded world exchanges its rows with NVLink stores into CUDA-IPC windows and
+    counter releases instead of a collective per tick — bit-identical to the NCCL route in both math modes, and to the
+    oracle in EXACT; two processes, one GPU each, two step calls per executor."""
+    if el.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+
+    from elodin_b200.sharding import Comm
+
+    uid = Comm.unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_window_worker, args=(r, uid, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, res, err in got:
+        assert err is None, err
+    if any(res["unsupported"] for _, res, _ in got):
+        pytest.skip("CUDA IPC between the two processes is not available here: " + str(got[0][1]["unsupported"]))
+    for rank, res, _ in got:
+        checks = {k: v for k, v in res.items() if k != "unsupported"}
+        assert len(checks) == 6 and all(checks.values()), (rank, checks)
+
+
 def test_numa_local_pinned_buffers_and_pcie_probe():
     """b200_host_alloc_local: page-locked memory bound to the NUMA node of the GPU's PCIe root (falls back to plain
     pinned memory when the node is unknown), usable as invoke_batch column buffers; b200_probe_pcie_gbs reports both
