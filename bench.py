@@ -531,7 +531,7 @@ def run_b200(args):
             del p2
             # spherical-harmonic gravity (GRAVITY_EGM08, degree 64 like the cube-sat example) on 2^16 satellites: its own
             # launch per tick, FP64-issue bound (synthetic Kaula-rule coefficients: the reference's tables are a download)
-            gM, gL = 1 << 16, 64
+            gM, gL = 1 << 18, 64
             grng = np.random.default_rng(8)
             cb, sb = np.zeros((gL + 1, gL + 1)), np.zeros((gL + 1, gL + 1))
             for l_ in range(2, gL + 1):
@@ -550,8 +550,12 @@ def run_b200(args):
             t_ms = q0.elapsed_time(q1) / 10
             extras["egm08_degree_64"] = {"worlds": gM, "us_per_tick": t_ms * 1e3, "value": gM / (t_ms * 1e-3), "unit": UNIT,
                                          "field_evaluations_per_s": 3 * gM / (t_ms * 1e-3),
+                                         "terms_per_s": 3 * gM * ((gL + 1) * (gL + 2) // 2) / (t_ms * 1e-3),
+                                         "fp64_pipe_frac": (3 * gM * ((gL + 1) * (gL + 2) // 2) / (t_ms * 1e-3) * 33.0 / (fp64_peak * 1e9 / 2.0)) if fp64_peak else None,
                                          "note": "cube-sat effector shape with the degree-64 series instead of J2: egm08_force_kernel (3 stage "
-                                                 "positions per body and tick, oracle arithmetic) + the wheel-fold body kernel"}
+                                                 "positions per body and tick, 2145 terms each, the oracle's IEEE operations: 33 FP64 "
+                                                 "instructions per term, none fused) + the wheel-fold body kernel; fp64_pipe_frac = those "
+                                                 "instructions / the DFMA issue rate of the probe"}
             gx.close()
             del gp
             # telemetry on every tick: the trajectory ring adds 104 B per body and tick (13 more planes written)

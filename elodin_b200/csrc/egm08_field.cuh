@@ -7,25 +7,24 @@ namespace b200 {
 // libs/nox-py/python/elodin/egm08.py (EGM08.compute_field) in the operation order of
 // oracle/sixdof_oracle.c:eff_gravity_egm08 — column by column (m outer, l = m..L inner), one running accumulator per
 // component, every IEEE operation explicit — so the result is bit-identical to the oracle in both math modes.
-// tab = [C | S | n1 | n2 | nq1 | nq2] each (L+1)^2 row-major [l][m], then diag[L+1], offc[L+1] (built at create by
-// sixdof_abi.cu:egm08_tables with the oracle's formulas).  Returns the force (mass included): ~30 k instructions per
-// evaluation at degree 64 and a 130-entry local array — which is why it lives in its own kernel and the body kernels
-// only add its result.
+// tab = the term stream sixdof_abi.cu:egm08_tables builds at create (eight doubles per (m, l) term in consumption
+// order: the warp-uniform loads of an evaluation walk 64 contiguous bytes per term).  The oracle evaluates the B
+// recursion twice per term (B_l and B_{l+1}); B_{l+1} of one term is bit for bit B_l of the next, so it is carried
+// instead.  Returns the force (mass included): ~35 FP64 instructions per term, 2145 terms at degree 64, and a local
+// array of the L+1 radial factors — which is why it lives in its own kernel and the body kernels only add its result.
 static __device__ __forceinline__ Vec3 egm08_field(const double *__restrict__ tab, int L, double mu, double r_ref, Vec3 p, double mass)
 {
     using namespace ex;
-    const int n = L + 1;
-    const double *C = tab, *S = C + n * n, *n1 = S + n * n, *n2 = n1 + n * n, *nq1 = n2 + n * n, *nq2 = nq1 + n * n;
-    const double *diag = nq2 + n * n, *offc = diag + n;
     const double r = sqr(add(add(mul(p.x, p.x), mul(p.y, p.y)), mul(p.z, p.z)));
     const double s = div(p.x, r), t = div(p.y, r), u = div(p.z, r);
-    double w[130]; // w[l] = rho_{l+1} / r_ref, rho_l = (mu / r) (r_ref / r)^l by repeated multiplication; w[L] = 0
+    double w[129]; // w[l] = rho_{l+1} / r_ref, rho_l = (mu / r) (r_ref / r)^l by repeated multiplication; w[L] = 0
     {
         double rho = div(mu, r);
         const double q = div(r_ref, r);
         for (int l = 1; l <= L; ++l) { rho = mul(rho, q); w[l - 1] = div(rho, r_ref); }
         w[L] = div(0.0, r_ref);
     }
+    const double4 *rec = reinterpret_cast<const double4 *>(tab); // two per term (cudaMalloc'd: 256-byte aligned)
     double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
     double im_prev = 0.0, rm_prev = 0.0, im = 0.0, rm = 1.0;
     for (int m = 0; m <= L; ++m) {
@@ -35,35 +34,45 @@ static __device__ __forceinline__ Vec3 egm08_field(const double *__restrict__ ta
         }
         const double rm1 = m == 0 ? 0.0 : rm_prev, im1 = m == 0 ? 0.0 : im_prev;
         const double mp = m == L ? 0.0 : (double)(m + 1);
-        double A0 = 0.0, A1 = 0.0, B0 = 0.0, B1 = 0.0;
-        for (int l = m; l <= L; ++l) {
-            double Al;
-            if (l == m) Al = diag[m];
-            else if (l == m + 1) Al = mul(offc[l], u);
-            else Al = sub(mul(mul(u, n1[l * n + m]), A0), mul(n2[l * n + m], A1));
+        // one term: Al = A_l at order m, Bl / Bn = B_l / B_{l+1} at order m+1, rc = C, S, nq1, nq2 of (l, m)
+        auto term = [&](double Al, double Bl, double Bn, const double4 rc, double wl) {
+            const double ee = add(mul(rc.x, rm1), mul(rc.y, im1)), ff = sub(mul(rc.y, rm1), mul(rc.x, im1)), dd = add(mul(rc.x, rm), mul(rc.y, im));
+            const double wa = mul(mul(wl, Al), mp);
+            a1 = add(a1, mul(wa, ee));
+            a2 = add(a2, mul(wa, ff));
+            a3 = add(a3, mul(mul(mul(mul(wl, Bl), mp), rc.z), dd));
+            a4 = sub(a4, mul(mul(mul(mul(wl, Bn), mp), rc.w), dd)); // the oracle adds the product times -1.0: the same value
+        };
+        // l = m: A_m = diag[m], B_m = 0, B_{m+1} = diag[m+1] (0 beyond degree L)
+        double4 ra = rec[0];
+        double A1 = 0.0, A0 = ra.x, Bm1 = 0.0, Bl = 0.0, Bn = m < L ? ra.z : 0.0;
+        term(A0, Bl, Bn, rec[1], w[m]);
+        rec += 2;
+        if (m == L) break;
+        // l = m + 1: A = offc[l] u, B_{l+1} = offc[l+1] u
+        ra = rec[0];
+        A1 = A0; A0 = mul(ra.x, u);
+        Bm1 = Bl; Bl = Bn; Bn = m + 1 < L ? mul(ra.z, u) : 0.0;
+        term(A0, Bl, Bn, rec[1], w[m + 1]);
+        rec += 2;
+        if (m + 1 == L) continue;
+        // m + 2 <= l < L: both three-term recursions
+#pragma unroll 2
+        for (int l = m + 2; l < L; ++l) {
+            ra = rec[0];
+            const double Al = sub(mul(mul(u, ra.x), A0), mul(ra.y, A1));
             A1 = A0; A0 = Al;
-            double Bl = 0.0;
-            if (m + 1 <= L) {
-                if (l == m + 1) Bl = diag[m + 1];
-                else if (l == m + 2) Bl = mul(offc[l], u);
-                else if (l > m + 2) Bl = sub(mul(mul(u, n1[l * n + m + 1]), B0), mul(n2[l * n + m + 1], B1));
-            }
-            double Bn = 0.0;
-            if (m + 1 <= L && l + 1 <= L) {
-                const int l1 = l + 1;
-                if (l1 == m + 1) Bn = diag[m + 1];
-                else if (l1 == m + 2) Bn = mul(offc[l1], u);
-                else Bn = sub(mul(mul(u, n1[l1 * n + m + 1]), Bl), mul(n2[l1 * n + m + 1], B0));
-            }
-            B1 = B0; B0 = Bl;
-            const double wl = w[l];
-            const double c = C[l * n + m], sv = S[l * n + m];
-            const double ee = add(mul(c, rm1), mul(sv, im1)), ff = sub(mul(sv, rm1), mul(c, im1)), dd = add(mul(c, rm), mul(sv, im));
-            a1 = add(a1, mul(mul(mul(wl, Al), mp), ee));
-            a2 = add(a2, mul(mul(mul(wl, Al), mp), ff));
-            a3 = add(a3, mul(mul(mul(mul(wl, Bl), mp), nq1[l * n + m]), dd));
-            a4 = add(a4, mul(mul(mul(mul(mul(wl, Bn), mp), nq2[l * n + m]), dd), -1.0));
+            const double Bq = sub(mul(mul(u, ra.z), Bn), mul(ra.w, Bl)); // B_{l+1} from B_l (= the carried Bn) and B_{l-1}
+            Bm1 = Bl; Bl = Bn; Bn = Bq;
+            term(Al, Bl, Bn, rec[1], w[l]);
+            rec += 2;
         }
+        // l = L: B_{L+1} lies beyond the table
+        ra = rec[0];
+        const double Al = sub(mul(mul(u, ra.x), A0), mul(ra.y, A1));
+        term(Al, Bn, 0.0, rec[1], w[L]);
+        rec += 2;
+        (void)Bm1;
     }
     return Vec3{mul(mass, add(a1, mul(s, a4))), mul(mass, add(a2, mul(t, a4))), mul(mass, add(a3, mul(u, a4)))};
 }

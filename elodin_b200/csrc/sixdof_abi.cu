@@ -103,19 +103,20 @@ int add_column(b200_sixdof *h, uint64_t id, uint32_t width, bool global)
     return B200_OK;
 }
 
-// Derived tables of the EGM08 recursion (python/elodin/egm08.py:84-144), laid out behind the caller's C / S tables:
-// [C | S | n1 | n2 | nq1 | nq2] each (L+1)^2 row-major [l][m], then diag[L+1], offc[L+1].  The same formulas, operation
-// for operation, as the test oracle's orc_egm08_tables, so both sides evaluate the series on bit-identical constants.
+// Derived tables of the EGM08 recursion (python/elodin/egm08.py:84-144) — the same formulas, operation for operation,
+// as the test oracle's orc_egm08_tables, so both sides evaluate the series on bit-identical constants — emitted as ONE
+// stream in the order egm08_field consumes it: column by column (m = 0..L), degree by degree (l = m..L), eight doubles
+// per term:
+//   [0] the A recursion's first constant: diag[m] (l = m), offc[l] (l = m+1), n1[l][m] otherwise      [1] n2[l][m] or 0
+//   [2] the same for B at (l+1, m+1): diag[m+1], offc[l+1], n1[l+1][m+1], or 0 beyond degree L         [3] n2[l+1][m+1] or 0
+//   [4] C[l][m]   [5] S[l][m]   [6] nq1[l][m]   [7] nq2[l][m]
+// so a warp reads the 137 KB of a degree-64 field front to back, 64 contiguous bytes per term.
 double kdelta(int d) { return d == 0 ? 1.0 : 2.0; }
 
 std::vector<double> egm08_tables(int L, const double *c_bar, const double *s_bar)
 {
     const int n = L + 1;
-    std::vector<double> t((size_t)6 * n * n + 2 * n, 0.0);
-    double *C = t.data(), *S = C + n * n, *n1 = S + n * n, *n2 = n1 + n * n, *nq1 = n2 + n * n, *nq2 = nq1 + n * n;
-    double *diag = nq2 + n * n, *offc = diag + n;
-    std::memcpy(C, c_bar, sizeof(double) * n * n);
-    std::memcpy(S, s_bar, sizeof(double) * n * n);
+    std::vector<double> n1((size_t)n * n, 0.0), n2((size_t)n * n, 0.0), nq1((size_t)n * n, 0.0), nq2((size_t)n * n, 0.0), diag(n), offc(n);
     for (int l = 0; l <= L; ++l)
         for (int m = 0; m <= L; ++m) {
             double v1 = 0.0, v2 = 0.0;
@@ -136,6 +137,21 @@ std::vector<double> egm08_tables(int L, const double *c_bar, const double *s_bar
         diag[l] = cur;
         offc[l] = l == 0 ? 0.0 : diag[l] * std::sqrt(((double)(2 * l) * kdelta(l - 1)) / kdelta(l));
     }
+    std::vector<double> t;
+    t.reserve((size_t)4 * n * (n + 1));
+    for (int m = 0; m <= L; ++m)
+        for (int l = m; l <= L; ++l) {
+            const int l1 = l + 1, m1 = m + 1;
+            const bool b_live = m1 <= L && l1 <= L;
+            t.push_back(l == m ? diag[m] : l == m + 1 ? offc[l] : n1[l * n + m]);
+            t.push_back(l >= m + 2 ? n2[l * n + m] : 0.0);
+            t.push_back(!b_live ? 0.0 : l1 == m1 ? diag[m1] : l1 == m1 + 1 ? offc[l1] : n1[l1 * n + m1]);
+            t.push_back(b_live && l1 >= m1 + 2 ? n2[l1 * n + m1] : 0.0);
+            t.push_back(c_bar[l * n + m]);
+            t.push_back(s_bar[l * n + m]);
+            t.push_back(nq1[l * n + m]);
+            t.push_back(nq2[l * n + m]);
+        }
     return t;
 }
 

@@ -133,19 +133,25 @@ __global__ void __launch_bounds__(256) peer_fill_kernel(const double *__restrict
     if (blockIdx.x == 0 && threadIdx.x < (unsigned)n_ranks) atomicMax(flags + threadIdx.x, T); // a faster peer may already be one ahead
 }
 
-// Holds the stream until every rank has delivered the rows of tick count `need` into this GPU's window.
-__global__ void peer_wait_kernel(const unsigned long long *flags, int n_ranks, unsigned long long need)
+// Spins until rank r has delivered the rows of tick count `need` into this GPU's window.
+__device__ __forceinline__ void peer_wait_one(const unsigned long long *flag, unsigned long long need)
 {
-    if (threadIdx.x >= (unsigned)n_ranks) return;
     unsigned long long t0, now, v;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
         if (v >= need) return;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         if (now - t0 > 20000000000ull) __trap(); // 20 s without the peer's rows: fail the handle instead of hanging the GPU
-        __nanosleep(100);
+        __nanosleep(64);
     }
+}
+
+// Holds the stream until every rank's rows of tick count `need` are here (first tick of a call; later ticks wait at
+// the end of the previous tick's push kernel).
+__global__ void peer_wait_kernel(const unsigned long long *flags, int n_ranks, unsigned long long need)
+{
+    if (threadIdx.x < (unsigned)n_ranks) peer_wait_one(flags + threadIdx.x, need);
 }
 
 struct PeerPush {
@@ -153,13 +159,16 @@ struct PeerPush {
     double *dst[B200_MAX_PEERS];  // X[next parity] of every rank, shifted to this rank's first row
     unsigned long long *flag[B200_MAX_PEERS]; // &flags_r[me]
     unsigned *ctr;
+    const unsigned long long *wait; // local delivery counters, or nullptr: do not wait for the peers' rows of `value`
     uint64_t ld_src, ld_dst;
     uint32_t rows;
     int n_ranks;
     unsigned long long value;     // tick count the rows belong to
 };
 
-// This rank's new rows -> every rank's window (NVLink stores), then one release per peer once every block is through.
+// This rank's new rows -> every rank's window (NVLink stores), then one release per peer once every block is through;
+// the same block then waits for the peers' rows of the same tick count, so the next tick's gravity launches straight
+// behind this kernel.
 __global__ void __launch_bounds__(128) peer_push_kernel(const __grid_constant__ PeerPush a)
 {
     const uint32_t i = blockIdx.x * 128u + threadIdx.x, k = blockIdx.y; // plane k of x y z vx vy vz
@@ -176,6 +185,8 @@ __global__ void __launch_bounds__(128) peer_push_kernel(const __grid_constant__ 
             __threadfence_system();
             for (int r = 0; r < a.n_ranks; ++r)
                 asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[r]), "l"(a.value) : "memory");
+            if (a.wait)
+                for (int r = 0; r < a.n_ranks; ++r) peer_wait_one(a.wait + r, a.value);
         }
     }
 }
@@ -477,8 +488,10 @@ int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks)
             const double *X = c->win.base[c->rank] + (T & 1ull) * 6ull * h->ld;
             G.pos = X - 4 * h->ld;
             G.vel = X;
-            peer_wait_kernel<<<1, 32, 0, h->stream>>>(flags, (int)R, T);
-            h->timings.kernel_launches++;
+            if (t == 0) { // later ticks: the previous tick's push kernel already waited
+                peer_wait_kernel<<<1, 32, 0, h->stream>>>(flags, (int)R, T);
+                h->timings.kernel_launches++;
+            }
         }
         CU(h, launch_graph_force(G, (int)h->desc.math_mode, true, h->stream));
         // the body kernel on this rank's rows only: shift every per-body plane, keep the entity numbering
@@ -497,6 +510,7 @@ int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks)
             // exchange: this rank's new x, v rows straight into every rank's next-parity half, then one counter release each
             PeerPush a{};
             a.pos = pos + i0; a.vel = vel + i0; a.ctr = c->win.ctr;
+            a.wait = last ? nullptr : flags;
             a.ld_src = a.ld_dst = h->ld; a.rows = (uint32_t)rows; a.n_ranks = (int)R; a.value = T + 1;
             for (uint64_t r = 0; r < R; ++r) {
                 a.dst[r] = c->win.base[r] + ((T + 1) & 1ull) * 6ull * h->ld + i0;

@@ -18,7 +18,7 @@ struct EffDev {
     uint32_t col_width;
     uint32_t pad;
     const uint8_t *mask; // [n_entities] or nullptr (query-join membership)
-    const double *table; // GRAVITY_EGM08: [C | S | n1 | n2 | nq1 | nq2] each (L+1)^2, then diag[L+1], offc[L+1] (device)
+    const double *table; // GRAVITY_EGM08: the term stream sixdof_abi.cu:egm08_tables builds (device)
 };
 
 // Launch parameters of the per-body integrator kernels.  All columns are SoA:
@@ -111,7 +111,7 @@ cudaError_t launch_small_world(const GraphParams &G, const StepParams &P, int ma
 struct EgmParams {
     const double *pos, *vel, *ine;
     double *aforce;
-    const double *table;     // [C | S | n1 | n2 | nq1 | nq2 | diag | offc] (device)
+    const double *table;     // term stream of sixdof_abi.cu:egm08_tables (device)
     const uint8_t *mask;     // entity mask of the effector or nullptr
     uint64_t ld, n_bodies;
     uint32_t n_entities, ent0;

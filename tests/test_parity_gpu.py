@@ -1559,6 +1559,13 @@ def test_egm08_gravity_effector(oracle, integrator):
         _assert_exact(got, want, f"exact {name}")
         fast = _run_gpu(pos, vel, ine, ge, cols, 0.05, n, "fast", integrator)
         _assert_close(fast, want, n * FAST_TOL_TICK, f"fast {name}")
+    # the degrees at the edges of the term stream (one term; two-term columns) and the bench's degree 64, one tick each
+    for Ld in (0, 1, 2, 64):
+        cd, sd = np.tril(rng.normal(0, 1e-5, (Ld + 1, Ld + 1))), np.tril(rng.normal(0, 1e-5, (Ld + 1, Ld + 1)), -1)
+        cd[0, 0] = 1.0
+        a, b, cc = effector_pair(O, "egm08", c_bar=cd, s_bar=sd, L=Ld)
+        want = _run_oracle(O, pos, vel, ine, [a], 0.05, 1, integrator)
+        _assert_exact(_run_gpu(pos, vel, ine, [b], cc, 0.05, 1, "exact", integrator), want, f"exact degree {Ld}")
     # C20 alone == GRAVITY_J2 (the reference's own closed form).  max_degree 3: the source zeroes rho_{L+1}
     # (egm08.py:150), so the terms of the top degree L drop out — degree 2 needs L >= 3
     c2, s2 = np.zeros((4, 4)), np.zeros((4, 4))
