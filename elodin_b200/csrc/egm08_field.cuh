@@ -45,14 +45,14 @@ static __device__ __forceinline__ Vec3 egm08_field(const double *__restrict__ ta
         };
         // l = m: A_m = diag[m], B_m = 0, B_{m+1} = diag[m+1] (0 beyond degree L)
         double4 ra = rec[0];
-        double A1 = 0.0, A0 = ra.x, Bm1 = 0.0, Bl = 0.0, Bn = m < L ? ra.z : 0.0;
+        double A1 = 0.0, A0 = ra.x, Bl = 0.0, Bn = m < L ? ra.z : 0.0;
         term(A0, Bl, Bn, rec[1], w[m]);
         rec += 2;
         if (m == L) break;
         // l = m + 1: A = offc[l] u, B_{l+1} = offc[l+1] u
         ra = rec[0];
         A1 = A0; A0 = mul(ra.x, u);
-        Bm1 = Bl; Bl = Bn; Bn = m + 1 < L ? mul(ra.z, u) : 0.0;
+        Bl = Bn; Bn = m + 1 < L ? mul(ra.z, u) : 0.0;
         term(A0, Bl, Bn, rec[1], w[m + 1]);
         rec += 2;
         if (m + 1 == L) continue;
@@ -63,7 +63,7 @@ static __device__ __forceinline__ Vec3 egm08_field(const double *__restrict__ ta
             const double Al = sub(mul(mul(u, ra.x), A0), mul(ra.y, A1));
             A1 = A0; A0 = Al;
             const double Bq = sub(mul(mul(u, ra.z), Bn), mul(ra.w, Bl)); // B_{l+1} from B_l (= the carried Bn) and B_{l-1}
-            Bm1 = Bl; Bl = Bn; Bn = Bq;
+            Bl = Bn; Bn = Bq;
             term(Al, Bl, Bn, rec[1], w[l]);
             rec += 2;
         }
@@ -72,7 +72,6 @@ static __device__ __forceinline__ Vec3 egm08_field(const double *__restrict__ ta
         const double Al = sub(mul(mul(u, ra.x), A0), mul(ra.y, A1));
         term(Al, Bn, 0.0, rec[1], w[L]);
         rec += 2;
-        (void)Bm1;
     }
     return Vec3{mul(mass, add(a1, mul(s, a4))), mul(mass, add(a2, mul(t, a4))), mul(mass, add(a3, mul(u, a4)))};
 }

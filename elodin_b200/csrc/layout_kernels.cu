@@ -2,6 +2,7 @@
 // and the FP64 throughput probe.
 #include <algorithm>
 
+#include "sixdof_device.cuh"
 #include "sixdof_internal.h"
 #include "sixdof_launch.h"
 
@@ -124,6 +125,81 @@ cudaError_t launch_multi_transpose(const MultiColumns &mc, uint64_t n_bodies, ui
 cudaError_t launch_probe_fp64(double *out, int iters, int blocks, cudaStream_t s)
 {
     probe_fp64_kernel<<<blocks, 256, 0, s>>>(out, iters);
+    return cudaGetLastError();
+}
+
+// ================================================================== self-test of the shared-divisor divisions
+//
+// ex::rcp_prep / ex::div_rcp (sixdof_device.cuh) against div.rn.f64, operand for operand: groups of four dividends over
+// one divisor, as the EXACT tick forms them (`ok` false -> the group is redone with __ddiv_rn), from a counter-based
+// generator that covers the whole encoding space and the corners of the range test.
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double with_exponent(uint64_t bits, unsigned lo, unsigned span)
+{
+    const uint64_t e = lo + (unsigned)((bits >> 52) % span); // biased exponent in [lo, lo + span)
+    return __longlong_as_double((long long)((bits & 0x800fffffffffffffull) | (e << 52)));
+}
+
+__global__ void __launch_bounds__(256) selftest_div_kernel(uint64_t seed, uint64_t n_groups, unsigned long long *counts)
+{
+    unsigned long long bad = 0, fast = 0;
+    for (uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x; g < n_groups; g += (uint64_t)gridDim.x * 256) {
+        const uint64_t h = mix64(seed + g * 5u);
+        const unsigned mode = (unsigned)(g % 10u);
+        double d, a[4];
+        const uint64_t hd = mix64(h);
+        uint64_t ha[4];
+        for (int i = 0; i < 4; ++i) ha[i] = mix64(h + 1 + i);
+        switch (mode) {
+        case 0: d = __longlong_as_double((long long)hd); for (int i = 0; i < 4; ++i) a[i] = __longlong_as_double((long long)ha[i]); break; // any encoding
+        case 1: d = with_exponent(hd, 993, 60); for (int i = 0; i < 4; ++i) a[i] = with_exponent(ha[i], 993, 60); break;                   // ordinary magnitudes
+        case 2: d = with_exponent(hd, 1000, 40); for (int i = 0; i < 4; ++i) a[i] = with_exponent(ha[i], 30, 50); break;                    // dividends around the tiny-exponent threshold
+        case 3: d = with_exponent(hd, 1, 80); for (int i = 0; i < 4; ++i) a[i] = with_exponent(ha[i], 1960, 86); break;                      // quotients at the overflow edge
+        case 4: d = with_exponent(hd, 1900, 146); for (int i = 0; i < 4; ++i) a[i] = with_exponent(ha[i], 0, 120); break;                    // quotients in the denormals, denormal dividends
+        case 5: d = with_exponent(hd, 0, 2047);                                                                                              // zero / denormal dividends over anything
+                for (int i = 0; i < 4; ++i) a[i] = (ha[i] & 1) ? __longlong_as_double((long long)(ha[i] & 0x8000000000000000ull)) : with_exponent(ha[i], 0, 1);
+                break;
+        case 6: d = __longlong_as_double((long long)((hd & 0xfff0000000000000ull) | ((hd & 1) ? 0x000fffffffffffffull : 0ull)));            // power of two / all-ones significand
+                d = with_exponent((uint64_t)__double_as_longlong(d), 900, 240);
+                for (int i = 0; i < 4; ++i) a[i] = with_exponent(ha[i], 900, 240);
+                break;
+        case 7: d = with_exponent(hd, 1000, 46); for (int i = 0; i < 4; ++i) a[i] = __dmul_rn(d, (double)(int)(ha[i] % 2001u) - 1000.0); break; // exact quotients
+        case 8: {                                                                                                                           // the workload: a unit quaternion over its norm
+            double q[4], n2 = 0.0;
+            for (int i = 0; i < 4; ++i) { q[i] = (double)(long long)(ha[i] >> 11) * 0x1p-52 - 1.0; n2 += q[i] * q[i]; }
+            const double n = sqrt(n2) * (1.0 + ((double)(hd & 0xff) - 128.0) * 0x1p-52);
+            d = (hd & 0x100) ? n : n * n;
+            for (int i = 0; i < 4; ++i) a[i] = q[i];
+            break;
+        }
+        default: d = with_exponent(hd, 1013, 20); for (int i = 0; i < 4; ++i) a[i] = (ha[i] & 3) ? with_exponent(ha[i], 1000, 46) : 0.0; break; // forces with zero components over a mass
+        }
+        const ex::Rcp r = ex::rcp_prep(d);
+        bool ok = true;
+        double got[4];
+        for (int i = 0; i < 4; ++i) got[i] = ex::div_rcp(a[i], r, ok);
+        if (!ok) { const double dd = ex::rare_path(d); for (int i = 0; i < 4; ++i) got[i] = __ddiv_rn(a[i], dd); }
+        fast += ok ? 1u : 0u;
+        for (int i = 0; i < 4; ++i) {
+            const double want = __ddiv_rn(a[i], d);
+            const bool same = __double_as_longlong(got[i]) == __double_as_longlong(want) || (got[i] != got[i] && want != want);
+            bad += same ? 0u : 1u;
+        }
+    }
+    if (bad) atomicAdd(counts, bad);
+    if (fast) atomicAdd(counts + 1, fast);
+}
+
+cudaError_t launch_selftest_div(uint64_t seed, uint64_t n_groups, unsigned long long *counts, cudaStream_t s)
+{
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n_groups + 255) / 256, 148u * 16u);
+    if (blocks) selftest_div_kernel<<<blocks, 256, 0, s>>>(seed, n_groups, counts);
     return cudaGetLastError();
 }
 

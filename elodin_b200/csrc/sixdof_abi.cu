@@ -1161,6 +1161,25 @@ double b200_probe_copy_gbs(int device, uint64_t bytes, int iters)
     return best;
 }
 
+// Self-test of the EXACT mode's shared-divisor divisions against div.rn.f64 (layout_kernels.cu:selftest_div_kernel):
+// n_groups groups of four dividends over one divisor; out[0] = results that differ in any bit (must be 0),
+// out[1] = groups answered without the __ddiv_rn fallback.
+int b200_selftest_shared_divisor(int device, uint64_t seed, uint64_t n_groups, uint64_t *out)
+{
+    if (!out) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (b200_device_count() <= 0) return B200_ERR_NO_DEVICE;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return cuda_fail(nullptr, cudaGetLastError(), "cudaSetDevice");
+    unsigned long long *counts = nullptr, host[2] = {0, 0};
+    if (cudaMalloc(&counts, sizeof host) != cudaSuccess) return cuda_fail(nullptr, cudaGetLastError(), "cudaMalloc(selftest)");
+    cudaError_t e = cudaMemset(counts, 0, sizeof host);
+    if (e == cudaSuccess) e = launch_selftest_div(seed, n_groups, counts, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(host, counts, sizeof host, cudaMemcpyDeviceToHost);
+    cudaFree(counts);
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "shared-divisor self-test");
+    out[0] = host[0]; out[1] = host[1];
+    return B200_OK;
+}
+
 double b200_probe_fp64_gflops(int device, int iters)
 {
     if (b200_device_count() <= 0) return -1.0;

@@ -127,5 +127,6 @@ cudaError_t launch_traj_to_aos(const double *traj, double *aos, uint64_t n_sampl
                                uint32_t width, cudaStream_t s);
 cudaError_t launch_multi_transpose(const MultiColumns &mc, uint64_t n_bodies, uint64_t ld, bool to_soa, cudaStream_t s);
 cudaError_t launch_probe_fp64(double *out, int iters, int blocks, cudaStream_t s);
+cudaError_t launch_selftest_div(uint64_t seed, uint64_t n_groups, unsigned long long *counts, cudaStream_t s);
 
 } // namespace b200

@@ -261,6 +261,7 @@ __device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose
                                            Motion &f_out, const Inertia &I, const GravReg &greg)
 {
     using namespace ex;
+    const InertiaRcp IR = inertia_rcp(I); // loop-invariant when a launch integrates several ticks
     if (INTEG == B200_INTEGRATOR_RK4) {
         // rk4.rs:85-123 (see the header comment of oracle/sixdof_oracle.c for the derivation)
         Motion sa = a_out; // du.a before stage 1 is the WorldAccel column
@@ -279,7 +280,7 @@ __device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose
                 const Motion sv = madd(v0, scale(dtf, sa));
                 if constexpr (SEQ == SEQ_INTERPRET) f_out = effectors_exact<GREG>(P, b, k, sx, pi, sv, I, greg);
                 else f_out = effectors_exact_seq<SEQ, GREG>(P, b, k, sx, pi, sv, I, greg);
-                sa = calc_accel_with(sx, pi, f_out, I);
+                sa = calc_accel_with(sx, pi, f_out, I, IR);
                 if (s == 0) { kv = sv; ka = sa; }
                 else if (s == 3) { kv = madd(kv, sv); ka = madd(ka, sa); }
                 else { kv = madd(kv, scale(2.0, sv)); ka = madd(ka, scale(2.0, sa)); }
@@ -294,7 +295,7 @@ __device__ __forceinline__ void exact_tick(const StepParams &P, uint64_t b, Pose
         const PoseInv pi = pose_inverses(x0.q);
         if constexpr (SEQ == SEQ_INTERPRET) f_out = effectors_exact<GREG>(P, b, 0, x0, pi, v0, I, greg);
         else f_out = effectors_exact_seq<SEQ, GREG>(P, b, 0, x0, pi, v0, I, greg);
-        a_out = calc_accel_with(x0, pi, f_out, I);
+        a_out = calc_accel_with(x0, pi, f_out, I, IR);
         v0 = madd(v0, scale(P.dt_final, a_out));
         x0 = tadd(x0, scale(P.dt_final, v0));
     }

@@ -342,6 +342,10 @@ int b200_probe_pcie_gbs(int device, void *host, uint64_t h2d_bytes, uint64_t d2h
  * numbers (device-timed, returns GB/s resp. GFLOP/s, <0 on error) */
 double b200_probe_copy_gbs(int device, uint64_t bytes, int iters);
 double b200_probe_fp64_gflops(int device, int iters);
+/* Self-test of the EXACT mode's division-by-a-shared-divisor route (sixdof_device.cuh ex::div_rcp) against the GPU's
+ * IEEE division on n_groups pseudo-random operand groups covering every encoding class: out[0] = results differing
+ * in any bit (0 on a correct build), out[1] = groups that did not need the __ddiv_rn fallback. */
+int b200_selftest_shared_divisor(int device, uint64_t seed, uint64_t n_groups, uint64_t *out);
 
 #ifdef __cplusplus
 }

@@ -1468,6 +1468,26 @@ def test_row_sharded_world_through_peer_windows_on_two_gpus():
         assert len(checks) == 6 and all(checks.values()), (rank, checks)
 
 
+def test_exact_shared_divisor_divisions():
+    """EXACT mode divides groups of dividends by one divisor (quaternion / norm, force / mass, torque / inertia) with the
+    divisor part of ptxas's div.rn.f64 expansion computed once (ex::rcp_prep / ex::div_rcp) and falls back to __ddiv_rn
+    outside the expansion's own range test: 2^26 groups (2.7e8 divisions) over every encoding class — any encoding,
+    ordinary magnitudes, the thresholds of the range test, overflow / denormal quotients, zeros, powers of two and
+    all-ones significands, exact quotients, unit quaternions over their norm — must agree with the GPU's IEEE division
+    in every bit, and the ordinary classes must not need the fallback."""
+    import ctypes as C
+
+    from elodin_b200 import _lib
+
+    L = _lib.lib()
+    out = (C.c_uint64 * 2)()
+    n = 1 << 26
+    for seed in (1, 0xB200):
+        _lib.check(L.b200_selftest_shared_divisor(0, seed, n, out))
+        assert out[0] == 0, f"{out[0]} of {4 * n} divisions differ from div.rn.f64"
+        assert out[1] >= 0.35 * n  # classes 1, 7, 8, 9 (4 of 10) stay inside the window
+
+
 def test_numa_local_pinned_buffers_and_pcie_probe():
     """b200_host_alloc_local: page-locked memory bound to the NUMA node of the GPU's PCIe root (falls back to plain
     pinned memory when the node is unknown), usable as invoke_batch column buffers; b200_probe_pcie_gbs reports both
