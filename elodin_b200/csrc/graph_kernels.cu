@@ -719,7 +719,12 @@ cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, d
 {
     constexpr size_t smem = (3 * 3 + 1) * 1024 * sizeof(double);
     const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
-    if (gridf >= 3u * 148u && G.n_entities >= 64 && G.n_entities <= 1024) {
+    // One to three worlds too: a world's (source pair, slot) items spread over as many CTAs as give every warp one item
+    // (scripts/tune_nbody_small.py: 1024 bodies x 1 / 2 / 3 worlds 15.4 / 26.7 / 37.7 -> 14.4 / 16.4 / 20.5 us per tick,
+    // 64 bodies 8.2 -> 6.2, same bits); B200_NBODY_WORLD_MIN=444 restores the small-grid kernel below 444 split-kernel CTAs
+    static const unsigned world_min = (unsigned)env_int("B200_NBODY_WORLD_MIN", 0);
+    static const unsigned world_rounds = (unsigned)std::max(1, env_int("B200_NBODY_WORLD_ROUNDS", 1));
+    if (gridf >= world_min && G.n_entities >= 64 && G.n_entities <= 1024) {
         // the persistent world-resident kernel with the integration fused in (same shapes as launch_graph_force picks)
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
@@ -731,7 +736,7 @@ cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, d
         if (G.n_worlds >= slots) grid_w = slots;
         else {
             const unsigned items = (G.n_entities + src - 1) / src * 3u;
-            grid_w = std::max(1u, std::min(slots / G.n_worlds, (items + 2 * warps - 1) / (2 * warps))) * G.n_worlds;
+            grid_w = std::max(1u, std::min(slots / G.n_worlds, (items + world_rounds * warps - 1) / (world_rounds * warps))) * G.n_worlds;
         }
         // gravity is usually the whole effector list (n-body): the integration is then compiled for that signature
         const bool only_graph = P.n_eff == 1 && !P.eff[0].mask;

@@ -1521,12 +1521,16 @@ def test_numa_local_pinned_buffers_and_pcie_probe():
 
 @pytest.mark.parametrize("n_ticks", [1, 4])
 @pytest.mark.parametrize("extra", [False, True])
-def test_world_resident_pair_kernel_with_fused_integration(oracle, n_ticks, extra):
-    """Batches of 64..1024-body worlds big enough for the persistent pair kernel (graph_dense_world_kernel): gravity
-    and integration in one launch per tick, ping-pong planes; odd / even tick counts, step() then chunked invoke_batch,
-    gravity alone (compiled signature) and with another effector (interpreter), ragged N."""
+@pytest.mark.parametrize("shape", [(41, 97), (1, 64), (2, 333), (3, 1024)])
+def test_world_resident_pair_kernel_with_fused_integration(oracle, n_ticks, extra, shape):
+    """Worlds of 64..1024 bodies run through the persistent pair kernel (graph_dense_world_kernel): gravity and
+    integration in one launch per tick, ping-pong planes; odd / even tick counts, step() then chunked invoke_batch,
+    gravity alone (compiled signature) and with another effector (interpreter), ragged N; a batch of many worlds (CTAs
+    take whole worlds) and one to three worlds (every CTA a slice of a world's sources)."""
     O = oracle
-    M, N = 41, 97
+    M, N = shape
+    if N == 1024 and (extra or n_ticks > 1):
+        pytest.skip("the 1024-body world is checked once (oracle cost)")
     pos, vel, ine = random_world(67, M, N)
     pos[..., 4:] *= 1e-2
     o, g, _ = effector_pair(O, "softened", edges=el.all_pairs_edges(N), k2=0.3, soft=1e-5)
@@ -1536,7 +1540,7 @@ def test_world_resident_pair_kernel_with_fused_integration(oracle, n_ticks, extr
         o2, g2, c2 = effector_pair(O, "thrust", thrust=thrust)
         oe.append(o2); ge.append(g2); cols.update(c2)
     want = _run_oracle(O, pos, vel, ine, oe, 0.01, 2 * n_ticks)
-    with el.B200Exec(N, M, 0.01, None, ge, "rk4", "fast", invoke_chunk_bodies=30 * N) as ex:
+    with el.B200Exec(N, M, 0.01, None, ge, "rk4", "fast", invoke_chunk_bodies=max(1, (M * 3) // 4) * N) as ex:
         ex.set_state(pos, vel, ine, **cols)
         ex.step(n_ticks, sync=True)
         mid = (ex.download(WORLD_POS), ex.download(WORLD_VEL))
