@@ -625,9 +625,11 @@ cudaError_t launch_graph_force(const GraphParams &G, int math_mode, bool dense, 
                     unsigned grid_w;
                     if (G.n_worlds >= slots) grid_w = slots;
                     else {
-                        // every CTA of a world takes at least ~2 rounds of items for its warps
+                        // few worlds: as many CTAs per world as the SMs allow, down to four busy warps per CTA (latency,
+                        // not throughput, is the price of a tick then: profiles/r02_tune_nbody_small.txt)
                         const unsigned items = (n_src + src - 1) / src * (rk4 ? 3u : 1u), warps = (unsigned)nt / 32u;
-                        const unsigned cpw = std::max(1u, std::min(slots / G.n_worlds, (items + 2 * warps - 1) / (2 * warps)));
+                        const unsigned busy = std::min(warps, 4u); // one busy warp per FP64 pipe when there is room to spread
+                        const unsigned cpw = std::max(1u, std::min(slots / G.n_worlds, (items + busy - 1) / busy));
                         grid_w = cpw * G.n_worlds;
                     }
                     const size_t smem = ((rk4 ? 3 : 1) * 3 + 1) * 1024 * sizeof(double);
@@ -736,7 +738,11 @@ cudaError_t launch_nbody_tick_fused(const GraphParams &G, const StepParams &P, d
         if (G.n_worlds >= slots) grid_w = slots;
         else {
             const unsigned items = (G.n_entities + src - 1) / src * 3u;
-            grid_w = std::max(1u, std::min(slots / G.n_worlds, (items + world_rounds * warps - 1) / (world_rounds * warps))) * G.n_worlds;
+            // few worlds: spread a world's items over the SMs until a CTA keeps only four warps busy — one per FP64 pipe
+            // (1024 bodies, one world: 14.4 -> 10.3 us per tick; profiles/r02_tune_nbody_small.txt)
+            static const unsigned spread = (unsigned)std::max(1, env_int("B200_NBODY_WORLD_SPREAD", 4));
+            const unsigned per_cta = world_rounds * std::min(warps, spread);
+            grid_w = std::max(1u, std::min(slots / G.n_worlds, (items + per_cta - 1) / per_cta)) * G.n_worlds;
         }
         // gravity is usually the whole effector list (n-body): the integration is then compiled for that signature
         const bool only_graph = P.n_eff == 1 && !P.eff[0].mask;

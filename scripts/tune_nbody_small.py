@@ -27,9 +27,9 @@ for N, Mw in ((64, 1), (64, 16), (200, 1), (256, 1), (256, 4), (512, 1), (512, 2
             a.record(st); ex.step(400); b.record(st); torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b) / 400)
     ex.close()
-    print(json.dumps({"world_min": os.environ.get("B200_NBODY_WORLD_MIN", "444"), "rounds": os.environ.get("B200_NBODY_WORLD_ROUNDS", "2"),
+    print(json.dumps({"world_min": os.environ.get("B200_NBODY_WORLD_MIN", "444"), "rounds": os.environ.get("B200_NBODY_WORLD_ROUNDS", "1"), "spread": os.environ.get("B200_NBODY_WORLD_SPREAD", "16"),
                       "N": N, "worlds": Mw, "us_per_tick": round(best * 1e3, 2), "checksum_after_5_ticks": chk}), flush=True)
 '''
-for wm, rounds in (("444", "2"), ("0", "1")):
-    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200_NBODY_WORLD_MIN=wm, B200_NBODY_WORLD_ROUNDS=rounds), capture_output=True, text=True)
+for wm, rounds, spread in (("0", "1", "16"), ("0", "1", "11"), ("0", "1", "8"), ("0", "1", "4")):
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200_NBODY_WORLD_MIN=wm, B200_NBODY_WORLD_ROUNDS=rounds, B200_NBODY_WORLD_SPREAD=spread), capture_output=True, text=True)
     print(out.stdout.strip()); print(out.stderr.strip()[-400:])
