@@ -61,3 +61,33 @@ for integ in ("rk4", "semi_implicit"):
         ex.set_state(p, v, I)
         ex.step(2, sync=True)
 print("egm done")
+# late round 2: EGM08 term stream at the degrees that exercise every column shape, the EXACT tick's shared-divisor
+# divisions (zero torque, zero force, ordinary operands), the division self-test kernel, worlds spread over CTA slices
+import ctypes as C
+from elodin_b200 import _lib
+for Ld in (0, 1, 2, 5):
+    cd, sd = np.tril(rng.normal(0, 1e-5, (Ld + 1, Ld + 1))), np.tril(rng.normal(0, 1e-5, (Ld + 1, Ld + 1)), -1)
+    cd[0, 0] = 1.0
+    with el.B200Exec(1, 33, 0.05, None, [el.GravityEGM08(cd, sd, Ld)], "rk4", "fast") as ex:
+        p, v, I = random_world(4, 33, 1)
+        p[..., 4:] += 6.9e6
+        ex.set_state(p, v, I)
+        ex.step(2, sync=True)
+for effs, names in (([], ()), ([el.GravityConst(), el.ThrustBody(), el.DragQuadratic(column="wind", per_body_params=True)], ("thrust", "wind"))):
+    M = 1000
+    pos, vel, ine = random_world(5, M, 1)
+    cols = {"thrust": rng.uniform(0, 5, (M, 1, 1)), "wind": rng.normal(0, 1, (M, 1, 5)) ** 2}
+    for integ in ("rk4", "semi_implicit"):
+        with el.B200Exec(1, M, 0.01, None, effs, integ, "exact") as ex:
+            ex.set_state(pos, vel, ine, **{k: cols[k] for k in names})
+            ex.step(3, sync=True)
+out = (C.c_uint64 * 2)()
+_lib.check(_lib.lib().b200_selftest_shared_divisor(0, 7, 1 << 16, out))
+assert out[0] == 0
+for N, M in ((1024, 1), (333, 2), (64, 1)):
+    p, v, I = random_world(N, M, N)
+    p[..., 4:] *= 1e-2
+    with el.B200Exec(N, M, 0.01, None, [el.GravityEdges("softened", k_squared=0.3, softening=1e-4, edges=el.all_pairs_edges(N))], "rk4", "fast") as ex:
+        ex.set_state(p, v, I)
+        ex.step(3, sync=True)
+print("late round 2 done")
