@@ -856,26 +856,7 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
                             uint64_t worlds_per_chunk)
 {
     const uint64_t N = h->desc.n_entities, M = h->desc.n_worlds;
-    // World ranges.  With the default range size the last ranges taper (each half of what is left, down to an eighth
-    // of a range): the upload engine is the bottleneck of a call, and what follows its last byte — that range's ticks
-    // and download — is pure tail, so the last range should be small.  An explicit invoke_chunk_bodies keeps uniform ranges.
-    std::vector<std::pair<uint64_t, uint64_t>> ranges;
-    {
-        static const int taper = [] { const char *e = getenv("B200_CHUNK_TAPER"); return e ? atoi(e) : 1; }();
-        const uint64_t align = (N == 1 && worlds_per_chunk >= 128) ? 128 : 1;
-        const uint64_t floor_w = std::max<uint64_t>(align, worlds_per_chunk / 8 / align * align);
-        for (uint64_t w = 0; w < M;) {
-            const uint64_t left = M - w;
-            uint64_t nw = std::min(worlds_per_chunk, left);
-            if (taper && !h->desc.invoke_chunk_bodies && left < 2 * worlds_per_chunk && left > floor_w) {
-                nw = std::max(floor_w, left / 2 / align * align);
-                if (left - nw < floor_w / 2) nw = left;
-            }
-            ranges.emplace_back(w, nw);
-            w += nw;
-        }
-    }
-    const uint64_t n_chunks = ranges.size();
+    const uint64_t n_chunks = (M + worlds_per_chunk - 1) / worlds_per_chunk;
     if (!h->copy_in) {
         CU(h, cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
         CU(h, cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
@@ -951,7 +932,7 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
     CU(h, cudaEventRecord(h->ev[0], h->copy_in));
 
     for (uint64_t k = 0; k < n_chunks; ++k) {
-        const uint64_t w0 = ranges[k].first, nw = ranges[k].second;
+        const uint64_t w0 = k * worlds_per_chunk, nw = std::min(worlds_per_chunk, M - w0);
         const uint64_t b0 = w0 * N, nb = nw * N;
         // H2D of this world range, every live input column (copy engine 1)
         for (size_t i = 0; i < h->input_ids.size(); ++i) {
