@@ -562,6 +562,15 @@ cudaError_t launch_body_step(const StepParams &P, int integrator, int math_mode,
         // bodies, profiles/r02_tune_misc.md); the interpreter kernel for every other list
         if (xcfg == 3) {
             const uint32_t seq = exact_sequence(P);
+#ifdef B200_TUNE
+            if (seq != SEQ_INTERPRET && rk4) switch (env_int("B200_EXACT_SEQ_CFG", 0)) { // registers vs warps for the compiled sequences
+            case 1: if (launch_exact_seq<B200_INTEGRATOR_RK4, 128, 3>(P, seq, s)) return cudaGetLastError(); break;
+            case 2: if (launch_exact_seq<B200_INTEGRATOR_RK4, 128, 2>(P, seq, s)) return cudaGetLastError(); break;
+            case 3: if (launch_exact_seq<B200_INTEGRATOR_RK4, 64, 6>(P, seq, s)) return cudaGetLastError(); break;
+            case 4: if (launch_exact_seq<B200_INTEGRATOR_RK4, 128, 5>(P, seq, s)) return cudaGetLastError(); break;
+            default: break;
+            }
+#endif
             if (seq != SEQ_INTERPRET &&
                 (rk4 ? launch_exact_seq<B200_INTEGRATOR_RK4, 128, 4>(P, seq, s) : launch_exact_seq<B200_INTEGRATOR_SEMI_IMPLICIT, 256, 1>(P, seq, s)))
                 return cudaGetLastError();

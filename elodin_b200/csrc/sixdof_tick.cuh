@@ -91,7 +91,7 @@ static __device__ __noinline__ Vec3 j2_field_exact(double mu, double J2, double 
 {
     using namespace ex;
     const double norm = sqr(dot3(r));
-    const Vec3 e_r = {div(r.x, norm), div(r.y, norm), div(r.z, norm)};
+    const Vec3 e_r = div3(r, norm);
     const double n3 = mul(mul(norm, norm), norm);
     const double c0 = mul(-mu, m);
     const double n2 = mul(norm, norm), n4 = mul(n2, n2), n5 = mul(norm, n4);
@@ -99,9 +99,10 @@ static __device__ __noinline__ Vec3 j2_field_exact(double mu, double J2, double 
     const double kz = div(mul(3.0, r.z), n5);
     const double kr = sub(div(3.0, mul(2.0, n4)), div(mul(15.0, mul(r.z, r.z)), mul(2.0, n6)));
     const double c1 = mul(mul(c0, J2), mul(r_ref, r_ref));
-    return Vec3{add(div(mul(c0, r.x), n3), mul(c1, add(mul(kz, 0.0), mul(kr, e_r.x)))),
-                add(div(mul(c0, r.y), n3), mul(c1, add(mul(kz, 0.0), mul(kr, e_r.y)))),
-                add(div(mul(c0, r.z), n3), mul(c1, add(mul(kz, 1.0), mul(kr, e_r.z))))};
+    const Vec3 pm = div3(Vec3{mul(c0, r.x), mul(c0, r.y), mul(c0, r.z)}, n3); // the point-mass term
+    return Vec3{add(pm.x, mul(c1, add(mul(kz, 0.0), mul(kr, e_r.x)))),
+                add(pm.y, mul(c1, add(mul(kz, 0.0), mul(kr, e_r.y)))),
+                add(pm.z, mul(c1, add(mul(kz, 1.0), mul(kr, e_r.z))))};
 }
 
 // clear_forces | effectors (array order) on the stage state; six_dof.rs:148-150,195
@@ -128,9 +129,9 @@ __device__ __forceinline__ void apply_effector_exact(uint32_t kind, const EffDev
         const double cd_rho = E.col_width == 5 ? ldp(E.col, P.ld, 3, b) : E.p[0];
         const double area = E.col_width == 5 ? ldp(E.col, P.ld, 4, b) : E.p[1];
         const double drag = mul(0.5, mul(mul(cd_rho, mul(speed, speed)), area));
+        const Vec3 dir = div3(fl, speed);
         F.ang = Vec3{0.0, 0.0, 0.0};
-        F.lin = Vec3{add(F.lin.x, mul(drag, div(fl.x, speed))), add(F.lin.y, mul(drag, div(fl.y, speed))),
-                     add(F.lin.z, mul(drag, div(fl.z, speed)))};
+        F.lin = Vec3{add(F.lin.x, mul(drag, dir.x)), add(F.lin.y, mul(drag, dir.y)), add(F.lin.z, mul(drag, dir.z))};
         break;
     }
     case B200_EFF_THRUST_BODY: { // rocket/main.py:429-431
@@ -159,7 +160,7 @@ __device__ __forceinline__ void apply_effector_exact(uint32_t kind, const EffDev
         const Vec3 r = sx.x, v = sv.lin;
         const double rn = sqr(dot3(r));
         const double rn3 = mul(mul(rn, rn), rn);
-        const Vec3 g = {div(mul(-mu, r.x), rn3), div(mul(-mu, r.y), rn3), div(mul(-mu, r.z), rn3)};
+        const Vec3 g = div3(Vec3{mul(-mu, r.x), mul(-mu, r.y), mul(-mu, r.z)}, rn3);
         const Vec3 c = cross(om, v);
         const Vec3 c2 = cross(om, cross(om, r));
         const Vec3 acc = {add(g.x, add(mul(-2.0, c.x), -c2.x)), add(g.y, add(mul(-2.0, c.y), -c2.y)),

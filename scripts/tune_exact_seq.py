@@ -32,6 +32,8 @@ for name, (effs, cols) in sets.items():
     ex.close()
     print(json.dumps({"cfg": os.environ.get("B200_EXACT_CFG", "3"), "set": name, "us_per_tick": best * 1e3, "entity_steps_per_s": M / (best * 1e-3), "sha1_after_3_ticks": h}), flush=True)
 '''
-for cfg in ("3", "12"):
-    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200_EXACT_CFG=cfg), capture_output=True, text=True)
-    print(out.stdout.strip()); print(out.stderr.strip()[-300:])
+# B200_EXACT_SEQ_CFG (tuning build only): launch bounds of the compiled sequences — 0 = 128 x 4 (default), 1 = 128 x 3,
+# 2 = 128 x 2, 3 = 64 x 6, 4 = 128 x 5
+for cfg, seq_cfg in (("3", "0"), ("12", "0")) + tuple(("3", c) for c in sys.argv[1:]):
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200_EXACT_CFG=cfg, B200_EXACT_SEQ_CFG=seq_cfg), capture_output=True, text=True)
+    print("seq_cfg", seq_cfg); print(out.stdout.strip()); print(out.stderr.strip()[-300:])
