@@ -10,6 +10,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <chrono>
 #include <map>
@@ -539,6 +540,8 @@ int b200_sixdof_create(const b200_sixdof_desc *d, b200_sixdof **out)
 
     b200_sixdof *h = new (std::nothrow) b200_sixdof();
     if (!h) return fail(B200_ERR_OUT_OF_MEMORY, "out of host memory");
+    static std::atomic<uint64_t> next_serial{1};
+    h->serial = next_serial.fetch_add(1);
     h->desc = *d;
     h->device = dev;
     h->effectors.assign(d->effectors, d->effectors + d->n_effectors);

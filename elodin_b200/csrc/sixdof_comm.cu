@@ -79,7 +79,7 @@ struct b200_comm {
     // other rank's address space through CUDA IPC, written over NVLink by the producing GPU
     struct Window {
         const b200_sixdof *owner = nullptr;
-        uint64_t ld = 0;
+        uint64_t owner_serial = 0, ld = 0;     // the handle the window was sized for (address + creation serial)
         double *base[B200_MAX_PEERS] = {};  // rank r's window as mapped here ([rank] = the local allocation)
         unsigned *ctr = nullptr;            // block counter of the push kernel (local)
     } win;
@@ -405,6 +405,7 @@ int b200_comm_peer_attach(b200_comm *c, b200_sixdof *h)
         return rc ? rc : fail(B200_ERR_UNSUPPORTED, "another rank could not map the peer windows");
     }
     w.owner = h;
+    w.owner_serial = h->serial;
     return B200_OK;
 }
 
@@ -458,7 +459,8 @@ int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks)
     const bool exact = h->desc.math_mode == B200_MATH_EXACT;
     const b200_effector &e = h->effectors[h->graph_eff];
     static const int peer_env = env_int("B200_ROW_PEER", 1);
-    const bool peer = peer_env && c->win.owner == h && c->win.ld == h->ld;
+    // (a window attached to another handle — or to a destroyed one whose address this handle reuses — is ignored)
+    const bool peer = peer_env && c->win.owner == h && c->win.owner_serial == h->serial && c->win.ld == h->ld;
     double *const pos = h->find(B200_ID_WORLD_POS)->dev, *const vel = h->find(B200_ID_WORLD_VEL)->dev;
     double *const acc = h->find(B200_ID_WORLD_ACCEL)->dev, *const frc = h->find(B200_ID_FORCE)->dev;
     auto gather_plane = [&](double *plane) { return nccl().AllGather(plane + i0, plane, rows, ncclDouble, c->comm, h->stream); };

@@ -25,6 +25,7 @@ inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 } // namespace b200
 
 struct b200_sixdof {
+    uint64_t serial = 0;               // unique per created handle: what a peer window remembers of its owner besides the address
     b200_sixdof_desc desc{};
     std::vector<b200_effector> effectors;
     std::vector<uint8_t *> eff_masks; // device copies of the per-effector entity masks (nullptr = all)
