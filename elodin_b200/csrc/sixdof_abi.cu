@@ -864,10 +864,16 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
         CU(h, cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
         CU(h, cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
     }
+    // B200_PIPE_TRACE=1: per-range completion times of the three engines on stderr (diagnostic; timing events)
+    static const bool trace = [] { const char *e = getenv("B200_PIPE_TRACE"); return e && atoi(e) != 0; }();
+    std::vector<cudaEvent_t> trace_d2h;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    double host_loop0 = 0.0, host_loop1 = 0.0;
     while (h->chunk_in.size() < n_chunks) {
         cudaEvent_t a, b;
-        CU(h, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        CU(h, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&a, trace ? cudaEventDefault : cudaEventDisableTiming));
+        CU(h, cudaEventCreateWithFlags(&b, trace ? cudaEventDefault : cudaEventDisableTiming));
         h->chunk_in.push_back(a);
         h->chunk_out.push_back(b);
     }
@@ -934,6 +940,7 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
     CU(h, cudaStreamWaitEvent(h->copy_out, h->ev[2], 0));
     CU(h, cudaEventRecord(h->ev[0], h->copy_in));
 
+    host_loop0 = host_ms();
     for (uint64_t k = 0; k < n_chunks; ++k) {
         const uint64_t w0 = k * worlds_per_chunk, nw = std::min(worlds_per_chunk, M - w0);
         const uint64_t b0 = w0 * N, nb = nw * N;
@@ -977,7 +984,14 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
             CU(h, cudaMemcpyAsync((double *)out_cols[i] + b0 * c->width, h->stage_out + out_off[i] + b0 * c->width,
                                   nb * c->width * 8, cudaMemcpyDefault, h->copy_out));
         }
+        if (trace) {
+            cudaEvent_t e;
+            CU(h, cudaEventCreate(&e));
+            CU(h, cudaEventRecord(e, h->copy_out));
+            trace_d2h.push_back(e);
+        }
     }
+    host_loop1 = host_ms();
     commit_ping_pong(h, n_ticks);
     h->ticks_done += n_ticks;
     h->tick += n_ticks;
@@ -994,6 +1008,15 @@ static int invoke_pipelined(b200_sixdof *h, const uint8_t *const *in_cols, uint8
         const Column *c = h->find(h->output_ids[i]);
         int rc = do_download(h, c->id, out_cols[i], h->n_bodies * c->width * 8ull);
         if (rc) return rc;
+    }
+    if (trace) {
+        fprintf(stderr, "[b200 pipe] host: enqueue loop %.3f..%.3f ms, synced at %.3f ms; device times from the first upload's start:\n",
+                host_loop0, host_loop1, host_ms());
+        for (uint64_t k = 0; k < n_chunks; ++k) {
+            fprintf(stderr, "[b200 pipe]  range %2llu: upload done %.3f  ticks done %.3f  download done %.3f ms\n", (unsigned long long)k,
+                    ev_ms(h->ev[0], h->chunk_in[k]), ev_ms(h->ev[0], h->chunk_out[k]), ev_ms(h->ev[0], trace_d2h[k]));
+            cudaEventDestroy(trace_d2h[k]);
+        }
     }
     // busy spans of the three engines; they overlap, so they do not add up to the call time
     h->timings.h2d_upload_ms = ev_ms(h->ev[0], h->ev[1]);

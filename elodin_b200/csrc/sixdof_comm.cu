@@ -191,6 +191,12 @@ __global__ void __launch_bounds__(128) peer_push_kernel(const __grid_constant__ 
     }
 }
 
+// plain grid-stride copy of 16-byte words: the PCIe probe's SM-driven leg (one side is mapped pinned host memory)
+__global__ void __launch_bounds__(256) copy16_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256) dst[i] = src[i];
+}
+
 } // namespace b200
 
 extern "C" {
@@ -545,6 +551,50 @@ int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks)
 // Concurrent host<->device bandwidth of one GPU (pinned `host` of >= max(h2d, d2h) * 2 bytes): an H2D stream and a
 // D2H stream run `iters` copies each at the same time; out[0] = H2D GB/s, out[1] = D2H GB/s.  bench.py runs it on
 // every rank at once to report the PCIe / host-memory ceiling its e2e number sits under.
+// The same measurement with kernels instead of the copy engines: SMs read mapped pinned host memory (H2D leg) and write it
+// (D2H leg), both at once on two streams, `blocks` CTAs of 256 threads per leg.  out[0] = H2D GB/s, out[1] = D2H GB/s.
+int b200_probe_zero_copy_gbs(int device, void *host, uint64_t h2d_bytes, uint64_t d2h_bytes, int iters, int blocks, double *out)
+{
+    if (!host || !out || iters < 1 || blocks < 1) return fail(B200_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (b200_device_count() <= 0) return B200_ERR_NO_DEVICE;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return cuda_fail(nullptr, cudaGetLastError(), "cudaSetDevice");
+    void *hdev = nullptr;
+    if (cudaHostGetDevicePointer(&hdev, host, 0) != cudaSuccess) { (void)cudaGetLastError(); return fail(B200_ERR_UNSUPPORTED, "host buffer is not mapped into the device address space"); }
+    void *din = nullptr, *dout = nullptr;
+    cudaStream_t s0 = nullptr, s1 = nullptr;
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    int rc = B200_OK;
+    if (cudaMalloc(&din, std::max<uint64_t>(h2d_bytes, 16)) != cudaSuccess || cudaMalloc(&dout, std::max<uint64_t>(d2h_bytes, 16)) != cudaSuccess)
+        rc = cuda_fail(nullptr, cudaGetLastError(), "cudaMalloc(probe)");
+    if (!rc) {
+        cudaStreamCreateWithFlags(&s0, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking);
+        for (auto &x : e) cudaEventCreate(&x);
+        char *hin = (char *)hdev, *hout = (char *)hdev + h2d_bytes;
+        for (int w = 0; w < 2; ++w) {
+            cudaEventRecord(e[0], s0); cudaEventRecord(e[2], s1);
+            for (int i = 0; i < (w ? iters : 1); ++i) {
+                if (h2d_bytes) copy16_kernel<<<blocks, 256, 0, s0>>>((const double2 *)hin, (double2 *)din, h2d_bytes / 16);
+                if (d2h_bytes) copy16_kernel<<<blocks, 256, 0, s1>>>((const double2 *)dout, (double2 *)hout, d2h_bytes / 16);
+            }
+            cudaEventRecord(e[1], s0); cudaEventRecord(e[3], s1);
+            cudaStreamSynchronize(s0); cudaStreamSynchronize(s1);
+        }
+        float m0 = 0.f, m1 = 0.f;
+        cudaEventElapsedTime(&m0, e[0], e[1]);
+        cudaEventElapsedTime(&m1, e[2], e[3]);
+        out[0] = m0 > 0 ? (double)h2d_bytes * iters / (m0 * 1e-3) / 1e9 : 0.0;
+        out[1] = m1 > 0 ? (double)d2h_bytes * iters / (m1 * 1e-3) / 1e9 : 0.0;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(B200_ERR_CUDA, "zero-copy probe failed");
+    }
+    for (auto &x : e) if (x) cudaEventDestroy(x);
+    if (s0) cudaStreamDestroy(s0);
+    if (s1) cudaStreamDestroy(s1);
+    if (din) cudaFree(din);
+    if (dout) cudaFree(dout);
+    return rc;
+}
+
 int b200_probe_pcie_gbs(int device, void *host, uint64_t h2d_bytes, uint64_t d2h_bytes, int iters, double *out)
 {
     if (!host || !out || iters < 1) return fail(B200_ERR_INVALID_ARGUMENT, "bad arguments");

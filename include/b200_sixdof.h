@@ -337,6 +337,9 @@ void b200_comm_peer_detach(b200_comm *c);
 /* Concurrent host<->device copy bandwidth of one GPU through pinned `host` (>= h2d_bytes + d2h_bytes): out[0] = H2D
  * GB/s, out[1] = D2H GB/s, both directions running at once — the ceiling an invoke_batch round trip sits under. */
 int b200_probe_pcie_gbs(int device, void *host, uint64_t h2d_bytes, uint64_t d2h_bytes, int iters, double *out);
+/* The same with kernels instead of the copy engines (SMs reading / writing mapped pinned host memory, `blocks` CTAs of
+ * 256 threads per direction): B200_ERR_UNSUPPORTED when `host` is not mapped into the device address space. */
+int b200_probe_zero_copy_gbs(int device, void *host, uint64_t h2d_bytes, uint64_t d2h_bytes, int iters, int blocks, double *out);
 
 /* FP64 / HBM probes used by bench.py to report the roofs next to the kernel
  * numbers (device-timed, returns GB/s resp. GFLOP/s, <0 on error) */
