@@ -61,18 +61,28 @@ __device__ __forceinline__ bool traj_due(const StepParams &P, uint64_t tick_afte
     slot = tick_after / P.traj_every - 1;
     return slot < P.traj_capacity;
 }
+// Trajectory samples are written once and never read back by a kernel: streaming stores (evict-first) keep them from
+// pushing the state planes out of the L2 the next launch starts from.
+__device__ __forceinline__ void stp_stream(double *base, uint64_t ld, int plane, uint64_t b, double v)
+{
+    __stcs(base + (uint64_t)plane * ld + b, v);
+}
 __device__ __forceinline__ void traj_store_state(const StepParams &P, uint64_t b, uint64_t slot, const Pose &x, const Motion &v)
 {
     double *t = P.traj + slot * (uint64_t)P.traj_planes * P.ld;
-    store_pose(t, P.ld, b, x);
-    store_motion(t + 7ull * P.ld, P.ld, b, v);
+    stp_stream(t, P.ld, 0, b, x.q.i); stp_stream(t, P.ld, 1, b, x.q.j); stp_stream(t, P.ld, 2, b, x.q.k); stp_stream(t, P.ld, 3, b, x.q.w);
+    stp_stream(t, P.ld, 4, b, x.x.x); stp_stream(t, P.ld, 5, b, x.x.y); stp_stream(t, P.ld, 6, b, x.x.z);
+    stp_stream(t, P.ld, 7, b, v.ang.x); stp_stream(t, P.ld, 8, b, v.ang.y); stp_stream(t, P.ld, 9, b, v.ang.z);
+    stp_stream(t, P.ld, 10, b, v.lin.x); stp_stream(t, P.ld, 11, b, v.lin.y); stp_stream(t, P.ld, 12, b, v.lin.z);
 }
 // B200_TRAJ_FULL: WorldAccel and Force as the tick leaves them in the ECS columns
 __device__ __forceinline__ void traj_store_af(const StepParams &P, uint64_t b, uint64_t slot, const Motion &a, const Motion &f)
 {
     double *t = P.traj + (slot * (uint64_t)P.traj_planes + 13ull) * P.ld;
-    store_motion(t, P.ld, b, a);
-    store_motion(t + 6ull * P.ld, P.ld, b, f);
+    stp_stream(t, P.ld, 0, b, a.ang.x); stp_stream(t, P.ld, 1, b, a.ang.y); stp_stream(t, P.ld, 2, b, a.ang.z);
+    stp_stream(t, P.ld, 3, b, a.lin.x); stp_stream(t, P.ld, 4, b, a.lin.y); stp_stream(t, P.ld, 5, b, a.lin.z);
+    stp_stream(t, P.ld, 6, b, f.ang.x); stp_stream(t, P.ld, 7, b, f.ang.y); stp_stream(t, P.ld, 8, b, f.ang.z);
+    stp_stream(t, P.ld, 9, b, f.lin.x); stp_stream(t, P.ld, 10, b, f.lin.y); stp_stream(t, P.ld, 11, b, f.lin.z);
 }
 
 // ================================================================== EXACT body kernel
