@@ -711,7 +711,7 @@ bool nbody_fused_applicable(const GraphParams &G, int math_mode, bool dense)
     static const int fcfg = [] { const char *e = getenv("B200_NBODY_FUSED"); return e ? atoi(e) : 1; }();
     if (fcfg == 0) return false;
     const unsigned gridf = ((G.n_entities + kFastSrc - 1) / kFastSrc) * G.n_worlds;
-    if (gridf < 3u * 148u) return true; // small grids: nbody_tick_fused_kernel (the "small grid" rule of the split gravity kernel)
+    if (gridf < 3u * 148u) return true; // small grids: one launch per tick (pair kernel for 64..1024 bodies, nbody_tick_fused_kernel otherwise)
     // worlds that fit the persistent kernel's tile set: fused at any batch size (measured: 43.1 -> 41.0 us per tick at 8
     // worlds of 1024 bodies, identical bits; B200_NBODY_FUSED=2 keeps the two-launch route)
     return fcfg != 2 && G.n_entities >= 64 && G.n_entities <= 1024;

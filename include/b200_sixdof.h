@@ -314,7 +314,7 @@ int b200_sixdof_trajectory_allgather(b200_sixdof *h, b200_comm *c, const uint64_
  * n_entities divisible by the rank count).  Every rank creates the same handle and uploads the same initial state,
  * then calls this instead of b200_sixdof_step: per tick it folds and integrates its own rows and all-gathers the
  * rows' new position / velocity planes over NCCL; after the call every rank holds the complete world.
- * At N = 1024 replicas (every GPU integrates the whole world, no exchange) are faster — the tick is a ~15 us
+ * At N = 1024 replicas (every GPU integrates the whole world, no exchange) are faster — the tick is a ~10 us
  * latency chain and the exchange adds to it; row shards pay off for worlds of several thousand bodies
  * (measured by bench.py `multi_gpu.nbody_1024_single_world`). */
 int b200_sixdof_step_row_sharded(b200_sixdof *h, b200_comm *c, uint64_t n_ticks);
