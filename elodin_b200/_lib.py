@@ -58,7 +58,7 @@ SYMBOLS = [
     "b200_comm_available", "b200_comm_version", "b200_comm_unique_id", "b200_comm_create", "b200_comm_destroy",
     "b200_comm_rank", "b200_comm_size", "b200_comm_last_ms", "b200_sixdof_trajectory_gather_bytes",
     "b200_sixdof_trajectory_allgather", "b200_sixdof_step_row_sharded", "b200_probe_pcie_gbs",
-    "b200_comm_peer_attach", "b200_comm_peer_attached", "b200_comm_peer_detach", "b200_selftest_shared_divisor", "b200_probe_zero_copy_gbs",
+    "b200_comm_peer_attach", "b200_comm_peer_attached", "b200_comm_peer_detach", "b200_selftest_shared_divisor", "b200_probe_zero_copy_gbs", "b200_egm08_stream_len", "b200_egm08_stream",
 ]
 COMM_ID_BYTES = 128
 
@@ -202,6 +202,9 @@ def lib():
     L.b200_sixdof_trajectory_gather_bytes.restype = u64
     L.b200_sixdof_trajectory_allgather.argtypes = [vp, vp, C.POINTER(u64), vp, u64]
     L.b200_sixdof_step_row_sharded.argtypes = [vp, vp, u64]
+    L.b200_egm08_stream_len.argtypes = [u32]
+    L.b200_egm08_stream_len.restype = u64
+    L.b200_egm08_stream.argtypes = [u32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), u64]
     L.b200_selftest_shared_divisor.argtypes = [C.c_int, u64, u64, C.POINTER(u64)]
     L.b200_probe_zero_copy_gbs.argtypes = [C.c_int, vp, u64, u64, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.b200_comm_peer_attach.argtypes = [vp, vp]

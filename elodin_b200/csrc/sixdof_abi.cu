@@ -1187,6 +1187,22 @@ double b200_probe_copy_gbs(int device, uint64_t bytes, int iters)
     return best;
 }
 
+// The EGM08 term stream the library builds at create (egm08_tables) for a degree-L coefficient pair: host-only, no GPU
+// needed — lets a host (and tests/test_host_logic.py, against the oracle's tables) check what the kernel will read.
+uint64_t b200_egm08_stream_len(uint32_t max_degree) { return 4ull * (max_degree + 1ull) * (max_degree + 2ull); }
+
+int b200_egm08_stream(uint32_t max_degree, const double *c_bar, const double *s_bar, double *out, uint64_t out_len)
+{
+    if (!c_bar || !s_bar || !out) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+    if (max_degree > 128) return fail(B200_ERR_INVALID_ARGUMENT, "EGM08 max_degree must be 0..128 (got %u)", max_degree);
+    if (out_len != b200_egm08_stream_len(max_degree))
+        return fail(B200_ERR_VALUE_SIZE_MISMATCH, "the degree-%u stream holds %llu f64 (got %llu)", max_degree,
+                    (unsigned long long)b200_egm08_stream_len(max_degree), (unsigned long long)out_len);
+    const std::vector<double> t = egm08_tables((int)max_degree, c_bar, s_bar);
+    std::memcpy(out, t.data(), t.size() * sizeof(double));
+    return B200_OK;
+}
+
 // Self-test of the EXACT mode's shared-divisor divisions against div.rn.f64 (layout_kernels.cu:selftest_div_kernel):
 // n_groups groups of four dividends over one divisor; out[0] = results that differ in any bit (must be 0),
 // out[1] = groups answered without the __ddiv_rn fallback.

@@ -345,6 +345,10 @@ int b200_probe_zero_copy_gbs(int device, void *host, uint64_t h2d_bytes, uint64_
  * numbers (device-timed, returns GB/s resp. GFLOP/s, <0 on error) */
 double b200_probe_copy_gbs(int device, uint64_t bytes, int iters);
 double b200_probe_fp64_gflops(int device, int iters);
+/* The term stream a GRAVITY_EGM08 effector of this degree is evaluated from: eight f64 per (m, l) term in
+ * consumption order — recursion constants of A at (l, m) and of B at (l+1, m+1), C, S, nq1, nq2.  Host-only. */
+uint64_t b200_egm08_stream_len(uint32_t max_degree);
+int b200_egm08_stream(uint32_t max_degree, const double *c_bar, const double *s_bar, double *out, uint64_t out_len);
 /* Self-test of the EXACT mode's division-by-a-shared-divisor route (sixdof_device.cuh ex::div_rcp) against the GPU's
  * IEEE division on n_groups pseudo-random operand groups covering every encoding class: out[0] = results differing
  * in any bit (0 on a correct build), out[1] = groups that did not need the __ddiv_rn fallback. */
