@@ -177,12 +177,29 @@ __global__ void __launch_bounds__(BLOCK, MINB) body_fast_spec_kernel(const __gri
         if (SIG & SIG_DRAG_PB) { B200_LDV(P.spec.drag, 3, in[k].cd_rho); B200_LDV(P.spec.drag, 4, in[k].area); }
     }
 
+    // A (WorldPos, WorldVel) sample on every launch of one tick: the pair stores it from here as one 16-byte store per
+    // plane — the per-body 8-byte stores inside fast_ticks fill half of every sector, and the other half arrives a whole
+    // tick of arithmetic later (telemetry on every tick: 254 -> see profiles/r02_tune_telemetry.txt)
+    const bool defer_traj = TRAJ && BPT == 2 && both && P.n_ticks == 1 && P.traj_planes == 13;
     Motion a_last[BPT], f_last[BPT];
 #pragma unroll
     for (int k = 0; k < BPT; ++k)
         if (k == 0 || both)
             fast_ticks<INTEG, TRAJ, false, SIG>(P, b0 + k, x[k], v[k], I[k], a_last[k], f_last[k], P.n_ticks, P.tick0,
-                                                P.write_fa != 0, GravReg{}, in[k]);
+                                                P.write_fa != 0, GravReg{}, in[k], !defer_traj);
+    if (TRAJ && BPT == 2 && defer_traj && P.traj_every) {
+        const uint64_t after = P.tick0 + 1;
+        const uint64_t slot = after / P.traj_every - 1;
+        if (after % P.traj_every == 0 && slot < P.traj_capacity) {
+            double *t = P.traj + slot * 13ull * P.ld + b0;
+            auto put = [&](int plane, double v0, double v1) { __stcs(reinterpret_cast<double2 *>(t + (uint64_t)plane * P.ld), make_double2(v0, v1)); };
+            constexpr int o = BPT - 1; // index of the pair's second body (0 when the kernel is compiled for one body per thread)
+            put(0, x[0].q.i, x[o].q.i); put(1, x[0].q.j, x[o].q.j); put(2, x[0].q.k, x[o].q.k); put(3, x[0].q.w, x[o].q.w);
+            put(4, x[0].x.x, x[o].x.x); put(5, x[0].x.y, x[o].x.y); put(6, x[0].x.z, x[o].x.z);
+            put(7, v[0].ang.x, v[o].ang.x); put(8, v[0].ang.y, v[o].ang.y); put(9, v[0].ang.z, v[o].ang.z);
+            put(10, v[0].lin.x, v[o].lin.x); put(11, v[0].lin.y, v[o].lin.y); put(12, v[0].lin.z, v[o].lin.z);
+        }
+    }
 
     B200_STV(P.pos, 0, x[k].q.i); B200_STV(P.pos, 1, x[k].q.j); B200_STV(P.pos, 2, x[k].q.k); B200_STV(P.pos, 3, x[k].q.w);
     B200_STV(P.pos, 4, x[k].x.x); B200_STV(P.pos, 5, x[k].x.y); B200_STV(P.pos, 6, x[k].x.z);
@@ -442,7 +459,7 @@ static void launch_spec_shape(const StepParams &Q, cudaStream_t s)
 
 static bool planes_16B_aligned(const StepParams &Q, uint32_t sig)
 {
-    uintptr_t a = (uintptr_t)Q.pos | (uintptr_t)Q.vel | (uintptr_t)Q.ine | (uintptr_t)Q.acc | (uintptr_t)Q.frc;
+    uintptr_t a = (uintptr_t)Q.pos | (uintptr_t)Q.vel | (uintptr_t)Q.ine | (uintptr_t)Q.acc | (uintptr_t)Q.frc | (uintptr_t)Q.traj;
     if (sig & SIG_THRUST) a |= (uintptr_t)Q.spec.thrust;
     if (sig & SIG_WRENCH) a |= (uintptr_t)Q.spec.wr_t | (uintptr_t)Q.spec.wr_f;
     if (sig & SIG_DRAG) a |= (uintptr_t)Q.spec.drag;

@@ -555,7 +555,7 @@ __device__ __forceinline__ Motion force_out_fast(const Vec3 &a_lin, const Vec3 &
 template <int INTEG, bool TRAJ, bool GREG = false, uint32_t SIG = SIG_GENERIC>
 __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose &x0, Motion &v0, const Inertia &I,
                                            Motion &a_last, Motion &f_last, uint32_t n_ticks, uint64_t tick0, bool want_f,
-                                           const GravReg &greg, const EffIn &in = EffIn{})
+                                           const GravReg &greg, const EffIn &in = EffIn{}, bool store_traj = true)
 {
     constexpr bool GEN = SIG == SIG_GENERIC;
     constexpr bool NEED_INVI = GEN || (SIG & (SIG_WRENCH | SIG_WHEELS | SIG_WWORLD));
@@ -652,7 +652,7 @@ __device__ __forceinline__ void fast_ticks(const StepParams &P, uint64_t b, Pose
             x0.x = Vec3{fma(d, v0.lin.x, x0.x.x), fma(d, v0.lin.y, x0.x.y), fma(d, v0.lin.z, x0.x.z)};
             a_last.ang = aa; a_last.lin = al; q_last = qn;
         }
-        if (TRAJ && P.traj_every) { // compiled out of the launches that record nothing (the roofline case)
+        if (TRAJ && P.traj_every && store_traj) { // compiled out of the launches that record nothing (the roofline case)
             if (++traj_phase == P.traj_every) {
                 traj_phase = 0;
                 if (traj_slot < P.traj_capacity) {

@@ -324,6 +324,32 @@ def test_trajectory_ring_matches_states():
         assert ex.tick == 60
 
 
+@pytest.mark.parametrize("effectors", [False, True])
+def test_trajectory_sample_on_every_tick_of_the_body_pair_kernel(effectors):
+    """Telemetry on every tick at a batch large enough for the body-pair kernel (two bodies per thread): the pair writes
+    its (WorldPos, WorldVel) sample as one 16-byte store per plane after the tick; the odd tail body and the 25-plane
+    ring keep the per-body stores.  Every sample must equal the state a download after that tick returns."""
+    M = 2 * 128 * 3 * 148 + 3  # one full wave of pairs + an odd tail
+    pos, vel, ine = random_world(21, M, 1)
+    effs, cols = [], {}
+    if effectors:
+        effs = [el.GravityConst(), el.ThrustBody((-1.0, 0, 0), "thrust")]
+        cols = {"thrust": np.random.default_rng(2).uniform(0, 5, (M, 1, 1))}
+    for full in (False, True):
+        with el.B200Exec(1, M, 0.01, None, effs, "rk4", "fast", max_fused_ticks=1, trajectory_every=1, trajectory_capacity=3,
+                         trajectory_full=full) as ex:
+            ex.set_state(pos, vel, ine, **cols)
+            snaps = []
+            for _ in range(4):
+                ex.step(1, sync=True)
+                snaps.append(np.concatenate([ex.download(WORLD_POS), ex.download(WORLD_VEL)], -1))
+            traj = ex.trajectory()
+            assert traj.shape == (3, M, 1, 25 if full else 13)
+            for k in range(3):
+                assert np.array_equal(traj[k][..., :13], snaps[k]), (full, k)
+            assert not np.array_equal(snaps[0], snaps[1])
+
+
 @pytest.mark.parametrize("math", ["exact", "fast"])
 @pytest.mark.parametrize("case", ["effectors", "nbody", "semi_implicit"])
 def test_full_trajectory_ring_carries_accel_and_force(math, case):
