@@ -22,6 +22,13 @@ int main(void)
     d.time_step = NAN;
     d.device = -1;
     if (b200_component_id("world_pos") != B200_ID_WORLD_POS) { printf("component id mismatch\n"); return 1; }
+    {   /* host-only entry: the EGM08 term stream of a degree-1 field (3 terms x 8 f64; a_bar[0][0] = 1 leads it) */
+        const double c[4] = {1.0, 0.0, 0.25, 0.5}, s[4] = {0.0, 0.0, 0.0, 0.125};
+        double st[24];
+        if (b200_egm08_stream_len(1) != 24 || b200_egm08_stream(1, c, s, st, 24) != B200_OK || st[0] != 1.0 || st[4] != 1.0 ||
+            st[8 + 4] != 0.25 || st[16 + 4] != 0.5 || st[16 + 5] != 0.125 ||
+            b200_egm08_stream(1, c, s, st, 23) != B200_ERR_VALUE_SIZE_MISMATCH) { printf("egm08 stream: %s\n", b200_last_error()); return 1; }
+    }
     if (b200_device_count() <= 0) {
         int rc = b200_sixdof_create(&d, &h);
         if (rc != B200_ERR_NO_DEVICE || h != 0) { printf("expected B200_ERR_NO_DEVICE, got %d\n", rc); return 1; }
